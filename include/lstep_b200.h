@@ -1,0 +1,190 @@
+/*
+ * lstep_b200.h — C ABI of the B200-native (sm_100a) L-STEP positional-encoding hot path.
+ *
+ * The reference (kthrn22/L-STEP) has no FFI layer: its hot path is Python/PyTorch code
+ * (SURVEY.md §8(b)). Each entry point below names the reference code it replaces, relative to
+ * /root/reference. A host binds these with ctypes; the in-tree Python host is
+ * l-step_b200/_lib.py.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - every function enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising; nothing allocates device memory — scratch comes from a caller
+ *     owned workspace whose size lstep_workspace_bytes() reports — so a call sequence can be
+ *     captured in a CUDA graph;
+ *   - the return value is an lstep_status; functions never throw; asynchronous data errors
+ *     (an out-of-range node id) are reported through a caller supplied device flag word;
+ *   - node / edge ids cross the ABI as int64 (the reference's numpy longlong), times as
+ *     float64, PE values and neighbour times as float32, exactly as in the reference.
+ */
+#ifndef LSTEP_B200_H
+#define LSTEP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSTEP_ABI_VERSION 1
+
+typedef enum lstep_status {
+  LSTEP_OK = 0,
+  LSTEP_ERR_INVALID_ARG = 1,   /* null pointer, negative size, K <= 0 (utils/utils.py:156 assert) */
+  LSTEP_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels were built for */
+  LSTEP_ERR_WORKSPACE = 3,     /* workspace too small */
+  LSTEP_ERR_CUDA = 4,          /* a CUDA runtime call failed; see lstep_last_cuda_error() */
+  LSTEP_ERR_ID_RANGE = 5       /* id does not fit the int32 device encoding */
+} lstep_status;
+
+/* bits set in the device `err_flag` word by kernels */
+#define LSTEP_FLAG_NODE_OUT_OF_RANGE 1u /* utils/utils.py:140 would raise IndexError */
+#define LSTEP_FLAG_UNSORTED_STREAM 2u
+
+const char* lstep_strerror(int status);
+const char* lstep_last_cuda_error(void);
+int lstep_abi_version(void);
+/* 1 when a CUDA device of compute capability 10.x is current; the library has no other path */
+int lstep_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------
+ * a1 — time-sorted CSR of the undirected temporal adjacency.
+ * Replaces get_neighbor_sampler + NeighborSampler.__init__ (utils/utils.py:282-301, 72-109):
+ * entry order per node = stable sort by time of the insertion order (edge order, source side
+ * before destination side).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lstep_csr {
+  const int64_t* indptr; /* [num_rows + 1] */
+  const int32_t* nbr;    /* [nnz] neighbour node id */
+  const int32_t* eid;    /* [nnz] edge id */
+  const double* t;       /* [nnz] interaction time, ascending within a row */
+  int64_t num_rows;      /* max node id + 1 (row 0 = padding node, empty) */
+  int64_t nnz;
+} lstep_csr;
+
+/* Bytes of scratch lstep_csr_build_* needs for `n_entries` adjacency entries. */
+size_t lstep_csr_build_workspace_bytes(int64_t n_entries, int64_t num_rows);
+
+/* Edge stream (src,dst,eid,t)[E] -> CSR with 2E entries. Outputs are caller allocated:
+ * indptr[num_rows+1], nbr/eid[2E], t[2E]. */
+int lstep_csr_build_from_edges(const int64_t* src, const int64_t* dst, const int64_t* eid, const double* t,
+                               int64_t num_edges, int64_t num_rows, int64_t* out_indptr, int32_t* out_nbr,
+                               int32_t* out_eid, double* out_t, void* workspace, size_t workspace_bytes,
+                               uint32_t* err_flag, void* stream);
+
+/* Flattened adjacency lists (owner node, neighbour, edge id, time)[n] in list order -> CSR
+ * (the NeighborSampler(adj_list=...) constructor form). */
+int lstep_csr_build_from_entries(const int64_t* owner, const int64_t* nbr, const int64_t* eid, const double* t,
+                                 int64_t n_entries, int64_t num_rows, int64_t* out_indptr, int32_t* out_nbr,
+                                 int32_t* out_eid, double* out_t, void* workspace, size_t workspace_bytes,
+                                 uint32_t* err_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a2 — most-recent-K temporal neighbour lookup (kernel K1).
+ * Replaces NeighborSampler.get_historical_neighbors, 'recent' strategy, and
+ * find_neighbors_before (utils/utils.py:129-146, 148-213). Row i < n_valid: c = #entries of
+ * q_node[i] with t < q_time[i] (strict, fp64), the last min(K,c) are written right-aligned into
+ * columns [K-len, K), the rest are 0. Rows n_valid <= i < n_rows are all zero (the reference's
+ * zip() truncation). Outputs [n_rows, K]; out_eid may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+int lstep_sample_recent(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows,
+                        int64_t n_valid, int K, int64_t* out_nbr, int64_t* out_eid, float* out_t,
+                        uint32_t* err_flag, void* stream);
+
+/* Device-internal compact form consumed by the aggregation kernels: int32 ids, no edge ids. */
+int lstep_sample_recent_compact(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows,
+                                int64_t n_valid, int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag,
+                                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a3 — learnable DFT filter over each node's PE history (kernel K3).
+ * Replaces LSTEP.fourier_transform_pe (models/LSTEP.py:104-137). FFT -> mask -> complex filter
+ * -> mask -> iFFT -> mask -> real -> Linear(T->1) is linear in the history, so it collapses to
+ *     out[n,c] = sum_{s < Th} G[s,c] * hist[ids[n], s, c]
+ * with a real table G[T,d] that depends on the parameters and on min(batch_idx, T) only.
+ * lstep_dft_collapse computes G (fp64 accumulation) from fft_filter.weight (complex64 [T,d],
+ * interleaved re/im) and fft_agg.weight ([T]); `b` is the mask length (T when unmasked).
+ * History element (node v, step s, column c) lives at
+ *     hist[v*node_stride + ((s0 + s) % ring) * time_stride + c]
+ * (reference layout [V1,Th,d]: node_stride=Th*d, time_stride=d, s0=0, ring=Th).
+ * ------------------------------------------------------------------------------------------ */
+int lstep_dft_collapse(const float* fft_filter_weight_c64, const float* fft_agg_weight, int T, int d, int b, float* G,
+                       void* stream);
+int lstep_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
+                     const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride, void* stream);
+/* dG[s,c] = sum_n hist[ids[n],s,c] * dout[n,c]  (s < Th; rows Th..T-1 of dG are left untouched) */
+int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
+                         const int64_t* ids, int64_t n_ids, const float* dout, float* dG, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * PE MLP parameters, packed for the kernels: every Linear weight transposed to [in][ldo]
+ * (ldo = lstep_packed_ld(d)), biases padded to ldo. lstep_pack_linear does one layer.
+ * ------------------------------------------------------------------------------------------ */
+int lstep_packed_ld(int out_features);
+int lstep_pack_linear(const float* weight /* [out,in] row major (torch) */, const float* bias /* [out] or NULL */,
+                      int out_features, int in_features, float* packed_w /* [in][ldo] */, float* packed_b /* [ldo] */,
+                      void* stream);
+
+typedef struct lstep_pe_mlp {
+  const float* w1; /* packed [d+t][ldo]  pe_mlp_1 / pe_neighbor_mlp_1 */
+  const float* b1;
+  const float* w2; /* packed [d][ldo]    pe_mlp_2 / pe_neighbor_mlp_2 */
+  const float* b2;
+  const float* ws; /* packed [d][ldo]    self_update_pe / self_update_neighbor_pe; NULL = no self term */
+  const float* bs;
+  const float* tw; /* [t] TimeEncoder frequencies (models/modules.py:20), fp32 */
+  int d;
+  int t;
+} lstep_pe_mlp;
+
+/* ------------------------------------------------------------------------------------------
+ * a6 — neighbourhood PE aggregate (kernel K2, gather side) + MLP.
+ * Replaces LSTEP.compute_neighborhood_pe (models/LSTEP.py:222-249) after the sampler call:
+ *   S[i] = sum_k [ pe[nbr[i,k]] || mask_k * cos(fp32(q_time[i] - nbr_t[i,k]) * tw) ]
+ *   out[i] = pe[q_node[i]] + tanh(Ws pe[q_node[i]] + bs + W2 relu(W1 S[i] + b1) + b2)
+ * lstep_nbr_aggregate writes S only (training path: the MLP then runs under autograd);
+ * lstep_nbr_aggregate_bwd scatters dS[:, :d] back into dpe (dpe[nbr[i,k]] += dS[i,:d]).
+ * ------------------------------------------------------------------------------------------ */
+int lstep_nbr_aggregate(const float* pe, int64_t pe_rows, const double* q_time, const int32_t* nbr,
+                        const float* nbr_t, int64_t n_rows, int K, const float* tw, int d, int t, float* S,
+                        void* stream);
+int lstep_nbr_aggregate_bwd(const float* dS, const int32_t* nbr, int64_t n_rows, int K, int d, int t, float* dpe,
+                            int64_t pe_rows, void* stream);
+int lstep_neighborhood_pe(const float* pe, int64_t pe_rows, const int64_t* q_node, const double* q_time,
+                          const int32_t* nbr, const float* nbr_t, int64_t n_rows, int K, const lstep_pe_mlp* mlp,
+                          float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* out[i] = base[i] + tanh(Ws base[i] + bs + W2 relu(W1 A[i] + b1) + b2) for n_rows rows of A [n, d+t];
+ * base[i] = pe[base_ids[i]]; result row i is written to out + i*out_stride, or, when out is NULL,
+ * back into pe[base_ids[i]] (in place). Exposed for tests. */
+int lstep_pe_mlp_apply(const float* A, const float* pe, const int64_t* base_ids, int64_t n_rows,
+                       const lstep_pe_mlp* mlp, float* out, int64_t out_stride, float* pe_inplace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7 + a8 — PE update with ordered write-back (kernels K2 scatter side + K4).
+ * Replaces LSTEP.update_pe (models/LSTEP.py:268-341), including its sampler call, on the
+ * caller's pe[pe_rows, d] table, in place:
+ *   phase A  every batch node gets the sum over its batch edges of [pe[other endpoint] || tf]
+ *            (source-side contributions first, then destination-side, edge order) -> MLP with
+ *            self term -> pe[ids] written;
+ *   pe[0] = 0;
+ *   phase B  most-recent-K lookup for (ids[i], times[i]), i < min(n_ids, n_edges) (Q1/Q1b);
+ *            every sampled neighbour u accumulates [pe[ids[i]] || tf] from the phase-A table;
+ *            all gathers complete before any row is written; MLP without self term (Q3);
+ *            pe[u] written for every distinct u, including u = 0 when any slot was padding.
+ * current_time is rounded to fp32 first (torch.Tensor([current_time]), Q4).
+ * ------------------------------------------------------------------------------------------ */
+size_t lstep_update_pe_workspace_bytes(int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows);
+int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids,
+                    const int64_t* src, const int64_t* dst, const double* times, int64_t n_edges,
+                    double current_time, int K, const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes,
+                    uint32_t* err_flag, void* stream);
+/* The update keeps a per-node int32 scratch map inside the workspace that must be zero on
+ * entry and is zero again on exit; call once after allocating the workspace. */
+int lstep_update_pe_workspace_init(void* workspace, size_t workspace_bytes, int64_t pe_rows, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSTEP_B200_H */

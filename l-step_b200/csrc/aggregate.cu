@@ -1,0 +1,148 @@
+// K2 (gather side) — neighbourhood PE aggregate of LSTEP.compute_neighborhood_pe
+// (/root/reference/models/LSTEP.py:228-238):
+//   S[i] = sum_k [ pe[nbr[i,k]] || (nbr[i,k] != 0) * cos(fp32(q_time[i] - nbr_t[i,k]) * w) ]
+// One CTA per query row, two warp-aligned roles working concurrently: `t` threads own one time
+// frequency each (K accurate cosines, never materialising the [K, d+t] concatenation), d/4
+// threads own one 128-bit column group of the PE row and add the K gathered rows in order
+// k = 0..K-1 (the PE table is L2 resident: 7.6 MB at Reddit size). Padded slots (id 0) read
+// pe[0] like any other row — it is non-zero after an update.
+#include "common.cuh"
+
+namespace lstep {
+
+template <int VEC>
+__global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restrict__ pe,
+                                                            const double* __restrict__ q_time,
+                                                            const int32_t* __restrict__ nbr,
+                                                            const float* __restrict__ nbr_t, int64_t n_rows, int K,
+                                                            const float* __restrict__ tw, int d, int t, int t_pad,
+                                                            float* __restrict__ S) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);
+  float* s_dt = reinterpret_cast<float*>(s_nbr + K);
+  const int tid = threadIdx.x;
+  const int dvec = d / VEC;
+  const int in1 = d + t;
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    const double tq = q_time[row];
+    for (int k = tid; k < K; k += blockDim.x) {
+      s_nbr[k] = nbr[row * K + k];
+      // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
+      s_dt[k] = (float)(tq - (double)nbr_t[row * K + k]);
+    }
+    __syncthreads();
+    if (tid < t) {
+      const float w = tw[tid];
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k)
+        if (s_nbr[k] != 0) acc += time_feature(s_dt[k], w);
+      S[row * in1 + d + tid] = acc;
+    } else if (tid >= t_pad && tid - t_pad < dvec) {
+      const int cv = tid - t_pad;
+      if (VEC == 4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = 0;
+        for (; k + 4 <= K; k += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            v[u] = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k + u] * d) + cv);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc.x += v[u].x;
+            acc.y += v[u].y;
+            acc.z += v[u].z;
+            acc.w += v[u].w;
+          }
+        }
+        for (; k < K; ++k) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k] * d) + cv);
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(S + row * in1)[cv] = acc;
+      } else {
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc += __ldg(pe + (int64_t)s_nbr[k] * d + cv);
+        S[row * in1 + cv] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// dpe[nbr[i,k], :] += dS[i, :d]   (training only; fp32 atomics)
+__global__ void __launch_bounds__(256) nbr_aggregate_bwd_kernel(const float* __restrict__ dS,
+                                                                const int32_t* __restrict__ nbr, int64_t n_rows, int K,
+                                                                int d, int t, float* __restrict__ dpe) {
+  const int in1 = d + t;
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      const float g = dS[row * in1 + c];
+      for (int k = 0; k < K; ++k) atomicAdd(dpe + (int64_t)nbr[row * K + k] * d + c, g);
+    }
+  }
+}
+
+int launch_pe_mlp(const float* A, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
+                  const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
+                  cudaStream_t st);
+
+static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* nbr, const float* nbr_t,
+                         int64_t n_rows, int K, const float* tw, int d, int t, float* S, cudaStream_t st) {
+  const bool v4 = d % 4 == 0 && aligned16(pe) && aligned16(S);
+  const int dvec = v4 ? d / 4 : d;
+  const int t_pad = (int)align_up((size_t)t, 32);
+  const int threads = (int)align_up((size_t)t_pad + dvec, 32);
+  if (threads > 512) return LSTEP_ERR_UNSUPPORTED;
+  const size_t smem = (size_t)K * 8;
+  if (smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
+  const int64_t grid = n_rows < (int64_t)kNumSMs * 16 ? n_rows : (int64_t)kNumSMs * 16;
+  if (v4)
+    nbr_aggregate_kernel<4><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S);
+  else
+    nbr_aggregate_kernel<1><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S);
+  return check_launch("nbr_aggregate");
+}
+
+}  // namespace lstep
+
+using namespace lstep;
+
+extern "C" int lstep_nbr_aggregate(const float* pe, int64_t pe_rows, const double* q_time, const int32_t* nbr,
+                                   const float* nbr_t, int64_t n_rows, int K, const float* tw, int d, int t, float* S,
+                                   void* stream) {
+  if (n_rows < 0 || K <= 0 || d <= 0 || t < 0 || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
+  if (n_rows == 0) return LSTEP_OK;
+  if (!pe || !q_time || !nbr || !nbr_t || !S || (t > 0 && !tw)) return LSTEP_ERR_INVALID_ARG;
+  return launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, S, as_stream(stream));
+}
+
+extern "C" int lstep_nbr_aggregate_bwd(const float* dS, const int32_t* nbr, int64_t n_rows, int K, int d, int t,
+                                       float* dpe, int64_t pe_rows, void* stream) {
+  if (n_rows < 0 || K <= 0 || d <= 0 || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
+  if (n_rows == 0) return LSTEP_OK;
+  if (!dS || !nbr || !dpe) return LSTEP_ERR_INVALID_ARG;
+  const int64_t grid = n_rows < (int64_t)kNumSMs * 8 ? n_rows : (int64_t)kNumSMs * 8;
+  nbr_aggregate_bwd_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(dS, nbr, n_rows, K, d, t, dpe);
+  return check_launch("nbr_aggregate_bwd");
+}
+
+extern "C" int lstep_neighborhood_pe(const float* pe, int64_t pe_rows, const int64_t* q_node, const double* q_time,
+                                     const int32_t* nbr, const float* nbr_t, int64_t n_rows, int K,
+                                     const lstep_pe_mlp* mlp, float* out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+  if (n_rows < 0 || K <= 0 || !mlp || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
+  if (n_rows == 0) return LSTEP_OK;
+  if (!pe || !q_node || !q_time || !nbr || !nbr_t || !out || !workspace) return LSTEP_ERR_INVALID_ARG;
+  const size_t need = (size_t)n_rows * (mlp->d + mlp->t) * sizeof(float);
+  if (workspace_bytes < need) return LSTEP_ERR_WORKSPACE;
+  float* S = reinterpret_cast<float*>(workspace);
+  int rc = launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, mlp->tw, mlp->d, mlp->t, S, as_stream(stream));
+  if (rc != LSTEP_OK) return rc;
+  return launch_pe_mlp(S, pe, q_node, n_rows, n_rows, nullptr, mlp, out, mlp->d, nullptr, as_stream(stream));
+}

@@ -1,0 +1,48 @@
+// Shared device/host helpers for the lstep_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lstep_b200.h"
+
+namespace lstep {
+
+constexpr int kWarp = 32;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+// last CUDA error text, for lstep_last_cuda_error()
+void set_cuda_error(cudaError_t e, const char* where);
+int check_launch(const char* where);
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// streaming 128-bit load that does not pollute L1 (history rows are read once)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_stream_f(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// TimeEncoder (models/modules.py:37): cos(fp32(dt) * w_j + 0). The product must be a separately
+// rounded fp32 multiply (no FMA contraction into the range reduction), cosf is the accurate
+// library version (arguments reach 1e8 rad).
+__device__ __forceinline__ float time_feature(float dt, float w) { return cosf(__fmul_rn(dt, w)); }
+
+}  // namespace lstep

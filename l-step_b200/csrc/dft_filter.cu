@@ -1,0 +1,250 @@
+// K3 — learnable DFT filter over each node's PE history.
+// Replaces LSTEP.fourier_transform_pe (/root/reference/models/LSTEP.py:104-137).
+//
+// The reference computes, per batch node n and PE column c,
+//   X = FFT_t(x[n,:,c]);  X *= m;  X *= W[:,c];  X *= m;  y = iFFT(X);  y *= m;
+//   out[n,c] = sum_t a[t] * Re(y[t])
+// with x zero-padded to T steps and m[j] = 1 for j < b (b = batch_idx when the history is
+// shorter than T, else no mask). Every step is linear in x, so
+//   out[n,c] = sum_s G[s,c] * x[n,s,c],
+//   G[s,c]   = (1/T) * sum_{f<b} Re( W[f,c] * A[f] * exp(-2*pi*i*f*s/T) ),
+//   A[f]     = sum_{t<b} a[t] * exp(+2*pi*i*f*t/T).
+// lstep_dft_collapse builds G in fp64 (phase reduced as an integer mod T, so the twiddles are
+// exact to fp64 rounding); lstep_dft_filter is then a pure streaming reduction: 2 flop per 4
+// bytes of history, bound by HBM bandwidth. It reads each node's history once with 128-bit
+// loads that bypass L1, keeps G in L1/L2 (68.8 KB at T=100, d=172), and reduces the per-thread
+// partial sums over time through shared memory in a fixed order (deterministic).
+#include "common.cuh"
+
+namespace lstep {
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dft_collapse_kernel(const float2* __restrict__ W, const float* __restrict__ a,
+                                                           int T, int d, int b, float* __restrict__ G) {
+  extern __shared__ double sm[];
+  double* tw_c = sm;           // [T] cos(2*pi*m/T)
+  double* tw_s = sm + T;       // [T] sin(2*pi*m/T)
+  double* A_re = sm + 2 * T;   // [T]
+  double* A_im = sm + 3 * T;   // [T]
+  for (int m = threadIdx.x; m < T; m += blockDim.x) {
+    double s, c;
+    sincospi(2.0 * (double)m / (double)T, &s, &c);
+    tw_c[m] = c;
+    tw_s[m] = s;
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < T; f += blockDim.x) {
+    double re = 0.0, im = 0.0;
+    if (f < b) {
+      for (int t = 0; t < b; ++t) {
+        const int m = (int)(((long long)f * t) % T);
+        const double at = (double)a[t];
+        re += at * tw_c[m];
+        im += at * tw_s[m];
+      }
+    }
+    A_re[f] = re;
+    A_im[f] = im;
+  }
+  __syncthreads();
+  const double invT = 1.0 / (double)T;
+  for (int s = blockIdx.x; s < T; s += gridDim.x) {
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      double acc = 0.0;
+      for (int f = 0; f < b; ++f) {
+        const float2 w = W[(size_t)f * d + c];
+        const double br = (double)w.x * A_re[f] - (double)w.y * A_im[f];
+        const double bi = (double)w.x * A_im[f] + (double)w.y * A_re[f];
+        const int m = (int)(((long long)f * s) % T);
+        acc += br * tw_c[m] + bi * tw_s[m];  // Re( B * exp(-i*theta) )
+      }
+      G[(size_t)s * d + c] = (float)(acc * invT);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int VEC>
+struct VecT;
+template <>
+struct VecT<4> {
+  using type = float4;
+};
+template <>
+struct VecT<1> {
+  using type = float;
+};
+
+__device__ __forceinline__ void fma_acc(float4& acc, const float4& g, const float4& x) {
+  acc.x = fmaf(g.x, x.x, acc.x);
+  acc.y = fmaf(g.y, x.y, acc.y);
+  acc.z = fmaf(g.z, x.z, acc.z);
+  acc.w = fmaf(g.w, x.w, acc.w);
+}
+__device__ __forceinline__ void fma_acc(float& acc, const float& g, const float& x) { acc = fmaf(g, x, acc); }
+__device__ __forceinline__ void add_acc(float4& a, const float4& b) {
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+  a.w += b.w;
+}
+__device__ __forceinline__ void add_acc(float& a, const float& b) { a += b; }
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return ld_stream_f4(p); }
+__device__ __forceinline__ float ld_stream(const float* p) { return ld_stream_f(p); }
+template <typename V>
+__device__ __forceinline__ V vzero();
+template <>
+__device__ __forceinline__ float4 vzero<float4>() {
+  return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <>
+__device__ __forceinline__ float vzero<float>() {
+  return 0.f;
+}
+
+constexpr int kDftThreads = 256;
+
+// threads = groups x dvec; thread (g, cv) owns vector column cv and history steps s = g, g+groups, ...
+template <int VEC>
+__global__ void __launch_bounds__(kDftThreads) dft_filter_kernel(const float* __restrict__ hist, int64_t node_stride,
+                                                                 int64_t time_stride, int s0, int ring, int Th, int d,
+                                                                 const int64_t* __restrict__ ids, int64_t n_ids,
+                                                                 const float* __restrict__ G, float* __restrict__ out,
+                                                                 int64_t out_stride) {
+  using V = typename VecT<VEC>::type;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V* red = reinterpret_cast<V*>(smem_raw);  // [groups][dvec]
+  const int dvec = d / VEC;
+  const int groups = kDftThreads / dvec;
+  const int g = threadIdx.x / dvec, cv = threadIdx.x % dvec;
+  const bool active = g < groups;
+  const V* Gv = reinterpret_cast<const V*>(G);
+  for (int64_t n = blockIdx.x; n < n_ids; n += gridDim.x) {
+    const float* base = hist + ids[n] * node_stride;
+    V acc = vzero<V>();
+    if (active) {
+      int s = g;
+      // 4 independent loads in flight per thread
+      for (; s + 3 * groups < Th; s += 4 * groups) {
+        V x[4], w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int ss = s + u * groups;
+          int ps = s0 + ss;
+          if (ps >= ring) ps -= ring;
+          x[u] = ld_stream(reinterpret_cast<const V*>(base + (int64_t)ps * time_stride) + cv);
+          w[u] = __ldg(Gv + (size_t)ss * dvec + cv);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) fma_acc(acc, w[u], x[u]);
+      }
+      for (; s < Th; s += groups) {
+        int ps = s0 + s;
+        if (ps >= ring) ps -= ring;
+        const V x = ld_stream(reinterpret_cast<const V*>(base + (int64_t)ps * time_stride) + cv);
+        const V w = __ldg(Gv + (size_t)s * dvec + cv);
+        fma_acc(acc, w, x);
+      }
+      red[g * dvec + cv] = acc;
+    }
+    __syncthreads();
+    if (active && g == 0) {
+      V tot = red[cv];
+      for (int gg = 1; gg < groups; ++gg) add_acc(tot, red[gg * dvec + cv]);
+      reinterpret_cast<V*>(out + n * out_stride)[cv] = tot;
+    }
+    __syncthreads();
+  }
+}
+
+// dG[s,c] += sum_{n in slice} x[n,s,c] * dout[n,c]; grid = (time groups, node slices)
+template <int VEC>
+__global__ void __launch_bounds__(kDftThreads) dft_filter_bwd_kernel(const float* __restrict__ hist,
+                                                                     int64_t node_stride, int64_t time_stride, int s0,
+                                                                     int ring, int Th, int d,
+                                                                     const int64_t* __restrict__ ids, int64_t n_ids,
+                                                                     const float* __restrict__ dout,
+                                                                     float* __restrict__ dG) {
+  using V = typename VecT<VEC>::type;
+  const int dvec = d / VEC;
+  const int groups = kDftThreads / dvec;
+  const int g = threadIdx.x / dvec, cv = threadIdx.x % dvec;
+  if (g >= groups) return;
+  const int s = blockIdx.x * groups + g;
+  if (s >= Th) return;
+  int ps = s0 + s;
+  if (ps >= ring) ps -= ring;
+  V acc = vzero<V>();
+  for (int64_t n = blockIdx.y; n < n_ids; n += gridDim.y) {
+    const V x = ld_stream(reinterpret_cast<const V*>(hist + ids[n] * node_stride + (int64_t)ps * time_stride) + cv);
+    const V go = __ldg(reinterpret_cast<const V*>(dout + n * (int64_t)d) + cv);
+    fma_acc(acc, go, x);
+  }
+  float* dst = dG + (size_t)s * d + (size_t)cv * VEC;
+  const float* a = reinterpret_cast<const float*>(&acc);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) atomicAdd(dst + i, a[i]);
+}
+
+static bool vec4_ok(const void* p, int64_t a, int64_t b, int d) {
+  return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && a % 4 == 0 && b % 4 == 0 && d % 4 == 0;
+}
+
+}  // namespace lstep
+
+using namespace lstep;
+
+extern "C" int lstep_dft_collapse(const float* W_c64, const float* a, int T, int d, int b, float* G, void* stream) {
+  if (!W_c64 || !a || !G || T <= 0 || d <= 0) return LSTEP_ERR_INVALID_ARG;
+  if (b < 0) b = 0;
+  if (b > T) b = T;
+  const size_t smem = sizeof(double) * 4 * (size_t)T;
+  if (smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
+  dft_collapse_kernel<<<T < kNumSMs ? T : kNumSMs, 256, smem, as_stream(stream)>>>(
+      reinterpret_cast<const float2*>(W_c64), a, T, d, b, G);
+  return check_launch("dft_collapse");
+}
+
+extern "C" int lstep_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th,
+                                int d, const int64_t* ids, int64_t n_ids, const float* G, float* out,
+                                int64_t out_stride, void* stream) {
+  if (n_ids < 0 || Th < 0 || d <= 0 || ring < Th || s0 < 0 || (ring > 0 && s0 >= ring)) return LSTEP_ERR_INVALID_ARG;
+  if (n_ids == 0) return LSTEP_OK;
+  if (!ids || !out || !G || (Th > 0 && !hist)) return LSTEP_ERR_INVALID_ARG;
+  const bool v4 = vec4_ok(hist, node_stride, time_stride, d) && vec4_ok(G, 0, 0, d) && vec4_ok(out, out_stride, 0, d);
+  const int dvec = v4 ? d / 4 : d;
+  if (dvec > kDftThreads) return LSTEP_ERR_UNSUPPORTED;
+  const int groups = kDftThreads / dvec;
+  const size_t smem = (size_t)groups * dvec * (v4 ? 16 : 4);
+  const int64_t grid = n_ids < (int64_t)kNumSMs * 6 ? n_ids : (int64_t)kNumSMs * 6;
+  if (v4)
+    dft_filter_kernel<4><<<(unsigned)grid, kDftThreads, smem, as_stream(stream)>>>(
+        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride);
+  else
+    dft_filter_kernel<1><<<(unsigned)grid, kDftThreads, smem, as_stream(stream)>>>(
+        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride);
+  return check_launch("dft_filter");
+}
+
+extern "C" int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring,
+                                    int Th, int d, const int64_t* ids, int64_t n_ids, const float* dout, float* dG,
+                                    void* stream) {
+  if (n_ids < 0 || Th < 0 || d <= 0 || ring < Th || s0 < 0) return LSTEP_ERR_INVALID_ARG;
+  if (n_ids == 0 || Th == 0) return LSTEP_OK;
+  if (!hist || !ids || !dout || !dG) return LSTEP_ERR_INVALID_ARG;
+  const bool v4 = vec4_ok(hist, node_stride, time_stride, d) && vec4_ok(dout, 0, 0, d);
+  const int dvec = v4 ? d / 4 : d;
+  if (dvec > kDftThreads) return LSTEP_ERR_UNSUPPORTED;
+  const int groups = kDftThreads / dvec;
+  int64_t slices = ceil_div((int64_t)kNumSMs * 4, ceil_div(Th, groups));
+  if (slices > n_ids) slices = n_ids;
+  if (slices < 1) slices = 1;
+  dim3 grid((unsigned)ceil_div(Th, groups), (unsigned)slices);
+  if (v4)
+    dft_filter_bwd_kernel<4><<<grid, kDftThreads, 0, as_stream(stream)>>>(hist, node_stride, time_stride, s0, ring, Th,
+                                                                          d, ids, n_ids, dout, dG);
+  else
+    dft_filter_bwd_kernel<1><<<grid, kDftThreads, 0, as_stream(stream)>>>(hist, node_stride, time_stride, s0, ring, Th,
+                                                                          d, ids, n_ids, dout, dG);
+  return check_launch("dft_filter_bwd");
+}

@@ -1,0 +1,484 @@
+// K2 (scatter side) + K4 — LSTEP.update_pe (/root/reference/models/LSTEP.py:268-341) on the
+// caller's PE table, in place, with the event order of the reference:
+//
+//   phase A   agg[v] = sum over batch edges of [pe[other endpoint] || tf]   (old table)
+//             pe[ids] <- pe[ids] + tanh(self(pe[ids]) + mlp(agg[ids]))
+//   pe[0] = 0
+//   phase B   sample most-recent-K neighbours of (ids[i], times[i]);
+//             agg2[u] = sum over slots (i,k) with nbr[i,k]==u of [pe[ids[i]] || tf]  (phase-A table)
+//             pe[U] <- pe[U] + tanh(mlp(agg2[U])),  U = distinct sampled ids (0 included if padded)
+//
+// The reference scatters into two zeroed [V1, d+t] buffers (10.9 GB at 10 M nodes). Here both
+// phases are pull-based segmented reductions over batch-local indices, so no V1-sized float
+// buffer exists and every destination row is reduced in a fixed order without float atomics:
+//   * phase A: one CTA per batch node scans the 2B endpoint ids (int32, L2 resident), compacts
+//     its matches in edge order (source side first, as the two scatter calls do) and adds the
+//     rows in exactly the reference's order;
+//   * phase B: an inverse index (destination -> slots) is built with integer atomics on a
+//     per-node counter map (count / scan / fill), one warp per destination sorts its slot list
+//     (<= 32 entries: ascending flat index = the reference's add order) and reduces it. The
+//     padding row 0 collects every empty slot — thousands of contributions at B=200 — so it is
+//     reduced by a two-level tree (z_i * pe[ids[i]] per row, then over rows) instead of a
+//     serial chain.
+// All gathers of a phase finish (kernel boundary) before its rows are written, which is what
+// makes the in-place write-back safe for nodes that are both source and destination (Q6).
+#include "common.cuh"
+
+namespace lstep {
+
+int launch_pe_mlp(const float* A, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
+                  const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
+                  cudaStream_t st);
+
+constexpr int kRow0Parts = 64;
+
+struct UpdateWs {
+  int32_t* cnt_of;   // [pe_rows]  zero between calls
+  int32_t* slot_of;  // [pe_rows]
+  int32_t* counters; // [8]: 0=M, 1=has_zero, 2=n_dest
+  int32_t* src32;    // [E]
+  int32_t* dst32;    // [E]
+  float* dtA;        // [E]
+  int32_t* nbrB;     // [N*K]
+  float* ntB;        // [N*K]
+  int32_t* rank;     // [N*K]
+  int32_t* list;     // [N*K]
+  int64_t* U;        // [N*K+1]
+  int32_t* off;      // [N*K+2]
+  float* row0_part;  // [kRow0Parts*d]
+  float* A;          // [max(N, N*K+1)*(d+t)]
+  size_t bytes;
+};
+
+static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows) {
+  UpdateWs w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + o : nullptr;
+    o = align_up(o + bytes, 256);
+    return p;
+  };
+  const size_t nk = (size_t)n_ids * K;
+  w.cnt_of = (int32_t*)take(sizeof(int32_t) * pe_rows);
+  w.slot_of = (int32_t*)take(sizeof(int32_t) * pe_rows);
+  w.counters = (int32_t*)take(sizeof(int32_t) * 8);
+  w.src32 = (int32_t*)take(sizeof(int32_t) * (n_edges + 4));
+  w.dst32 = (int32_t*)take(sizeof(int32_t) * (n_edges + 4));
+  w.dtA = (float*)take(sizeof(float) * (n_edges + 4));
+  w.nbrB = (int32_t*)take(sizeof(int32_t) * nk);
+  w.ntB = (float*)take(sizeof(float) * nk);
+  w.rank = (int32_t*)take(sizeof(int32_t) * nk);
+  w.list = (int32_t*)take(sizeof(int32_t) * nk);
+  w.U = (int64_t*)take(sizeof(int64_t) * (nk + 1));
+  w.off = (int32_t*)take(sizeof(int32_t) * (nk + 2));
+  w.row0_part = (float*)take(sizeof(float) * kRow0Parts * d);
+  const size_t rowsA = nk + 1 > (size_t)n_ids ? nk + 1 : (size_t)n_ids;
+  w.A = (float*)take(sizeof(float) * rowsA * (d + t));
+  w.bytes = o;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// int64 endpoints -> int32, per-edge fp32 time delta of phase A, counters reset
+__global__ void prep_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                  const double* __restrict__ times, int64_t n_edges, float tc, int64_t pe_rows,
+                                  int32_t* __restrict__ src32, int32_t* __restrict__ dst32, float* __restrict__ dtA,
+                                  int32_t* __restrict__ counters, uint32_t* err_flag) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (blockIdx.x == 0 && threadIdx.x < 8) counters[threadIdx.x] = 0;
+  if (e >= n_edges) return;
+  int64_t s = src[e], dd = dst[e];
+  if (s < 0 || s >= pe_rows || dd < 0 || dd >= pe_rows) {
+    if (err_flag) atomicOr(err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
+    s = 0;
+    dd = 0;
+  }
+  src32[e] = (int32_t)s;
+  dst32[e] = (int32_t)dd;
+  // torch.Tensor([current_time]) is fp32; fp32 - fp64 promotes to fp64; then .float()  (LSTEP.py:277, Q4)
+  dtA[e] = (float)((double)tc - times[e]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase A: one CTA per batch node. Threads [0,t): time frequencies; [t_pad, t_pad+d/4): PE columns.
+constexpr int kSegPerThread = 4;
+
+__global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __restrict__ pe,
+                                                             const int64_t* __restrict__ ids, int64_t n_ids,
+                                                             const int32_t* __restrict__ src32,
+                                                             const int32_t* __restrict__ dst32,
+                                                             const float* __restrict__ dtA, int64_t n_edges,
+                                                             const float* __restrict__ tw, int d, int t, int t_pad,
+                                                             float* __restrict__ A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nthr = blockDim.x;
+  const int seg = nthr * kSegPerThread;
+  int32_t* s_other = reinterpret_cast<int32_t*>(smem_raw);  // [seg]
+  float* s_dt = reinterpret_cast<float*>(s_other + seg);    // [seg]
+  int32_t* s_warp = reinterpret_cast<int32_t*>(s_dt + seg); // [32] warp totals
+  __shared__ int s_total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int dvec = d / 4;
+  const int in1 = d + t;
+  const bool is_tf = tid < t;
+  const bool is_pe = tid >= t_pad && tid - t_pad < dvec;
+  const int cv = tid - t_pad;
+
+  for (int64_t n = blockIdx.x; n < n_ids; n += gridDim.x) {
+    const int32_t node = (int32_t)ids[n];
+    float acc_tf = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float w = is_tf ? tw[tid] : 0.f;
+    for (int side = 0; side < 2; ++side) {
+      const int32_t* match = side == 0 ? src32 : dst32;  // scatter #1 indexes by src (LSTEP.py:283-286), #2 by dst
+      const int32_t* other = side == 0 ? dst32 : src32;
+      for (int64_t lo = 0; lo < n_edges; lo += seg) {
+        // ordered compaction of the matches in [lo, lo+seg)
+        const int64_t e0 = lo + (int64_t)tid * kSegPerThread;
+        int32_t mv[kSegPerThread];
+        int cnt = 0;
+#pragma unroll
+        for (int u = 0; u < kSegPerThread; ++u) {
+          mv[u] = (e0 + u < n_edges) ? match[e0 + u] : -1;
+          cnt += (mv[u] == node);
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(kFull, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_warp[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+          const int nw = nthr >> 5;
+          int v = lane < nw ? s_warp[lane] : 0;
+          int iv = v;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int x = __shfl_up_sync(kFull, iv, o);
+            if (lane >= o) iv += x;
+          }
+          if (lane < nw) s_warp[lane] = iv - v;  // exclusive
+          if (lane == 31) s_total = iv;
+        }
+        __syncthreads();
+        int pos = s_warp[wid] + incl - cnt;
+#pragma unroll
+        for (int u = 0; u < kSegPerThread; ++u) {
+          if (mv[u] == node) {
+            s_other[pos] = other[e0 + u];
+            s_dt[pos] = dtA[e0 + u];
+            ++pos;
+          }
+        }
+        __syncthreads();
+        const int total = s_total;
+        if (is_tf) {
+          for (int j = 0; j < total; ++j) acc_tf += time_feature(s_dt[j], w);
+        } else if (is_pe) {
+          int j = 0;
+          for (; j + 4 <= total; j += 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)s_other[j + u] * d) + cv);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              acc.x += v[u].x;
+              acc.y += v[u].y;
+              acc.z += v[u].z;
+              acc.w += v[u].w;
+            }
+          }
+          for (; j < total; ++j) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)s_other[j] * d) + cv);
+            acc.x += v.x;
+            acc.y += v.y;
+            acc.z += v.z;
+            acc.w += v.w;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    if (is_tf) A[n * in1 + d + tid] = acc_tf;
+    if (is_pe) reinterpret_cast<float4*>(A + n * in1)[cv] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// phase B index, step 1: per-destination counts, arrival ranks, distinct list; also pe[0] = 0
+__global__ void __launch_bounds__(256) phaseB_count_kernel(const int32_t* __restrict__ nbrB, int64_t total,
+                                                           int32_t* __restrict__ cnt_of, int32_t* __restrict__ rank,
+                                                           int64_t* __restrict__ U, int32_t* __restrict__ counters,
+                                                           float* pe, int d) {
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // LSTEP.py:317
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int32_t u = -1;
+  if (i < total) u = nbrB[i];
+  if (u > 0) {
+    const int c = atomicAdd(cnt_of + u, 1);
+    rank[i] = c;
+    if (c == 0) {
+      const int s = atomicAdd(counters + 0, 1);
+      U[s] = u;
+    }
+  }
+  const unsigned z = __ballot_sync(kFull, u == 0);
+  if (z && (threadIdx.x & 31) == 0) counters[1] = 1;
+}
+
+// step 2 (one CTA): offsets by exclusive scan over U order; slot map; counter map reset
+__global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__ cnt_of, int32_t* __restrict__ slot_of,
+                                                           int64_t* __restrict__ U, int32_t* __restrict__ off,
+                                                           int32_t* __restrict__ counters) {
+  __shared__ int s_warp[32];
+  const int M = counters[0];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int chunk = (M + blockDim.x - 1) / blockDim.x;
+  const int lo = tid * chunk, hi = min(M, lo + chunk);
+  int sum = 0;
+  for (int s = lo; s < hi; ++s) sum += cnt_of[U[s]];
+  int incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(kFull, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int v = s_warp[lane], iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int x = __shfl_up_sync(kFull, iv, o);
+      if (lane >= o) iv += x;
+    }
+    s_warp[lane] = iv - v;
+  }
+  __syncthreads();
+  int run = s_warp[wid] + incl - sum;
+  for (int s = lo; s < hi; ++s) {
+    const int64_t u = U[s];
+    off[s] = run;
+    run += cnt_of[u];
+    cnt_of[u] = 0;  // restore the all-zero invariant
+    slot_of[u] = s;
+  }
+  if (hi == M && lo <= M && (lo < M || tid == 0) && (tid == (M == 0 ? 0 : (M - 1) / max(chunk, 1)))) off[M] = run;
+  if (tid == 0) {
+    const int hz = counters[1];
+    counters[2] = M + hz;
+    if (hz) U[M] = 0;
+  }
+}
+
+// step 3: fill slot lists; extra blocks: per-part partial sums of the padding row
+__global__ void __launch_bounds__(256) phaseB_fill_kernel(const int32_t* __restrict__ nbrB, int64_t total, int K,
+                                                          const int32_t* __restrict__ slot_of,
+                                                          const int32_t* __restrict__ off,
+                                                          const int32_t* __restrict__ rank, int32_t* __restrict__ list,
+                                                          int fill_blocks, const int32_t* __restrict__ counters,
+                                                          const float* __restrict__ pe, const int64_t* __restrict__ ids,
+                                                          int64_t n_ids, int d, float* __restrict__ row0_part) {
+  if ((int)blockIdx.x < fill_blocks) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < total) {
+      const int32_t u = nbrB[i];
+      if (u > 0) list[off[slot_of[u]] + rank[i]] = (int32_t)i;
+    }
+    return;
+  }
+  if (counters[1] == 0) return;
+  const int part = blockIdx.x - fill_blocks;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    float acc = 0.f;
+    for (int64_t n = part; n < n_ids; n += kRow0Parts) {
+      int z = 0;
+      for (int k = 0; k < K; ++k) z += (nbrB[n * K + k] == 0);
+      if (z) acc = fmaf((float)z, pe[ids[n] * (int64_t)d + c], acc);
+    }
+    row0_part[part * d + c] = acc;
+  }
+}
+
+// step 4: one warp per destination reduces its slot list; last block finishes the padding row
+template <int DVPL, int TFPL>
+__global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restrict__ pe,
+                                                            const int64_t* __restrict__ ids, int K,
+                                                            const float* __restrict__ ntB,
+                                                            const int32_t* __restrict__ off,
+                                                            const int32_t* __restrict__ list,
+                                                            const int32_t* __restrict__ counters, float tc,
+                                                            const float* __restrict__ tw, int d, int t,
+                                                            const float* __restrict__ row0_part, float* __restrict__ A) {
+  const int in1 = d + t;
+  const int M = counters[0];
+  if (blockIdx.x == gridDim.x - 1) {
+    if (counters[1]) {
+      for (int c = threadIdx.x; c < in1; c += blockDim.x) {
+        float acc = 0.f;
+        if (c < d)
+          for (int p = 0; p < kRow0Parts; ++p) acc += row0_part[p * d + c];
+        A[(int64_t)M * in1 + c] = acc;  // time features of padded slots are zeroed (LSTEP.py:316)
+      }
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (s >= M) return;
+  const int dvec = d >> 2;
+  const int o0 = off[s], len = off[s + 1] - o0;
+  float4 acc[DVPL];
+  float acc_tf[TFPL], w[TFPL];
+#pragma unroll
+  for (int q = 0; q < DVPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < TFPL; ++q) {
+    acc_tf[q] = 0.f;
+    w[q] = (lane + 32 * q < t) ? tw[lane + 32 * q] : 0.f;
+  }
+  for (int c0 = 0; c0 < len; c0 += 32) {
+    int e = (c0 + lane < len) ? list[o0 + c0 + lane] : 0x7fffffff;
+    if (len <= 32) {
+      // bitonic sort ascending across the warp: restores flat-index (reference) order
+#pragma unroll
+      for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          const int o = __shfl_xor_sync(kFull, e, j);
+          const bool up = ((lane & k) == 0);
+          const bool lower = ((lane & j) == 0);
+          e = (lower == up) ? min(e, o) : max(e, o);
+        }
+      }
+    }
+    const int m = min(32, len - c0);
+    for (int j = 0; j < m; ++j) {
+      const int i = __shfl_sync(kFull, e, j);
+      const int n = i / K;
+      const float dt = tc - ntB[i];  // fp32 - fp32 (LSTEP.py:314)
+      const float4* row = reinterpret_cast<const float4*>(pe + ids[n] * (int64_t)d);
+#pragma unroll
+      for (int q = 0; q < DVPL; ++q) {
+        const int cv = lane + 32 * q;
+        if (cv < dvec) {
+          const float4 v = __ldg(row + cv);
+          acc[q].x += v.x;
+          acc[q].y += v.y;
+          acc[q].z += v.z;
+          acc[q].w += v.w;
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < TFPL; ++q)
+        if (lane + 32 * q < t) acc_tf[q] += time_feature(dt, w[q]);
+    }
+  }
+  float* arow = A + (int64_t)s * in1;
+#pragma unroll
+  for (int q = 0; q < DVPL; ++q)
+    if (lane + 32 * q < dvec) reinterpret_cast<float4*>(arow)[lane + 32 * q] = acc[q];
+#pragma unroll
+  for (int q = 0; q < TFPL; ++q)
+    if (lane + 32 * q < t) arow[d + lane + 32 * q] = acc_tf[q];
+}
+
+}  // namespace lstep
+
+using namespace lstep;
+
+extern "C" size_t lstep_update_pe_workspace_bytes(int64_t n_ids, int64_t n_edges, int K, int d, int t,
+                                                  int64_t pe_rows) {
+  if (n_ids < 0 || n_edges < 0 || K <= 0 || d <= 0 || t < 0 || pe_rows <= 0) return 0;
+  return carve(nullptr, n_ids, n_edges, K, d, t, pe_rows).bytes;
+}
+
+extern "C" int lstep_update_pe_workspace_init(void* workspace, size_t workspace_bytes, int64_t pe_rows, void* stream) {
+  if (!workspace || pe_rows <= 0 || workspace_bytes < sizeof(int32_t) * (size_t)pe_rows) return LSTEP_ERR_INVALID_ARG;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t) * (size_t)pe_rows, as_stream(stream));
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "workspace_init");
+    return LSTEP_ERR_CUDA;
+  }
+  return LSTEP_OK;
+}
+
+extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids,
+                               const int64_t* src, const int64_t* dst, const double* times, int64_t n_edges,
+                               double current_time, int K, const lstep_pe_mlp* mlp, void* workspace,
+                               size_t workspace_bytes, uint32_t* err_flag, void* stream) {
+  if (!pe || !csr || !mlp || pe_rows <= 0 || n_ids < 0 || n_edges < 0 || K <= 0) return LSTEP_ERR_INVALID_ARG;
+  if (n_ids > 0 && !ids) return LSTEP_ERR_INVALID_ARG;
+  if (n_edges > 0 && (!src || !dst || !times)) return LSTEP_ERR_INVALID_ARG;
+  const int d = mlp->d, t = mlp->t;
+  if (d % 4 != 0 || reinterpret_cast<uintptr_t>(pe) % 16 != 0) return LSTEP_ERR_UNSUPPORTED;
+  if (csr->num_rows > pe_rows) return LSTEP_ERR_INVALID_ARG;
+  if (pe_rows > 0x7fffffffLL || (int64_t)n_ids * K > 0x7fffffffLL) return LSTEP_ERR_ID_RANGE;
+  const size_t need = carve(nullptr, n_ids, n_edges, K, d, t, pe_rows).bytes;
+  if (!workspace || workspace_bytes < need) return LSTEP_ERR_WORKSPACE;
+  UpdateWs w = carve(workspace, n_ids, n_edges, K, d, t, pe_rows);
+  cudaStream_t st = as_stream(stream);
+  const float tc = (float)current_time;
+  int rc;
+
+  // ---- phase A
+  {
+    const int64_t blocks = ceil_div(n_edges > 0 ? n_edges : 1, 256);
+    prep_edges_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, times, n_edges, tc, pe_rows, w.src32, w.dst32, w.dtA,
+                                                        w.counters, err_flag);
+    if ((rc = check_launch("prep_edges")) != LSTEP_OK) return rc;
+  }
+  const int dvec = d / 4;
+  const int t_pad = (int)align_up((size_t)t, 32);
+  const int threads = (int)align_up((size_t)t_pad + dvec, 32);
+  if (threads > 512 || dvec > 8 * 32 || t > 8 * 32) return LSTEP_ERR_UNSUPPORTED;
+  if (n_ids > 0) {
+    const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
+    const int64_t grid = n_ids < (int64_t)kNumSMs * 16 ? n_ids : (int64_t)kNumSMs * 16;
+    edge_aggregate_kernel<<<(unsigned)grid, threads, smem, st>>>(pe, ids, n_ids, w.src32, w.dst32, w.dtA, n_edges,
+                                                                 mlp->tw, d, t, t_pad, w.A);
+    if ((rc = check_launch("edge_aggregate")) != LSTEP_OK) return rc;
+    if ((rc = launch_pe_mlp(w.A, pe, ids, n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st)) != LSTEP_OK) return rc;
+  }
+
+  // ---- phase B
+  const int64_t n_valid = n_ids < n_edges ? n_ids : n_edges;  // zip(node_ids, times) truncation (Q1)
+  const int64_t total = n_ids * (int64_t)K;
+  if (n_ids > 0) {
+    rc = lstep_sample_recent_compact(csr, ids, times, n_ids, n_valid, K, w.nbrB, w.ntB, err_flag, stream);
+    if (rc != LSTEP_OK) return rc;
+  }
+  {
+    const int64_t blocks = ceil_div(total > 0 ? total : 1, 256);
+    phaseB_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(w.nbrB, total, w.cnt_of, w.rank, w.U, w.counters, pe, d);
+    if ((rc = check_launch("phaseB_count")) != LSTEP_OK) return rc;
+  }
+  if (total == 0) return LSTEP_OK;
+  phaseB_scan_kernel<<<1, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.counters);
+  if ((rc = check_launch("phaseB_scan")) != LSTEP_OK) return rc;
+  {
+    const int fill_blocks = (int)ceil_div(total, 256);
+    phaseB_fill_kernel<<<fill_blocks + kRow0Parts, 256, 0, st>>>(w.nbrB, total, K, w.slot_of, w.off, w.rank, w.list,
+                                                                 fill_blocks, w.counters, pe, ids, n_ids, d,
+                                                                 w.row0_part);
+    if ((rc = check_launch("phaseB_fill")) != LSTEP_OK) return rc;
+  }
+  const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;  // distinct non-zero destinations
+  {
+    const int64_t blocks = ceil_div(max_dest > 0 ? max_dest : 1, 8) + 1;
+    if (dvec <= 64 && t <= 128)
+      phaseB_gather_kernel<2, 4><<<(unsigned)blocks, 256, 0, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.counters, tc,
+                                                                   mlp->tw, d, t, w.row0_part, w.A);
+    else
+      phaseB_gather_kernel<8, 8><<<(unsigned)blocks, 256, 0, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.counters, tc,
+                                                                   mlp->tw, d, t, w.row0_part, w.A);
+    if ((rc = check_launch("phaseB_gather")) != LSTEP_OK) return rc;
+  }
+  lstep_pe_mlp noself = *mlp;
+  noself.ws = nullptr;  // the self term is computed and discarded by the reference (LSTEP.py:334-335, Q3)
+  noself.bs = nullptr;
+  return launch_pe_mlp(w.A, pe, w.U, max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe, st);
+}
