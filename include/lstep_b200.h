@@ -118,20 +118,23 @@ int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int64_t time_st
                          const int64_t* ids, int64_t n_ids, const float* dout, float* dG, void* stream);
 
 /* ------------------------------------------------------------------------------------------
- * PE MLP parameters, packed for the kernels: every Linear weight transposed to [in][ldo]
- * (ldo = lstep_packed_ld(d)), biases padded to ldo. lstep_pack_linear does one layer.
+ * PE MLP parameters, packed for the kernels: every Linear weight transposed and zero padded to
+ * [in_pad][ldo] (in_pad = lstep_packed_rows(in), ldo = lstep_packed_ld(out)) so that a tile of 16
+ * input rows is one contiguous block a bulk async copy can stream; biases padded to ldo.
+ * lstep_pack_linear does one layer.
  * ------------------------------------------------------------------------------------------ */
 int lstep_packed_ld(int out_features);
+int lstep_packed_rows(int in_features);
 int lstep_pack_linear(const float* weight /* [out,in] row major (torch) */, const float* bias /* [out] or NULL */,
-                      int out_features, int in_features, float* packed_w /* [in][ldo] */, float* packed_b /* [ldo] */,
-                      void* stream);
+                      int out_features, int in_features, float* packed_w /* [in_pad][ldo] */,
+                      float* packed_b /* [ldo] */, void* stream);
 
 typedef struct lstep_pe_mlp {
-  const float* w1; /* packed [d+t][ldo]  pe_mlp_1 / pe_neighbor_mlp_1 */
+  const float* w1; /* packed [rows(d+t)][ldo]  pe_mlp_1 / pe_neighbor_mlp_1 */
   const float* b1;
-  const float* w2; /* packed [d][ldo]    pe_mlp_2 / pe_neighbor_mlp_2 */
+  const float* w2; /* packed [rows(d)][ldo]    pe_mlp_2 / pe_neighbor_mlp_2 */
   const float* b2;
-  const float* ws; /* packed [d][ldo]    self_update_pe / self_update_neighbor_pe; NULL = no self term */
+  const float* ws; /* packed [rows(d)][ldo]    self_update_pe / self_update_neighbor_pe; NULL = no self term */
   const float* bs;
   const float* tw; /* [t] TimeEncoder frequencies (models/modules.py:20), fp32 */
   int d;

@@ -46,6 +46,7 @@ _SIGS = {
     "lstep_dft_filter": (i32, [vp, i64, i64, i32, i32, i32, i32, vp, i64, vp, vp, i64, vp]),
     "lstep_dft_filter_bwd": (i32, [vp, i64, i64, i32, i32, i32, i32, vp, i64, vp, vp, vp]),
     "lstep_packed_ld": (i32, [i32]),
+    "lstep_packed_rows": (i32, [i32]),
     "lstep_pack_linear": (i32, [vp, vp, i32, i32, vp, vp, vp]),
     "lstep_nbr_aggregate": (i32, [vp, i64, vp, vp, vp, i64, i32, vp, i32, i32, vp, vp]),
     "lstep_nbr_aggregate_bwd": (i32, [vp, vp, i64, i32, i32, i32, vp, i64, vp]),

@@ -16,13 +16,12 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
                                                             const int32_t* __restrict__ nbr,
                                                             const float* __restrict__ nbr_t, int64_t n_rows, int K,
                                                             const float* __restrict__ tw, int d, int t, int t_pad,
-                                                            float* __restrict__ S) {
+                                                            float* __restrict__ S, int64_t ldS) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);
   float* s_dt = reinterpret_cast<float*>(s_nbr + K);
   const int tid = threadIdx.x;
   const int dvec = d / VEC;
-  const int in1 = d + t;
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const double tq = q_time[row];
     for (int k = tid; k < K; k += blockDim.x) {
@@ -36,7 +35,7 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
       float acc = 0.f;
       for (int k = 0; k < K; ++k)
         if (s_nbr[k] != 0) acc += time_feature(s_dt[k], w);
-      S[row * in1 + d + tid] = acc;
+      S[row * ldS + d + tid] = acc;
     } else if (tid >= t_pad && tid - t_pad < dvec) {
       const int cv = tid - t_pad;
       if (VEC == 4) {
@@ -62,11 +61,11 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
           acc.z += v.z;
           acc.w += v.w;
         }
-        reinterpret_cast<float4*>(S + row * in1)[cv] = acc;
+        reinterpret_cast<float4*>(S + row * ldS)[cv] = acc;
       } else {
         float acc = 0.f;
         for (int k = 0; k < K; ++k) acc += __ldg(pe + (int64_t)s_nbr[k] * d + cv);
-        S[row * in1 + cv] = acc;
+        S[row * ldS + cv] = acc;
       }
     }
     __syncthreads();
@@ -86,15 +85,15 @@ __global__ void __launch_bounds__(256) nbr_aggregate_bwd_kernel(const float* __r
   }
 }
 
-int launch_pe_mlp(const float* A, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
+int launch_pe_mlp(const float* A, int64_t lda, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st);
 
 static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
 int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* nbr, const float* nbr_t,
-                         int64_t n_rows, int K, const float* tw, int d, int t, float* S, cudaStream_t st) {
-  const bool v4 = d % 4 == 0 && aligned16(pe) && aligned16(S);
+                         int64_t n_rows, int K, const float* tw, int d, int t, float* S, int64_t ldS, cudaStream_t st) {
+  const bool v4 = d % 4 == 0 && ldS % 4 == 0 && aligned16(pe) && aligned16(S);
   const int dvec = v4 ? d / 4 : d;
   const int t_pad = (int)align_up((size_t)t, 32);
   const int threads = (int)align_up((size_t)t_pad + dvec, 32);
@@ -103,9 +102,9 @@ int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* n
   if (smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
   const int64_t grid = n_rows < (int64_t)kNumSMs * 16 ? n_rows : (int64_t)kNumSMs * 16;
   if (v4)
-    nbr_aggregate_kernel<4><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S);
+    nbr_aggregate_kernel<4><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS);
   else
-    nbr_aggregate_kernel<1><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S);
+    nbr_aggregate_kernel<1><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS);
   return check_launch("nbr_aggregate");
 }
 
@@ -119,7 +118,7 @@ extern "C" int lstep_nbr_aggregate(const float* pe, int64_t pe_rows, const doubl
   if (n_rows < 0 || K <= 0 || d <= 0 || t < 0 || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
   if (n_rows == 0) return LSTEP_OK;
   if (!pe || !q_time || !nbr || !nbr_t || !S || (t > 0 && !tw)) return LSTEP_ERR_INVALID_ARG;
-  return launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, S, as_stream(stream));
+  return launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, S, d + t, as_stream(stream));
 }
 
 extern "C" int lstep_nbr_aggregate_bwd(const float* dS, const int32_t* nbr, int64_t n_rows, int K, int d, int t,
@@ -139,10 +138,11 @@ extern "C" int lstep_neighborhood_pe(const float* pe, int64_t pe_rows, const int
   if (n_rows < 0 || K <= 0 || !mlp || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
   if (n_rows == 0) return LSTEP_OK;
   if (!pe || !q_node || !q_time || !nbr || !nbr_t || !out || !workspace) return LSTEP_ERR_INVALID_ARG;
-  const size_t need = (size_t)n_rows * (mlp->d + mlp->t) * sizeof(float);
+  const int64_t ldS = (int64_t)align_up((size_t)(mlp->d + mlp->t), 4);  // 16-byte aligned rows
+  const size_t need = (size_t)n_rows * ldS * sizeof(float);
   if (workspace_bytes < need) return LSTEP_ERR_WORKSPACE;
   float* S = reinterpret_cast<float*>(workspace);
-  int rc = launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, mlp->tw, mlp->d, mlp->t, S, as_stream(stream));
+  int rc = launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, mlp->tw, mlp->d, mlp->t, S, ldS, as_stream(stream));
   if (rc != LSTEP_OK) return rc;
-  return launch_pe_mlp(S, pe, q_node, n_rows, n_rows, nullptr, mlp, out, mlp->d, nullptr, as_stream(stream));
+  return launch_pe_mlp(S, ldS, pe, q_node, n_rows, n_rows, nullptr, mlp, out, mlp->d, nullptr, as_stream(stream));
 }

@@ -16,7 +16,8 @@
 //     rows in exactly the reference's order;
 //   * phase B: an inverse index (destination -> slots) is built with integer atomics on a
 //     per-node counter map (count / scan / fill), one warp per destination sorts its slot list
-//     (<= 32 entries: ascending flat index = the reference's add order) and reduces it. The
+//     (<= 32 entries: ascending flat index = the reference's add order) and reduces it; longer
+//     lists (hubs) are summed in 32.32 fixed point, which is exact and hence order independent. The
 //     padding row 0 collects every empty slot — thousands of contributions at B=200 — so it is
 //     reduced by a two-level tree (z_i * pe[ids[i]] per row, then over rows) instead of a
 //     serial chain.
@@ -26,7 +27,7 @@
 
 namespace lstep {
 
-int launch_pe_mlp(const float* A, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
+int launch_pe_mlp(const float* A, int64_t lda, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st);
 
@@ -35,7 +36,7 @@ constexpr int kRow0Parts = 64;
 struct UpdateWs {
   int32_t* cnt_of;   // [pe_rows]  zero between calls
   int32_t* slot_of;  // [pe_rows]
-  int32_t* counters; // [8]: 0=M, 1=has_zero, 2=n_dest
+  int32_t* counters; // [8]: 0=M, 1=has_zero, 2=n_dest, 3=n_hubs
   int32_t* src32;    // [E]
   int32_t* dst32;    // [E]
   float* dtA;        // [E]
@@ -45,8 +46,10 @@ struct UpdateWs {
   int32_t* list;     // [N*K]
   int64_t* U;        // [N*K+1]
   int32_t* off;      // [N*K+2]
+  int32_t* hubs;     // [N*K/32+1] destinations with more than 32 slots
   float* row0_part;  // [kRow0Parts*d]
-  float* A;          // [max(N, N*K+1)*(d+t)]
+  float* A;          // [max(N, N*K+1)][lda], lda = d+t rounded up to 4 floats
+  int64_t lda;
   size_t bytes;
 };
 
@@ -71,9 +74,11 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
   w.list = (int32_t*)take(sizeof(int32_t) * nk);
   w.U = (int64_t*)take(sizeof(int64_t) * (nk + 1));
   w.off = (int32_t*)take(sizeof(int32_t) * (nk + 2));
+  w.hubs = (int32_t*)take(sizeof(int32_t) * (nk / 32 + 2));
   w.row0_part = (float*)take(sizeof(float) * kRow0Parts * d);
   const size_t rowsA = nk + 1 > (size_t)n_ids ? nk + 1 : (size_t)n_ids;
-  w.A = (float*)take(sizeof(float) * rowsA * (d + t));
+  w.lda = (int64_t)align_up((size_t)(d + t), 4);
+  w.A = (float*)take(sizeof(float) * rowsA * w.lda);
   w.bytes = o;
   return w;
 }
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
                                                              const int32_t* __restrict__ dst32,
                                                              const float* __restrict__ dtA, int64_t n_edges,
                                                              const float* __restrict__ tw, int d, int t, int t_pad,
-                                                             float* __restrict__ A) {
+                                                             float* __restrict__ A, int64_t lda) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nthr = blockDim.x;
   const int seg = nthr * kSegPerThread;
@@ -119,7 +124,6 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
   __shared__ int s_total;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int dvec = d / 4;
-  const int in1 = d + t;
   const bool is_tf = tid < t;
   const bool is_pe = tid >= t_pad && tid - t_pad < dvec;
   const int cv = tid - t_pad;
@@ -201,8 +205,8 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
         __syncthreads();
       }
     }
-    if (is_tf) A[n * in1 + d + tid] = acc_tf;
-    if (is_pe) reinterpret_cast<float4*>(A + n * in1)[cv] = acc;
+    if (is_tf) A[n * lda + d + tid] = acc_tf;
+    if (is_pe) reinterpret_cast<float4*>(A + n * lda)[cv] = acc;
   }
 }
 
@@ -229,15 +233,17 @@ __global__ void __launch_bounds__(256) phaseB_count_kernel(const int32_t* __rest
   if (z && (threadIdx.x & 31) == 0) counters[1] = 1;
 }
 
-// step 2 (one CTA): offsets by exclusive scan over U order; slot map; counter map reset
+// step 2 (one CTA): offsets by exclusive scan over U order; slot map; counter map reset; hub list
+constexpr int kHubLen = 32;  // lists longer than a warp are hubs and get a whole CTA
+
 __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__ cnt_of, int32_t* __restrict__ slot_of,
                                                            int64_t* __restrict__ U, int32_t* __restrict__ off,
-                                                           int32_t* __restrict__ counters) {
+                                                           int32_t* __restrict__ hubs, int32_t* __restrict__ counters) {
   __shared__ int s_warp[32];
   const int M = counters[0];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int chunk = (M + blockDim.x - 1) / blockDim.x;
-  const int lo = tid * chunk, hi = min(M, lo + chunk);
+  const int lo = min(M, tid * chunk), hi = min(M, lo + chunk);
   int sum = 0;
   for (int s = lo; s < hi; ++s) sum += cnt_of[U[s]];
   int incl = sum;
@@ -256,17 +262,19 @@ __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__
       if (lane >= o) iv += x;
     }
     s_warp[lane] = iv - v;
+    if (lane == 31) off[M] = iv;  // total number of non-padding slots
   }
   __syncthreads();
   int run = s_warp[wid] + incl - sum;
   for (int s = lo; s < hi; ++s) {
     const int64_t u = U[s];
+    const int deg = cnt_of[u];
     off[s] = run;
-    run += cnt_of[u];
+    run += deg;
     cnt_of[u] = 0;  // restore the all-zero invariant
     slot_of[u] = s;
+    if (deg > kHubLen) hubs[atomicAdd(counters + 3, 1)] = s;
   }
-  if (hi == M && lo <= M && (lo < M || tid == 0) && (tid == (M == 0 ? 0 : (M - 1) / max(chunk, 1)))) off[M] = run;
   if (tid == 0) {
     const int hz = counters[1];
     counters[2] = M + hz;
@@ -303,64 +311,84 @@ __global__ void __launch_bounds__(256) phaseB_fill_kernel(const int32_t* __restr
   }
 }
 
-// step 4: one warp per destination reduces its slot list; last block finishes the padding row
+// One list entry = slot i = (row n, column k): contributes [pe[ids[n]] || cos((tc - nt[i]) * w)].
+// The per-entry metadata (source row pointer, dt) is resolved for 32 entries at once (one lane each),
+// so the dependent index loads are paid once per chunk, not once per entry.
+template <int DVPL, int TFPL>
+struct GatherAcc {
+  float4 pe[DVPL];
+  float tf[TFPL];
+};
+
+// step 4: blocks [0, warp_blocks): one warp per destination with a short list (sorted, fp32, reference
+// order); blocks [warp_blocks, warp_blocks + hub_blocks): one CTA per hub (32.32 fixed point, exact, so
+// the arrival order of the list does not matter); last block: finishes the padding row.
 template <int DVPL, int TFPL>
 __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restrict__ pe,
                                                             const int64_t* __restrict__ ids, int K,
                                                             const float* __restrict__ ntB,
                                                             const int32_t* __restrict__ off,
                                                             const int32_t* __restrict__ list,
+                                                            const int32_t* __restrict__ hubs,
                                                             const int32_t* __restrict__ counters, float tc,
                                                             const float* __restrict__ tw, int d, int t,
-                                                            const float* __restrict__ row0_part, float* __restrict__ A) {
+                                                            const float* __restrict__ row0_part, float* __restrict__ A,
+                                                            int64_t lda, int warp_blocks, int hub_blocks) {
+  extern __shared__ unsigned long long s_fix[];  // [d + t] fixed-point accumulators (hub blocks only)
   const int in1 = d + t;
   const int M = counters[0];
-  if (blockIdx.x == gridDim.x - 1) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int dvec = d >> 2;
+  float w[TFPL];
+#pragma unroll
+  for (int q = 0; q < TFPL; ++q) w[q] = (lane + 32 * q < t) ? tw[lane + 32 * q] : 0.f;
+
+  if ((int)blockIdx.x == warp_blocks + hub_blocks) {  // ---- padding row
     if (counters[1]) {
       for (int c = threadIdx.x; c < in1; c += blockDim.x) {
         float acc = 0.f;
         if (c < d)
           for (int p = 0; p < kRow0Parts; ++p) acc += row0_part[p * d + c];
-        A[(int64_t)M * in1 + c] = acc;  // time features of padded slots are zeroed (LSTEP.py:316)
+        A[(int64_t)M * lda + c] = acc;  // time features of padded slots are zeroed (LSTEP.py:316)
       }
     }
     return;
   }
-  const int lane = threadIdx.x & 31;
-  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (s >= M) return;
-  const int dvec = d >> 2;
-  const int o0 = off[s], len = off[s + 1] - o0;
-  float4 acc[DVPL];
-  float acc_tf[TFPL], w[TFPL];
+
+  if ((int)blockIdx.x < warp_blocks) {  // ---- short lists
+    const int s = blockIdx.x * (blockDim.x >> 5) + wid;
+    if (s >= M) return;
+    const int o0 = off[s], len = off[s + 1] - o0;
+    if (len > kHubLen) return;  // a hub block owns this destination
+    int e = (lane < len) ? list[o0 + lane] : 0x7fffffff;
+    // bitonic sort ascending across the warp: restores flat-index (= reference add) order
 #pragma unroll
-  for (int q = 0; q < DVPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 2; k <= 32; k <<= 1) {
 #pragma unroll
-  for (int q = 0; q < TFPL; ++q) {
-    acc_tf[q] = 0.f;
-    w[q] = (lane + 32 * q < t) ? tw[lane + 32 * q] : 0.f;
-  }
-  for (int c0 = 0; c0 < len; c0 += 32) {
-    int e = (c0 + lane < len) ? list[o0 + c0 + lane] : 0x7fffffff;
-    if (len <= 32) {
-      // bitonic sort ascending across the warp: restores flat-index (reference) order
-#pragma unroll
-      for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          const int o = __shfl_xor_sync(kFull, e, j);
-          const bool up = ((lane & k) == 0);
-          const bool lower = ((lane & j) == 0);
-          e = (lower == up) ? min(e, o) : max(e, o);
-        }
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const int o = __shfl_xor_sync(kFull, e, j);
+        const bool up = ((lane & k) == 0);
+        const bool lower = ((lane & j) == 0);
+        e = (lower == up) ? min(e, o) : max(e, o);
       }
     }
-    const int m = min(32, len - c0);
-    for (int j = 0; j < m; ++j) {
-      const int i = __shfl_sync(kFull, e, j);
-      const int n = i / K;
-      const float dt = tc - ntB[i];  // fp32 - fp32 (LSTEP.py:314)
-      const float4* row = reinterpret_cast<const float4*>(pe + ids[n] * (int64_t)d);
+    // per-lane metadata of entry `lane`
+    const float* my_row = pe;
+    float my_dt = 0.f;
+    if (lane < len) {
+      my_row = pe + ids[e / K] * (int64_t)d;
+      my_dt = tc - ntB[e];  // fp32 - fp32 (LSTEP.py:314)
+    }
+    float4 acc[DVPL];
+    float acc_tf[TFPL];
+#pragma unroll
+    for (int q = 0; q < DVPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < TFPL; ++q) acc_tf[q] = 0.f;
+    for (int j = 0; j < len; ++j) {
+      const float4* row = reinterpret_cast<const float4*>(
+          reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)my_row, j)));
+      const float dt = __shfl_sync(kFull, my_dt, j);
 #pragma unroll
       for (int q = 0; q < DVPL; ++q) {
         const int cv = lane + 32 * q;
@@ -376,14 +404,76 @@ __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restr
       for (int q = 0; q < TFPL; ++q)
         if (lane + 32 * q < t) acc_tf[q] += time_feature(dt, w[q]);
     }
+    float* arow = A + (int64_t)s * lda;
+#pragma unroll
+    for (int q = 0; q < DVPL; ++q)
+      if (lane + 32 * q < dvec) reinterpret_cast<float4*>(arow)[lane + 32 * q] = acc[q];
+#pragma unroll
+    for (int q = 0; q < TFPL; ++q)
+      if (lane + 32 * q < t) arow[d + lane + 32 * q] = acc_tf[q];
+    return;
   }
-  float* arow = A + (int64_t)s * in1;
+
+  // ---- hubs: CTA per hub, warps take 32-entry chunks round-robin, exact fixed-point accumulation
+  constexpr float kScale = 4294967296.f;  // 2^32
+  constexpr double kInv = 1.0 / 4294967296.0;
+  const int n_hubs = counters[3];
+  const int nw = blockDim.x >> 5;
+  for (int h = blockIdx.x - warp_blocks; h < n_hubs; h += hub_blocks) {
+    const int s = hubs[h];
+    const int o0 = off[s], len = off[s + 1] - o0;
+    for (int c = threadIdx.x; c < in1; c += blockDim.x) s_fix[c] = 0ull;
+    __syncthreads();
+    long long facc[DVPL][4], ftf[TFPL];
 #pragma unroll
-  for (int q = 0; q < DVPL; ++q)
-    if (lane + 32 * q < dvec) reinterpret_cast<float4*>(arow)[lane + 32 * q] = acc[q];
+    for (int q = 0; q < DVPL; ++q) facc[q][0] = facc[q][1] = facc[q][2] = facc[q][3] = 0;
 #pragma unroll
-  for (int q = 0; q < TFPL; ++q)
-    if (lane + 32 * q < t) arow[d + lane + 32 * q] = acc_tf[q];
+    for (int q = 0; q < TFPL; ++q) ftf[q] = 0;
+    for (int c0 = wid * 32; c0 < len; c0 += nw * 32) {
+      const float* my_row = pe;
+      float my_dt = 0.f;
+      if (c0 + lane < len) {
+        const int e = list[o0 + c0 + lane];
+        my_row = pe + ids[e / K] * (int64_t)d;
+        my_dt = tc - ntB[e];
+      }
+      const int m = min(32, len - c0);
+      for (int j = 0; j < m; ++j) {
+        const float4* row = reinterpret_cast<const float4*>(
+            reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)my_row, j)));
+        const float dt = __shfl_sync(kFull, my_dt, j);
+#pragma unroll
+        for (int q = 0; q < DVPL; ++q) {
+          const int cv = lane + 32 * q;
+          if (cv < dvec) {
+            const float4 v = __ldg(row + cv);
+            facc[q][0] += __float2ll_rn(v.x * kScale);
+            facc[q][1] += __float2ll_rn(v.y * kScale);
+            facc[q][2] += __float2ll_rn(v.z * kScale);
+            facc[q][3] += __float2ll_rn(v.w * kScale);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < TFPL; ++q)
+          if (lane + 32 * q < t) ftf[q] += __float2ll_rn(time_feature(dt, w[q]) * kScale);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < DVPL; ++q) {
+      const int cv = lane + 32 * q;
+      if (cv < dvec) {
+#pragma unroll
+        for (int x = 0; x < 4; ++x) atomicAdd(&s_fix[4 * cv + x], (unsigned long long)facc[q][x]);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < TFPL; ++q)
+      if (lane + 32 * q < t) atomicAdd(&s_fix[d + lane + 32 * q], (unsigned long long)ftf[q]);
+    __syncthreads();
+    float* arow = A + (int64_t)s * lda;
+    for (int c = threadIdx.x; c < in1; c += blockDim.x) arow[c] = (float)((double)(long long)s_fix[c] * kInv);
+    __syncthreads();
+  }
 }
 
 }  // namespace lstep
@@ -439,9 +529,9 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
     const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
     const int64_t grid = n_ids < (int64_t)kNumSMs * 16 ? n_ids : (int64_t)kNumSMs * 16;
     edge_aggregate_kernel<<<(unsigned)grid, threads, smem, st>>>(pe, ids, n_ids, w.src32, w.dst32, w.dtA, n_edges,
-                                                                 mlp->tw, d, t, t_pad, w.A);
+                                                                 mlp->tw, d, t, t_pad, w.A, w.lda);
     if ((rc = check_launch("edge_aggregate")) != LSTEP_OK) return rc;
-    if ((rc = launch_pe_mlp(w.A, pe, ids, n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st)) != LSTEP_OK) return rc;
+    if ((rc = launch_pe_mlp(w.A, w.lda, pe, ids, n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st)) != LSTEP_OK) return rc;
   }
 
   // ---- phase B
@@ -457,7 +547,7 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
     if ((rc = check_launch("phaseB_count")) != LSTEP_OK) return rc;
   }
   if (total == 0) return LSTEP_OK;
-  phaseB_scan_kernel<<<1, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.counters);
+  phaseB_scan_kernel<<<1, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.counters);
   if ((rc = check_launch("phaseB_scan")) != LSTEP_OK) return rc;
   {
     const int fill_blocks = (int)ceil_div(total, 256);
@@ -468,17 +558,21 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
   }
   const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;  // distinct non-zero destinations
   {
-    const int64_t blocks = ceil_div(max_dest > 0 ? max_dest : 1, 8) + 1;
+    const int warp_blocks = (int)ceil_div(max_dest > 0 ? max_dest : 1, 8);
+    int hub_blocks = (int)(total / (kHubLen + 1)) + 1;  // at most this many lists can be longer than kHubLen
+    if (hub_blocks > 2 * kNumSMs) hub_blocks = 2 * kNumSMs;
+    const unsigned blocks = (unsigned)(warp_blocks + hub_blocks + 1);
+    const size_t smem = sizeof(unsigned long long) * (size_t)(d + t);
     if (dvec <= 64 && t <= 128)
-      phaseB_gather_kernel<2, 4><<<(unsigned)blocks, 256, 0, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.counters, tc,
-                                                                   mlp->tw, d, t, w.row0_part, w.A);
+      phaseB_gather_kernel<2, 4><<<blocks, 256, smem, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw,
+                                                            d, t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
     else
-      phaseB_gather_kernel<8, 8><<<(unsigned)blocks, 256, 0, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.counters, tc,
-                                                                   mlp->tw, d, t, w.row0_part, w.A);
+      phaseB_gather_kernel<8, 8><<<blocks, 256, smem, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw,
+                                                            d, t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
     if ((rc = check_launch("phaseB_gather")) != LSTEP_OK) return rc;
   }
   lstep_pe_mlp noself = *mlp;
   noself.ws = nullptr;  // the self term is computed and discarded by the reference (LSTEP.py:334-335, Q3)
   noself.bs = nullptr;
-  return launch_pe_mlp(w.A, pe, w.U, max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe, st);
+  return launch_pe_mlp(w.A, w.lda, pe, w.U, max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe, st);
 }

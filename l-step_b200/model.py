@@ -203,7 +203,7 @@ class LSTEP(nn.Module):
         with torch.cuda.device(dev):
             for n, in_f in zip(names, (d + t, d, d)):
                 lin = getattr(self, n)
-                pw = torch.empty((in_f, ldo), dtype=torch.float32, device=dev)
+                pw = torch.empty((lib.lstep_packed_rows(in_f), ldo), dtype=torch.float32, device=dev)
                 pb = torch.empty(ldo, dtype=torch.float32, device=dev)
                 w = lin.weight.detach().contiguous()
                 b = lin.bias.detach().contiguous()
@@ -286,20 +286,31 @@ class LSTEP(nn.Module):
         else:
             b = T
         (ids_dev,) = self._upload([(node_ids, I64)])
+        return self.fourier_transform_pe_device(ids_dev, pe, b, bool(use_dropout)).squeeze()
+
+    def fourier_transform_pe_device(self, ids_dev, pe, b: int, residual: bool = False, s0: int = 0, ring: int = None, Th: int = None,
+                                    node_stride: int = None, time_stride: int = None, out=None):
+        """Device-resident form: ids already in HBM, mask length b resolved. With `ring`/`s0`/strides the
+        history may be a ring buffer (logical step s lives in slot (s0+s) % ring)."""
+        T, d = self.num_fft_batches, self.pe_dim
+        Th = pe.shape[1] if Th is None else Th
+        ring = max(Th, 1) if ring is None else ring
+        node_stride = pe.stride(0) if node_stride is None else node_stride
+        time_stride = pe.stride(1) if time_stride is None else time_stride
         n = ids_dev.shape[0]
         lib = _lib.load()
         with torch.cuda.device(pe.device):
             needs_grad = torch.is_grad_enabled() and (self.fft_filter.weight.requires_grad or self.fft_agg.weight.requires_grad)
             if needs_grad:
-                G = self._collapsed_filter_autograd(b, bool(use_dropout))
+                G = self._collapsed_filter_autograd(b, residual)
                 out = _DftFilterFn.apply(G, pe.detach(), ids_dev, Th)
             else:
-                G = self._collapsed_filter(b, bool(use_dropout))
-                out = torch.empty((n, d), dtype=torch.float32, device=pe.device)
-                _lib.check(lib.lstep_dft_filter(_lib.ptr(pe), pe.stride(0), pe.stride(1), 0, max(Th, 1), Th, d, _lib.ptr(ids_dev), n,
-                                                _lib.ptr(G), _lib.ptr(out), d, _lib.stream_ptr()), "lstep_dft_filter")
-        return out.squeeze()
-
+                G = self._collapsed_filter(b, residual)
+                if out is None:
+                    out = torch.empty((n, d), dtype=torch.float32, device=pe.device)
+                _lib.check(lib.lstep_dft_filter(_lib.ptr(pe), node_stride, time_stride, s0, ring, Th, d, _lib.ptr(ids_dev), n,
+                                                _lib.ptr(G), _lib.ptr(out), out.stride(0), _lib.stream_ptr()), "lstep_dft_filter")
+        return out
     # ---- feature branch (PyTorch; lookups on the device sampler) ------------------------------
     def _sample_full(self, ids_dev, t_dev, n_rows, n_valid, K):
         s = self.neighbor_sampler
@@ -366,8 +377,14 @@ class LSTEP(nn.Module):
         self._check_ids(node_ids, pe.shape[0], "pe")
         if s.num_rows > pe.shape[0]:
             raise IndexError(f"pe has {pe.shape[0]} rows but the sampler knows node ids up to {s.num_rows - 1}")
-        K = int(num_neighbors)
         ids_dev, t_dev = self._upload([(node_ids, I64), (node_interact_times, F64)])
+        return self.compute_neighborhood_pe_device(pe, ids_dev, t_dev, int(num_neighbors))
+
+    def compute_neighborhood_pe_device(self, pe, ids_dev, t_dev, K: int, out=None):
+        """Device-resident form (ids int64 / times float64 already in HBM, validated by the caller)."""
+        s = self.neighbor_sampler
+        d, t = self.pe_dim, self.time_feat_dim
+        n = ids_dev.shape[0]
         lib = _lib.load()
         with torch.cuda.device(pe.device):
             nbr, nt = s.sample_device(ids_dev, t_dev, n, n, K)
@@ -378,8 +395,9 @@ class LSTEP(nn.Module):
                 h = self.pe_neighbor_mlp_2(F.relu(self.pe_neighbor_mlp_1(S)))
                 return node_pe + torch.tanh(self.self_update_neighbor_pe(node_pe) + h)
             pec = pe if pe.is_contiguous() else pe.contiguous()
-            out = torch.empty((n, d), dtype=torch.float32, device=pe.device)
-            ws = torch.empty(max(n, 1) * (d + t), dtype=torch.float32, device=pe.device)
+            if out is None:
+                out = torch.empty((n, d), dtype=torch.float32, device=pe.device)
+            ws = torch.empty(max(n, 1) * (d + t + 3), dtype=torch.float32, device=pe.device)
             _lib.check(lib.lstep_neighborhood_pe(_lib.ptr(pec), pec.shape[0], _lib.ptr(ids_dev), _lib.ptr(t_dev), _lib.ptr(nbr),
                                                  _lib.ptr(nt), n, K, self._mlp_ref("nbr"), _lib.ptr(out), _lib.ptr(ws), ws.numel() * 4,
                                                  _lib.stream_ptr()), "lstep_neighborhood_pe")
@@ -418,8 +436,15 @@ class LSTEP(nn.Module):
         self._check_ids(node_ids[:min(n_ids, n_edges)], s.num_rows, "neighbor sampler")
         if s.num_rows > V1:
             raise IndexError(f"pe has {V1} rows but the sampler knows node ids up to {s.num_rows - 1}")
-        K = int(num_neighbors)
         ids_dev, src_dev, dst_dev, t_dev = self._upload([(node_ids, I64), (src, I64), (dst, I64), (times, F64)])
+        return self.update_pe_device(pe, ids_dev, src_dev, dst_dev, t_dev, float(current_time), int(num_neighbors))
+
+    def update_pe_device(self, pe, ids_dev, src_dev, dst_dev, t_dev, current_time: float, K: int):
+        """Device-resident form of update_pe (inputs validated by the caller)."""
+        s = self.neighbor_sampler
+        d, t = self.pe_dim, self.time_feat_dim
+        V1 = pe.shape[0]
+        n_ids, n_edges = ids_dev.shape[0], src_dev.shape[0]
         lib = _lib.load()
         need = lib.lstep_update_pe_workspace_bytes(n_ids, n_edges, K, d, t, V1)
         with torch.cuda.device(pe.device):
@@ -429,7 +454,7 @@ class LSTEP(nn.Module):
                 _lib.check(lib.lstep_update_pe_workspace_init(_lib.ptr(buf), buf.numel(), V1, _lib.stream_ptr()), "workspace_init")
                 ws = self._update_ws = (buf, V1)
             _lib.check(lib.lstep_update_pe(_lib.ptr(pe), V1, s.csr_ref, _lib.ptr(ids_dev), n_ids, _lib.ptr(src_dev), _lib.ptr(dst_dev),
-                                           _lib.ptr(t_dev), n_edges, float(current_time), K, self._mlp_ref("update"), _lib.ptr(ws[0]),
+                                           _lib.ptr(t_dev), n_edges, current_time, K, self._mlp_ref("update"), _lib.ptr(ws[0]),
                                            ws[0].numel(), _lib.ptr(s._err), _lib.stream_ptr()), "lstep_update_pe")
             with torch.no_grad():
                 pe.narrow(0, 0, 0).zero_()  # in-place no-op: bumps the autograd version counter of the caller's tensor

@@ -18,9 +18,26 @@ restructuring itself is what the parity tests check. Citations are relative to /
 """
 from __future__ import annotations
 
-import numpy as np
+import contextlib
 
-F32 = np.float32
+import numpy as np
+import scipy.fft as _sfft
+
+F32 = np.float32   # fixed-precision casts that are part of the reference's contract (fp32 time deltas, fp32 tables)
+ACC = np.float32   # arithmetic precision of sums / matmuls / cos / tanh; float64 under `high_precision()`
+
+
+@contextlib.contextmanager
+def high_precision():
+    """Evaluate the same functions with float64 arithmetic (inputs still quantised exactly as the
+    reference quantises them). Used by tests as the 'exact' answer against which the fp32 error of the
+    reference-style evaluation and of the CUDA kernels are both measured."""
+    global ACC
+    old, ACC = ACC, np.float64
+    try:
+        yield
+    finally:
+        ACC = old
 
 
 # --------------------------------------------------------------------------------------------
@@ -92,15 +109,17 @@ def time_encoder_weights(time_dim: int) -> np.ndarray:
 
 def time_encode(dt_f32: np.ndarray, w: np.ndarray) -> np.ndarray:
     dt_f32 = np.asarray(dt_f32, dtype=F32)
-    arg = dt_f32[..., None] * w.astype(F32)  # exact fp32 product; Linear(1->t) with zero bias
-    return np.cos(arg, dtype=F32)
+    arg = dt_f32[..., None] * w.astype(F32)  # fp32 product, as Linear(1->t) with zero bias computes it
+    # cos evaluated in float64 and rounded: the correctly rounded value every fp32 cosf approximates to <= 1 ulp
+    # (numpy's own float32 cos drops to scalar libm for |x| > 7e4, 25x slower on these arguments)
+    return np.cos(arg.astype(np.float64)).astype(ACC)
 
 
 # --------------------------------------------------------------------------------------------
 # parameters — names are the reference's state_dict keys
 # --------------------------------------------------------------------------------------------
 def _linear(x, p, name):
-    return x.astype(F32) @ p[name + ".weight"].T.astype(F32) + p[name + ".bias"].astype(F32)
+    return x.astype(ACC) @ p[name + ".weight"].T.astype(ACC) + p[name + ".bias"].astype(ACC)
 
 
 def init_params(pe_dim=172, time_dim=100, T=100, seed=0) -> dict:
@@ -126,23 +145,24 @@ def init_params(pe_dim=172, time_dim=100, T=100, seed=0) -> dict:
 # --------------------------------------------------------------------------------------------
 def fourier_transform_pe(p: dict, node_ids, pe_hist: np.ndarray, batch_idx: int, num_fft_batches: int):
     x = pe_hist[node_ids].astype(F32)  # [N, Th, d]  (:105)
+    cdt = np.complex64 if ACC is np.float32 else np.complex128
     mask = None
     T = num_fft_batches
     if x.shape[1] < T:  # :108-113 — zero-pad to T; mask is keyed on batch_idx (Q5)
         x = np.concatenate([x, np.zeros((x.shape[0], T - x.shape[1], x.shape[2]), F32)], axis=1)
         mask = np.zeros(x.shape, F32)
         mask[:, :batch_idx, :] += 1
-    X = np.fft.fft(x.astype(np.complex64), axis=1).astype(np.complex64)  # :116-117
+    X = _sfft.fft(x.astype(cdt), axis=1, workers=-1).astype(cdt)  # :116-117
     if mask is not None:
         X = X * mask
-    X = p["fft_filter.weight"][None].astype(np.complex64) * X  # [T,d] table, elementwise (:121)
+    X = p["fft_filter.weight"][None].astype(cdt) * X  # [T,d] table, elementwise (:121)
     if mask is not None:
         X = X * mask
-    y = np.fft.ifft(X, axis=1).astype(np.complex64)  # :125
+    y = _sfft.ifft(X, axis=1, workers=-1).astype(cdt)  # :125
     if mask is not None:
         y = y * mask
-    y = y.real.astype(F32)  # complex -> float32 keeps the real part (:129)
-    out = y.transpose(0, 2, 1) @ p["fft_agg.weight"].astype(F32).T  # Linear(T->1), no bias (:135)
+    y = y.real.astype(ACC)  # complex -> float32 keeps the real part (:129)
+    out = y.transpose(0, 2, 1) @ p["fft_agg.weight"].astype(ACC).T  # Linear(T->1), no bias (:135)
     return np.squeeze(out[..., 0]) if out.shape[0] == 1 else out[..., 0]  # .squeeze()
 
 
@@ -158,12 +178,12 @@ def compute_neighborhood_pe(p: dict, adj: Adjacency, pe: np.ndarray, node_ids, n
     tf[nbr == 0] = 0.0  # :231
     nbr_pe = pe[nbr]  # [B,K,d]; padded slots read pe[0] (nonzero after an update — Q2) (:233)
     node_pe = pe[node_ids]  # :235
-    s = np.concatenate([nbr_pe, tf], axis=-1).sum(axis=1, dtype=F32)  # :238
+    s = np.concatenate([nbr_pe.astype(ACC), tf], axis=-1).sum(axis=1, dtype=ACC)  # :238
     h = _linear(s, p, "pe_neighbor_mlp_1")
     h = np.maximum(h, 0)
     h = _linear(h, p, "pe_neighbor_mlp_2")
     h = _linear(node_pe, p, "self_update_neighbor_pe") + h  # :244
-    return (node_pe + np.tanh(h, dtype=F32)).astype(F32)  # :245-247
+    return (node_pe + np.tanh(h, dtype=ACC)).astype(ACC)  # :245-247
 
 
 # --------------------------------------------------------------------------------------------
@@ -188,12 +208,12 @@ def update_pe(p: dict, adj: Adjacency, pe: np.ndarray, node_ids, batch_src_node_
     # ---- phase A (:277-303)
     dt = (np.float64(tc) - np.asarray(node_interact_times, dtype=np.float64)).astype(F32)  # f32 - f64 -> f64 -> float
     tf = time_encode(dt, w)  # [E,t]
-    agg = np.zeros((pe.shape[0], d + tf.shape[1]), F32)  # :282
-    scatter_sum_rows(np.concatenate([pe[batch_dst_node_ids], tf], axis=-1), batch_src_node_ids, agg)  # :283-286
-    scatter_sum_rows(np.concatenate([pe[batch_src_node_ids], tf], axis=-1), batch_dst_node_ids, agg)  # :287-290
+    agg = np.zeros((pe.shape[0], d + tf.shape[1]), ACC)  # :282
+    scatter_sum_rows(np.concatenate([pe[batch_dst_node_ids].astype(ACC), tf], axis=-1), batch_src_node_ids, agg)  # :283-286
+    scatter_sum_rows(np.concatenate([pe[batch_src_node_ids].astype(ACC), tf], axis=-1), batch_dst_node_ids, agg)  # :287-290
     a = agg[node_ids]  # :292
     h = _linear(np.maximum(_linear(a, p, "pe_mlp_1"), 0), p, "pe_mlp_2")  # :294-297
-    upd = node_pe + np.tanh(_linear(node_pe, p, "self_update_pe") + h, dtype=F32)  # :299-301
+    upd = node_pe + np.tanh(_linear(node_pe, p, "self_update_pe") + h, dtype=ACC)  # :299-301
     pe[node_ids] = upd  # :303
     # ---- phase B (:306-339)
     nbr, _, nt = sample_recent(adj, node_ids, node_interact_times, num_neighbors)  # N ids zipped with B times (Q1/Q1b)
@@ -204,14 +224,14 @@ def update_pe(p: dict, adj: Adjacency, pe: np.ndarray, node_ids, batch_src_node_
     tf2 = time_encode(dt2, w)
     tf2[nbr_flat == 0] = 0.0  # :316
     pe[0] = 0.0  # :317
-    agg2 = np.zeros((pe.shape[0], d + tf2.shape[1]), F32)  # :319
-    scatter_sum_rows(np.concatenate([pe[src_flat], tf2], axis=-1), nbr_flat, agg2)  # :320-322, phase-A-updated pe
+    agg2 = np.zeros((pe.shape[0], d + tf2.shape[1]), ACC)  # :319
+    scatter_sum_rows(np.concatenate([pe[src_flat].astype(ACC), tf2], axis=-1), nbr_flat, agg2)  # :320-322, phase-A-updated pe
     uniq = np.unique(nbr_flat)  # sorted; contains 0 when any slot is padding (:324)
     a2 = agg2[uniq]
     node_pe2 = pe[uniq]  # :325
     h2 = _linear(np.maximum(_linear(a2, p, "pe_mlp_1"), 0), p, "pe_mlp_2")  # :329-332
     # :334-335 — the self_update_pe term is computed and then overwritten: tanh(h2) only (Q3)
-    pe[uniq] = node_pe2 + np.tanh(h2, dtype=F32)  # :336-339 (row 0 becomes nonzero — Q2)
+    pe[uniq] = node_pe2 + np.tanh(h2, dtype=ACC)  # :336-339 (row 0 becomes nonzero — Q2)
     return pe  # same object (Q7)
 
 
