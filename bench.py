@@ -151,7 +151,7 @@ def run_ours(args, rank, world):
         lo, hi, _, _ = stream.batch_arrays(b)
         return [stream.src[lo:hi], stream.dst[lo:hi], stream.src[lo:hi], neg_dev[lo - e0:hi - e0]]
 
-    outs = [torch.empty((B, D), dtype=torch.float32, device=dev) for _ in range(C_CALLS)]
+    outs = torch.empty((C_CALLS, B, D), dtype=torch.float32, device=dev)
     W, Ksteps = args.warmup, args.steps
     W = max(W, 3)
     step_no = 0
@@ -195,9 +195,9 @@ def run_ours(args, rank, world):
     bm = bytes_model(B, N_mean, M_mean, K, V1=V1)
     hbm_peak, peak_src = peaks()
     # dominant kernel: the one with the largest share of the step
-    dom = max(kern, key=lambda k: kern[k]["ms"] * kern[k]["launches_per_step"])
-    alg = {"dft_filter": bm["F"], "nbr_aggregate": bm["P"] / C_CALLS, "sample_recent": bm["S"] * (B / (C_CALLS * B + N_mean)),
-           "pe_mlp(nbr)": (B * 4 * D * 3 + 4 * ((D + T_DIM) * D + 2 * D * D)) }
+    dom = max((k for k in kern if not k.startswith("_")), key=lambda k: kern[k]["ms"])
+    alg = {"dft_filter": bm["F"], "nbr_aggregate": bm["P"], "sample_recent": bm["S"] * (C_CALLS * B / (C_CALLS * B + N_mean)),
+           "pe_mlp(nbr)": (C_CALLS * B * 4 * D * 3 + 4 * ((D + T_DIM) * D + 2 * D * D))}
     roof = None
     if dom in alg:
         ach = alg[dom] / (kern[dom]["ms"] * 1e-3) / 1e9
@@ -239,15 +239,15 @@ def run_ours(args, rank, world):
 
 
 def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, lib):
-    """Per-stage times of the step (events around each stage) and stand-alone times of the four
-    kernels through their own C-ABI entry points on the same batch data."""
+    """Stand-alone CUDA-event times of the kernels of one step, each through its own C-ABI entry point
+    on the live state of the stream (the update runs on a scratch copy of the table); the stream is
+    then advanced by a normal step so the next measurement sees fresh data."""
     import torch
     from lstep_b200 import _lib
     m = model
     T, d, t = T_HIST, D, T_DIM
-    names = ["dft_filter(a3)", "table_clone+index_copy", "neighborhood x4 (a6)", "update_pe (a7+a8)", "ring_append"]
-    acc = {k: 0.0 for k in names}
-    kacc = {"dft_filter": 0.0, "sample_recent": 0.0, "nbr_aggregate": 0.0, "pe_mlp(nbr)": 0.0}
+    acc = {"dft_filter": 0.0, "sample_recent": 0.0, "nbr_aggregate": 0.0, "pe_mlp(nbr)": 0.0, "update_pe(9 kernels)": 0.0,
+           "ring_append": 0.0, "whole_step(lstep_pe_step)": 0.0}
     M_meas = []
 
     def timed(fn):
@@ -257,63 +257,53 @@ def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, l
         b.record()
         return a, b, r
 
-    S = torch.empty((stream.B, d + t), dtype=torch.float32, device=dev)
+    tw = m.time_encoder.w.weight.detach().reshape(-1)
+    scratch = torch.empty_like(stream.cur)
     with torch.no_grad():
         for i in range(n):
             b = (step_no + i) % nb
             lo, hi, io, ie = stream.batch_arrays(b)
+            nB, N = hi - lo, ie - io
             ids = stream.ids[io:ie]
             src, dst, tt = stream.src[lo:hi], stream.dst[lo:hi], stream.t[lo:hi]
             qs = queries(b)
-            evs = []
-            evs.append(timed(lambda: m.fourier_transform_pe_device(ids, stream.ring, T if stream.len >= T else min(stream.batch_idx, T), False,
-                                                                   s0=stream.head, ring=T, Th=stream.len, node_stride=T * d, time_stride=d)))
-            fft = evs[-1][2]
-
-            def clone():
-                stream.cur.copy_(stream.ring[:, stream._last_slot(), :])
-                stream.cur.index_copy_(0, ids, fft)
-            evs.append(timed(clone))
-            evs.append(timed(lambda: [m.compute_neighborhood_pe_device(stream.cur, q, tt, K) for q in qs]))
-            # stand-alone kernels on this batch (before the update changes the table)
-            nB = hi - lo
-            k1 = timed(lambda: sampler.sample_device(qs[1], tt, nB, nB, K))
-            nbr, nt = k1[2]
-            tw = m.time_encoder.w.weight.detach().reshape(-1)
-            k2 = timed(lambda: _lib.check(lib.lstep_nbr_aggregate(_lib.ptr(stream.cur), stream.V1, _lib.ptr(tt), _lib.ptr(nbr), _lib.ptr(nt), nB, K,
-                                                                  _lib.ptr(tw), d, t, _lib.ptr(S), _lib.stream_ptr()), "agg"))
-            outb = torch.empty((nB, d), dtype=torch.float32, device=dev)
-            k3 = timed(lambda: _lib.check(lib.lstep_pe_mlp_apply(_lib.ptr(S), _lib.ptr(stream.cur), _lib.ptr(qs[1]), nB, m._mlp_ref("nbr"),
-                                                                 _lib.ptr(outb), d, None, _lib.stream_ptr()), "mlp"))
-            evs.append(timed(lambda: m.update_pe_device(stream.cur, ids, src, dst, tt, float(stream.t_np[lo:hi].max()), K)))
-
-            def append():
-                if stream.len < T:
-                    slot = (stream.head + stream.len) % T
-                    stream.len += 1
-                else:
-                    slot = stream.head
-                    stream.head = (stream.head + 1) % T
-                stream.ring[:, slot, :] = stream.cur
-            evs.append(timed(append))
-            stream.batch_idx += 1
+            qcat = torch.cat(qs)
+            tcat = tt.repeat(len(qs))
+            rows = qcat.shape[0]
+            G = m._collapsed_filter(T if stream.len >= T else min(stream.batch_idx, T), False)
+            fft = torch.empty((N, d), dtype=torch.float32, device=dev)
+            nbr = torch.empty((rows, K), dtype=torch.int32, device=dev)
+            nt = torch.empty((rows, K), dtype=torch.float32, device=dev)
+            S = torch.empty((rows, d + t), dtype=torch.float32, device=dev)
+            outb = torch.empty((rows, d), dtype=torch.float32, device=dev)
+            scratch.copy_(stream.cur)
             torch.cuda.synchronize()
-            for name, (a, bb, _) in zip(names, evs):
-                acc[name] += a.elapsed_time(bb)
-            kacc["dft_filter"] += evs[0][0].elapsed_time(evs[0][1])
-            kacc["sample_recent"] += k1[0].elapsed_time(k1[1])
-            kacc["nbr_aggregate"] += k2[0].elapsed_time(k2[1])
-            kacc["pe_mlp(nbr)"] += k3[0].elapsed_time(k3[1])
-            if m._update_ws is not None:  # measured M of this batch: counters live after the two int32 maps
-                pass
-    stages = {k: v / n for k, v in acc.items()}
-    kern = {"dft_filter": {"ms": kacc["dft_filter"] / n, "launches_per_step": 1},
-            "sample_recent": {"ms": kacc["sample_recent"] / n, "launches_per_step": C_CALLS + 1},
-            "nbr_aggregate": {"ms": kacc["nbr_aggregate"] / n, "launches_per_step": C_CALLS},
-            "pe_mlp(nbr)": {"ms": kacc["pe_mlp(nbr)"] / n, "launches_per_step": C_CALLS},
-            # own kernels per step: K3 1; a6 3 x C (sample, aggregate, mlp); update_pe 8 (prep, edge agg, mlp, sample, count, scan, fill, gather) + mlp
-            "_launches_per_step": {"n": 1 + 3 * C_CALLS + 9, "ms": 0.0, "launches_per_step": 0}}
-    # measured M: distinct sampled neighbours per batch, recomputed on the host for a few batches (cheap)
+            ev = {}
+            ev["dft_filter"] = timed(lambda: _lib.check(lib.lstep_dft_filter(_lib.ptr(stream.ring), T * d, d, stream.head, T, stream.len, d,
+                                                                            _lib.ptr(ids), N, _lib.ptr(G), _lib.ptr(fft), d, _lib.stream_ptr()), "dft"))
+            ev["sample_recent"] = timed(lambda: _lib.check(lib.lstep_sample_recent_compact(sampler.csr_ref, _lib.ptr(qcat), _lib.ptr(tcat), rows, rows, K,
+                                                                                          _lib.ptr(nbr), _lib.ptr(nt), _lib.ptr(sampler._err),
+                                                                                          _lib.stream_ptr()), "k1"))
+            ev["nbr_aggregate"] = timed(lambda: _lib.check(lib.lstep_nbr_aggregate(_lib.ptr(stream.cur), stream.V1, _lib.ptr(tcat), _lib.ptr(nbr), _lib.ptr(nt),
+                                                                                  rows, K, _lib.ptr(tw), d, t, _lib.ptr(S), _lib.stream_ptr()), "agg"))
+            ev["pe_mlp(nbr)"] = timed(lambda: _lib.check(lib.lstep_pe_mlp_apply(_lib.ptr(S), _lib.ptr(stream.cur), _lib.ptr(qcat), rows, m._mlp_ref("nbr"),
+                                                                               _lib.ptr(outb), d, None, _lib.stream_ptr()), "mlp"))
+            ev["update_pe(9 kernels)"] = timed(lambda: m.update_pe_device(scratch, ids, src, dst, tt, stream.batch_tmax[b], K))
+            nxt = (stream.head + stream.len) % T if stream.len < T else stream.head  # the slot the coming step overwrites anyway
+            ev["ring_append"] = timed(lambda: stream.ring[:, nxt, :].copy_(stream.cur))
+            ev["whole_step(lstep_pe_step)"] = timed(lambda: stream.step(b, qs))
+            torch.cuda.synchronize()
+            for k2, (a, bb, _) in ev.items():
+                acc[k2] += a.elapsed_time(bb)
+    stages = {k2: v / n for k2, v in acc.items()}
+    kern = {"dft_filter": {"ms": stages["dft_filter"], "launches_per_step": 1},
+            "sample_recent": {"ms": stages["sample_recent"], "launches_per_step": 2},
+            "nbr_aggregate": {"ms": stages["nbr_aggregate"], "launches_per_step": 1},
+            "pe_mlp(nbr)": {"ms": stages["pe_mlp(nbr)"], "launches_per_step": 1},
+            # own kernels per step: DFT 1; a6 3 (sample, aggregate, mlp; all C query sets per launch);
+            # update_pe 9 (prep, edge aggregate, mlp, sample, count, scan, fill, gather, mlp); ring append 1
+            "_launches_per_step": {"n": 1 + 3 + 9 + 1, "ms": 0.0, "launches_per_step": 0}}
+    # measured M: distinct sampled neighbours per batch
     for i in range(min(n, 20)):
         b = (step_no + i) % nb
         lo, hi, io, ie = stream.batch_arrays(b)
@@ -334,7 +324,7 @@ def e2e_pass(stream, g, e0, neg_all, step_no, nb, n, B, world, dev):
         b = (step_no + i) % nb
         lo, hi, _, _ = stream.batch_arrays(b)
         stream.step_host(g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.node_interact_times[lo:hi],
-                         [g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.src_node_ids[lo:hi], neg_all[lo - e0:hi - e0]])
+                         [g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.src_node_ids[lo:hi], neg_all[lo - e0:hi - e0]], lo=lo)
     step_no += 3
     torch.cuda.synchronize()
     if world > 1:
@@ -348,7 +338,7 @@ def e2e_pass(stream, g, e0, neg_all, step_no, nb, n, B, world, dev):
         b = (step_no + i) % nb
         lo, hi, _, _ = stream.batch_arrays(b)
         r = stream.step_host(g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.node_interact_times[lo:hi],
-                             [g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.src_node_ids[lo:hi], neg_all[lo - e0:hi - e0]])
+                             [g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.src_node_ids[lo:hi], neg_all[lo - e0:hi - e0]], lo=lo)
         d2h += r.nbytes
         edges += hi - lo
     ev1.record()

@@ -187,6 +187,40 @@ int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int6
  * entry and is zero again on exit; call once after allocating the workspace. */
 int lstep_update_pe_workspace_init(void* workspace, size_t workspace_bytes, int64_t pe_rows, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f1 — streaming PE step on device-resident state (an addition to the reference API; the loops'
+ * trim / clone / cat of the history, train_LSTEP_link_prediction.py:205,224-230,301-306 and
+ * evaluate_model_utils.py:57-63,131-135, become one ring-slot write).
+ *   ring  [V1][T][d] node-major history ring; logical step j lives in slot (head + j) % T, j < len
+ *   cur   [V1][d]    current table; equals the newest ring slot between steps (lstep_ring_load
+ *                    initialises it after an import)
+ * lstep_pe_step runs, for the batch of edges [lo, lo + n_edges) of the resident stream:
+ *   the DFT filter of the batch nodes `ids` (G = collapsed filter for this step's mask) scattered into
+ *   cur; compute_neighborhood_pe for n_queries id sets (host array of device pointers, each
+ *   [n_edges], queried at the batch's edge times) -> nbr_out [n_queries][n_edges][d]; update_pe on
+ *   cur; cur -> ring[:, append_slot].
+ * The workspace starts with the update_pe workspace: initialise it with
+ * lstep_update_pe_workspace_init.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lstep_pe_stream {
+  const int64_t* src; /* [E] whole edge stream, resident */
+  const int64_t* dst;
+  const double* t;
+  float* ring;
+  float* cur;
+  int64_t V1;
+  int T;
+  int d;
+} lstep_pe_stream;
+
+size_t lstep_pe_step_workspace_bytes(int64_t max_ids, int64_t max_edges, int n_queries, int K, int d, int t, int64_t V1);
+int lstep_ring_load(const float* ring, float* cur, int64_t V1, int T, int d, int slot, void* stream);
+int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, int64_t n_edges, const int64_t* ids,
+                  int64_t n_ids, double current_time, int head, int len, int append_slot, const float* G,
+                  const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
+                  const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                  uint32_t* err_flag, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,6 +27,11 @@ class CSR(C.Structure):
     _fields_ = [("indptr", vp), ("nbr", vp), ("eid", vp), ("t", vp), ("num_rows", i64), ("nnz", i64)]
 
 
+class PEStreamDesc(C.Structure):
+    """struct lstep_pe_stream"""
+    _fields_ = [("src", vp), ("dst", vp), ("t", vp), ("ring", vp), ("cur", vp), ("V1", i64), ("T", i32), ("d", i32)]
+
+
 class PEMLP(C.Structure):
     """struct lstep_pe_mlp"""
     _fields_ = [("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("ws", vp), ("bs", vp), ("tw", vp), ("d", i32), ("t", i32)]
@@ -56,6 +61,10 @@ _SIGS = {
     "lstep_update_pe": (i32, [vp, i64, C.POINTER(CSR), vp, i64, vp, vp, vp, i64, C.c_double, i32, C.POINTER(PEMLP), vp, sz,
                               vp, vp]),
     "lstep_update_pe_workspace_init": (i32, [vp, sz, i64, vp]),
+    "lstep_pe_step_workspace_bytes": (sz, [i64, i64, i32, i32, i32, i32, i64]),
+    "lstep_ring_load": (i32, [vp, vp, i64, i32, i32, i32, vp]),
+    "lstep_pe_step": (i32, [C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, i32, i32, i32, vp,
+                            C.POINTER(C.c_void_p), i32, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
 }
 
 EXPORTS = tuple(_SIGS)

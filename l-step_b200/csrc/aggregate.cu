@@ -16,14 +16,14 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
                                                             const int32_t* __restrict__ nbr,
                                                             const float* __restrict__ nbr_t, int64_t n_rows, int K,
                                                             const float* __restrict__ tw, int d, int t, int t_pad,
-                                                            float* __restrict__ S, int64_t ldS) {
+                                                            float* __restrict__ S, int64_t ldS, int64_t period) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);
   float* s_dt = reinterpret_cast<float*>(s_nbr + K);
   const int tid = threadIdx.x;
   const int dvec = d / VEC;
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    const double tq = q_time[row];
+    const double tq = q_time[period ? row % period : row];
     for (int k = tid; k < K; k += blockDim.x) {
       s_nbr[k] = nbr[row * K + k];
       // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
@@ -85,14 +85,15 @@ __global__ void __launch_bounds__(256) nbr_aggregate_bwd_kernel(const float* __r
   }
 }
 
-int launch_pe_mlp(const float* A, int64_t lda, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
+int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st);
 
 static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
 int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* nbr, const float* nbr_t,
-                         int64_t n_rows, int K, const float* tw, int d, int t, float* S, int64_t ldS, cudaStream_t st) {
+                         int64_t n_rows, int K, const float* tw, int d, int t, float* S, int64_t ldS, int64_t period,
+                         cudaStream_t st) {
   const bool v4 = d % 4 == 0 && ldS % 4 == 0 && aligned16(pe) && aligned16(S);
   const int dvec = v4 ? d / 4 : d;
   const int t_pad = (int)align_up((size_t)t, 32);
@@ -102,9 +103,9 @@ int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* n
   if (smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
   const int64_t grid = n_rows < (int64_t)kNumSMs * 16 ? n_rows : (int64_t)kNumSMs * 16;
   if (v4)
-    nbr_aggregate_kernel<4><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS);
+    nbr_aggregate_kernel<4><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period);
   else
-    nbr_aggregate_kernel<1><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS);
+    nbr_aggregate_kernel<1><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period);
   return check_launch("nbr_aggregate");
 }
 
@@ -118,7 +119,7 @@ extern "C" int lstep_nbr_aggregate(const float* pe, int64_t pe_rows, const doubl
   if (n_rows < 0 || K <= 0 || d <= 0 || t < 0 || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
   if (n_rows == 0) return LSTEP_OK;
   if (!pe || !q_time || !nbr || !nbr_t || !S || (t > 0 && !tw)) return LSTEP_ERR_INVALID_ARG;
-  return launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, S, d + t, as_stream(stream));
+  return launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, S, d + t, 0, as_stream(stream));
 }
 
 extern "C" int lstep_nbr_aggregate_bwd(const float* dS, const int32_t* nbr, int64_t n_rows, int K, int d, int t,
@@ -142,7 +143,7 @@ extern "C" int lstep_neighborhood_pe(const float* pe, int64_t pe_rows, const int
   const size_t need = (size_t)n_rows * ldS * sizeof(float);
   if (workspace_bytes < need) return LSTEP_ERR_WORKSPACE;
   float* S = reinterpret_cast<float*>(workspace);
-  int rc = launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, mlp->tw, mlp->d, mlp->t, S, ldS, as_stream(stream));
+  int rc = launch_nbr_aggregate(pe, q_time, nbr, nbr_t, n_rows, K, mlp->tw, mlp->d, mlp->t, S, ldS, 0, as_stream(stream));
   if (rc != LSTEP_OK) return rc;
-  return launch_pe_mlp(S, ldS, pe, q_node, n_rows, n_rows, nullptr, mlp, out, mlp->d, nullptr, as_stream(stream));
+  return launch_pe_mlp(S, ldS, pe, single_ids(q_node), n_rows, n_rows, nullptr, mlp, out, mlp->d, nullptr, as_stream(stream));
 }

@@ -40,6 +40,21 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Row -> node id for kernels that serve several query sets in one launch (the eval loop's C calls of
+// compute_neighborhood_pe share one batch of edge times): row r belongs to set r / period.
+struct RowIds {
+  const int64_t* p[8];
+  int64_t period;  // 0: single set, p[0][row]
+  __device__ __forceinline__ int64_t at(int64_t row) const { return period ? p[row / period][row % period] : p[0][row]; }
+  __device__ __forceinline__ int64_t time_index(int64_t row) const { return period ? row % period : row; }
+};
+inline RowIds single_ids(const int64_t* ids) {
+  RowIds r{};
+  r.p[0] = ids;
+  r.period = 0;
+  return r;
+}
+
 // TimeEncoder (models/modules.py:37): cos(fp32(dt) * w_j + 0). The product must be a separately
 // rounded fp32 multiply (no FMA contraction into the range reduction), cosf is the accurate
 // library version (arguments reach 1e8 rad).

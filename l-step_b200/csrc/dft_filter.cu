@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_kernel(const float* __
                                                                  int64_t time_stride, int s0, int ring, int Th, int d,
                                                                  const int64_t* __restrict__ ids, int64_t n_ids,
                                                                  const float* __restrict__ G, float* __restrict__ out,
-                                                                 int64_t out_stride) {
+                                                                 int64_t out_stride, int scatter) {
   using V = typename VecT<VEC>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V* red = reinterpret_cast<V*>(smem_raw);  // [groups][dvec]
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_kernel(const float* __
     if (active && g == 0) {
       V tot = red[cv];
       for (int gg = 1; gg < groups; ++gg) add_acc(tot, red[gg * dvec + cv]);
-      reinterpret_cast<V*>(out + n * out_stride)[cv] = tot;
+      reinterpret_cast<V*>(out + (scatter ? ids[n] : n) * out_stride)[cv] = tot;
     }
     __syncthreads();
   }
@@ -205,9 +205,10 @@ extern "C" int lstep_dft_collapse(const float* W_c64, const float* a, int T, int
   return check_launch("dft_collapse");
 }
 
-extern "C" int lstep_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th,
-                                int d, const int64_t* ids, int64_t n_ids, const float* G, float* out,
-                                int64_t out_stride, void* stream) {
+namespace lstep {
+int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
+                      const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride, int scatter,
+                      void* stream) {
   if (n_ids < 0 || Th < 0 || d <= 0 || ring < Th || s0 < 0 || (ring > 0 && s0 >= ring)) return LSTEP_ERR_INVALID_ARG;
   if (n_ids == 0) return LSTEP_OK;
   if (!ids || !out || !G || (Th > 0 && !hist)) return LSTEP_ERR_INVALID_ARG;
@@ -219,11 +220,18 @@ extern "C" int lstep_dft_filter(const float* hist, int64_t node_stride, int64_t 
   const int64_t grid = n_ids < (int64_t)kNumSMs * 6 ? n_ids : (int64_t)kNumSMs * 6;
   if (v4)
     dft_filter_kernel<4><<<(unsigned)grid, kDftThreads, smem, as_stream(stream)>>>(
-        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride);
+        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, scatter);
   else
     dft_filter_kernel<1><<<(unsigned)grid, kDftThreads, smem, as_stream(stream)>>>(
-        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride);
+        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, scatter);
   return check_launch("dft_filter");
+}
+}  // namespace lstep
+
+extern "C" int lstep_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th,
+                                int d, const int64_t* ids, int64_t n_ids, const float* G, float* out,
+                                int64_t out_stride, void* stream) {
+  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, 0, stream);
 }
 
 extern "C" int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring,

@@ -78,7 +78,7 @@ __device__ __forceinline__ void consumer_sync(int nthreads) {  // named barrier 
 //             groups only meet at the end of a segment, where the partials are summed through smem.
 template <int RT, int G>
 __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float* __restrict__ A, int64_t lda, const float* pe,
-                                                              const int64_t* __restrict__ base_ids, int64_t n_rows,
+                                                              RowIds base_ids, int64_t n_rows,
                                                               const int32_t* __restrict__ n_rows_dev, lstep_pe_mlp m,
                                                               int ldo, float* __restrict__ out, int64_t out_stride,
                                                               float* pe_inplace) {
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
       for (int u = 0; u < 4; ++u) {
         const int idx = base + u * ncons + tid;
         const int r = idx / d_pad, k = idx % d_pad;
-        v[u] = (idx < totalB && row0 + r < n_rows && k < d) ? pe[base_ids[row0 + r] * (int64_t)d + k] : 0.f;
+        v[u] = (idx < totalB && row0 + r < n_rows && k < d) ? pe[base_ids.at(row0 + r) * (int64_t)d + k] : 0.f;
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
       const int rr = rg * RT + r;
       const int64_t row = row0 + rr;
       if (row >= n_rows) continue;
-      float* dst = out ? out + row * out_stride : pe_inplace + base_ids[row] * (int64_t)d;
+      float* dst = out ? out + row * out_stride : pe_inplace + base_ids.at(row) * (int64_t)d;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int c = c0 + j;
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
 }
 
 template <int RT, int G>
-static int launch_mlp_r(const float* A, int64_t lda, const float* pe, const int64_t* base_ids, int64_t n_rows,
+static int launch_mlp_r(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows,
                         const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride,
                         float* pe_inplace, cudaStream_t st) {
   constexpr int R = 2 * RT;
@@ -285,11 +285,11 @@ static int launch_mlp_r(const float* A, int64_t lda, const float* pe, const int6
 }
 
 // n_rows is the host-side upper bound of rows; *n_rows_dev (optional) the device-side count.
-int launch_pe_mlp(const float* A, int64_t lda, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
+int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st) {
   if (n_rows <= 0) return LSTEP_OK;
-  if (!A || !pe || !base_ids || !m || (!out && !pe_inplace)) return LSTEP_ERR_INVALID_ARG;
+  if (!A || !pe || !base_ids.p[0] || !m || (!out && !pe_inplace)) return LSTEP_ERR_INVALID_ARG;
   const int ldo = lstep_packed_ld(m->d);
   // rows per CTA: the largest tile that still gives about one CTA per SM; k-split while the CTA stays <= 1024 threads
   if (ldo <= 192) {  // 4 k-split groups of <= 192 threads + the producer warp = 800 threads
@@ -321,6 +321,6 @@ extern "C" int lstep_pe_mlp_apply(const float* A, const float* pe, const int64_t
                                   void* stream) {
   if (n_rows < 0) return LSTEP_ERR_INVALID_ARG;
   if (!mlp) return LSTEP_ERR_INVALID_ARG;
-  return launch_pe_mlp(A, mlp->d + mlp->t, pe, base_ids, n_rows, n_rows, nullptr, mlp, out, out_stride, pe_inplace,
+  return launch_pe_mlp(A, mlp->d + mlp->t, pe, single_ids(base_ids), n_rows, n_rows, nullptr, mlp, out, out_stride, pe_inplace,
                        as_stream(stream));
 }

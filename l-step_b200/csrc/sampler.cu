@@ -15,8 +15,7 @@ template <typename IdT, bool kWithEid>
 __global__ void __launch_bounds__(256) sample_recent_kernel(const int64_t* __restrict__ indptr,
                                                             const int32_t* __restrict__ c_nbr,
                                                             const int32_t* __restrict__ c_eid,
-                                                            const double* __restrict__ c_t, int64_t num_rows,
-                                                            const int64_t* __restrict__ q_node,
+                                                            const double* __restrict__ c_t, int64_t num_rows, RowIds q_node,
                                                             const double* __restrict__ q_time, int64_t n_rows,
                                                             int64_t n_valid, int K, IdT* __restrict__ out_nbr,
                                                             IdT* __restrict__ out_eid, float* __restrict__ out_t,
@@ -28,13 +27,13 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(const int64_t* __res
   int64_t end = 0;  // one past the last strictly-earlier entry
   int64_t cnt = 0;
   if (row < n_valid) {
-    const int64_t node = q_node[row];
+    const int64_t node = q_node.at(row);
     if (node < 0 || node >= num_rows) {
       if (lane == 0 && err_flag) atomicOr(err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
     } else {
       const int64_t lo = indptr[node];
       int64_t a = lo, b = indptr[node + 1];
-      const double tq = q_time[row];
+      const double tq = q_time[q_node.time_index(row)];
       // invariant: entries < a are earlier than tq, entries >= b are not
       while (b - a > 32) {
         const int64_t len = b - a;
@@ -70,12 +69,12 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(const int64_t* __res
 }
 
 template <typename IdT, bool kWithEid>
-static int launch_sample(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows,
+int launch_sample(const lstep_csr* csr, RowIds q_node, const double* q_time, int64_t n_rows,
                          int64_t n_valid, int K, IdT* out_nbr, IdT* out_eid, float* out_t, uint32_t* err_flag,
                          void* stream) {
   if (!csr || K <= 0 || n_rows < 0 || n_valid < 0) return LSTEP_ERR_INVALID_ARG;
   if (n_rows == 0) return LSTEP_OK;
-  if (!out_nbr || !out_t || (n_valid > 0 && (!q_node || !q_time))) return LSTEP_ERR_INVALID_ARG;
+  if (!out_nbr || !out_t || (n_valid > 0 && (!q_node.p[0] || !q_time))) return LSTEP_ERR_INVALID_ARG;
   if (n_valid > n_rows) n_valid = n_rows;
   const int warps = 8;
   const int64_t blocks = ceil_div(n_rows, warps);
@@ -85,21 +84,24 @@ static int launch_sample(const lstep_csr* csr, const int64_t* q_node, const doub
   return check_launch("sample_recent");
 }
 
+template int launch_sample<int32_t, false>(const lstep_csr*, RowIds, const double*, int64_t, int64_t, int, int32_t*, int32_t*, float*,
+                                           uint32_t*, void*);
+
 }  // namespace lstep
 
 extern "C" int lstep_sample_recent(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows,
                                    int64_t n_valid, int K, int64_t* out_nbr, int64_t* out_eid, float* out_t,
                                    uint32_t* err_flag, void* stream) {
   if (out_eid)
-    return lstep::launch_sample<int64_t, true>(csr, q_node, q_time, n_rows, n_valid, K, out_nbr, out_eid, out_t,
+    return lstep::launch_sample<int64_t, true>(csr, lstep::single_ids(q_node), q_time, n_rows, n_valid, K, out_nbr, out_eid, out_t,
                                                err_flag, stream);
-  return lstep::launch_sample<int64_t, false>(csr, q_node, q_time, n_rows, n_valid, K, out_nbr, nullptr, out_t,
+  return lstep::launch_sample<int64_t, false>(csr, lstep::single_ids(q_node), q_time, n_rows, n_valid, K, out_nbr, nullptr, out_t,
                                               err_flag, stream);
 }
 
 extern "C" int lstep_sample_recent_compact(const lstep_csr* csr, const int64_t* q_node, const double* q_time,
                                            int64_t n_rows, int64_t n_valid, int K, int32_t* out_nbr, float* out_t,
                                            uint32_t* err_flag, void* stream) {
-  return lstep::launch_sample<int32_t, false>(csr, q_node, q_time, n_rows, n_valid, K, out_nbr, nullptr, out_t,
+  return lstep::launch_sample<int32_t, false>(csr, lstep::single_ids(q_node), q_time, n_rows, n_valid, K, out_nbr, nullptr, out_t,
                                               err_flag, stream);
 }

@@ -1,0 +1,142 @@
+// Streaming PE step: the whole per-batch sequence of the eval loop
+// (evaluate_model_utils.py:54-135) as one C call on device-resident state:
+//
+//   a3   cur[ids] <- sum_s G[s] * ring[ids, (head+s) % T]            (DFT filter, scattered into the table)
+//   a6   out[c]   <- neighbourhood PE of query set c at the batch's edge times, all C sets in ONE
+//                    sampler / aggregate / MLP launch (C*B rows)
+//   a7/8 cur      <- update_pe(cur)                                   (in place)
+//        ring[:, slot] <- cur                                          (append: overwrite the oldest slot)
+//
+// `cur` always equals the newest ring slot between steps, so the loops' clone(hist[:, -1]) disappears,
+// and the history is never trimmed or concatenated: one [V1, d] table copy per step remains (the H term
+// of SURVEY §8(d)) instead of ~3 GB of clone + cat at Reddit size.
+#include "common.cuh"
+
+namespace lstep {
+
+template <typename IdT, bool kWithEid>
+int launch_sample(const lstep_csr* csr, RowIds q_node, const double* q_time, int64_t n_rows, int64_t n_valid, int K,
+                  IdT* out_nbr, IdT* out_eid, float* out_t, uint32_t* err_flag, void* stream);
+int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* nbr, const float* nbr_t, int64_t n_rows,
+                         int K, const float* tw, int d, int t, float* S, int64_t ldS, int64_t period, cudaStream_t st);
+int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
+                  const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
+                  cudaStream_t st);
+int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
+                      const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride, int scatter,
+                      void* stream);
+
+// ring[v][slot][:] = cur[v][:]  (node-major ring: 688-byte rows at a 68.8 KB pitch)
+__global__ void __launch_bounds__(256) ring_append_kernel(const float* __restrict__ cur, float* __restrict__ ring,
+                                                          int64_t V1, int T, int d, int slot) {
+  const int dvec = d >> 2;
+  const int64_t total = V1 * dvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / dvec;
+    const int c = (int)(i % dvec);
+    reinterpret_cast<float4*>(ring + (v * T + slot) * (int64_t)d)[c] = reinterpret_cast<const float4*>(cur + v * (int64_t)d)[c];
+  }
+}
+
+__global__ void __launch_bounds__(256) ring_load_kernel(const float* __restrict__ ring, float* __restrict__ cur, int64_t V1,
+                                                        int T, int d, int slot) {
+  const int dvec = d >> 2;
+  const int64_t total = V1 * dvec;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t v = i / dvec;
+    const int c = (int)(i % dvec);
+    reinterpret_cast<float4*>(cur + v * (int64_t)d)[c] = reinterpret_cast<const float4*>(ring + (v * T + slot) * (int64_t)d)[c];
+  }
+}
+
+struct StepWs {
+  void* update;  // lstep_update_pe workspace (first: its per-node counter map sits at offset 0)
+  size_t update_bytes;
+  int32_t* nbrQ;  // [C*B*K]
+  float* ntQ;     // [C*B*K]
+  float* S;       // [C*B][lda]
+  int64_t lda;
+  size_t bytes;
+};
+
+static StepWs carve_step(void* base, int64_t max_ids, int64_t max_edges, int C, int K, int d, int t, int64_t V1) {
+  StepWs w;
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? static_cast<char*>(base) + o : nullptr;
+    o = align_up(o + bytes, 256);
+    return p;
+  };
+  w.update_bytes = lstep_update_pe_workspace_bytes(max_ids, max_edges, K, d, t, V1);
+  w.update = take(w.update_bytes);
+  const size_t rows = (size_t)C * max_edges;
+  w.nbrQ = (int32_t*)take(4 * rows * K);
+  w.ntQ = (float*)take(4 * rows * K);
+  w.lda = (int64_t)align_up((size_t)(d + t), 4);
+  w.S = (float*)take(4 * rows * w.lda);
+  w.bytes = o;
+  return w;
+}
+
+}  // namespace lstep
+
+using namespace lstep;
+
+extern "C" size_t lstep_pe_step_workspace_bytes(int64_t max_ids, int64_t max_edges, int n_queries, int K, int d, int t,
+                                                int64_t V1) {
+  if (max_ids < 0 || max_edges < 0 || n_queries < 0 || n_queries > 8 || K <= 0 || d <= 0 || t < 0 || V1 <= 0) return 0;
+  return carve_step(nullptr, max_ids, max_edges, n_queries, K, d, t, V1).bytes;
+}
+
+extern "C" int lstep_ring_load(const float* ring, float* cur, int64_t V1, int T, int d, int slot, void* stream) {
+  if (!ring || !cur || V1 <= 0 || T <= 0 || d <= 0 || d % 4 != 0 || slot < 0 || slot >= T) return LSTEP_ERR_INVALID_ARG;
+  ring_load_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(ring, cur, V1, T, d, slot);
+  return check_launch("ring_load");
+}
+
+extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, int64_t n_edges,
+                             const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
+                             const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
+                             const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace,
+                             size_t workspace_bytes, uint32_t* err_flag, void* stream) {
+  if (!s || !csr || !mlp_nbr || !mlp_upd || !G || n_edges < 0 || n_ids < 0 || K <= 0 || n_queries < 0 || n_queries > 8)
+    return LSTEP_ERR_INVALID_ARG;
+  if (!s->ring || !s->cur || !s->src || !s->dst || !s->t || s->V1 <= 0 || s->T <= 0 || s->d != mlp_nbr->d || s->d % 4 != 0)
+    return LSTEP_ERR_INVALID_ARG;
+  if (head < 0 || head >= s->T || len < 0 || len > s->T || append_slot < 0 || append_slot >= s->T) return LSTEP_ERR_INVALID_ARG;
+  if (n_queries > 0 && (!query_ids_host || !nbr_out)) return LSTEP_ERR_INVALID_ARG;
+  const int d = s->d, t = mlp_nbr->t, T = s->T;
+  const StepWs need = carve_step(nullptr, n_ids, n_edges, n_queries, K, d, t, s->V1);
+  if (!workspace || workspace_bytes < need.bytes) return LSTEP_ERR_WORKSPACE;
+  StepWs w = carve_step(workspace, n_ids, n_edges, n_queries, K, d, t, s->V1);
+  cudaStream_t st = as_stream(stream);
+  int rc;
+  // a3: filtered history of the batch nodes straight into the current table
+  if (n_ids > 0) {
+    rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, 1, stream);
+    if (rc != LSTEP_OK) return rc;
+  }
+  // a6: all query sets in one pass
+  const int64_t rows = (int64_t)n_queries * n_edges;
+  if (rows > 0) {
+    RowIds q{};
+    for (int c = 0; c < n_queries; ++c) {
+      if (!query_ids_host[c]) return LSTEP_ERR_INVALID_ARG;
+      q.p[c] = query_ids_host[c];
+    }
+    q.period = n_edges;
+    const double* tq = s->t + lo;
+    rc = launch_sample<int32_t, false>(csr, q, tq, rows, rows, K, w.nbrQ, nullptr, w.ntQ, err_flag, stream);
+    if (rc != LSTEP_OK) return rc;
+    rc = launch_nbr_aggregate(s->cur, tq, w.nbrQ, w.ntQ, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, n_edges, st);
+    if (rc != LSTEP_OK) return rc;
+    rc = launch_pe_mlp(w.S, w.lda, s->cur, q, rows, rows, nullptr, mlp_nbr, nbr_out, d, nullptr, st);
+    if (rc != LSTEP_OK) return rc;
+  }
+  // a7 + a8
+  rc = lstep_update_pe(s->cur, s->V1, csr, ids, n_ids, s->src + lo, s->dst + lo, s->t + lo, n_edges, current_time, K,
+                       mlp_upd, w.update, w.update_bytes, err_flag, stream);
+  if (rc != LSTEP_OK) return rc;
+  ring_append_kernel<<<kNumSMs * 8, 256, 0, st>>>(s->cur, s->ring, s->V1, T, d, append_slot);
+  return check_launch("ring_append");
+}

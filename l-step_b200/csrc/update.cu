@@ -27,7 +27,7 @@
 
 namespace lstep {
 
-int launch_pe_mlp(const float* A, int64_t lda, const float* pe, const int64_t* base_ids, int64_t n_rows, int64_t expected_rows,
+int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st);
 
@@ -531,7 +531,7 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
     edge_aggregate_kernel<<<(unsigned)grid, threads, smem, st>>>(pe, ids, n_ids, w.src32, w.dst32, w.dtA, n_edges,
                                                                  mlp->tw, d, t, t_pad, w.A, w.lda);
     if ((rc = check_launch("edge_aggregate")) != LSTEP_OK) return rc;
-    if ((rc = launch_pe_mlp(w.A, w.lda, pe, ids, n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st)) != LSTEP_OK) return rc;
+    if ((rc = launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st)) != LSTEP_OK) return rc;
   }
 
   // ---- phase B
@@ -574,5 +574,5 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
   lstep_pe_mlp noself = *mlp;
   noself.ws = nullptr;  // the self term is computed and discarded by the reference (LSTEP.py:334-335, Q3)
   noself.bs = nullptr;
-  return launch_pe_mlp(w.A, w.lda, pe, w.U, max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe, st);
+  return launch_pe_mlp(w.A, w.lda, pe, single_ids(w.U), max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe, st);
 }

@@ -20,11 +20,16 @@ adopts one (utils/EarlyStopping.py:79-82,100-104).
 """
 from __future__ import annotations
 
+import ctypes
+
 import numpy as np
 import torch
 
 from . import _lib
 from .model import LSTEP
+
+C_void_p = ctypes.c_void_p
+C_byref = ctypes.byref
 
 
 class PEStream:
@@ -61,6 +66,8 @@ class PEStream:
         self.ids_np = np.concatenate(ids) if ids else np.zeros(0, np.int64)
         self.ids = torch.from_numpy(self.ids_np).to(dev)
         self.num_batches = len(self.batch_lo)
+        self.batch_tmax = [float(self.t_np[lo:min(lo + self.B, self.stop)].max()) for lo in self.batch_lo]
+        self._host_cursor = self.start
         self.V1 = None
         self.batch_idx = 0
         if history is not None:
@@ -83,8 +90,17 @@ class PEStream:
         self.len = Th  # number of valid steps
         self.head = 0  # slot of the oldest valid step
         self.cur = torch.empty((V1, d), dtype=torch.float32, device=self.dev)
+        lib = _lib.load()
+        with torch.cuda.device(self.dev):
+            _lib.check(lib.lstep_ring_load(_lib.ptr(self.ring), _lib.ptr(self.cur), V1, self.T, d, self._last_slot(),
+                                           _lib.stream_ptr()), "lstep_ring_load")
+        self.desc = _lib.PEStreamDesc(self.src.data_ptr(), self.dst.data_ptr(), self.t.data_ptr(), self.ring.data_ptr(),
+                                      self.cur.data_ptr(), V1, self.T, d)
+        self._ws = None
+        self.steps_done = 0
 
     def export_history(self) -> torch.Tensor:
+        """The history in the reference's layout [V1, Th, d], oldest first (for save_pe / torch.cat)."""
         idx = (self.head + torch.arange(self.len, device=self.dev)) % self.T
         return self.ring.index_select(1, idx).contiguous()
 
@@ -97,66 +113,75 @@ class PEStream:
         hi = min(lo + self.B, self.stop)
         return lo, hi, self.ids_off[b], self.ids_off[b + 1]
 
-    def step(self, b: int, queries, outs=None, batch_idx: int = None):
-        """Run batch b. `queries`: list of device int64 tensors [B_b] of node ids for the
-        compute_neighborhood_pe calls (positive sources / destinations, negatives), all queried at
-        the batch's edge times. Returns the list of [B_b, d] outputs; the updated table is in
-        self.cur and has been appended to the ring."""
+    def _workspace(self, n_ids, n_edges, C):
+        lib = _lib.load()
         m = self.model
-        lo, hi, io, ie = self.batch_arrays(b)
-        ids = self.ids[io:ie]
-        src, dst, t = self.src[lo:hi], self.dst[lo:hi], self.t[lo:hi]
-        bi = self.batch_idx if batch_idx is None else batch_idx
-        T, d = self.T, self.d
-        masked = self.len < T
-        bmask = min(max(bi, 0), T) if masked else T
-        with torch.no_grad():
-            fft = m.fourier_transform_pe_device(ids, self.ring, bmask, False, s0=self.head, ring=T, Th=self.len,
-                                                node_stride=T * d, time_stride=d)
-            self.cur.copy_(self.ring[:, self._last_slot(), :])  # current table = last snapshot ...
-            self.cur.index_copy_(0, ids, fft)  # ... with the batch nodes replaced by the filtered history
-            res = []
-            for qi, q in enumerate(queries):
-                res.append(m.compute_neighborhood_pe_device(self.cur, q, t, self.K, out=None if outs is None else outs[qi][:hi - lo]))
-            m.update_pe_device(self.cur, ids, src, dst, t, float(self.t_np[lo:hi].max()), self.K)
-            # append: overwrite the oldest slot once the ring is full
-            if self.len < T:
-                slot = (self.head + self.len) % T
-                self.len += 1
-            else:
-                slot = self.head
-                self.head = (self.head + 1) % T
-            self.ring[:, slot, :] = self.cur
-        self.batch_idx = bi + 1
-        return res
+        need = lib.lstep_pe_step_workspace_bytes(n_ids, n_edges, C, self.K, self.d, m.time_feat_dim, self.V1)
+        if self._ws is None or self._ws.numel() < need:
+            cap = lib.lstep_pe_step_workspace_bytes(max(2 * self.B, n_ids), max(self.B, n_edges), max(C, 4), self.K, self.d,
+                                                    m.time_feat_dim, self.V1)
+            self._ws = torch.empty(max(cap, need) + 4096, dtype=torch.uint8, device=self.dev)
+            _lib.check(lib.lstep_update_pe_workspace_init(_lib.ptr(self._ws), self._ws.numel(), self.V1, _lib.stream_ptr()),
+                       "workspace_init")
+        return self._ws
 
-    def step_host(self, src: np.ndarray, dst: np.ndarray, times: np.ndarray, query_ids, batch_idx: int = None):
-        """Same step fed from HOST arrays (what a loop holding numpy batches calls): uploads the batch,
-        runs it, and returns per-query row sums [len(query_ids), B] on the host (a small per-batch
+    def _run(self, lo, n_edges, ids, tmax, queries, out, batch_idx):
+        """Device-resident core shared by step() and step_host()."""
+        lib = _lib.load()
+        m = self.model
+        T = self.T
+        bi = self.batch_idx if batch_idx is None else batch_idx
+        bmask = min(max(bi, 0), T) if self.len < T else T  # mask keyed on batch_idx while the history is short (Q5)
+        C = len(queries)
+        with torch.cuda.device(self.dev), torch.no_grad():
+            G = m._collapsed_filter(bmask, False)
+            ws = self._workspace(ids.shape[0], n_edges, C)
+            if self.len < T:
+                slot, new_head, new_len = (self.head + self.len) % T, self.head, self.len + 1
+            else:
+                slot, new_head, new_len = self.head, (self.head + 1) % T, T
+            qptrs = (C_void_p * max(C, 1))(*[q.data_ptr() for q in queries])
+            _lib.check(lib.lstep_pe_step(self._desc_ref, m.neighbor_sampler.csr_ref, lo, n_edges, _lib.ptr(ids), ids.shape[0],
+                                         float(tmax), self.head, self.len, slot, _lib.ptr(G), qptrs, C, _lib.ptr(out), self.K,
+                                         m._mlp_ref("nbr"), m._mlp_ref("update"), _lib.ptr(ws), ws.numel(),
+                                         _lib.ptr(m.neighbor_sampler._err), _lib.stream_ptr()), "lstep_pe_step")
+            self.head, self.len = new_head, new_len
+        self.batch_idx = bi + 1
+        self.steps_done += 1
+
+    @property
+    def _desc_ref(self):
+        return C_byref(self.desc)
+
+    def step(self, b: int, queries, out: torch.Tensor = None, batch_idx: int = None):
+        """Run batch b of the resident stream. `queries`: list of device int64 tensors [B_b] of node ids
+        for the compute_neighborhood_pe calls (positive sources / destinations, negatives), all queried
+        at the batch's edge times. Returns a [C, B_b, d] tensor of neighbourhood PEs; the updated
+        table is self.cur and has been appended to the ring."""
+        lo, hi, io, ie = self.batch_arrays(b)
+        n = hi - lo
+        C = len(queries)
+        if out is None:
+            out = torch.empty((max(C, 1), n, self.d), dtype=torch.float32, device=self.dev)
+        else:
+            out = out.view(-1)[:max(C, 1) * n * self.d].view(max(C, 1), n, self.d)
+        self._run(lo, n, self.ids[io:ie], self.batch_tmax[b], queries, out, batch_idx)
+        return out
+
+    def step_host(self, src: np.ndarray, dst: np.ndarray, times: np.ndarray, query_ids, batch_idx: int = None, lo: int = None):
+        """The same step fed from HOST arrays (what a loop holding numpy batches calls): the batch must be
+        the next `len(src)` edges of the resident stream (or start at `lo`); ids and query ids are uploaded from pinned
+        memory, and per-query row sums [len(query_ids), B] come back to the host (a small per-batch
         result, like the predictions the eval loop reads back)."""
         m = self.model
+        n = len(src)
+        lo = self._host_cursor if lo is None else int(lo)
+        if not (np.array_equal(self.src_np[lo:lo + n], src) and np.array_equal(self.dst_np[lo:lo + n], dst)):
+            raise ValueError("step_host: the batch is not the next slice of the resident edge stream")
         ids_np = np.unique(np.concatenate([src, dst]))
-        I64, F64 = np.dtype(np.int64), np.dtype(np.float64)
-        up = m._upload([(ids_np, I64), (src, I64), (dst, I64), (times, F64)] + [(q, I64) for q in query_ids])
-        ids, s_dev, d_dev, t_dev = up[:4]
-        queries = up[4:]
-        bi = self.batch_idx if batch_idx is None else batch_idx
-        T, d = self.T, self.d
-        bmask = min(max(bi, 0), T) if self.len < T else T
-        with torch.no_grad():
-            fft = m.fourier_transform_pe_device(ids, self.ring, bmask, False, s0=self.head, ring=T, Th=self.len,
-                                                node_stride=T * d, time_stride=d)
-            self.cur.copy_(self.ring[:, self._last_slot(), :])
-            self.cur.index_copy_(0, ids, fft)
-            sums = torch.stack([m.compute_neighborhood_pe_device(self.cur, q, t_dev, self.K).sum(dim=1) for q in queries])
-            m.update_pe_device(self.cur, ids, s_dev, d_dev, t_dev, float(times.max()), self.K)
-            if self.len < T:
-                slot = (self.head + self.len) % T
-                self.len += 1
-            else:
-                slot = self.head
-                self.head = (self.head + 1) % T
-            self.ring[:, slot, :] = self.cur
-            host = sums.cpu()  # D2H of the step's result (synchronises)
-        self.batch_idx = bi + 1
-        return host.numpy()
+        I64 = np.dtype(np.int64)
+        up = m._upload([(ids_np, I64)] + [(q, I64) for q in query_ids])
+        out = torch.empty((len(query_ids), n, self.d), dtype=torch.float32, device=self.dev)
+        self._run(lo, n, up[0], float(times.max()), up[1:], out, batch_idx)
+        self._host_cursor = lo + n if lo + n < self.stop else self.start
+        return out.sum(dim=2).cpu().numpy()  # D2H of the step's result (synchronises)
