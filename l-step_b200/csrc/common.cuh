@@ -55,6 +55,18 @@ inline RowIds single_ids(const int64_t* ids) {
   return r;
 }
 
+// Optional tail of the lookup kernel used by update_pe phase B: while a row's K neighbours are still in
+// registers, count them per destination (integer atomics on the per-node map), record the arrival rank
+// and the list of distinct destinations, flag padding; block 0 also zeroes pe[0] (LSTEP.py:317).
+struct PhaseBHook {
+  int32_t* cnt_of;
+  int32_t* rank;
+  int64_t* U;
+  int32_t* counters;  // [0] = number of distinct destinations, [1] = any padded slot
+  float* pe0;
+  int d;
+};
+
 // TimeEncoder (models/modules.py:37): cos(fp32(dt) * w_j + 0). The product must be a separately
 // rounded fp32 multiply (no FMA contraction into the range reduction), cosf is the accurate
 // library version (arguments reach 1e8 rad).

@@ -11,7 +11,7 @@
 
 namespace lstep {
 
-template <typename IdT, bool kWithEid>
+template <typename IdT, bool kWithEid, bool kHook>
 __global__ void __launch_bounds__(256) sample_recent_kernel(const int64_t* __restrict__ indptr,
                                                             const int32_t* __restrict__ c_nbr,
                                                             const int32_t* __restrict__ c_eid,
@@ -19,8 +19,10 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(const int64_t* __res
                                                             const double* __restrict__ q_time, int64_t n_rows,
                                                             int64_t n_valid, int K, IdT* __restrict__ out_nbr,
                                                             IdT* __restrict__ out_eid, float* __restrict__ out_t,
-                                                            uint32_t* err_flag) {
+                                                            uint32_t* err_flag, PhaseBHook hook) {
   const int lane = threadIdx.x & 31;
+  if (kHook && blockIdx.x == 0)
+    for (int c = threadIdx.x; c < hook.d; c += blockDim.x) hook.pe0[c] = 0.f;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n_rows) return;
 
@@ -53,6 +55,7 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(const int64_t* __res
   const int pad = K - take;
   const int64_t obase = row * (int64_t)K;
   const int64_t first = end - take;
+  bool has_zero = false;
   for (int k = lane; k < K; k += 32) {
     IdT n = 0, e = 0;
     float tt = 0.f;
@@ -65,6 +68,18 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(const int64_t* __res
     out_nbr[obase + k] = n;
     if (kWithEid) out_eid[obase + k] = e;
     out_t[obase + k] = tt;
+    if (kHook) {
+      if (n > 0) {
+        const int c = atomicAdd(hook.cnt_of + n, 1);
+        hook.rank[obase + k] = c;
+        if (c == 0) hook.U[atomicAdd(hook.counters + 0, 1)] = (int64_t)n;
+      } else {
+        has_zero = true;
+      }
+    }
+  }
+  if (kHook) {
+    if (__any_sync(kFull, has_zero) && lane == 0) hook.counters[1] = 1;
   }
 }
 
@@ -78,10 +93,23 @@ int launch_sample(const lstep_csr* csr, RowIds q_node, const double* q_time, int
   if (n_valid > n_rows) n_valid = n_rows;
   const int warps = 8;
   const int64_t blocks = ceil_div(n_rows, warps);
-  sample_recent_kernel<IdT, kWithEid><<<(unsigned)blocks, warps * 32, 0, as_stream(stream)>>>(
+  sample_recent_kernel<IdT, kWithEid, false><<<(unsigned)blocks, warps * 32, 0, as_stream(stream)>>>(
       csr->indptr, csr->nbr, csr->eid, csr->t, csr->num_rows, q_node, q_time, n_rows, n_valid, K, out_nbr, out_eid,
-      out_t, err_flag);
+      out_t, err_flag, PhaseBHook{});
   return check_launch("sample_recent");
+}
+
+// lookup + per-destination counting for update_pe phase B (one launch instead of two)
+int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int64_t n_valid,
+                        int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag, PhaseBHook hook, void* stream) {
+  if (!csr || K <= 0 || n_rows <= 0 || !out_nbr || !out_t || !q_node || !q_time) return LSTEP_ERR_INVALID_ARG;
+  if (n_valid > n_rows) n_valid = n_rows;
+  const int warps = 8;
+  const int64_t blocks = ceil_div(n_rows, warps);
+  sample_recent_kernel<int32_t, false, true><<<(unsigned)blocks, warps * 32, 0, as_stream(stream)>>>(
+      csr->indptr, csr->nbr, csr->eid, csr->t, csr->num_rows, single_ids(q_node), q_time, n_rows, n_valid, K, out_nbr,
+      nullptr, out_t, err_flag, hook);
+  return check_launch("sample_recent+count");
 }
 
 template int launch_sample<int32_t, false>(const lstep_csr*, RowIds, const double*, int64_t, int64_t, int, int32_t*, int32_t*, float*,

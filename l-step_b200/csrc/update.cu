@@ -30,6 +30,8 @@ namespace lstep {
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st);
+int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int64_t n_valid,
+                        int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag, PhaseBHook hook, void* stream);
 
 constexpr int kRow0Parts = 64;
 
@@ -84,37 +86,17 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// int64 endpoints -> int32, per-edge fp32 time delta of phase A, counters reset
-__global__ void prep_edges_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
-                                  const double* __restrict__ times, int64_t n_edges, float tc, int64_t pe_rows,
-                                  int32_t* __restrict__ src32, int32_t* __restrict__ dst32, float* __restrict__ dtA,
-                                  int32_t* __restrict__ counters, uint32_t* err_flag) {
-  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (blockIdx.x == 0 && threadIdx.x < 8) counters[threadIdx.x] = 0;
-  if (e >= n_edges) return;
-  int64_t s = src[e], dd = dst[e];
-  if (s < 0 || s >= pe_rows || dd < 0 || dd >= pe_rows) {
-    if (err_flag) atomicOr(err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
-    s = 0;
-    dd = 0;
-  }
-  src32[e] = (int32_t)s;
-  dst32[e] = (int32_t)dd;
-  // torch.Tensor([current_time]) is fp32; fp32 - fp64 promotes to fp64; then .float()  (LSTEP.py:277, Q4)
-  dtA[e] = (float)((double)tc - times[e]);
-}
-
-// ---------------------------------------------------------------------------------------------
 // phase A: one CTA per batch node. Threads [0,t): time frequencies; [t_pad, t_pad+d/4): PE columns.
 constexpr int kSegPerThread = 4;
 
 __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __restrict__ pe,
                                                              const int64_t* __restrict__ ids, int64_t n_ids,
-                                                             const int32_t* __restrict__ src32,
-                                                             const int32_t* __restrict__ dst32,
-                                                             const float* __restrict__ dtA, int64_t n_edges,
+                                                             const int64_t* __restrict__ src,
+                                                             const int64_t* __restrict__ dst,
+                                                             const double* __restrict__ times, int64_t n_edges, float tc,
                                                              const float* __restrict__ tw, int d, int t, int t_pad,
-                                                             float* __restrict__ A, int64_t lda) {
+                                                             float* __restrict__ A, int64_t lda,
+                                                             int32_t* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nthr = blockDim.x;
   const int seg = nthr * kSegPerThread;
@@ -127,19 +109,20 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
   const bool is_tf = tid < t;
   const bool is_pe = tid >= t_pad && tid - t_pad < dvec;
   const int cv = tid - t_pad;
+  if (blockIdx.x == 0 && tid < 8) counters[tid] = 0;  // phase-B counters, consumed by later launches
 
   for (int64_t n = blockIdx.x; n < n_ids; n += gridDim.x) {
-    const int32_t node = (int32_t)ids[n];
+    const int64_t node = ids[n];
     float acc_tf = 0.f;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float w = is_tf ? tw[tid] : 0.f;
     for (int side = 0; side < 2; ++side) {
-      const int32_t* match = side == 0 ? src32 : dst32;  // scatter #1 indexes by src (LSTEP.py:283-286), #2 by dst
-      const int32_t* other = side == 0 ? dst32 : src32;
+      const int64_t* match = side == 0 ? src : dst;  // scatter #1 indexes by src (LSTEP.py:283-286), #2 by dst
+      const int64_t* other = side == 0 ? dst : src;
       for (int64_t lo = 0; lo < n_edges; lo += seg) {
         // ordered compaction of the matches in [lo, lo+seg)
         const int64_t e0 = lo + (int64_t)tid * kSegPerThread;
-        int32_t mv[kSegPerThread];
+        int64_t mv[kSegPerThread];
         int cnt = 0;
 #pragma unroll
         for (int u = 0; u < kSegPerThread; ++u) {
@@ -171,8 +154,9 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
 #pragma unroll
         for (int u = 0; u < kSegPerThread; ++u) {
           if (mv[u] == node) {
-            s_other[pos] = other[e0 + u];
-            s_dt[pos] = dtA[e0 + u];
+            s_other[pos] = (int32_t)other[e0 + u];
+            // torch.Tensor([current_time]) is fp32; fp32 - fp64 promotes to fp64; then .float() (LSTEP.py:277, Q4)
+            s_dt[pos] = (float)((double)tc - times[e0 + u]);
             ++pos;
           }
         }
@@ -211,34 +195,33 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase B index, step 1: per-destination counts, arrival ranks, distinct list; also pe[0] = 0
-__global__ void __launch_bounds__(256) phaseB_count_kernel(const int32_t* __restrict__ nbrB, int64_t total,
-                                                           int32_t* __restrict__ cnt_of, int32_t* __restrict__ rank,
-                                                           int64_t* __restrict__ U, int32_t* __restrict__ counters,
-                                                           float* pe, int d) {
-  if (blockIdx.x == 0)
-    for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // LSTEP.py:317
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  int32_t u = -1;
-  if (i < total) u = nbrB[i];
-  if (u > 0) {
-    const int c = atomicAdd(cnt_of + u, 1);
-    rank[i] = c;
-    if (c == 0) {
-      const int s = atomicAdd(counters + 0, 1);
-      U[s] = u;
-    }
-  }
-  const unsigned z = __ballot_sync(kFull, u == 0);
-  if (z && (threadIdx.x & 31) == 0) counters[1] = 1;
-}
-
 // step 2 (one CTA): offsets by exclusive scan over U order; slot map; counter map reset; hub list
 constexpr int kHubLen = 32;  // lists longer than a warp are hubs and get a whole CTA
 
+// Block 0 scans (and, for small batches, also fills the slot lists); blocks 1.. compute the per-part
+// partial sums of the padding row.
 __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__ cnt_of, int32_t* __restrict__ slot_of,
                                                            int64_t* __restrict__ U, int32_t* __restrict__ off,
-                                                           int32_t* __restrict__ hubs, int32_t* __restrict__ counters) {
+                                                           int32_t* __restrict__ hubs, int32_t* __restrict__ counters,
+                                                           const int32_t* __restrict__ nbrB, int64_t total, int K,
+                                                           const int32_t* __restrict__ rank, int32_t* __restrict__ list,
+                                                           int fill_here, const float* __restrict__ pe,
+                                                           const int64_t* __restrict__ ids, int64_t n_ids, int d,
+                                                           float* __restrict__ row0_part) {
+  if (blockIdx.x > 0) {
+    if (counters[1] == 0) return;
+    const int part = blockIdx.x - 1;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float acc = 0.f;
+      for (int64_t n = part; n < n_ids; n += kRow0Parts) {
+        int z = 0;
+        for (int k = 0; k < K; ++k) z += (nbrB[n * K + k] == 0);
+        if (z) acc = fmaf((float)z, pe[ids[n] * (int64_t)d + c], acc);
+      }
+      row0_part[part * d + c] = acc;
+    }
+    return;
+  }
   __shared__ int s_warp[32];
   const int M = counters[0];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -280,49 +263,76 @@ __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__
     counters[2] = M + hz;
     if (hz) U[M] = 0;
   }
-}
-
-// step 3: fill slot lists; extra blocks: per-part partial sums of the padding row
-__global__ void __launch_bounds__(256) phaseB_fill_kernel(const int32_t* __restrict__ nbrB, int64_t total, int K,
-                                                          const int32_t* __restrict__ slot_of,
-                                                          const int32_t* __restrict__ off,
-                                                          const int32_t* __restrict__ rank, int32_t* __restrict__ list,
-                                                          int fill_blocks, const int32_t* __restrict__ counters,
-                                                          const float* __restrict__ pe, const int64_t* __restrict__ ids,
-                                                          int64_t n_ids, int d, float* __restrict__ row0_part) {
-  if ((int)blockIdx.x < fill_blocks) {
-    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i < total) {
+  if (fill_here) {
+    __syncthreads();  // off[] / slot_of[] written above are visible to the whole CTA
+    for (int64_t i = tid; i < total; i += blockDim.x) {
       const int32_t u = nbrB[i];
       if (u > 0) list[off[slot_of[u]] + rank[i]] = (int32_t)i;
     }
-    return;
   }
-  if (counters[1] == 0) return;
-  const int part = blockIdx.x - fill_blocks;
-  for (int c = threadIdx.x; c < d; c += blockDim.x) {
-    float acc = 0.f;
-    for (int64_t n = part; n < n_ids; n += kRow0Parts) {
-      int z = 0;
-      for (int k = 0; k < K; ++k) z += (nbrB[n * K + k] == 0);
-      if (z) acc = fmaf((float)z, pe[ids[n] * (int64_t)d + c], acc);
-    }
-    row0_part[part * d + c] = acc;
+}
+
+// step 3 (large batches only): fill slot lists
+__global__ void __launch_bounds__(256) phaseB_fill_kernel(const int32_t* __restrict__ nbrB, int64_t total,
+                                                          const int32_t* __restrict__ slot_of,
+                                                          const int32_t* __restrict__ off,
+                                                          const int32_t* __restrict__ rank, int32_t* __restrict__ list) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < total) {
+    const int32_t u = nbrB[i];
+    if (u > 0) list[off[slot_of[u]] + rank[i]] = (int32_t)i;
   }
 }
 
 // One list entry = slot i = (row n, column k): contributes [pe[ids[n]] || cos((tc - nt[i]) * w)].
 // The per-entry metadata (source row pointer, dt) is resolved for 32 entries at once (one lane each),
-// so the dependent index loads are paid once per chunk, not once per entry.
+// so the dependent index loads are paid once per chunk, not once per entry; the rows of 4 consecutive
+// entries are then loaded together before they are added, in list order.
 template <int DVPL, int TFPL>
-struct GatherAcc {
-  float4 pe[DVPL];
-  float tf[TFPL];
-};
+__device__ __forceinline__ void accumulate_chunk(const float* my_row, float my_dt, int m, int lane, int dvec, int t,
+                                                 const float (&w)[TFPL], float4 (&acc)[DVPL], float (&acc_tf)[TFPL]) {
+  for (int j0 = 0; j0 < m; j0 += 4) {
+    const float4* row[4];
+    float dt[4];
+    float4 v[4][DVPL];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = min(j0 + u, m - 1);
+      row[u] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)my_row, j)));
+      dt[u] = __shfl_sync(kFull, my_dt, j);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int q = 0; q < DVPL; ++q)
+        if (lane + 32 * q < dvec) v[u][q] = __ldg(row[u] + lane + 32 * q);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (j0 + u < m) {
+#pragma unroll
+        for (int q = 0; q < DVPL; ++q)
+          if (lane + 32 * q < dvec) {
+            acc[q].x += v[u][q].x;
+            acc[q].y += v[u][q].y;
+            acc[q].z += v[u][q].z;
+            acc[q].w += v[u][q].w;
+          }
+#pragma unroll
+        for (int q = 0; q < TFPL; ++q)
+          if (lane + 32 * q < t) acc_tf[q] += time_feature(dt[u], w[q]);
+      }
+    }
+  }
+}
 
-// step 4: blocks [0, warp_blocks): one warp per destination with a short list (sorted, fp32, reference
-// order); blocks [warp_blocks, warp_blocks + hub_blocks): one CTA per hub (32.32 fixed point, exact, so
-// the arrival order of the list does not matter); last block: finishes the padding row.
+constexpr int kHubSortMax = 4096;  // hub lists up to this length are sorted in shared memory
+
+// step 4: blocks [0, warp_blocks): one warp per destination with a short list (sorted: fp32 adds in the
+// reference's flat order); blocks [warp_blocks, warp_blocks + hub_blocks): one CTA per hub — its slot
+// list is sorted in shared memory (bitonic), split into 8 contiguous slices, one per warp, and the 8
+// fp32 partial rows are added in warp order: a fixed summation tree, reproducible run to run (lists
+// beyond 4096 slots fall back to exact 32.32 fixed-point accumulation, also order independent);
+// last block: finishes the padding row.
 template <int DVPL, int TFPL>
 __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restrict__ pe,
                                                             const int64_t* __restrict__ ids, int K,
@@ -334,8 +344,11 @@ __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restr
                                                             const float* __restrict__ tw, int d, int t,
                                                             const float* __restrict__ row0_part, float* __restrict__ A,
                                                             int64_t lda, int warp_blocks, int hub_blocks) {
-  extern __shared__ unsigned long long s_fix[];  // [d + t] fixed-point accumulators (hub blocks only)
+  extern __shared__ __align__(16) unsigned char gsm[];
   const int in1 = d + t;
+  int* s_list = reinterpret_cast<int*>(gsm);                                             // [kHubSortMax]
+  float* s_part = reinterpret_cast<float*>(s_list + kHubSortMax);                        // [8][in1]
+  unsigned long long* s_fix = reinterpret_cast<unsigned long long*>(s_part + 8 * in1 + (in1 & 1));  // [in1]
   const int M = counters[0];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int dvec = d >> 2;
@@ -355,6 +368,13 @@ __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restr
     return;
   }
 
+  float4 acc[DVPL];
+  float acc_tf[TFPL];
+#pragma unroll
+  for (int q = 0; q < DVPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < TFPL; ++q) acc_tf[q] = 0.f;
+
   if ((int)blockIdx.x < warp_blocks) {  // ---- short lists
     const int s = blockIdx.x * (blockDim.x >> 5) + wid;
     if (s >= M) return;
@@ -372,38 +392,13 @@ __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restr
         e = (lower == up) ? min(e, o) : max(e, o);
       }
     }
-    // per-lane metadata of entry `lane`
     const float* my_row = pe;
     float my_dt = 0.f;
     if (lane < len) {
       my_row = pe + ids[e / K] * (int64_t)d;
       my_dt = tc - ntB[e];  // fp32 - fp32 (LSTEP.py:314)
     }
-    float4 acc[DVPL];
-    float acc_tf[TFPL];
-#pragma unroll
-    for (int q = 0; q < DVPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int q = 0; q < TFPL; ++q) acc_tf[q] = 0.f;
-    for (int j = 0; j < len; ++j) {
-      const float4* row = reinterpret_cast<const float4*>(
-          reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)my_row, j)));
-      const float dt = __shfl_sync(kFull, my_dt, j);
-#pragma unroll
-      for (int q = 0; q < DVPL; ++q) {
-        const int cv = lane + 32 * q;
-        if (cv < dvec) {
-          const float4 v = __ldg(row + cv);
-          acc[q].x += v.x;
-          acc[q].y += v.y;
-          acc[q].z += v.z;
-          acc[q].w += v.w;
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < TFPL; ++q)
-        if (lane + 32 * q < t) acc_tf[q] += time_feature(dt, w[q]);
-    }
+    accumulate_chunk<DVPL, TFPL>(my_row, my_dt, len, lane, dvec, t, w, acc, acc_tf);
     float* arow = A + (int64_t)s * lda;
 #pragma unroll
     for (int q = 0; q < DVPL; ++q)
@@ -414,14 +409,70 @@ __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restr
     return;
   }
 
-  // ---- hubs: CTA per hub, warps take 32-entry chunks round-robin, exact fixed-point accumulation
-  constexpr float kScale = 4294967296.f;  // 2^32
-  constexpr double kInv = 1.0 / 4294967296.0;
+  // ---- hubs
   const int n_hubs = counters[3];
   const int nw = blockDim.x >> 5;
   for (int h = blockIdx.x - warp_blocks; h < n_hubs; h += hub_blocks) {
     const int s = hubs[h];
     const int o0 = off[s], len = off[s + 1] - o0;
+    float* arow = A + (int64_t)s * lda;
+    if (len <= kHubSortMax) {
+      int n2 = 64;
+      while (n2 < len) n2 <<= 1;
+      for (int i = threadIdx.x; i < n2; i += blockDim.x) s_list[i] = i < len ? list[o0 + i] : 0x7fffffff;
+      __syncthreads();
+      for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+            const int p = i ^ j;
+            if (p > i) {
+              const int a = s_list[i], b = s_list[p];
+              const bool up = ((i & k) == 0);
+              if ((a > b) == up) {
+                s_list[i] = b;
+                s_list[p] = a;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      // warp `wid` reduces the contiguous slice [lo, hi) of the sorted list
+      const int per = (len + nw - 1) / nw;
+      const int lo = min(len, wid * per), hi = min(len, lo + per);
+#pragma unroll
+      for (int q = 0; q < DVPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int q = 0; q < TFPL; ++q) acc_tf[q] = 0.f;
+      for (int c0 = lo; c0 < hi; c0 += 32) {
+        const float* my_row = pe;
+        float my_dt = 0.f;
+        if (c0 + lane < hi) {
+          const int e = s_list[c0 + lane];
+          my_row = pe + ids[e / K] * (int64_t)d;
+          my_dt = tc - ntB[e];
+        }
+        accumulate_chunk<DVPL, TFPL>(my_row, my_dt, min(32, hi - c0), lane, dvec, t, w, acc, acc_tf);
+      }
+      float* part = s_part + wid * in1;
+#pragma unroll
+      for (int q = 0; q < DVPL; ++q)
+        if (lane + 32 * q < dvec) reinterpret_cast<float4*>(part)[lane + 32 * q] = acc[q];
+#pragma unroll
+      for (int q = 0; q < TFPL; ++q)
+        if (lane + 32 * q < t) part[d + lane + 32 * q] = acc_tf[q];
+      __syncthreads();
+      for (int c = threadIdx.x; c < in1; c += blockDim.x) {
+        float v = 0.f;
+        for (int ww = 0; ww < nw; ++ww) v += s_part[ww * in1 + c];
+        arow[c] = v;
+      }
+      __syncthreads();
+      continue;
+    }
+    // giant hub: exact 32.32 fixed-point accumulation in arrival order
+    constexpr float kScale = 4294967296.f;  // 2^32
+    constexpr double kInv = 1.0 / 4294967296.0;
     for (int c = threadIdx.x; c < in1; c += blockDim.x) s_fix[c] = 0ull;
     __syncthreads();
     long long facc[DVPL][4], ftf[TFPL];
@@ -470,7 +521,6 @@ __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restr
     for (int q = 0; q < TFPL; ++q)
       if (lane + 32 * q < t) atomicAdd(&s_fix[d + lane + 32 * q], (unsigned long long)ftf[q]);
     __syncthreads();
-    float* arow = A + (int64_t)s * lda;
     for (int c = threadIdx.x; c < in1; c += blockDim.x) arow[c] = (float)((double)(long long)s_fix[c] * kInv);
     __syncthreads();
   }
@@ -514,47 +564,45 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
   const float tc = (float)current_time;
   int rc;
 
-  // ---- phase A
-  {
-    const int64_t blocks = ceil_div(n_edges > 0 ? n_edges : 1, 256);
-    prep_edges_kernel<<<(unsigned)blocks, 256, 0, st>>>(src, dst, times, n_edges, tc, pe_rows, w.src32, w.dst32, w.dtA,
-                                                        w.counters, err_flag);
-    if ((rc = check_launch("prep_edges")) != LSTEP_OK) return rc;
-  }
   const int dvec = d / 4;
   const int t_pad = (int)align_up((size_t)t, 32);
   const int threads = (int)align_up((size_t)t_pad + dvec, 32);
   if (threads > 512 || dvec > 8 * 32 || t > 8 * 32) return LSTEP_ERR_UNSUPPORTED;
-  if (n_ids > 0) {
+  if (n_ids == 0) {  // nothing to update; the reference still zeroes the padding row (LSTEP.py:317)
+    cudaError_t e = cudaMemsetAsync(pe, 0, sizeof(float) * d, st);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "update_pe memset");
+      return LSTEP_ERR_CUDA;
+    }
+    return LSTEP_OK;
+  }
+  // ---- phase A (also resets the phase-B counters)
+  {
     const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
     const int64_t grid = n_ids < (int64_t)kNumSMs * 16 ? n_ids : (int64_t)kNumSMs * 16;
-    edge_aggregate_kernel<<<(unsigned)grid, threads, smem, st>>>(pe, ids, n_ids, w.src32, w.dst32, w.dtA, n_edges,
-                                                                 mlp->tw, d, t, t_pad, w.A, w.lda);
+    edge_aggregate_kernel<<<(unsigned)grid, threads, smem, st>>>(pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d, t,
+                                                                 t_pad, w.A, w.lda, w.counters);
     if ((rc = check_launch("edge_aggregate")) != LSTEP_OK) return rc;
     if ((rc = launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st)) != LSTEP_OK) return rc;
   }
 
-  // ---- phase B
+  // ---- phase B: lookup + per-destination count in one launch (also pe[0] = 0)
   const int64_t n_valid = n_ids < n_edges ? n_ids : n_edges;  // zip(node_ids, times) truncation (Q1)
   const int64_t total = n_ids * (int64_t)K;
-  if (n_ids > 0) {
-    rc = lstep_sample_recent_compact(csr, ids, times, n_ids, n_valid, K, w.nbrB, w.ntB, err_flag, stream);
+  {
+    PhaseBHook hook{w.cnt_of, w.rank, w.U, w.counters, pe, d};
+    rc = launch_sample_count(csr, ids, times, n_ids, n_valid, K, w.nbrB, w.ntB, err_flag, hook, stream);
     if (rc != LSTEP_OK) return rc;
   }
   {
-    const int64_t blocks = ceil_div(total > 0 ? total : 1, 256);
-    phaseB_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(w.nbrB, total, w.cnt_of, w.rank, w.U, w.counters, pe, d);
-    if ((rc = check_launch("phaseB_count")) != LSTEP_OK) return rc;
-  }
-  if (total == 0) return LSTEP_OK;
-  phaseB_scan_kernel<<<1, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.counters);
-  if ((rc = check_launch("phaseB_scan")) != LSTEP_OK) return rc;
-  {
-    const int fill_blocks = (int)ceil_div(total, 256);
-    phaseB_fill_kernel<<<fill_blocks + kRow0Parts, 256, 0, st>>>(w.nbrB, total, K, w.slot_of, w.off, w.rank, w.list,
-                                                                 fill_blocks, w.counters, pe, ids, n_ids, d,
-                                                                 w.row0_part);
-    if ((rc = check_launch("phaseB_fill")) != LSTEP_OK) return rc;
+    const int fill_here = total <= 16384 ? 1 : 0;
+    phaseB_scan_kernel<<<1 + kRow0Parts, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.counters, w.nbrB, total, K,
+                                                        w.rank, w.list, fill_here, pe, ids, n_ids, d, w.row0_part);
+    if ((rc = check_launch("phaseB_scan")) != LSTEP_OK) return rc;
+    if (!fill_here) {
+      phaseB_fill_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w.nbrB, total, w.slot_of, w.off, w.rank, w.list);
+      if ((rc = check_launch("phaseB_fill")) != LSTEP_OK) return rc;
+    }
   }
   const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;  // distinct non-zero destinations
   {
@@ -562,7 +610,7 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
     int hub_blocks = (int)(total / (kHubLen + 1)) + 1;  // at most this many lists can be longer than kHubLen
     if (hub_blocks > 2 * kNumSMs) hub_blocks = 2 * kNumSMs;
     const unsigned blocks = (unsigned)(warp_blocks + hub_blocks + 1);
-    const size_t smem = sizeof(unsigned long long) * (size_t)(d + t);
+    const size_t smem = sizeof(int) * kHubSortMax + sizeof(float) * (8 * (size_t)(d + t) + 2) + sizeof(unsigned long long) * (size_t)(d + t);
     if (dvec <= 64 && t <= 128)
       phaseB_gather_kernel<2, 4><<<blocks, 256, smem, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw,
                                                             d, t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
