@@ -183,6 +183,30 @@ int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int6
                     const int64_t* src, const int64_t* dst, const double* times, int64_t n_edges,
                     double current_time, int K, const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes,
                     uint32_t* err_flag, void* stream);
+/* The same update as separate phases, for a node-id sharded table (l-step_b200/shard.py): rank r owns
+ * the rows v with v % G == r, runs phase A for the batch nodes it owns, then the aggregation half of
+ * phase B for the (node, time) pairs it owns (csr_ids index the rank's local CSR, row_ids the table),
+ * ships the partial aggregate rows to the owners of the destinations, which combine them
+ * (lstep_segment_sum_rows, fixed order) and apply the MLP (lstep_pe_mlp_apply without self term).
+ * lstep_update_pe_workspace_layout reports where phase B left its results inside the workspace:
+ * offsets[0] counters int32[8] (0: #distinct non-zero destinations M, 1: padding seen), offsets[1] U
+ * int64[M (+1)], offsets[2] A float[M (+1)][lda], offsets[3] = lda. */
+int lstep_update_pe_phase_a(float* pe, int64_t pe_rows, const int64_t* ids, int64_t n_ids, const int64_t* src,
+                            const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K,
+                            const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes, void* stream);
+int lstep_update_pe_phase_b_partial(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* csr_ids,
+                                    const int64_t* row_ids, int64_t n_ids, const double* q_times, int64_t n_valid,
+                                    int64_t n_edges_layout, double current_time, int K, const lstep_pe_mlp* mlp,
+                                    void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream);
+int lstep_update_pe_workspace_layout(int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows, int64_t* offsets);
+int lstep_segment_sum_rows(const float* rows, int64_t ld, const int64_t* seg_off, int64_t n_seg, int width, float* out,
+                           int64_t ldo, void* stream);
+int lstep_dft_filter_scatter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
+                             const int64_t* ids, const int64_t* out_ids, int64_t n_ids, const float* G, float* out,
+                             int64_t out_stride, void* stream);
+int lstep_ring_copy_rows(float* ring, float* cur, int64_t ring_rows, int T, int d, int slot, int64_t row_mul,
+                         int64_t row_add, int to_ring, void* stream);
+
 /* The update keeps a per-node int32 scratch map inside the workspace that must be zero on
  * entry and is zero again on exit; call once after allocating the workspace. */
 int lstep_update_pe_workspace_init(void* workspace, size_t workspace_bytes, int64_t pe_rows, void* stream);

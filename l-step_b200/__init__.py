@@ -15,6 +15,10 @@ _LAZY = {
     "TimeEncoder": "modules",
     "MergeLayer": "modules",
     "PEStream": "stream",
+    "ShardRank": "shard",
+    "LocalGroup": "shard",
+    "DistGroup": "shard",
+    "ShardedPEStream": "shard",
 }
 
 

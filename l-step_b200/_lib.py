@@ -61,6 +61,13 @@ _SIGS = {
     "lstep_update_pe": (i32, [vp, i64, C.POINTER(CSR), vp, i64, vp, vp, vp, i64, C.c_double, i32, C.POINTER(PEMLP), vp, sz,
                               vp, vp]),
     "lstep_update_pe_workspace_init": (i32, [vp, sz, i64, vp]),
+    "lstep_update_pe_phase_a": (i32, [vp, i64, vp, i64, vp, vp, vp, i64, C.c_double, i32, C.POINTER(PEMLP), vp, sz, vp]),
+    "lstep_update_pe_phase_b_partial": (i32, [vp, i64, C.POINTER(CSR), vp, vp, i64, vp, i64, i64, C.c_double, i32, C.POINTER(PEMLP),
+                                              vp, sz, vp, vp]),
+    "lstep_update_pe_workspace_layout": (i32, [i64, i64, i32, i32, i32, i64, C.POINTER(i64)]),
+    "lstep_segment_sum_rows": (i32, [vp, i64, vp, i64, i32, vp, i64, vp]),
+    "lstep_dft_filter_scatter": (i32, [vp, i64, i64, i32, i32, i32, i32, vp, vp, i64, vp, vp, i64, vp]),
+    "lstep_ring_copy_rows": (i32, [vp, vp, i64, i32, i32, i32, i64, i64, i32, vp]),
     "lstep_pe_step_workspace_bytes": (sz, [i64, i64, i32, i32, i32, i32, i64]),
     "lstep_ring_load": (i32, [vp, vp, i64, i32, i32, i32, vp]),
     "lstep_pe_step": (i32, [C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, i32, i32, i32, vp,

@@ -110,7 +110,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_kernel(const float* __
                                                                  int64_t time_stride, int s0, int ring, int Th, int d,
                                                                  const int64_t* __restrict__ ids, int64_t n_ids,
                                                                  const float* __restrict__ G, float* __restrict__ out,
-                                                                 int64_t out_stride, int scatter) {
+                                                                 int64_t out_stride, const int64_t* __restrict__ out_ids) {
   using V = typename VecT<VEC>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V* red = reinterpret_cast<V*>(smem_raw);  // [groups][dvec]
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_kernel(const float* __
     if (active && g == 0) {
       V tot = red[cv];
       for (int gg = 1; gg < groups; ++gg) add_acc(tot, red[gg * dvec + cv]);
-      reinterpret_cast<V*>(out + (scatter ? ids[n] : n) * out_stride)[cv] = tot;
+      reinterpret_cast<V*>(out + (out_ids ? out_ids[n] : n) * out_stride)[cv] = tot;
     }
     __syncthreads();
   }
@@ -207,8 +207,8 @@ extern "C" int lstep_dft_collapse(const float* W_c64, const float* a, int T, int
 
 namespace lstep {
 int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
-                      const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride, int scatter,
-                      void* stream) {
+                      const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride,
+                      const int64_t* out_ids, void* stream) {
   if (n_ids < 0 || Th < 0 || d <= 0 || ring < Th || s0 < 0 || (ring > 0 && s0 >= ring)) return LSTEP_ERR_INVALID_ARG;
   if (n_ids == 0) return LSTEP_OK;
   if (!ids || !out || !G || (Th > 0 && !hist)) return LSTEP_ERR_INVALID_ARG;
@@ -220,10 +220,10 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
   const int64_t grid = n_ids < (int64_t)kNumSMs * 6 ? n_ids : (int64_t)kNumSMs * 6;
   if (v4)
     dft_filter_kernel<4><<<(unsigned)grid, kDftThreads, smem, as_stream(stream)>>>(
-        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, scatter);
+        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids);
   else
     dft_filter_kernel<1><<<(unsigned)grid, kDftThreads, smem, as_stream(stream)>>>(
-        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, scatter);
+        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids);
   return check_launch("dft_filter");
 }
 }  // namespace lstep
@@ -231,7 +231,16 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
 extern "C" int lstep_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th,
                                 int d, const int64_t* ids, int64_t n_ids, const float* G, float* out,
                                 int64_t out_stride, void* stream) {
-  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, 0, stream);
+  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, nullptr, stream);
+}
+
+/* Same filter with the result row n written to out + out_ids[n]*out_stride (history rows and table rows
+ * may use different id spaces: local ring rows vs global table rows in the sharded layout). */
+extern "C" int lstep_dft_filter_scatter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th,
+                                        int d, const int64_t* ids, const int64_t* out_ids, int64_t n_ids, const float* G,
+                                        float* out, int64_t out_stride, void* stream) {
+  if (!out_ids && n_ids > 0) return LSTEP_ERR_INVALID_ARG;
+  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids, stream);
 }
 
 extern "C" int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring,

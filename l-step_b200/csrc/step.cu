@@ -23,29 +23,32 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st);
 int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
-                      const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride, int scatter,
-                      void* stream);
+                      const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride,
+                      const int64_t* out_ids, void* stream);
 
 // ring[v][slot][:] = cur[v][:]  (node-major ring: 688-byte rows at a 68.8 KB pitch)
+// table row of ring row v is v*row_mul + row_add (1, 0 for a single GPU; G, rank for a node-id sharded ring)
 __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restrict__ cur, float* __restrict__ ring,
-                                                          int64_t V1, int T, int d, int slot) {
+                                                          int64_t V1, int T, int d, int slot, int64_t row_mul, int64_t row_add) {
   const int dvec = d >> 2;
   const int64_t total = V1 * dvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = i / dvec;
     const int c = (int)(i % dvec);
-    reinterpret_cast<float4*>(ring + (v * T + slot) * (int64_t)d)[c] = reinterpret_cast<const float4*>(cur + v * (int64_t)d)[c];
+    reinterpret_cast<float4*>(ring + (v * T + slot) * (int64_t)d)[c] =
+        reinterpret_cast<const float4*>(cur + (v * row_mul + row_add) * (int64_t)d)[c];
   }
 }
 
 __global__ void __launch_bounds__(256) ring_load_kernel(const float* __restrict__ ring, float* __restrict__ cur, int64_t V1,
-                                                        int T, int d, int slot) {
+                                                        int T, int d, int slot, int64_t row_mul, int64_t row_add) {
   const int dvec = d >> 2;
   const int64_t total = V1 * dvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = i / dvec;
     const int c = (int)(i % dvec);
-    reinterpret_cast<float4*>(cur + v * (int64_t)d)[c] = reinterpret_cast<const float4*>(ring + (v * T + slot) * (int64_t)d)[c];
+    reinterpret_cast<float4*>(cur + (v * row_mul + row_add) * (int64_t)d)[c] =
+        reinterpret_cast<const float4*>(ring + (v * T + slot) * (int64_t)d)[c];
   }
 }
 
@@ -90,8 +93,21 @@ extern "C" size_t lstep_pe_step_workspace_bytes(int64_t max_ids, int64_t max_edg
 
 extern "C" int lstep_ring_load(const float* ring, float* cur, int64_t V1, int T, int d, int slot, void* stream) {
   if (!ring || !cur || V1 <= 0 || T <= 0 || d <= 0 || d % 4 != 0 || slot < 0 || slot >= T) return LSTEP_ERR_INVALID_ARG;
-  ring_load_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(ring, cur, V1, T, d, slot);
+  ring_load_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(ring, cur, V1, T, d, slot, 1, 0);
   return check_launch("ring_load");
+}
+
+/* Sharded ring (rows v of the local ring <-> table rows v*row_mul + row_add): load / append one slot. */
+extern "C" int lstep_ring_copy_rows(float* ring, float* cur, int64_t ring_rows, int T, int d, int slot, int64_t row_mul,
+                                    int64_t row_add, int to_ring, void* stream) {
+  if (!ring || !cur || ring_rows < 0 || T <= 0 || d <= 0 || d % 4 != 0 || slot < 0 || slot >= T || row_mul <= 0 || row_add < 0)
+    return LSTEP_ERR_INVALID_ARG;
+  if (ring_rows == 0) return LSTEP_OK;
+  if (to_ring)
+    ring_append_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(cur, ring, ring_rows, T, d, slot, row_mul, row_add);
+  else
+    ring_load_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(ring, cur, ring_rows, T, d, slot, row_mul, row_add);
+  return check_launch("ring_copy_rows");
 }
 
 extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, int64_t n_edges,
@@ -113,7 +129,7 @@ extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int
   int rc;
   // a3: filtered history of the batch nodes straight into the current table
   if (n_ids > 0) {
-    rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, 1, stream);
+    rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, ids, stream);
     if (rc != LSTEP_OK) return rc;
   }
   // a6: all query sets in one pass
@@ -137,6 +153,6 @@ extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int
   rc = lstep_update_pe(s->cur, s->V1, csr, ids, n_ids, s->src + lo, s->dst + lo, s->t + lo, n_edges, current_time, K,
                        mlp_upd, w.update, w.update_bytes, err_flag, stream);
   if (rc != LSTEP_OK) return rc;
-  ring_append_kernel<<<kNumSMs * 8, 256, 0, st>>>(s->cur, s->ring, s->V1, T, d, append_slot);
+  ring_append_kernel<<<kNumSMs * 8, 256, 0, st>>>(s->cur, s->ring, s->V1, T, d, append_slot, 1, 0);
   return check_launch("ring_append");
 }

@@ -546,28 +546,105 @@ extern "C" int lstep_update_pe_workspace_init(void* workspace, size_t workspace_
   return LSTEP_OK;
 }
 
+namespace lstep {
+
+static int check_update_args(const float* pe, int64_t pe_rows, const lstep_pe_mlp* mlp, int64_t n_ids, int64_t n_edges, int K,
+                             void* workspace, size_t workspace_bytes) {
+  if (!pe || !mlp || pe_rows <= 0 || n_ids < 0 || n_edges < 0 || K <= 0) return LSTEP_ERR_INVALID_ARG;
+  const int d = mlp->d, t = mlp->t;
+  if (d % 4 != 0 || reinterpret_cast<uintptr_t>(pe) % 16 != 0) return LSTEP_ERR_UNSUPPORTED;
+  if (pe_rows > 0x7fffffffLL || (int64_t)n_ids * K > 0x7fffffffLL) return LSTEP_ERR_ID_RANGE;
+  const int dvec = d / 4;
+  const int threads = (int)align_up(align_up((size_t)t, 32) + dvec, 32);
+  if (threads > 512 || dvec > 8 * 32 || t > 8 * 32) return LSTEP_ERR_UNSUPPORTED;
+  const size_t need = carve(nullptr, n_ids, n_edges, K, d, t, pe_rows).bytes;
+  if (!workspace || workspace_bytes < need) return LSTEP_ERR_WORKSPACE;
+  return LSTEP_OK;
+}
+
+// phase A: aggregate over the batch edges for the rows `ids`, MLP with self term, in place. Also resets
+// the phase-B counters.
+static int phase_a(float* pe, const UpdateWs& w, const int64_t* ids, int64_t n_ids, const int64_t* src, const int64_t* dst,
+                   const double* times, int64_t n_edges, float tc, const lstep_pe_mlp* mlp, cudaStream_t st) {
+  const int d = mlp->d, t = mlp->t;
+  const int dvec = d / 4;
+  const int t_pad = (int)align_up((size_t)t, 32);
+  const int threads = (int)align_up((size_t)t_pad + dvec, 32);
+  const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
+  const int64_t grid = n_ids < (int64_t)kNumSMs * 16 ? n_ids : (int64_t)kNumSMs * 16;
+  edge_aggregate_kernel<<<(unsigned)grid, threads, smem, st>>>(pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d, t,
+                                                               t_pad, w.A, w.lda, w.counters);
+  int rc = check_launch("edge_aggregate");
+  if (rc != LSTEP_OK) return rc;
+  return launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st);
+}
+
+// phase B, aggregation half: lookup of (csr_ids[i], q_times[i]) for i < n_valid, inverse index, per
+// destination reduction of [pe[row_ids[i]] || tf]. Leaves U (distinct destinations, + 0 when any slot
+// was padding), the aggregate rows A and the device counters in the workspace.
+static int phase_b_partial(float* pe, int64_t pe_rows, const UpdateWs& w, const lstep_csr* csr, const int64_t* csr_ids,
+                           const int64_t* row_ids, int64_t n_ids, const double* q_times, int64_t n_valid, float tc, int K,
+                           const lstep_pe_mlp* mlp, uint32_t* err_flag, void* stream) {
+  const int d = mlp->d, t = mlp->t;
+  const int dvec = d / 4;
+  cudaStream_t st = as_stream(stream);
+  const int64_t total = n_ids * (int64_t)K;
+  int rc;
+  {
+    PhaseBHook hook{w.cnt_of, w.rank, w.U, w.counters, pe, d};
+    rc = launch_sample_count(csr, csr_ids, q_times, n_ids, n_valid, K, w.nbrB, w.ntB, err_flag, hook, stream);
+    if (rc != LSTEP_OK) return rc;
+  }
+  {
+    const int fill_here = total <= 16384 ? 1 : 0;
+    phaseB_scan_kernel<<<1 + kRow0Parts, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.counters, w.nbrB, total, K,
+                                                        w.rank, w.list, fill_here, pe, row_ids, n_ids, d, w.row0_part);
+    if ((rc = check_launch("phaseB_scan")) != LSTEP_OK) return rc;
+    if (!fill_here) {
+      phaseB_fill_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w.nbrB, total, w.slot_of, w.off, w.rank, w.list);
+      if ((rc = check_launch("phaseB_fill")) != LSTEP_OK) return rc;
+    }
+  }
+  const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;  // distinct non-zero destinations
+  const int warp_blocks = (int)ceil_div(max_dest > 0 ? max_dest : 1, 8);
+  int hub_blocks = (int)(total / (kHubLen + 1)) + 1;  // at most this many lists can be longer than kHubLen
+  if (hub_blocks > 2 * kNumSMs) hub_blocks = 2 * kNumSMs;
+  const unsigned blocks = (unsigned)(warp_blocks + hub_blocks + 1);
+  const size_t smem = sizeof(int) * kHubSortMax + sizeof(float) * (8 * (size_t)(d + t) + 2) + sizeof(unsigned long long) * (size_t)(d + t);
+  if (dvec <= 64 && t <= 128)
+    phaseB_gather_kernel<2, 4><<<blocks, 256, smem, st>>>(pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw, d,
+                                                          t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
+  else
+    phaseB_gather_kernel<8, 8><<<blocks, 256, smem, st>>>(pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw, d,
+                                                          t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
+  return check_launch("phaseB_gather");
+}
+
+// phase B, write-back half: pe[U] += tanh(mlp(A)), no self term (Q3)
+static int phase_b_apply(float* pe, int64_t pe_rows, const UpdateWs& w, int64_t n_ids, int K, const lstep_pe_mlp* mlp,
+                         cudaStream_t st) {
+  const int64_t total = n_ids * (int64_t)K;
+  const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;
+  lstep_pe_mlp noself = *mlp;
+  noself.ws = nullptr;  // the self term is computed and discarded by the reference (LSTEP.py:334-335, Q3)
+  noself.bs = nullptr;
+  return launch_pe_mlp(w.A, w.lda, pe, single_ids(w.U), max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe, st);
+}
+
+}  // namespace lstep
+
 extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids,
                                const int64_t* src, const int64_t* dst, const double* times, int64_t n_edges,
                                double current_time, int K, const lstep_pe_mlp* mlp, void* workspace,
                                size_t workspace_bytes, uint32_t* err_flag, void* stream) {
-  if (!pe || !csr || !mlp || pe_rows <= 0 || n_ids < 0 || n_edges < 0 || K <= 0) return LSTEP_ERR_INVALID_ARG;
-  if (n_ids > 0 && !ids) return LSTEP_ERR_INVALID_ARG;
-  if (n_edges > 0 && (!src || !dst || !times)) return LSTEP_ERR_INVALID_ARG;
-  const int d = mlp->d, t = mlp->t;
-  if (d % 4 != 0 || reinterpret_cast<uintptr_t>(pe) % 16 != 0) return LSTEP_ERR_UNSUPPORTED;
+  int rc = check_update_args(pe, pe_rows, mlp, n_ids, n_edges, K, workspace, workspace_bytes);
+  if (rc != LSTEP_OK) return rc;
+  if (!csr || (n_ids > 0 && !ids) || (n_edges > 0 && (!src || !dst || !times))) return LSTEP_ERR_INVALID_ARG;
   if (csr->num_rows > pe_rows) return LSTEP_ERR_INVALID_ARG;
-  if (pe_rows > 0x7fffffffLL || (int64_t)n_ids * K > 0x7fffffffLL) return LSTEP_ERR_ID_RANGE;
-  const size_t need = carve(nullptr, n_ids, n_edges, K, d, t, pe_rows).bytes;
-  if (!workspace || workspace_bytes < need) return LSTEP_ERR_WORKSPACE;
+  const int d = mlp->d, t = mlp->t;
   UpdateWs w = carve(workspace, n_ids, n_edges, K, d, t, pe_rows);
   cudaStream_t st = as_stream(stream);
   const float tc = (float)current_time;
-  int rc;
-
-  const int dvec = d / 4;
-  const int t_pad = (int)align_up((size_t)t, 32);
-  const int threads = (int)align_up((size_t)t_pad + dvec, 32);
-  if (threads > 512 || dvec > 8 * 32 || t > 8 * 32) return LSTEP_ERR_UNSUPPORTED;
   if (n_ids == 0) {  // nothing to update; the reference still zeroes the padding row (LSTEP.py:317)
     cudaError_t e = cudaMemsetAsync(pe, 0, sizeof(float) * d, st);
     if (e != cudaSuccess) {
@@ -576,51 +653,77 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
     }
     return LSTEP_OK;
   }
-  // ---- phase A (also resets the phase-B counters)
-  {
-    const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
-    const int64_t grid = n_ids < (int64_t)kNumSMs * 16 ? n_ids : (int64_t)kNumSMs * 16;
-    edge_aggregate_kernel<<<(unsigned)grid, threads, smem, st>>>(pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d, t,
-                                                                 t_pad, w.A, w.lda, w.counters);
-    if ((rc = check_launch("edge_aggregate")) != LSTEP_OK) return rc;
-    if ((rc = launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st)) != LSTEP_OK) return rc;
-  }
-
-  // ---- phase B: lookup + per-destination count in one launch (also pe[0] = 0)
+  if ((rc = phase_a(pe, w, ids, n_ids, src, dst, times, n_edges, tc, mlp, st)) != LSTEP_OK) return rc;
   const int64_t n_valid = n_ids < n_edges ? n_ids : n_edges;  // zip(node_ids, times) truncation (Q1)
-  const int64_t total = n_ids * (int64_t)K;
-  {
-    PhaseBHook hook{w.cnt_of, w.rank, w.U, w.counters, pe, d};
-    rc = launch_sample_count(csr, ids, times, n_ids, n_valid, K, w.nbrB, w.ntB, err_flag, hook, stream);
-    if (rc != LSTEP_OK) return rc;
+  if ((rc = phase_b_partial(pe, pe_rows, w, csr, ids, ids, n_ids, times, n_valid, tc, K, mlp, err_flag, stream)) != LSTEP_OK) return rc;
+  return phase_b_apply(pe, pe_rows, w, n_ids, K, mlp, st);
+}
+
+// ---- the same phases as separate entry points (node-id sharded tables: the phases are separated by
+// ---- row exchanges between ranks, see l-step_b200/shard.py)
+extern "C" int lstep_update_pe_phase_a(float* pe, int64_t pe_rows, const int64_t* ids, int64_t n_ids, const int64_t* src,
+                                       const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K,
+                                       const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_update_args(pe, pe_rows, mlp, n_ids, n_edges, K, workspace, workspace_bytes);
+  if (rc != LSTEP_OK) return rc;
+  if (n_ids == 0) return LSTEP_OK;
+  if (!ids || (n_edges > 0 && (!src || !dst || !times))) return LSTEP_ERR_INVALID_ARG;
+  UpdateWs w = carve(workspace, n_ids, n_edges, K, mlp->d, mlp->t, pe_rows);
+  return phase_a(pe, w, ids, n_ids, src, dst, times, n_edges, (float)current_time, mlp, as_stream(stream));
+}
+
+extern "C" int lstep_update_pe_phase_b_partial(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* csr_ids,
+                                               const int64_t* row_ids, int64_t n_ids, const double* q_times, int64_t n_valid,
+                                               int64_t n_edges_layout, double current_time, int K, const lstep_pe_mlp* mlp,
+                                               void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream) {
+  int rc = check_update_args(pe, pe_rows, mlp, n_ids, n_edges_layout, K, workspace, workspace_bytes);
+  if (rc != LSTEP_OK) return rc;
+  if (!csr || n_ids <= 0 || !csr_ids || !row_ids || !q_times || n_valid < 0) return LSTEP_ERR_INVALID_ARG;
+  UpdateWs w = carve(workspace, n_ids, n_edges_layout, K, mlp->d, mlp->t, pe_rows);
+  cudaError_t e = cudaMemsetAsync(w.counters, 0, sizeof(int32_t) * 8, as_stream(stream));
+  if (e != cudaSuccess) {
+    set_cuda_error(e, "phase_b counters");
+    return LSTEP_ERR_CUDA;
   }
-  {
-    const int fill_here = total <= 16384 ? 1 : 0;
-    phaseB_scan_kernel<<<1 + kRow0Parts, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.counters, w.nbrB, total, K,
-                                                        w.rank, w.list, fill_here, pe, ids, n_ids, d, w.row0_part);
-    if ((rc = check_launch("phaseB_scan")) != LSTEP_OK) return rc;
-    if (!fill_here) {
-      phaseB_fill_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w.nbrB, total, w.slot_of, w.off, w.rank, w.list);
-      if ((rc = check_launch("phaseB_fill")) != LSTEP_OK) return rc;
+  return phase_b_partial(pe, pe_rows, w, csr, csr_ids, row_ids, n_ids, q_times, n_valid, (float)current_time, K, mlp, err_flag,
+                         stream);
+}
+
+extern "C" int lstep_update_pe_workspace_layout(int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows,
+                                                int64_t* offsets /* [4]: counters, U, A (bytes), lda (floats) */) {
+  if (!offsets || n_ids < 0 || n_edges < 0 || K <= 0 || d <= 0 || t < 0 || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
+  char base[1];
+  UpdateWs w = carve(base, n_ids, n_edges, K, d, t, pe_rows);
+  offsets[0] = reinterpret_cast<char*>(w.counters) - base;
+  offsets[1] = reinterpret_cast<char*>(w.U) - base;
+  offsets[2] = reinterpret_cast<char*>(w.A) - base;
+  offsets[3] = w.lda;
+  return LSTEP_OK;
+}
+
+// out[s][:] = sum of rows[seg_off[s] .. seg_off[s+1]) in order (fixed order => reproducible): combines
+// the per-rank partial aggregates of a destination.
+namespace lstep {
+__global__ void __launch_bounds__(256) segment_sum_rows_kernel(const float* __restrict__ rows, int64_t ld,
+                                                               const int64_t* __restrict__ seg_off, int64_t n_seg, int width,
+                                                               float* __restrict__ out, int64_t ldo) {
+  for (int64_t s = blockIdx.x; s < n_seg; s += gridDim.x) {
+    const int64_t lo = seg_off[s], hi = seg_off[s + 1];
+    for (int c = threadIdx.x; c < width; c += blockDim.x) {
+      float acc = 0.f;
+      for (int64_t r = lo; r < hi; ++r) acc += rows[r * ld + c];
+      out[s * ldo + c] = acc;
     }
   }
-  const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;  // distinct non-zero destinations
-  {
-    const int warp_blocks = (int)ceil_div(max_dest > 0 ? max_dest : 1, 8);
-    int hub_blocks = (int)(total / (kHubLen + 1)) + 1;  // at most this many lists can be longer than kHubLen
-    if (hub_blocks > 2 * kNumSMs) hub_blocks = 2 * kNumSMs;
-    const unsigned blocks = (unsigned)(warp_blocks + hub_blocks + 1);
-    const size_t smem = sizeof(int) * kHubSortMax + sizeof(float) * (8 * (size_t)(d + t) + 2) + sizeof(unsigned long long) * (size_t)(d + t);
-    if (dvec <= 64 && t <= 128)
-      phaseB_gather_kernel<2, 4><<<blocks, 256, smem, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw,
-                                                            d, t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
-    else
-      phaseB_gather_kernel<8, 8><<<blocks, 256, smem, st>>>(pe, ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw,
-                                                            d, t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
-    if ((rc = check_launch("phaseB_gather")) != LSTEP_OK) return rc;
-  }
-  lstep_pe_mlp noself = *mlp;
-  noself.ws = nullptr;  // the self term is computed and discarded by the reference (LSTEP.py:334-335, Q3)
-  noself.bs = nullptr;
-  return launch_pe_mlp(w.A, w.lda, pe, single_ids(w.U), max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe, st);
+}
+}  // namespace lstep
+
+extern "C" int lstep_segment_sum_rows(const float* rows, int64_t ld, const int64_t* seg_off, int64_t n_seg, int width,
+                                      float* out, int64_t ldo, void* stream) {
+  if (n_seg < 0 || width <= 0) return LSTEP_ERR_INVALID_ARG;
+  if (n_seg == 0) return LSTEP_OK;
+  if (!rows || !seg_off || !out) return LSTEP_ERR_INVALID_ARG;
+  const int64_t grid = n_seg < (int64_t)kNumSMs * 8 ? n_seg : (int64_t)kNumSMs * 8;
+  segment_sum_rows_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(rows, ld, seg_off, n_seg, width, out, ldo);
+  return check_launch("segment_sum_rows");
 }
