@@ -233,9 +233,128 @@ def run_ours(args, rank, world):
             "stages_ms": stages, "kernels_ms": {k: v for k, v in kern.items() if not k.startswith("_")},
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_sharded(args, rank, world):
+    """BASELINE config 5: scale-out graph (10 M nodes), node-id sharded PE history / CSR, NCCL all-to-all row
+    exchanges (l-step_b200/shard.py). The batch is replicated, so the total work is fixed as N grows
+    (strong scaling). T = 20 history steps so that the ring (137.6 GB in total) fits from N = 1 upwards."""
+    import torch
+    import torch.distributed as dist
+    from lstep_b200 import LSTEP, DistGroup, ShardedPEStream, ShardRank, _lib
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    else:  # degenerate group of one: same code path, no peers
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29533")
+        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
+    lib = _lib.load()
+    assert lib.lstep_device_ok() == 1
+    B, K, T = 2000, 20, args.scaleout_T
+    V, E = args.scaleout_nodes, args.scaleout_edges
+    t0 = time.time()
+    g = synth.make_graph("scaleout", seed=0, num_nodes=V, num_edges=E)
+    t_gen = time.time() - t0
+    torch.manual_seed(0)
+    node_feats = np.zeros((2, 172), dtype=np.float32)
+    m = LSTEP(node_feats, np.zeros((1, 172), dtype=np.float32), None, None, pe_dim=D, num_neighbors=20, time_feat_dim=T_DIM,
+              num_fft_batches=T, device=dev).to(dev).eval()
+    gen = torch.Generator(device=dev).manual_seed(1)
+    init = torch.randn((V + 1, D), device=dev, generator=gen) * 0.1
+    init[0] = 0
+    e0 = int(E * 0.7) // B * B
+    t0 = time.time()
+    rk = ShardRank(m, rank, world, g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids, V, B, K, init, start=e0)
+    del init
+    torch.cuda.synchronize()
+    t_setup = time.time() - t0
+    sh = ShardedPEStream(rk, DistGroup())
+    nb = (E - e0 + B - 1) // B
+    rng = np.random.default_rng(2)
+    dst_pool = np.unique(g.dst_node_ids[:2_000_000])
+
+    def queries(b):
+        lo, hi = rk.batch(b)
+        return [g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.src_node_ids[lo:hi], rng.choice(dst_pool, hi - lo)]
+
+    W, Ksteps = max(args.warmup, 3), args.steps
+    step_no = 0
+    for _ in range(W):
+        sh.step(step_no % nb, queries(step_no % nb))
+        step_no += 1
+    torch.cuda.synchronize()
+    dist.barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rk.bytes_x1 = rk.bytes_x2 = 0
+    edges = 0
+    ev0.record()
+    for _ in range(Ksteps):
+        b = step_no % nb
+        sh.step(b, queries(b))
+        lo, hi = rk.batch(b)
+        edges += hi - lo
+        step_no += 1
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop()
+    tm = torch.tensor([ms], device=dev)
+    dist.barrier()
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_max = float(tm.item())
+    value = edges / (ms_max * 1e-3)  # the batch is replicated: edges of the job, not per rank
+    # end to end: same step with the per-query row sums read back to the host every step
+    n_e2e = min(Ksteps, 100)
+    d2h = 0
+    e_edges = 0
+    h0 = m.h2d_bytes
+    dist.barrier()
+    ev0.record()
+    for _ in range(n_e2e):
+        b = step_no % nb
+        out = sh.step(b, queries(b))
+        r = out.sum(dim=2).cpu()
+        d2h += r.numel() * 4
+        lo, hi = rk.batch(b)
+        e_edges += hi - lo
+        step_no += 1
+    ev1.record()
+    torch.cuda.synchronize()
+    tm = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    dist.barrier()
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e = {"value": e_edges / (float(tm.item()) * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": (m.h2d_bytes - h0) / n_e2e,
+           "d2h_bytes_per_step": d2h / n_e2e, "steps": n_e2e, "api": "ShardedPEStream.step (numpy queries in, per-query row sums out), per rank"}
+    x = torch.tensor([rk.bytes_x1, rk.bytes_x2], dtype=torch.float64, device=dev)
+    dist.all_reduce(x)
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        out = {
+            "metric": "temporal edges/sec through PE update+aggregation; % HBM roofline", "value": value, "unit": "edges/s",
+            "n_gpus": world, "steps": Ksteps, "warmup": W, "ms_per_step": ms_max / Ksteps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"scale-out synthetic temporal graph, V={V}, first E={E} edges of the stream, B={B}, K={K}, T={T}, d={D}, "
+                                   f"t={T_DIM}, C={C_CALLS}",
+                       "parallelism": f"PE history ring + CSR sharded by node id over {world} GPU(s) (owner = id mod N), current table cached "
+                                      "per rank, 2 NCCL all-to-all row exchanges per step",
+                       "l2_policy": f"inputs larger than L2: history ring {(V + 1) * T * D * 4 / 1e9 / world:.1f} GB per rank",
+                       "graph_gen_s": t_gen, "shard_setup_s": t_setup,
+                       "nvlink_bytes_per_step_all_ranks": {"rows_fetch": float(x[0].item()) / Ksteps, "partials": float(x[1].item()) / Ksteps}},
+            "clocks": clk, "e2e": e2e,
+            "gpu_launches": int(Ksteps * 12 * world),
+            "roofline": None, "cpu_baseline": None,
+        }
+        emit(out)
+    dist.destroy_process_group()
 
 
 def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, lib):
@@ -410,6 +529,10 @@ def run_reference(args, rank, world):
     /root/reference are not on the GPU box and may not be copied), so this arm times the oracle port."""
     if rank != 0:
         return
+    global T_HIST
+    if args.workload == "scaleout" or (world > 1 and not args.replicas):
+        # the sharded arm's config: batch shape of the Flights config (B=2000, K=20), T = --scaleout-T
+        args.workload, T_HIST = "flights", args.scaleout_T
     B, K = WORKLOADS[args.workload]
     steps, warm = args.steps, max(args.warmup, 1)
     steps = min(steps, 60)  # each step is one batch of CPU work (~0.1 s); bounded
@@ -430,23 +553,54 @@ def run_reference(args, rank, world):
            "config": {"workload": f"{args.workload}-shaped synthetic temporal graph, B={B}, K={K}, T={T_HIST}, d={D}, t={T_DIM}, C={C_CALLS}"},
            "cpu_baseline": {"value": value, "unit": "edges/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
            "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL prints its version banner) write to fd 1; the driver wants exactly one JSON line there.
+    Route fd 1 to stderr for the duration of the run; emit() restores it for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=1000)
-    ap.add_argument("--warmup", type=int, default=120)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS) + ["scaleout"])
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas of the single-GPU workload instead of the sharded scale-out graph")
+    ap.add_argument("--scaleout-nodes", type=int, default=10_000_000)
+    ap.add_argument("--scaleout-edges", type=int, default=40_000_000)
+    ap.add_argument("--scaleout-T", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batches", type=int, default=40)
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 1000 if (int(os.environ.get("WORLD_SIZE", 1)) == 1 and args.workload != "scaleout") else 100
+    if args.warmup is None:
+        args.warmup = 120 if (int(os.environ.get("WORLD_SIZE", 1)) == 1 and args.workload != "scaleout") else 30
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "scaleout" or (world > 1 and not args.replicas):
+        run_sharded(args, rank, world)
     else:
         run_ours(args, rank, world)
 

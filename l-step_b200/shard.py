@@ -82,15 +82,19 @@ class DistGroup:
         self.dist, self.group = dist, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
 
-    def alltoallv(self, send: torch.Tensor, counts):
+    def alltoallv(self, send: torch.Tensor, counts, recv_counts=None):
         """send: rows grouped by destination rank (counts[r] rows for rank r). Returns (recv rows grouped by
-        source rank, recv counts)."""
+        source rank, recv counts). When the receive counts are already known (the reply of a request, a
+        second payload with the same split) the count exchange and its host sync are skipped."""
         dist = self.dist
         dev = send.device
-        c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
-        c_in = torch.empty_like(c_out)
-        dist.all_to_all_single(c_in, c_out, group=self.group)
-        rc = c_in.cpu().tolist()
+        if recv_counts is None:
+            c_out = torch.tensor(counts, dtype=torch.int64, device=dev)
+            c_in = torch.empty_like(c_out)
+            dist.all_to_all_single(c_in, c_out, group=self.group)
+            rc = c_in.cpu().tolist()
+        else:
+            rc = list(recv_counts)
         recv = torch.empty((sum(rc),) + tuple(send.shape[1:]), dtype=send.dtype, device=dev)
         dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=list(counts), group=self.group)
         return recv, rc
@@ -105,7 +109,7 @@ def fetch_rows(comm, table: torch.Tensor, need_sorted: torch.Tensor, counts, wor
     them into this rank's copy. Every rank of the group must call it (collective)."""
     req, rc = comm.alltoallv(need_sorted, counts)      # ids other ranks ask me for
     rows = table.index_select(0, req)                  # my authoritative rows
-    got, _ = comm.alltoallv(rows, rc)                  # rows I asked for, in the order I asked
+    got, _ = comm.alltoallv(rows, rc, recv_counts=counts)  # rows I asked for, in the order I asked
     if need_sorted.numel():
         table.index_copy_(0, need_sorted, got)
     return int(need_sorted.numel()), int(req.numel())
@@ -348,8 +352,8 @@ class ShardedPEStream:
         out = torch.zeros((len(queries) * st["nB"], rk.d), dtype=torch.float32, device=rk.dev)
         st = rk.p2(st, out)
         comm.allreduce_sum(out)  # every row is non-zero on exactly one rank: an exact, order-free combine
-        ru, _ = comm.alltoallv(st["send_u"], st["send_counts"])
-        rr, _ = comm.alltoallv(st["send_rows"], st["send_counts"])
+        ru, rc = comm.alltoallv(st["send_u"], st["send_counts"])
+        rr, _ = comm.alltoallv(st["send_rows"], st["send_counts"], recv_counts=rc)
         rk.bytes_x2 += int(st["send_rows"].numel() * 4 + rr.numel() * 4)
         rk.p3(st, ru, rr)
         return out.view(len(queries), st["nB"], rk.d)
