@@ -67,9 +67,31 @@ struct PhaseBHook {
   int d;
 };
 
-// TimeEncoder (models/modules.py:37): cos(fp32(dt) * w_j + 0). The product must be a separately
-// rounded fp32 multiply (no FMA contraction into the range reduction), cosf is the accurate
-// library version (arguments reach 1e8 rad).
-__device__ __forceinline__ float time_feature(float dt, float w) { return cosf(__fmul_rn(dt, w)); }
+// TimeEncoder (models/modules.py:37): cos(fp32(dt) * w_j + 0). The product is a separately rounded fp32
+// multiply (that is what Linear(1->t) computes), then an accurate cosine: arguments reach 1e6..1e8 rad
+// (dt in seconds times w_0 = 1), where cosf() takes its slow Payne-Hanek path (hundreds of instructions,
+// and divergent: only the low-frequency lanes need it). accurate_cos() instead reduces the argument in
+// fp64 — k = rint(x * 2/pi), r = x - k*pi/2 with a two-term pi/2 and FMAs, exact to ~1e-16 for
+// |x| < 2^31 — and evaluates the Cephes single-precision minimax polynomials on |r| <= pi/4:
+// branch-free, ~20 instructions, within 1 ulp of the correctly rounded cos like cosf itself.
+__device__ __forceinline__ float accurate_cos(float x) {
+  if (!(fabsf(x) < 2.0e9f)) return cosf(x);  // beyond int32 quadrant range (never reached by real timestamps); NaN/inf too
+  const double xd = (double)x;
+  const double kd = rint(xd * 0.63661977236758134308);  // 2/pi
+  double r = fma(-kd, 1.57079632679489655800e+00, xd);   // pi/2 high part
+  r = fma(-kd, 6.12323399573676603587e-17, r);           // pi/2 low part
+  const int q = (int)kd;
+  const float rf = (float)r;
+  const float z = rf * rf;
+  // sin(r) = r + r^3 * S(z),  cos(r) = 1 - z/2 + z^2 * C(z)   on |r| <= pi/4
+  const float s = fmaf(rf * z, fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), rf);
+  const float c = fmaf(z * z, fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
+                       fmaf(-0.5f, z, 1.0f));
+  // cos(x) = cos(r + q*pi/2): q mod 4 = 0: c, 1: -s, 2: -c, 3: s
+  const float v = (q & 1) ? s : c;
+  return (((q + 1) & 2) ? -v : v);
+}
+
+__device__ __forceinline__ float time_feature(float dt, float w) { return accurate_cos(__fmul_rn(dt, w)); }
 
 }  // namespace lstep
