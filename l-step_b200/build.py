@@ -36,7 +36,7 @@ def _digest() -> str:
         with open(f, "rb") as fh:
             h.update(f.encode())
             h.update(fh.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update((" ".join(NVCC_FLAGS) + os.environ.get("LSTEP_NVCC_EXTRA", "")).encode())
     return h.hexdigest()
 
 
@@ -44,7 +44,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     dig = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + \
+    extra = os.environ.get("LSTEP_NVCC_EXTRA", "").split()  # e.g. -DLSTEP_PROFILE_GATHER for instrumented builds
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr

@@ -68,28 +68,57 @@ struct PhaseBHook {
 };
 
 // TimeEncoder (models/modules.py:37): cos(fp32(dt) * w_j + 0). The product is a separately rounded fp32
-// multiply (that is what Linear(1->t) computes), then an accurate cosine: arguments reach 1e6..1e8 rad
+// multiply (that is what Linear(1->t) computes), then an accurate cosine. Arguments reach 1e6..1e8 rad
 // (dt in seconds times w_0 = 1), where cosf() takes its slow Payne-Hanek path (hundreds of instructions,
-// and divergent: only the low-frequency lanes need it). accurate_cos() instead reduces the argument in
-// fp64 — k = rint(x * 2/pi), r = x - k*pi/2 with a two-term pi/2 and FMAs, exact to ~1e-16 for
-// |x| < 2^31 — and evaluates the Cephes single-precision minimax polynomials on |r| <= pi/4:
-// branch-free, ~20 instructions, within 1 ulp of the correctly rounded cos like cosf itself.
-__device__ __forceinline__ float accurate_cos(float x) {
-  if (!(fabsf(x) < 2.0e9f)) return cosf(x);  // beyond int32 quadrant range (never reached by real timestamps); NaN/inf too
-  const double xd = (double)x;
-  const double kd = rint(xd * 0.63661977236758134308);  // 2/pi
-  double r = fma(-kd, 1.57079632679489655800e+00, xd);   // pi/2 high part
-  r = fma(-kd, 6.12323399573676603587e-17, r);           // pi/2 low part
-  const int q = (int)kd;
-  const float rf = (float)r;
+// divergent: only the low-frequency lanes need it) and where an fp64 reduction is no alternative (the
+// scalar fp64 pipe of this part issues ~4 lanes/clk/SM: measured, it made one hub CTA the step's long
+// pole). accurate_cos() does the Payne-Hanek reduction in 64-bit integer arithmetic instead: with
+// |x| = m * 2^E (m the 24-bit significand), (x * 2/pi) mod 4 in 2.62 fixed point is m * W mod 2^64, where
+// W is the 64-bit window of the bits of 2/pi that starts E+62 bits after the binary point (bits further
+// left only contribute multiples of 4 quadrants). The top two bits are the quadrant, the rest the
+// fraction of a quadrant (error < 2^-38), folded to [-1/2, 1/2), scaled by pi/2 and fed to the Cephes
+// single-precision minimax polynomials: ~35 integer / fp32 instructions, absolute error <= 1.1e-7
+// (checked against libm on 15 000 arguments up to 2e9). Arguments below 2^14 — 72 % of the (dt, w_j)
+// pairs, all of them for j >= 28 — take a 3-term Cody-Waite reduction in fp32 FMAs instead (6 instructions).
+__device__ __forceinline__ float cos_poly(float rf, int q) {
   const float z = rf * rf;
   // sin(r) = r + r^3 * S(z),  cos(r) = 1 - z/2 + z^2 * C(z)   on |r| <= pi/4
   const float s = fmaf(rf * z, fmaf(fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f), rf);
   const float c = fmaf(z * z, fmaf(fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f),
                        fmaf(-0.5f, z, 1.0f));
-  // cos(x) = cos(r + q*pi/2): q mod 4 = 0: c, 1: -s, 2: -c, 3: s
+  // cos(r + q*pi/2): q mod 4 = 0: c, 1: -s, 2: -c, 3: s
   const float v = (q & 1) ? s : c;
   return (((q + 1) & 2) ? -v : v);
+}
+
+__device__ __forceinline__ float accurate_cos(float x) {
+  if (fabsf(x) < 16384.f) {
+    const float k = rintf(x * 0.63661977236758134f);
+    float r = fmaf(-k, 1.5703125f, x);                 // pi/2 = 1.5703125 + 4.837512969970703125e-4 + 7.549789954891882e-8 + ...
+    r = fmaf(-k, 4.837512969970703125e-4f, r);
+    r = fmaf(-k, 7.549789954891882e-8f, r);
+    return cos_poly(r, (int)k);
+  }
+  const uint32_t bits = __float_as_uint(x);
+  int e = (int)((bits >> 23) & 0xffu);
+  if (e >= 214) return cosf(x);  // inf / nan / beyond the 128 stored bits of 2/pi (never a real timestamp)
+  const uint32_t m = (bits & 0x7fffffu) | (e ? 0x800000u : 0u);
+  e = e ? e : 1;
+  const int sh = e - 88;  // E + 62 with E = e - 150
+  const unsigned long long P_hi = 0xa2f9836e4e441529ull, P_lo = 0xfc2757d1f534ddc0ull;  // floor(2/pi * 2^128)
+  unsigned long long W = 0ull;
+  if (sh > 64)
+    W = (P_hi << (sh - 64)) | (P_lo >> (128 - sh));
+  else if (sh > 0)
+    W = P_hi >> (64 - sh);
+  const unsigned long long R = (unsigned long long)m * W;  // mod 2^64: 2 quadrant bits . 62 fraction bits
+  int q = (int)(R >> 62);
+  long long f = (long long)(R & 0x3fffffffffffffffull);
+  if (f >= (1ll << 61)) {
+    f -= (1ll << 62);
+    q += 1;
+  }
+  return cos_poly((float)f * 3.4061215800865545e-19f /* (pi/2) * 2^-62 */, q);
 }
 
 __device__ __forceinline__ float time_feature(float dt, float w) { return accurate_cos(__fmul_rn(dt, w)); }

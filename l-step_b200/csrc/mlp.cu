@@ -94,8 +94,8 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
     const int64_t nd = *n_rows_dev;
     n_rows = nd < n_rows ? nd : n_rows;
   }
-  const int64_t row0 = (int64_t)blockIdx.x * R;
-  if (row0 >= n_rows) return;
+  const int64_t n_row_tiles = (n_rows + R - 1) / R;
+  if ((int64_t)blockIdx.x >= n_row_tiles) return;
   const int tile_elems = kKTile * ldo;
   float* Wst = smem;
   float* As = Wst + (size_t)NS * tile_elems;
@@ -108,6 +108,10 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
   const int t1 = in1_pad / kKTile, t2 = d_pad / kKTile;
   const int ntiles = t1 + t2 + (has_self ? t2 : 0);
   const uint32_t tile_bytes = (uint32_t)tile_elems * 4u;
+  // persistent: this CTA walks row tiles blockIdx.x, blockIdx.x + gridDim.x, ...; the weight-tile ring keeps
+  // running across row tiles (global tile counter `it`), so the next row tile's first weights are already in
+  // flight while the current epilogue runs.
+  const int64_t my_tiles = (n_row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
@@ -120,51 +124,20 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
 
   if (tid >= ncons) {  // ---- producer warp
     if (tid == ncons) {
-      for (int i = 0; i < ntiles; ++i) {
-        const int s = i % NS;
-        if (i >= NS) mbar_wait(&empty_bar[s], (uint32_t)(((i / NS) - 1) & 1));
-        const float* src = i < t1 ? m.w1 + (size_t)i * tile_elems
-                                  : (i < t1 + t2 ? m.w2 + (size_t)(i - t1) * tile_elems : m.ws + (size_t)(i - t1 - t2) * tile_elems);
-        mbar_expect_tx(&full_bar[s], tile_bytes);
-        bulk_g2s(Wst + (size_t)s * tile_elems, src, tile_bytes, &full_bar[s]);
+      int64_t it = 0;
+      for (int64_t rt = 0; rt < my_tiles; ++rt) {
+        for (int i = 0; i < ntiles; ++i, ++it) {
+          const int s = (int)(it % NS);
+          if (it >= NS) mbar_wait(&empty_bar[s], (uint32_t)(((it / NS) - 1) & 1));
+          const float* src = i < t1 ? m.w1 + (size_t)i * tile_elems
+                                    : (i < t1 + t2 ? m.w2 + (size_t)(i - t1) * tile_elems : m.ws + (size_t)(i - t1 - t2) * tile_elems);
+          mbar_expect_tx(&full_bar[s], tile_bytes);
+          bulk_g2s(Wst + (size_t)s * tile_elems, src, tile_bytes, &full_bar[s]);
+        }
       }
     }
     return;
   }
-
-  // ---- consumers: stage the activation tiles k-major (loads batched ahead of the stores)
-  {
-    const int totalA = R * in1_pad, totalB = R * d_pad;
-    for (int base = 0; base < totalA; base += ncons * 4) {
-      float v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * ncons + tid;
-        const int r = idx / in1_pad, k = idx % in1_pad;
-        v[u] = (idx < totalA && row0 + r < n_rows && k < in1) ? A[(row0 + r) * lda + k] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * ncons + tid;
-        if (idx < totalA) As[(idx % in1_pad) * R + idx / in1_pad] = v[u];
-      }
-    }
-    for (int base = 0; base < totalB; base += ncons * 4) {
-      float v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * ncons + tid;
-        const int r = idx / d_pad, k = idx % d_pad;
-        v[u] = (idx < totalB && row0 + r < n_rows && k < d) ? pe[base_ids.at(row0 + r) * (int64_t)d + k] : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int idx = base + u * ncons + tid;
-        if (idx < totalB) Bs[(idx % d_pad) * R + idx / d_pad] = v[u];
-      }
-    }
-  }
-  consumer_sync(ncons);
 
   const int g = tid / ldo, lt = tid % ldo;  // k-split group, thread within group
   const int npairs = ldo >> 1;
@@ -200,14 +173,14 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
       }
     }
   };
-  // one segment: tiles [first, first+count) against the k-major input `in`; partial sums -> red[g]
-  auto run_segment = [&](int first, int count, const float* in) {
+  // one segment: weight tiles [first, first+count) of the current row tile (global ring index it0 + i)
+  auto run_segment = [&](int64_t it0, int first, int count, const float* in) {
 #pragma unroll
     for (int r = 0; r < RT; ++r) acc[r][0] = acc[r][1] = 0.f;
     for (int j = g; j < count; j += G) {
-      const int i = first + j;
-      const int s = i % NS;
-      mbar_wait(&full_bar[s], (uint32_t)((i / NS) & 1));
+      const int64_t it = it0 + first + j;
+      const int s = (int)(it % NS);
+      mbar_wait(&full_bar[s], (uint32_t)((it / NS) & 1));
       fma_tile(Wst + (size_t)s * tile_elems, in + (size_t)j * kKTile * R);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);  // this warp is done with the stage
@@ -224,39 +197,78 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
     return v;
   };
 
-  // ---- layer 1: h = relu(W1 a + b1), written k-major; padded columns stay zero
-  run_segment(0, t1, As);
-  if (g == 0) {
+  for (int64_t rt = 0; rt < my_tiles; ++rt) {
+    const int64_t row0 = ((int64_t)blockIdx.x + rt * gridDim.x) * R;
+    const int64_t it0 = rt * ntiles;
+    // ---- stage the activation tiles k-major (loads batched ahead of the stores)
+    {
+      const int totalA = R * in1_pad, totalB = R * d_pad;
+      for (int base = 0; base < totalA; base += ncons * 4) {
+        float v[4];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int c = c0 + j;
-      if (c < d_pad) {
-        const float b = c < d ? m.b1[c] : 0.f;
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * ncons + tid;
+          const int r = idx / in1_pad, k = idx % in1_pad;
+          v[u] = (idx < totalA && row0 + r < n_rows && k < in1) ? A[(row0 + r) * lda + k] : 0.f;
+        }
 #pragma unroll
-        for (int r = 0; r < RT; ++r) Hs[c * R + rg * RT + r] = c < d ? fmaxf(reduced(r, j) + b, 0.f) : 0.f;
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * ncons + tid;
+          if (idx < totalA) As[(idx % in1_pad) * R + idx / in1_pad] = v[u];
+        }
       }
-    }
-  }
-  consumer_sync(ncons);
-
-  // ---- layer 2 (+ self term): z = W2 h + b2 [+ Ws base + bs] as one k-run over [h ; base]
-  run_segment(t1, ntiles - t1, Hs);
-  if (g == 0) {
+      for (int base = 0; base < totalB; base += ncons * 4) {
+        float v[4];
 #pragma unroll
-    for (int r = 0; r < RT; ++r) {
-      const int rr = rg * RT + r;
-      const int64_t row = row0 + rr;
-      if (row >= n_rows) continue;
-      float* dst = out ? out + row * out_stride : pe_inplace + base_ids.at(row) * (int64_t)d;
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * ncons + tid;
+          const int r = idx / d_pad, k = idx % d_pad;
+          v[u] = (idx < totalB && row0 + r < n_rows && k < d) ? pe[base_ids.at(row0 + r) * (int64_t)d + k] : 0.f;
+        }
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int c = c0 + j;
-        if (c < d) {
-          const float z = reduced(r, j) + m.b2[c] + (has_self ? m.bs[c] : 0.f);
-          dst[c] = Bs[c * R + rr] + tanhf(z);
+        for (int u = 0; u < 4; ++u) {
+          const int idx = base + u * ncons + tid;
+          if (idx < totalB) Bs[(idx % d_pad) * R + idx / d_pad] = v[u];
         }
       }
     }
+    consumer_sync(ncons);
+
+    // ---- layer 1: h = relu(W1 a + b1), written k-major; padded columns stay zero
+    run_segment(it0, 0, t1, As);
+    if (g == 0) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int c = c0 + j;
+        if (c < d_pad) {
+          const float b = c < d ? m.b1[c] : 0.f;
+#pragma unroll
+          for (int r = 0; r < RT; ++r) Hs[c * R + rg * RT + r] = c < d ? fmaxf(reduced(r, j) + b, 0.f) : 0.f;
+        }
+      }
+    }
+    consumer_sync(ncons);
+
+    // ---- layer 2 (+ self term): z = W2 h + b2 [+ Ws base + bs] as one k-run over [h ; base]
+    run_segment(it0, t1, ntiles - t1, Hs);
+    if (g == 0) {
+#pragma unroll
+      for (int r = 0; r < RT; ++r) {
+        const int rr = rg * RT + r;
+        const int64_t row = row0 + rr;
+        if (row >= n_rows) continue;
+        float* dst = out ? out + row * out_stride : pe_inplace + base_ids.at(row) * (int64_t)d;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int c = c0 + j;
+          if (c < d) {
+            const float z = reduced(r, j) + m.b2[c] + (has_self ? m.bs[c] : 0.f);
+            dst[c] = Bs[c * R + rr] + tanhf(z);
+          }
+        }
+      }
+    }
+    consumer_sync(ncons);  // red / As / Bs are reused by the next row tile
   }
 }
 
@@ -279,7 +291,8 @@ static int launch_mlp_r(const float* A, int64_t lda, const float* pe, RowIds bas
     }
     attr_set = true;
   }
-  const int64_t blocks = ceil_div(n_rows, R);
+  int64_t blocks = ceil_div(n_rows, R);
+  if (blocks > kNumSMs) blocks = kNumSMs;  // persistent: one CTA per SM walks the row tiles
   kern<<<(unsigned)blocks, G * ldo + 32, smem, st>>>(A, lda, pe, base_ids, n_rows, n_rows_dev, *m, ldo, out, out_stride, pe_inplace);
   return check_launch("pe_mlp");
 }
@@ -293,7 +306,7 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
   const int ldo = lstep_packed_ld(m->d);
   // rows per CTA: the largest tile that still gives about one CTA per SM; k-split while the CTA stays <= 1024 threads
   if (ldo <= 192) {  // 4 k-split groups of <= 192 threads + the producer warp = 800 threads
-    if (expected_rows >= (int64_t)kNumSMs * 12) return launch_mlp_r<8, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
+    if (expected_rows >= (int64_t)kNumSMs * 24) return launch_mlp_r<8, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
     if (expected_rows >= (int64_t)kNumSMs * 5) return launch_mlp_r<4, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
     return launch_mlp_r<2, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
   }

@@ -34,11 +34,15 @@ int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const doubl
                         int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag, PhaseBHook hook, void* stream);
 
 constexpr int kRow0Parts = 64;
+constexpr int kHubLen = 4;     // a warp reduces a destination's slot list serially (~430 dependent instructions per
+                              // slot), so lists longer than this are split into chunk tasks spread over the GPU
+constexpr int kChunkLog2 = 2;  // slots per chunk task = 4
 
 struct UpdateWs {
   int32_t* cnt_of;   // [pe_rows]  zero between calls
   int32_t* slot_of;  // [pe_rows]
-  int32_t* counters; // [8]: 0=M, 1=has_zero, 2=n_dest, 3=n_hubs
+  unsigned long long* hub_acc;  // [#long lists][d+t] 32.32 fixed-point accumulators (zeroed per call by the scan kernel)
+  int32_t* counters; // [8]: 0=M, 1=has_zero, 2=n_dest, 3=n_hubs, 4=n_hub_tasks
   int32_t* src32;    // [E]
   int32_t* dst32;    // [E]
   float* dtA;        // [E]
@@ -49,6 +53,9 @@ struct UpdateWs {
   int64_t* U;        // [N*K+1]
   int32_t* off;      // [N*K+2]
   int32_t* hubs;     // [N*K/32+1] destinations with more than 32 slots
+  int32_t* hub_remaining;  // chunk tasks of the hub still running
+  int32_t* task_hub;       // [2*N*K/32+2] hub index of a chunk task
+  int32_t* task_chunk;     // [2*N*K/32+2] chunk index of a chunk task
   float* row0_part;  // [kRow0Parts*d]
   float* A;          // [max(N, N*K+1)][lda], lda = d+t rounded up to 4 floats
   int64_t lda;
@@ -76,7 +83,11 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
   w.list = (int32_t*)take(sizeof(int32_t) * nk);
   w.U = (int64_t*)take(sizeof(int64_t) * (nk + 1));
   w.off = (int32_t*)take(sizeof(int32_t) * (nk + 2));
-  w.hubs = (int32_t*)take(sizeof(int32_t) * (nk / 32 + 2));
+  w.hubs = (int32_t*)take(sizeof(int32_t) * (nk / (kHubLen + 1) + 2));
+  w.hub_remaining = (int32_t*)take(sizeof(int32_t) * (nk / (kHubLen + 1) + 2));
+  w.task_hub = (int32_t*)take(sizeof(int32_t) * ((nk >> kChunkLog2) + nk / (kHubLen + 1) + 4));
+  w.task_chunk = (int32_t*)take(sizeof(int32_t) * ((nk >> kChunkLog2) + nk / (kHubLen + 1) + 4));
+  w.hub_acc = (unsigned long long*)take(sizeof(unsigned long long) * (nk / (kHubLen + 1) + 1) * (size_t)(d + t));
   w.row0_part = (float*)take(sizeof(float) * kRow0Parts * d);
   const size_t rowsA = nk + 1 > (size_t)n_ids ? nk + 1 : (size_t)n_ids;
   w.lda = (int64_t)align_up((size_t)(d + t), 4);
@@ -196,13 +207,15 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
 
 // ---------------------------------------------------------------------------------------------
 // step 2 (one CTA): offsets by exclusive scan over U order; slot map; counter map reset; hub list
-constexpr int kHubLen = 32;  // lists longer than a warp are hubs and get a whole CTA
 
 // Block 0 scans (and, for small batches, also fills the slot lists); blocks 1.. compute the per-part
 // partial sums of the padding row.
 __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__ cnt_of, int32_t* __restrict__ slot_of,
                                                            int64_t* __restrict__ U, int32_t* __restrict__ off,
-                                                           int32_t* __restrict__ hubs, int32_t* __restrict__ counters,
+                                                           int32_t* __restrict__ hubs, int32_t* __restrict__ hub_remaining,
+                                                           int32_t* __restrict__ task_hub, int32_t* __restrict__ task_chunk,
+                                                           unsigned long long* __restrict__ hub_acc, int in1,
+                                                           int32_t* __restrict__ counters,
                                                            const int32_t* __restrict__ nbrB, int64_t total, int K,
                                                            const int32_t* __restrict__ rank, int32_t* __restrict__ list,
                                                            int fill_here, const float* __restrict__ pe,
@@ -256,15 +269,30 @@ __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__
     run += deg;
     cnt_of[u] = 0;  // restore the all-zero invariant
     slot_of[u] = s;
-    if (deg > kHubLen) hubs[atomicAdd(counters + 3, 1)] = s;
+    if (deg > kHubLen) {  // long list: reduced by ceil(deg/8) chunk tasks spread over the grid
+      const int h = atomicAdd(counters + 3, 1);
+      const int nch = (deg + (1 << kChunkLog2) - 1) >> kChunkLog2;
+      const int t0 = atomicAdd(counters + 4, nch);
+      hubs[h] = s;
+      hub_remaining[h] = nch;
+      for (int c = 0; c < nch; ++c) {
+        task_hub[t0 + c] = h;
+        task_chunk[t0 + c] = c;
+      }
+    }
   }
   if (tid == 0) {
     const int hz = counters[1];
     counters[2] = M + hz;
     if (hz) U[M] = 0;
   }
+  __syncthreads();  // off[] / slot_of[] / the hub list written above are visible to the whole CTA
+  {
+    const int64_t nacc = (int64_t)counters[3] * in1;  // accumulator rows of this call's long lists start from zero
+    ulonglong2* z = reinterpret_cast<ulonglong2*>(hub_acc);
+    for (int64_t i = tid; i < (nacc + 1) / 2; i += blockDim.x) z[i] = make_ulonglong2(0ull, 0ull);
+  }
   if (fill_here) {
-    __syncthreads();  // off[] / slot_of[] written above are visible to the whole CTA
     for (int64_t i = tid; i < total; i += blockDim.x) {
       const int32_t u = nbrB[i];
       if (u > 0) list[off[slot_of[u]] + rank[i]] = (int32_t)i;
@@ -325,32 +353,29 @@ __device__ __forceinline__ void accumulate_chunk(const float* my_row, float my_d
   }
 }
 
-constexpr int kHubSortMax = 4096;  // hub lists up to this length are sorted in shared memory
-
 // step 4: blocks [0, warp_blocks): one warp per destination with a short list (sorted: fp32 adds in the
-// reference's flat order); blocks [warp_blocks, warp_blocks + hub_blocks): one CTA per hub — its slot
-// list is sorted in shared memory (bitonic), split into 8 contiguous slices, one per warp, and the 8
-// fp32 partial rows are added in warp order: a fixed summation tree, reproducible run to run (lists
-// beyond 4096 slots fall back to exact 32.32 fixed-point accumulation, also order independent);
-// last block: finishes the padding row.
+// reference's flat order). Blocks [warp_blocks, warp_blocks + hub_blocks): hub chunk tasks — every 32-slot
+// chunk of a hub's list is an independent task taken by one warp anywhere on the GPU, accumulated in 32.32
+// fixed point and added to the hub's accumulator row with 64-bit integer atomics (exact, so neither the
+// arrival order of the list nor the order of the tasks matters: reproducible run to run); the warp that
+// finishes a hub's last task converts the row to fp32 and re-zeroes the accumulator. One CTA per hub would
+// serialise ~430 dependent instructions per slot on one SM (measured: 29 us for a 225-slot hub). Last block:
+// finishes the padding row.
 template <int DVPL, int TFPL>
-__global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restrict__ pe,
-                                                            const int64_t* __restrict__ ids, int K,
-                                                            const float* __restrict__ ntB,
-                                                            const int32_t* __restrict__ off,
-                                                            const int32_t* __restrict__ list,
-                                                            const int32_t* __restrict__ hubs,
-                                                            const int32_t* __restrict__ counters, float tc,
-                                                            const float* __restrict__ tw, int d, int t,
-                                                            const float* __restrict__ row0_part, float* __restrict__ A,
-                                                            int64_t lda, int warp_blocks, int hub_blocks) {
-  extern __shared__ __align__(16) unsigned char gsm[];
+__global__ void __launch_bounds__(256, DVPL <= 2 ? 2 : 1) phaseB_gather_kernel(
+    const float* __restrict__ pe, const int64_t* __restrict__ ids, int K, const float* __restrict__ ntB,
+    const int32_t* __restrict__ off, const int32_t* __restrict__ list, const int32_t* __restrict__ hubs,
+    int32_t* __restrict__ hub_remaining, const int32_t* __restrict__ task_hub, const int32_t* __restrict__ task_chunk,
+    unsigned long long* __restrict__ hub_acc, const int32_t* __restrict__ counters, float tc, const float* __restrict__ tw, int d,
+    int t, const float* __restrict__ row0_part, float* __restrict__ A, int64_t lda, int warp_blocks, int hub_blocks) {
   const int in1 = d + t;
-  int* s_list = reinterpret_cast<int*>(gsm);                                             // [kHubSortMax]
-  float* s_part = reinterpret_cast<float*>(s_list + kHubSortMax);                        // [8][in1]
-  unsigned long long* s_fix = reinterpret_cast<unsigned long long*>(s_part + 8 * in1 + (in1 & 1));  // [in1]
   const int M = counters[0];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int nw = blockDim.x >> 5;
+  // the grid is sized for the worst case (every slot a distinct destination); surplus CTAs leave at once
+  if ((int)blockIdx.x < warp_blocks && (int)blockIdx.x * nw >= M) return;
+  const int n_tasks = counters[4];
+  if ((int)blockIdx.x >= warp_blocks && (int)blockIdx.x < warp_blocks + hub_blocks && ((int)blockIdx.x - warp_blocks) * nw >= n_tasks) return;
   const int dvec = d >> 2;
   float w[TFPL];
 #pragma unroll
@@ -376,10 +401,10 @@ __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restr
   for (int q = 0; q < TFPL; ++q) acc_tf[q] = 0.f;
 
   if ((int)blockIdx.x < warp_blocks) {  // ---- short lists
-    const int s = blockIdx.x * (blockDim.x >> 5) + wid;
+    const int s = blockIdx.x * nw + wid;
     if (s >= M) return;
     const int o0 = off[s], len = off[s + 1] - o0;
-    if (len > kHubLen) return;  // a hub block owns this destination
+    if (len > kHubLen) return;  // reduced by hub chunk tasks
     int e = (lane < len) ? list[o0 + lane] : 0x7fffffff;
     // bitonic sort ascending across the warp: restores flat-index (= reference add) order
 #pragma unroll
@@ -409,120 +434,79 @@ __global__ void __launch_bounds__(256) phaseB_gather_kernel(const float* __restr
     return;
   }
 
-  // ---- hubs
-  const int n_hubs = counters[3];
-  const int nw = blockDim.x >> 5;
-  for (int h = blockIdx.x - warp_blocks; h < n_hubs; h += hub_blocks) {
+  // ---- hub chunk tasks
+  constexpr float kScale = 4294967296.f;           // 2^32
+  constexpr float kInv = 2.3283064365386963e-10f;  // 2^-32
+  for (int task = ((int)blockIdx.x - warp_blocks) * nw + wid; task < n_tasks; task += hub_blocks * nw) {
+    const int h = task_hub[task], c0 = task_chunk[task] << kChunkLog2;
     const int s = hubs[h];
     const int o0 = off[s], len = off[s + 1] - o0;
-    float* arow = A + (int64_t)s * lda;
-    if (len <= kHubSortMax) {
-      int n2 = 64;
-      while (n2 < len) n2 <<= 1;
-      for (int i = threadIdx.x; i < n2; i += blockDim.x) s_list[i] = i < len ? list[o0 + i] : 0x7fffffff;
-      __syncthreads();
-      for (int k = 2; k <= n2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-            const int p = i ^ j;
-            if (p > i) {
-              const int a = s_list[i], b = s_list[p];
-              const bool up = ((i & k) == 0);
-              if ((a > b) == up) {
-                s_list[i] = b;
-                s_list[p] = a;
-              }
-            }
-          }
-          __syncthreads();
-        }
-      }
-      // warp `wid` reduces the contiguous slice [lo, hi) of the sorted list
-      const int per = (len + nw - 1) / nw;
-      const int lo = min(len, wid * per), hi = min(len, lo + per);
-#pragma unroll
-      for (int q = 0; q < DVPL; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int q = 0; q < TFPL; ++q) acc_tf[q] = 0.f;
-      for (int c0 = lo; c0 < hi; c0 += 32) {
-        const float* my_row = pe;
-        float my_dt = 0.f;
-        if (c0 + lane < hi) {
-          const int e = s_list[c0 + lane];
-          my_row = pe + ids[e / K] * (int64_t)d;
-          my_dt = tc - ntB[e];
-        }
-        accumulate_chunk<DVPL, TFPL>(my_row, my_dt, min(32, hi - c0), lane, dvec, t, w, acc, acc_tf);
-      }
-      float* part = s_part + wid * in1;
-#pragma unroll
-      for (int q = 0; q < DVPL; ++q)
-        if (lane + 32 * q < dvec) reinterpret_cast<float4*>(part)[lane + 32 * q] = acc[q];
-#pragma unroll
-      for (int q = 0; q < TFPL; ++q)
-        if (lane + 32 * q < t) part[d + lane + 32 * q] = acc_tf[q];
-      __syncthreads();
-      for (int c = threadIdx.x; c < in1; c += blockDim.x) {
-        float v = 0.f;
-        for (int ww = 0; ww < nw; ++ww) v += s_part[ww * in1 + c];
-        arow[c] = v;
-      }
-      __syncthreads();
-      continue;
+    const int m = min(1 << kChunkLog2, len - c0);
+    const float* my_row = pe;
+    float my_dt = 0.f;
+    if (lane < m) {
+      const int e = list[o0 + c0 + lane];
+      my_row = pe + ids[e / K] * (int64_t)d;
+      my_dt = tc - ntB[e];
     }
-    // giant hub: exact 32.32 fixed-point accumulation in arrival order
-    constexpr float kScale = 4294967296.f;  // 2^32
-    constexpr double kInv = 1.0 / 4294967296.0;
-    for (int c = threadIdx.x; c < in1; c += blockDim.x) s_fix[c] = 0ull;
-    __syncthreads();
     long long facc[DVPL][4], ftf[TFPL];
 #pragma unroll
     for (int q = 0; q < DVPL; ++q) facc[q][0] = facc[q][1] = facc[q][2] = facc[q][3] = 0;
 #pragma unroll
     for (int q = 0; q < TFPL; ++q) ftf[q] = 0;
-    for (int c0 = wid * 32; c0 < len; c0 += nw * 32) {
-      const float* my_row = pe;
-      float my_dt = 0.f;
-      if (c0 + lane < len) {
-        const int e = list[o0 + c0 + lane];
-        my_row = pe + ids[e / K] * (int64_t)d;
-        my_dt = tc - ntB[e];
+    for (int j0 = 0; j0 < m; j0 += 4) {
+      const float4* row[4];
+      float dt[4];
+      float4 v[4][DVPL];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = min(j0 + u, m - 1);
+        row[u] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)my_row, j)));
+        dt[u] = __shfl_sync(kFull, my_dt, j);
       }
-      const int m = min(32, len - c0);
-      for (int j = 0; j < m; ++j) {
-        const float4* row = reinterpret_cast<const float4*>(
-            reinterpret_cast<const float*>(__shfl_sync(kFull, (unsigned long long)my_row, j)));
-        const float dt = __shfl_sync(kFull, my_dt, j);
 #pragma unroll
-        for (int q = 0; q < DVPL; ++q) {
-          const int cv = lane + 32 * q;
-          if (cv < dvec) {
-            const float4 v = __ldg(row + cv);
-            facc[q][0] += __float2ll_rn(v.x * kScale);
-            facc[q][1] += __float2ll_rn(v.y * kScale);
-            facc[q][2] += __float2ll_rn(v.z * kScale);
-            facc[q][3] += __float2ll_rn(v.w * kScale);
-          }
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int q = 0; q < DVPL; ++q)
+          if (lane + 32 * q < dvec) v[u][q] = __ldg(row[u] + lane + 32 * q);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (j0 + u < m) {
+#pragma unroll
+          for (int q = 0; q < DVPL; ++q)
+            if (lane + 32 * q < dvec) {
+              facc[q][0] += __float2ll_rn(v[u][q].x * kScale);
+              facc[q][1] += __float2ll_rn(v[u][q].y * kScale);
+              facc[q][2] += __float2ll_rn(v[u][q].z * kScale);
+              facc[q][3] += __float2ll_rn(v[u][q].w * kScale);
+            }
+#pragma unroll
+          for (int q = 0; q < TFPL; ++q)
+            if (lane + 32 * q < t) ftf[q] += __float2ll_rn(time_feature(dt[u], w[q]) * kScale);
         }
-#pragma unroll
-        for (int q = 0; q < TFPL; ++q)
-          if (lane + 32 * q < t) ftf[q] += __float2ll_rn(time_feature(dt, w[q]) * kScale);
       }
     }
+    unsigned long long* hrow = hub_acc + (size_t)h * in1;
 #pragma unroll
     for (int q = 0; q < DVPL; ++q) {
       const int cv = lane + 32 * q;
       if (cv < dvec) {
 #pragma unroll
-        for (int x = 0; x < 4; ++x) atomicAdd(&s_fix[4 * cv + x], (unsigned long long)facc[q][x]);
+        for (int x = 0; x < 4; ++x) atomicAdd(hrow + 4 * cv + x, (unsigned long long)facc[q][x]);
       }
     }
 #pragma unroll
     for (int q = 0; q < TFPL; ++q)
-      if (lane + 32 * q < t) atomicAdd(&s_fix[d + lane + 32 * q], (unsigned long long)ftf[q]);
-    __syncthreads();
-    for (int c = threadIdx.x; c < in1; c += blockDim.x) arow[c] = (float)((double)(long long)s_fix[c] * kInv);
-    __syncthreads();
+      if (lane + 32 * q < t) atomicAdd(hrow + d + lane + 32 * q, (unsigned long long)ftf[q]);
+    __threadfence();
+    int last = 0;
+    if (lane == 0) last = (atomicSub(hub_remaining + h, 1) == 1);
+    last = __shfl_sync(kFull, last, 0);
+    if (last) {  // every task of this list has added its part: convert the row
+      __threadfence();
+      float* arow = A + (int64_t)s * lda;
+      for (int c = lane; c < in1; c += 32) arow[c] = (float)(long long)__ldcg(hrow + c) * kInv;
+    }
   }
 }
 
@@ -538,6 +522,7 @@ extern "C" size_t lstep_update_pe_workspace_bytes(int64_t n_ids, int64_t n_edges
 
 extern "C" int lstep_update_pe_workspace_init(void* workspace, size_t workspace_bytes, int64_t pe_rows, void* stream) {
   if (!workspace || pe_rows <= 0 || workspace_bytes < sizeof(int32_t) * (size_t)pe_rows) return LSTEP_ERR_INVALID_ARG;
+  // the per-node counter map must be zero on entry (every call leaves it zero)
   cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t) * (size_t)pe_rows, as_stream(stream));
   if (e != cudaSuccess) {
     set_cuda_error(e, "workspace_init");
@@ -597,7 +582,8 @@ static int phase_b_partial(float* pe, int64_t pe_rows, const UpdateWs& w, const 
   }
   {
     const int fill_here = total <= 16384 ? 1 : 0;
-    phaseB_scan_kernel<<<1 + kRow0Parts, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.counters, w.nbrB, total, K,
+    phaseB_scan_kernel<<<1 + kRow0Parts, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.hub_remaining, w.task_hub,
+                                                        w.task_chunk, w.hub_acc, d + t, w.counters, w.nbrB, total, K,
                                                         w.rank, w.list, fill_here, pe, row_ids, n_ids, d, w.row0_part);
     if ((rc = check_launch("phaseB_scan")) != LSTEP_OK) return rc;
     if (!fill_here) {
@@ -607,16 +593,17 @@ static int phase_b_partial(float* pe, int64_t pe_rows, const UpdateWs& w, const 
   }
   const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;  // distinct non-zero destinations
   const int warp_blocks = (int)ceil_div(max_dest > 0 ? max_dest : 1, 8);
-  int hub_blocks = (int)(total / (kHubLen + 1)) + 1;  // at most this many lists can be longer than kHubLen
-  if (hub_blocks > 2 * kNumSMs) hub_blocks = 2 * kNumSMs;
+  int hub_blocks = (int)(((total >> kChunkLog2) + total / (kHubLen + 1)) / 8) + 1;  // enough warps for every possible chunk task
+  if (hub_blocks > 4 * kNumSMs) hub_blocks = 4 * kNumSMs;
   const unsigned blocks = (unsigned)(warp_blocks + hub_blocks + 1);
-  const size_t smem = sizeof(int) * kHubSortMax + sizeof(float) * (8 * (size_t)(d + t) + 2) + sizeof(unsigned long long) * (size_t)(d + t);
   if (dvec <= 64 && t <= 128)
-    phaseB_gather_kernel<2, 4><<<blocks, 256, smem, st>>>(pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw, d,
-                                                          t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
+    phaseB_gather_kernel<2, 4><<<blocks, 256, 0, st>>>(pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.hub_remaining, w.task_hub,
+                                                       w.task_chunk, w.hub_acc, w.counters, tc, mlp->tw, d, t, w.row0_part, w.A, w.lda,
+                                                       warp_blocks, hub_blocks);
   else
-    phaseB_gather_kernel<8, 8><<<blocks, 256, smem, st>>>(pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.counters, tc, mlp->tw, d,
-                                                          t, w.row0_part, w.A, w.lda, warp_blocks, hub_blocks);
+    phaseB_gather_kernel<8, 8><<<blocks, 256, 0, st>>>(pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.hub_remaining, w.task_hub,
+                                                       w.task_chunk, w.hub_acc, w.counters, tc, mlp->tw, d, t, w.row0_part, w.A, w.lda,
+                                                       warp_blocks, hub_blocks);
   return check_launch("phaseB_gather");
 }
 
