@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LSTEP_ABI_VERSION 1
+#define LSTEP_ABI_VERSION 2
 
 typedef enum lstep_status {
   LSTEP_OK = 0,
@@ -125,6 +125,9 @@ int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int64_t time_st
  * ------------------------------------------------------------------------------------------ */
 int lstep_packed_ld(int out_features);
 int lstep_packed_rows(int in_features);
+size_t lstep_packed_tc_floats(int out_features, int in_features);
+int lstep_pack_linear_tc(const float* weight /* [out,in] row major (torch) */, int out_features, int in_features,
+                         float* packed /* lstep_packed_tc_floats() floats */, void* stream);
 int lstep_pack_linear(const float* weight /* [out,in] row major (torch) */, const float* bias /* [out] or NULL */,
                       int out_features, int in_features, float* packed_w /* [in_pad][ldo] */,
                       float* packed_b /* [ldo] */, void* stream);
@@ -139,6 +142,11 @@ typedef struct lstep_pe_mlp {
   const float* tw; /* [t] TimeEncoder frequencies (models/modules.py:20), fp32 */
   int d;
   int t;
+  /* the same three weight matrices packed for the tensor-core kernel (lstep_pack_linear_tc: B-fragment
+   * order, TF32 hi / lo split); all NULL = fp32 SIMT kernel only */
+  const float* w1_tc;
+  const float* w2_tc;
+  const float* ws_tc;
 } lstep_pe_mlp;
 
 /* ------------------------------------------------------------------------------------------

@@ -34,7 +34,8 @@ class PEStreamDesc(C.Structure):
 
 class PEMLP(C.Structure):
     """struct lstep_pe_mlp"""
-    _fields_ = [("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("ws", vp), ("bs", vp), ("tw", vp), ("d", i32), ("t", i32)]
+    _fields_ = [("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("ws", vp), ("bs", vp), ("tw", vp), ("d", i32), ("t", i32),
+                ("w1_tc", vp), ("w2_tc", vp), ("ws_tc", vp)]
 
 
 _SIGS = {
@@ -53,6 +54,8 @@ _SIGS = {
     "lstep_packed_ld": (i32, [i32]),
     "lstep_packed_rows": (i32, [i32]),
     "lstep_pack_linear": (i32, [vp, vp, i32, i32, vp, vp, vp]),
+    "lstep_packed_tc_floats": (sz, [i32, i32]),
+    "lstep_pack_linear_tc": (i32, [vp, i32, i32, vp, vp]),
     "lstep_nbr_aggregate": (i32, [vp, i64, vp, vp, vp, i64, i32, vp, i32, i32, vp, vp]),
     "lstep_nbr_aggregate_bwd": (i32, [vp, vp, i64, i32, i32, i32, vp, i64, vp]),
     "lstep_neighborhood_pe": (i32, [vp, i64, vp, vp, vp, vp, i64, i32, C.POINTER(PEMLP), vp, vp, sz, vp]),
@@ -102,7 +105,7 @@ def load(require_device: bool = True):
             for name, (res, args) in _SIGS.items():
                 fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
                 fn.restype, fn.argtypes = res, args
-            if lib.lstep_abi_version() != 1:
+            if lib.lstep_abi_version() != 2:
                 raise LstepError("liblstep_b200.so ABI version mismatch; rebuild")
             _LIB = lib
     if require_device:

@@ -16,6 +16,8 @@
 //   * activations sit in shared memory k-major ([k][R]) so one 128-bit broadcast load feeds RT rows;
 //     thread (rg, cp) keeps an RT x 2 register tile: rows rg*RT.., columns 2cp, 2cp+1 (one 64-bit
 //     conflict-free weight load per k).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lstep {
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(G == 4 ? 800 : 288) pe_mlp_kernel(const float*
                                                               int ldo, float* __restrict__ out, int64_t out_stride,
                                                               float* pe_inplace) {
   constexpr int R = 2 * RT;
-  constexpr int NS = 2 * G;
+  constexpr int NS = (RT >= 8 ? 2 : 3) * G;  // as many weight tiles in flight as shared memory allows
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t full_bar[NS];
   __shared__ __align__(8) uint64_t empty_bar[NS];
@@ -279,7 +281,7 @@ static int launch_mlp_r(const float* A, int64_t lda, const float* pe, RowIds bas
   constexpr int R = 2 * RT;
   const int ldo = lstep_packed_ld(m->d);
   const int in1_pad = lstep_packed_rows(m->d + m->t), d_pad = lstep_packed_rows(m->d);
-  const size_t smem = sizeof(float) * ((size_t)2 * G * kKTile * ldo + (size_t)R * (in1_pad + 2 * (size_t)d_pad) + (size_t)G * R * ldo);
+  const size_t smem = sizeof(float) * ((size_t)(RT >= 8 ? 2 : 3) * G * kKTile * ldo + (size_t)R * (in1_pad + 2 * (size_t)d_pad) + (size_t)G * R * ldo);
   if (smem > 220 * 1024 || G * ldo + 32 > 1024) return LSTEP_ERR_UNSUPPORTED;
   auto kern = pe_mlp_kernel<RT, G>;
   static bool attr_set = false;
@@ -297,12 +299,26 @@ static int launch_mlp_r(const float* A, int64_t lda, const float* pe, RowIds bas
   return check_launch("pe_mlp");
 }
 
+int launch_pe_mlp_tc(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
+                     const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
+                     cudaStream_t st);
+
 // n_rows is the host-side upper bound of rows; *n_rows_dev (optional) the device-side count.
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st) {
   if (n_rows <= 0) return LSTEP_OK;
   if (!A || !pe || !base_ids.p[0] || !m || (!out && !pe_inplace)) return LSTEP_ERR_INVALID_ARG;
+  {
+    // The 3xTF32 tensor-core variant (csrc/mlp_tc.cu) is opt-in: measured on B200 it is not faster than the
+    // fp32 kernel at these sizes (both are bound by streaming the weights into each SM, and it streams twice
+    // the bytes) and its rounding is slightly outside the update_pe parity bar.
+    static const bool use_tc = getenv("LSTEP_MLP_TC") != nullptr;
+    if (use_tc) {
+      const int rc = launch_pe_mlp_tc(A, lda, pe, base_ids, n_rows, expected_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
+      if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
+    }
+  }
   const int ldo = lstep_packed_ld(m->d);
   // rows per CTA: the largest tile that still gives about one CTA per SM; k-split while the CTA stays <= 1024 threads
   if (ldo <= 192) {  // 4 k-split groups of <= 192 threads + the producer warp = 800 threads

@@ -222,6 +222,12 @@ __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__
                                                            const int64_t* __restrict__ ids, int64_t n_ids, int d,
                                                            float* __restrict__ row0_part) {
   if (blockIdx.x > 0) {
+    {  // accumulator rows of this call's long lists start from zero: at most min(M, N*K/(kHubLen+1)) lists are long
+      const int64_t cap = min((int64_t)counters[0], total / (kHubLen + 1) + 1) * in1;
+      ulonglong2* z = reinterpret_cast<ulonglong2*>(hub_acc);
+      for (int64_t i = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; i < (cap + 1) / 2; i += (int64_t)(gridDim.x - 1) * blockDim.x)
+        z[i] = make_ulonglong2(0ull, 0ull);
+    }
     if (counters[1] == 0) return;
     const int part = blockIdx.x - 1;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -287,11 +293,6 @@ __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__
     if (hz) U[M] = 0;
   }
   __syncthreads();  // off[] / slot_of[] / the hub list written above are visible to the whole CTA
-  {
-    const int64_t nacc = (int64_t)counters[3] * in1;  // accumulator rows of this call's long lists start from zero
-    ulonglong2* z = reinterpret_cast<ulonglong2*>(hub_acc);
-    for (int64_t i = tid; i < (nacc + 1) / 2; i += blockDim.x) z[i] = make_ulonglong2(0ull, 0ull);
-  }
   if (fill_here) {
     for (int64_t i = tid; i < total; i += blockDim.x) {
       const int32_t u = nbrB[i];
@@ -615,6 +616,7 @@ static int phase_b_apply(float* pe, int64_t pe_rows, const UpdateWs& w, int64_t 
   lstep_pe_mlp noself = *mlp;
   noself.ws = nullptr;  // the self term is computed and discarded by the reference (LSTEP.py:334-335, Q3)
   noself.bs = nullptr;
+  noself.ws_tc = nullptr;
   return launch_pe_mlp(w.A, w.lda, pe, single_ids(w.U), max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe, st);
 }
 

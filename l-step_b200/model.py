@@ -199,7 +199,7 @@ class LSTEP(nn.Module):
         ldo = lib.lstep_packed_ld(d)
         if bool(torch.count_nonzero(self.time_encoder.w.bias)):
             raise _lib.LstepError("TimeEncoder bias must be zero (it is frozen at zero in the reference, models/modules.py:21)")
-        bufs = []
+        bufs, tc = [], []
         with torch.cuda.device(dev):
             for n, in_f in zip(names, (d + t, d, d)):
                 lin = getattr(self, n)
@@ -210,10 +210,13 @@ class LSTEP(nn.Module):
                 _lib.check(lib.lstep_pack_linear(_lib.ptr(w), _lib.ptr(b), d, in_f, _lib.ptr(pw), _lib.ptr(pb), _lib.stream_ptr()),
                            "lstep_pack_linear")
                 bufs += [pw, pb]
+                pt = torch.empty(lib.lstep_packed_tc_floats(d, in_f), dtype=torch.float32, device=dev)
+                _lib.check(lib.lstep_pack_linear_tc(_lib.ptr(w), d, in_f, _lib.ptr(pt), _lib.stream_ptr()), "lstep_pack_linear_tc")
+                tc.append(pt)
         tw = self.time_encoder.w.weight.detach().reshape(-1).contiguous()
         bufs.append(tw)
-        st = _lib.PEMLP(*(b.data_ptr() for b in bufs), d, t)
-        entry = (key, st, bufs, C.byref(st))
+        st = _lib.PEMLP(*(b.data_ptr() for b in bufs), d, t, *(x.data_ptr() for x in tc))
+        entry = (key, st, bufs + tc, C.byref(st))
         self._pack_cache[which] = entry
         return st
 

@@ -164,7 +164,7 @@ class ShardRank:
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.batch_idx = 0
         pk = model._packed_mlp("update")
-        self._noself = _lib.PEMLP(pk.w1, pk.b1, pk.w2, pk.b2, None, None, pk.tw, pk.d, pk.t)  # phase B: no self term (Q3)
+        self._noself = _lib.PEMLP(pk.w1, pk.b1, pk.w2, pk.b2, None, None, pk.tw, pk.d, pk.t, pk.w1_tc, pk.w2_tc, None)  # phase B: no self term (Q3)
         self.bytes_x1 = self.bytes_x2 = 0
 
     # ---- helpers ------------------------------------------------------------------------------

@@ -28,7 +28,7 @@ def test_library_builds_and_exports_header_symbols():
 
 def test_status_strings_and_sizes():
     lib = _lib.load(require_device=False)
-    assert lib.lstep_abi_version() == 1
+    assert lib.lstep_abi_version() == 2
     assert lib.lstep_strerror(0) == b"ok"
     assert lib.lstep_packed_ld(172) == 192
     small = lib.lstep_update_pe_workspace_bytes(10, 10, 4, 12, 10, 61)
