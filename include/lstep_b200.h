@@ -253,6 +253,32 @@ int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, in
                   const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
                   uint32_t* err_flag, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Host-fed streaming step (csrc/host_step.cu): what a loop that holds the batch as HOST arrays calls
+ * per batch (the hand-over train_LSTEP_link_prediction.py:204-313 / evaluate_model_utils.py:38-142 do
+ * with numpy arrays and .cpu() reads). A stepper owns `slots` pinned input/result slots and their
+ * device mirrors (allocated once by _create: the only entry points that allocate).
+ * lstep_pe_step_host packs (src, dst, t, sorted unique batch nodes, the query id sets) into a pinned
+ * slot, moves them with one async copy, enqueues lstep_pe_step's kernels on the staged batch
+ * (current_time = max t, LSTEP.update_pe's caller passes that), reduces nbr_out to per-query row sums
+ * [n_queries][n_edges] and copies them to the slot's pinned result, all on `stream`, without
+ * synchronising; *ticket identifies the step. ids_host may be NULL (computed here by sort + unique).
+ * nbr_out may be NULL (the stepper's own [n_queries][n_edges][d] buffer is used).
+ * lstep_host_step_result waits for the ticket's event and returns the pinned result (valid until the
+ * slot is reused `slots` steps later).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lstep_host_stepper lstep_host_stepper;
+int lstep_host_stepper_create(int slots, int64_t max_edges, int max_queries, int d, lstep_host_stepper** out);
+void lstep_host_stepper_destroy(lstep_host_stepper* h);
+int lstep_pe_step_host(lstep_host_stepper* h, const lstep_pe_stream* s, const lstep_csr* csr, int64_t n_edges,
+                       const int64_t* src_host, const int64_t* dst_host, const double* t_host, const int64_t* ids_host,
+                       int64_t n_ids, int head, int len, int append_slot, const float* G,
+                       const int64_t* const* query_ids_host_arrays, int n_queries, float* nbr_out, int K,
+                       const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                       uint32_t* err_flag, void* stream, int64_t* ticket);
+int lstep_host_step_result(lstep_host_stepper* h, int64_t ticket, const float** result_host, int64_t* n_floats);
+void lstep_host_stepper_bytes(const lstep_host_stepper* h, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,6 +75,13 @@ _SIGS = {
     "lstep_ring_load": (i32, [vp, vp, i64, i32, i32, i32, vp]),
     "lstep_pe_step": (i32, [C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, i32, i32, i32, vp,
                             C.POINTER(C.c_void_p), i32, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
+    "lstep_host_stepper_create": (i32, [i32, i64, i32, i32, C.POINTER(C.c_void_p)]),
+    "lstep_host_stepper_destroy": (None, [vp]),
+    "lstep_pe_step_host": (i32, [vp, C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, vp, vp, vp, vp, i64, i32, i32, i32, vp,
+                                 C.POINTER(C.c_void_p), i32, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp,
+                                 C.POINTER(i64)]),
+    "lstep_host_step_result": (i32, [vp, i64, C.POINTER(C.POINTER(C.c_float)), C.POINTER(i64)]),
+    "lstep_host_stepper_bytes": (None, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 
 EXPORTS = tuple(_SIGS)

@@ -1,0 +1,201 @@
+// Host-fed streaming step: the per-batch call a loop holding HOST (numpy) batches makes.
+//
+// The reference's loops hand every batch to the model as host arrays and read the predictions back
+// (train_LSTEP_link_prediction.py:204-313, evaluate_model_utils.py:38-142). lstep_pe_step_host is the
+// native form of that hand-over for the PE path: one call packs the batch (endpoints, times, the sorted
+// unique batch nodes, the C query id sets) into a pinned slot, moves it with ONE async copy, enqueues the
+// whole step (pe_step_core, csrc/step.cu), reduces the [C][n][d] neighbourhood PEs to the per-query row
+// sums a caller reads back, and copies those to a pinned result slot, all on the caller's stream, without
+// synchronising. lstep_host_step_result waits for a ticket's event and hands out the pinned result, so a
+// loop can keep `slots - 1` steps in flight (results read one step behind hide the host's own time).
+#include <algorithm>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+
+namespace lstep {
+
+int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* src, const int64_t* dst, const double* tq,
+                 int64_t n_edges, const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
+                 const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
+                 const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                 uint32_t* err_flag, void* stream);
+
+// res[row] = sum_c x[row][c]: one warp per row, lanes stride the columns, fixed-order shuffle tree
+__global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ x, int64_t n_rows, int d, float* __restrict__ res) {
+  const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const float* p = x + row * d;
+  float acc = 0.f;
+  for (int c = lane; c < d; c += 32) acc += p[c];
+  acc = warp_sum(acc);
+  if (lane == 0) res[row] = acc;
+}
+
+constexpr int kMaxSlots = 8;
+
+}  // namespace lstep
+
+using namespace lstep;
+
+struct lstep_host_stepper {
+  int slots;
+  int64_t max_edges;
+  int max_queries;
+  int d;
+  size_t in_bytes;   // capacity of one input slot
+  size_t res_floats; // capacity of one result slot
+  char* h_in[kMaxSlots];
+  char* d_in[kMaxSlots];
+  float* h_res[kMaxSlots];
+  float* d_res[kMaxSlots];
+  cudaEvent_t done[kMaxSlots];
+  int64_t res_n[kMaxSlots];
+  int64_t ticket_of[kMaxSlots];  // ticket currently held by the slot, -1 = none
+  float* d_nbr_out;              // [max_queries][max_edges][d] when the caller keeps no copy of its own
+  int64_t next_ticket;
+  uint64_t h2d_bytes, d2h_bytes;
+};
+
+static int cuda_fail(cudaError_t e, const char* where) {
+  set_cuda_error(e, where);
+  return LSTEP_ERR_CUDA;
+}
+
+extern "C" void lstep_host_stepper_destroy(lstep_host_stepper* h) {
+  if (!h) return;
+  for (int i = 0; i < h->slots; ++i) {
+    if (h->done[i]) cudaEventDestroy(h->done[i]);
+    if (h->h_in[i]) cudaFreeHost(h->h_in[i]);
+    if (h->h_res[i]) cudaFreeHost(h->h_res[i]);
+    if (h->d_in[i]) cudaFree(h->d_in[i]);
+    if (h->d_res[i]) cudaFree(h->d_res[i]);
+  }
+  if (h->d_nbr_out) cudaFree(h->d_nbr_out);
+  delete h;
+}
+
+extern "C" int lstep_host_stepper_create(int slots, int64_t max_edges, int max_queries, int d, lstep_host_stepper** out) {
+  if (!out || slots < 1 || slots > kMaxSlots || max_edges <= 0 || max_queries < 0 || max_queries > 8 || d <= 0)
+    return LSTEP_ERR_INVALID_ARG;
+  lstep_host_stepper* h = new (std::nothrow) lstep_host_stepper();
+  if (!h) return LSTEP_ERR_INVALID_ARG;
+  h->slots = slots;
+  h->max_edges = max_edges;
+  h->max_queries = max_queries;
+  h->d = d;
+  // src | dst | t | ids (<= 2n) | C query sets, 8 bytes each
+  h->in_bytes = sizeof(int64_t) * (size_t)max_edges * (size_t)(5 + max_queries);
+  h->res_floats = (size_t)std::max(1, max_queries) * (size_t)max_edges;
+  h->next_ticket = 0;
+  h->h2d_bytes = h->d2h_bytes = 0;
+  h->d_nbr_out = nullptr;
+  for (int i = 0; i < kMaxSlots; ++i) {
+    h->h_in[i] = h->d_in[i] = nullptr;
+    h->h_res[i] = h->d_res[i] = nullptr;
+    h->done[i] = nullptr;
+    h->ticket_of[i] = -1;
+    h->res_n[i] = 0;
+  }
+  cudaError_t e = cudaSuccess;
+  for (int i = 0; i < slots && e == cudaSuccess; ++i) {
+    if ((e = cudaHostAlloc((void**)&h->h_in[i], h->in_bytes, cudaHostAllocDefault)) != cudaSuccess) break;
+    if ((e = cudaHostAlloc((void**)&h->h_res[i], sizeof(float) * h->res_floats, cudaHostAllocDefault)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&h->d_in[i], h->in_bytes)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&h->d_res[i], sizeof(float) * h->res_floats)) != cudaSuccess) break;
+    if ((e = cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming)) != cudaSuccess) break;
+  }
+  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_nbr_out, sizeof(float) * h->res_floats * (size_t)d);
+  if (e != cudaSuccess) {
+    lstep_host_stepper_destroy(h);
+    return cuda_fail(e, "host_stepper_create");
+  }
+  *out = h;
+  return LSTEP_OK;
+}
+
+extern "C" int lstep_pe_step_host(lstep_host_stepper* h, const lstep_pe_stream* s, const lstep_csr* csr, int64_t n_edges,
+                                  const int64_t* src_host, const int64_t* dst_host, const double* t_host,
+                                  const int64_t* ids_host, int64_t n_ids, int head, int len, int append_slot, const float* G,
+                                  const int64_t* const* query_ids_host_arrays, int n_queries, float* nbr_out, int K,
+                                  const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace,
+                                  size_t workspace_bytes, uint32_t* err_flag, void* stream, int64_t* ticket) {
+  if (!h || !s || !ticket || n_edges <= 0 || n_edges > h->max_edges || n_queries < 0 || n_queries > h->max_queries)
+    return LSTEP_ERR_INVALID_ARG;
+  if (!src_host || !dst_host || !t_host || (n_queries > 0 && !query_ids_host_arrays)) return LSTEP_ERR_INVALID_ARG;
+  if (ids_host && (n_ids < 0 || n_ids > 2 * n_edges)) return LSTEP_ERR_INVALID_ARG;
+  for (int c = 0; c < n_queries; ++c)
+    if (!query_ids_host_arrays[c]) return LSTEP_ERR_INVALID_ARG;
+  if (s->d != h->d) return LSTEP_ERR_INVALID_ARG;
+  cudaStream_t st = as_stream(stream);
+  const int slot = (int)(h->next_ticket % h->slots);
+  cudaError_t e;
+  if (h->ticket_of[slot] >= 0) {  // the slot's previous step (copy in, kernels, copy out) must have drained
+    if ((e = cudaEventSynchronize(h->done[slot])) != cudaSuccess) return cuda_fail(e, "pe_step_host slot wait");
+  }
+  const size_t n = (size_t)n_edges;
+  int64_t* hp = reinterpret_cast<int64_t*>(h->h_in[slot]);
+  int64_t* h_src = hp;
+  int64_t* h_dst = hp + n;
+  double* h_t = reinterpret_cast<double*>(hp + 2 * n);
+  int64_t* h_ids = hp + 3 * n;  // room for 2n
+  int64_t* h_q = hp + 5 * n;
+  memcpy(h_src, src_host, 8 * n);
+  memcpy(h_dst, dst_host, 8 * n);
+  memcpy(h_t, t_host, 8 * n);
+  double tmax = t_host[0];
+  for (size_t i = 1; i < n; ++i) tmax = t_host[i] > tmax ? t_host[i] : tmax;
+  if (ids_host) {
+    memcpy(h_ids, ids_host, 8 * (size_t)n_ids);
+  } else {  // sorted unique endpoints (evaluate_model_utils.py:54-55 does this with torch.unique on the host)
+    memcpy(h_ids, src_host, 8 * n);
+    memcpy(h_ids + n, dst_host, 8 * n);
+    std::sort(h_ids, h_ids + 2 * n);
+    n_ids = std::unique(h_ids, h_ids + 2 * n) - h_ids;
+  }
+  for (int c = 0; c < n_queries; ++c) memcpy(h_q + (size_t)c * n, query_ids_host_arrays[c], 8 * n);
+  const size_t bytes = 8 * n * (size_t)(5 + n_queries);
+  if ((e = cudaMemcpyAsync(h->d_in[slot], h->h_in[slot], bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
+    return cuda_fail(e, "pe_step_host h2d");
+  h->h2d_bytes += bytes;
+  const int64_t* dp = reinterpret_cast<const int64_t*>(h->d_in[slot]);
+  const int64_t* qdev[8];
+  for (int c = 0; c < n_queries; ++c) qdev[c] = dp + 5 * n + (size_t)c * n;
+  float* outp = nbr_out ? nbr_out : h->d_nbr_out;
+  int rc = pe_step_core(s, csr, dp, dp + n, reinterpret_cast<const double*>(dp + 2 * n), n_edges, dp + 3 * n, n_ids, tmax, head,
+                        len, append_slot, G, qdev, n_queries, outp, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag,
+                        stream);
+  if (rc != LSTEP_OK) return rc;
+  const int64_t rows = (int64_t)n_queries * n_edges;
+  if (rows > 0) {
+    row_sum_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(outp, rows, h->d, h->d_res[slot]);
+    if ((rc = check_launch("row_sum")) != LSTEP_OK) return rc;
+    if ((e = cudaMemcpyAsync(h->h_res[slot], h->d_res[slot], sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+      return cuda_fail(e, "pe_step_host d2h");
+    h->d2h_bytes += sizeof(float) * (size_t)rows;
+  }
+  if ((e = cudaEventRecord(h->done[slot], st)) != cudaSuccess) return cuda_fail(e, "pe_step_host event");
+  h->res_n[slot] = rows;
+  h->ticket_of[slot] = h->next_ticket;
+  *ticket = h->next_ticket++;
+  return LSTEP_OK;
+}
+
+extern "C" int lstep_host_step_result(lstep_host_stepper* h, int64_t ticket, const float** result_host, int64_t* n_floats) {
+  if (!h || ticket < 0 || ticket >= h->next_ticket) return LSTEP_ERR_INVALID_ARG;
+  const int slot = (int)(ticket % h->slots);
+  if (h->ticket_of[slot] != ticket) return LSTEP_ERR_INVALID_ARG;  // the slot has been reused: result gone
+  cudaError_t e = cudaEventSynchronize(h->done[slot]);
+  if (e != cudaSuccess) return cuda_fail(e, "host_step_result");
+  if (result_host) *result_host = h->h_res[slot];
+  if (n_floats) *n_floats = h->res_n[slot];
+  return LSTEP_OK;
+}
+
+extern "C" void lstep_host_stepper_bytes(const lstep_host_stepper* h, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+  if (!h) return;
+  if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
+  if (d2h_bytes) *d2h_bytes = h->d2h_bytes;
+}

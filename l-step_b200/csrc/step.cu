@@ -110,14 +110,16 @@ extern "C" int lstep_ring_copy_rows(float* ring, float* cur, int64_t ring_rows, 
   return check_launch("ring_copy_rows");
 }
 
-extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, int64_t n_edges,
-                             const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
-                             const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
-                             const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace,
-                             size_t workspace_bytes, uint32_t* err_flag, void* stream) {
+namespace lstep {
+// The step on explicit batch pointers (src/dst/tq = the batch's n_edges endpoints and times on the device).
+int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* src, const int64_t* dst, const double* tq,
+                 int64_t n_edges, const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
+                 const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
+                 const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                 uint32_t* err_flag, void* stream) {
   if (!s || !csr || !mlp_nbr || !mlp_upd || !G || n_edges < 0 || n_ids < 0 || K <= 0 || n_queries < 0 || n_queries > 8)
     return LSTEP_ERR_INVALID_ARG;
-  if (!s->ring || !s->cur || !s->src || !s->dst || !s->t || s->V1 <= 0 || s->T <= 0 || s->d != mlp_nbr->d || s->d % 4 != 0)
+  if (!s->ring || !s->cur || !src || !dst || !tq || s->V1 <= 0 || s->T <= 0 || s->d != mlp_nbr->d || s->d % 4 != 0)
     return LSTEP_ERR_INVALID_ARG;
   if (head < 0 || head >= s->T || len < 0 || len > s->T || append_slot < 0 || append_slot >= s->T) return LSTEP_ERR_INVALID_ARG;
   if (n_queries > 0 && (!query_ids_host || !nbr_out)) return LSTEP_ERR_INVALID_ARG;
@@ -141,7 +143,6 @@ extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int
       q.p[c] = query_ids_host[c];
     }
     q.period = n_edges;
-    const double* tq = s->t + lo;
     rc = launch_sample<int32_t, false>(csr, q, tq, rows, rows, K, w.nbrQ, nullptr, w.ntQ, err_flag, stream);
     if (rc != LSTEP_OK) return rc;
     rc = launch_nbr_aggregate(s->cur, tq, w.nbrQ, w.ntQ, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, n_edges, st);
@@ -150,9 +151,20 @@ extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int
     if (rc != LSTEP_OK) return rc;
   }
   // a7 + a8
-  rc = lstep_update_pe(s->cur, s->V1, csr, ids, n_ids, s->src + lo, s->dst + lo, s->t + lo, n_edges, current_time, K,
-                       mlp_upd, w.update, w.update_bytes, err_flag, stream);
+  rc = lstep_update_pe(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update,
+                       w.update_bytes, err_flag, stream);
   if (rc != LSTEP_OK) return rc;
   ring_append_kernel<<<kNumSMs * 8, 256, 0, st>>>(s->cur, s->ring, s->V1, T, d, append_slot, 1, 0);
   return check_launch("ring_append");
+}
+}  // namespace lstep
+
+extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, int64_t n_edges,
+                             const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
+                             const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
+                             const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace,
+                             size_t workspace_bytes, uint32_t* err_flag, void* stream) {
+  if (!s || !s->src || !s->dst || !s->t || lo < 0) return LSTEP_ERR_INVALID_ARG;
+  return pe_step_core(s, csr, s->src + lo, s->dst + lo, s->t + lo, n_edges, ids, n_ids, current_time, head, len, append_slot, G,
+                      query_ids_host, n_queries, nbr_out, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag, stream);
 }

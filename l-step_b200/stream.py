@@ -168,20 +168,97 @@ class PEStream:
         self._run(lo, n, self.ids[io:ie], self.batch_tmax[b], queries, out, batch_idx)
         return out
 
-    def step_host(self, src: np.ndarray, dst: np.ndarray, times: np.ndarray, query_ids, batch_idx: int = None, lo: int = None):
-        """The same step fed from HOST arrays (what a loop holding numpy batches calls): the batch must be
-        the next `len(src)` edges of the resident stream (or start at `lo`); ids and query ids are uploaded from pinned
-        memory, and per-query row sums [len(query_ids), B] come back to the host (a small per-batch
-        result, like the predictions the eval loop reads back)."""
+    # ---- host-fed steps (native stager: csrc/host_step.cu) -----------------------------------------
+    def _stepper(self, n_edges: int, C: int):
+        lib = _lib.load()
+        st = getattr(self, "_host_stepper", None)
+        if st is None or st[1] < n_edges or st[2] < C:
+            if st is not None:
+                lib.lstep_host_stepper_destroy(st[0])
+            h = C_void_p()
+            cap_e, cap_c = max(self.B, n_edges), max(C, 4)
+            with torch.cuda.device(self.dev):
+                _lib.check(lib.lstep_host_stepper_create(self.HOST_SLOTS, cap_e, cap_c, self.d, C_byref(h)), "lstep_host_stepper_create")
+            self._host_stepper = st = (h, cap_e, cap_c)
+            self._host_bytes = [0, 0]
+        return st[0]
+
+    HOST_SLOTS = 4  # steps that may be in flight before step_host_async blocks on the oldest
+
+    def __del__(self):
+        st = getattr(self, "_host_stepper", None)
+        if st is not None:
+            try:
+                _lib.load(False).lstep_host_stepper_destroy(st[0])
+            except Exception:
+                pass
+            self._host_stepper = None
+
+    def step_host_async(self, src: np.ndarray, dst: np.ndarray, times: np.ndarray, query_ids, batch_idx: int = None,
+                        ids: np.ndarray = None, out: torch.Tensor = None) -> int:
+        """One step fed from HOST arrays (what a loop holding numpy batches calls): the batch's endpoints,
+        times and the query id sets are packed into a pinned slot and uploaded by one async copy inside the
+        native call, the step's kernels are enqueued behind it, and the per-query row sums [C, n] of the
+        neighbourhood PEs are copied back to a pinned result slot. Returns a ticket at once (nothing
+        synchronises); `result(ticket)` waits for that step only, so a loop can read results one step behind.
+        `ids` (sorted unique batch nodes) is computed natively when omitted; `out` [C, n, d] keeps the full
+        neighbourhood PEs on the device."""
+        lib = _lib.load()
         m = self.model
         n = len(src)
-        lo = self._host_cursor if lo is None else int(lo)
-        if not (np.array_equal(self.src_np[lo:lo + n], src) and np.array_equal(self.dst_np[lo:lo + n], dst)):
-            raise ValueError("step_host: the batch is not the next slice of the resident edge stream")
-        ids_np = np.unique(np.concatenate([src, dst]))
-        I64 = np.dtype(np.int64)
-        up = m._upload([(ids_np, I64)] + [(q, I64) for q in query_ids])
-        out = torch.empty((len(query_ids), n, self.d), dtype=torch.float32, device=self.dev)
-        self._run(lo, n, up[0], float(times.max()), up[1:], out, batch_idx)
-        self._host_cursor = lo + n if lo + n < self.stop else self.start
-        return out.sum(dim=2).cpu().numpy()  # D2H of the step's result (synchronises)
+        C = len(query_ids)
+        I64, F64 = np.dtype(np.int64), np.dtype(np.float64)
+        src = np.ascontiguousarray(src, dtype=I64)
+        dst = np.ascontiguousarray(dst, dtype=I64)
+        times = np.ascontiguousarray(times, dtype=F64)
+        qs = [np.ascontiguousarray(q, dtype=I64) for q in query_ids]
+        if len(dst) != n or len(times) != n or any(len(q) != n for q in qs):
+            raise ValueError("step_host: src, dst, times and every query set must have the same length")
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=I64)
+        n_ids_bound = len(ids) if ids is not None else 2 * n
+        T = self.T
+        bi = self.batch_idx if batch_idx is None else batch_idx
+        bmask = min(max(bi, 0), T) if self.len < T else T
+        with torch.cuda.device(self.dev), torch.no_grad():
+            h = self._stepper(n, C)
+            G = m._collapsed_filter(bmask, False)
+            ws = self._workspace(n_ids_bound, n, C)
+            if self.len < T:
+                slot, new_head, new_len = (self.head + self.len) % T, self.head, self.len + 1
+            else:
+                slot, new_head, new_len = self.head, (self.head + 1) % T, T
+            qptrs = (C_void_p * max(C, 1))(*[q.ctypes.data for q in qs])
+            ticket = ctypes.c_int64(-1)
+            _lib.check(lib.lstep_pe_step_host(h, self._desc_ref, m.neighbor_sampler.csr_ref, n, src.ctypes.data, dst.ctypes.data,
+                                              times.ctypes.data, ids.ctypes.data if ids is not None else None,
+                                              len(ids) if ids is not None else 0, self.head, self.len, slot, _lib.ptr(G), qptrs, C,
+                                              _lib.ptr(out), self.K, m._mlp_ref("nbr"), m._mlp_ref("update"), _lib.ptr(ws),
+                                              ws.numel(), _lib.ptr(m.neighbor_sampler._err), _lib.stream_ptr(), C_byref(ticket)),
+                       "lstep_pe_step_host")
+            self.head, self.len = new_head, new_len
+        self.batch_idx = bi + 1
+        self.steps_done += 1
+        self._ticket_shape = getattr(self, "_ticket_shape", {})
+        self._ticket_shape[ticket.value] = (C, n)
+        self._ticket_shape.pop(ticket.value - 2 * self.HOST_SLOTS, None)
+        a, b = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        lib.lstep_host_stepper_bytes(h, C_byref(a), C_byref(b))
+        m.h2d_bytes += a.value - self._host_bytes[0]
+        self._host_bytes = [a.value, b.value]
+        return ticket.value
+
+    def result(self, ticket: int) -> np.ndarray:
+        """Per-query row sums [C, n] of step `ticket` (waits for that step's device-to-host copy)."""
+        lib = _lib.load()
+        p = ctypes.POINTER(ctypes.c_float)()
+        nf = ctypes.c_int64(0)
+        _lib.check(lib.lstep_host_step_result(self._host_stepper[0], ticket, C_byref(p), C_byref(nf)), "lstep_host_step_result")
+        C, n = self._ticket_shape[ticket]
+        if nf.value == 0:
+            return np.zeros((C, n), np.float32)
+        return np.ctypeslib.as_array(p, shape=(nf.value,)).reshape(C, n).copy()
+
+    def step_host(self, src: np.ndarray, dst: np.ndarray, times: np.ndarray, query_ids, batch_idx: int = None, ids: np.ndarray = None):
+        """Synchronous form: run the step and return its per-query row sums [len(query_ids), n]."""
+        return self.result(self.step_host_async(src, dst, times, query_ids, batch_idx, ids))

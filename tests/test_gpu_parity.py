@@ -403,6 +403,46 @@ def test_stream_api_matches_reference_replay(torch_cuda, tag):
     assert torch.equal(st2.cur, st.cur) and torch.equal(st2.export_history(), h)
 
 
+def test_host_fed_step_matches_device_resident_step(torch_cuda):
+    """PEStream.step_host_async (native stager: pinned slot -> one H2D copy -> step -> row sums -> pinned D2H,
+    results read one step behind) against PEStream.step on a twin stream: tables bit-identical after every
+    step, row sums equal to the row sums of the device-resident outputs, ids computed natively == np.unique."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream
+    g = synth.make_graph("tiny_bip", seed=5)
+    V, d, T, K, B = g.num_nodes, 172, 100, 20, 64
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin("full", g, s, 172, d, 100, T, K)[0].eval()
+    init = seeded_normal(11, (V + 1, d), 0.3)
+    init[0] = 0
+    e0 = g.num_edges - 12 * B - 17  # last batch is ragged
+    a = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=torch.from_numpy(init).cuda(), start=e0)
+    b = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=torch.from_numpy(init).cuda(), start=e0)
+    rng = np.random.default_rng(0)
+    pending, want_prev = None, None
+    for i in range(a.num_batches):
+        lo, hi, io, ie = a.batch_arrays(i)
+        neg = rng.integers(1, V + 1, hi - lo).astype(np.int64)
+        q_np = [g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], neg]
+        out = a.step(i, [torch.from_numpy(np.ascontiguousarray(q)).cuda() for q in q_np])
+        want = out.sum(dim=2).cpu().numpy()
+        # odd steps pass precomputed ids, even steps let the native side sort + unique
+        ids = a.ids_np[io:ie] if i % 2 else None
+        tk = b.step_host_async(g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.node_interact_times[lo:hi], q_np, ids=ids)
+        if pending is not None:
+            got = b.result(pending)
+            assert got.shape == want_prev.shape
+            np.testing.assert_allclose(got, want_prev, rtol=1e-5, atol=1e-5)
+        pending, want_prev = tk, want
+        assert torch.equal(a.cur, b.cur), i
+    np.testing.assert_allclose(b.result(pending), want_prev, rtol=1e-5, atol=1e-5)
+    assert torch.equal(a.export_history(), b.export_history())
+    with pytest.raises(ValueError):
+        b.step_host_async(g.src_node_ids[:4], g.dst_node_ids[:3], g.node_interact_times[:4], [])
+    s.check_errors()
+
+
 # ------------------------------------------------------------------------------------------ (e) sharded table
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_ranks_match_single_gpu_stream(torch_cuda, world):
