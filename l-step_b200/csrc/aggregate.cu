@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
                                                             const float* __restrict__ nbr_t, int64_t n_rows, int K,
                                                             const float* __restrict__ tw, int d, int t, int t_pad,
                                                             float* __restrict__ S, int64_t ldS, int64_t period) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);
   float* s_dt = reinterpret_cast<float*>(s_nbr + K);
@@ -25,9 +27,9 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const double tq = q_time[period ? row % period : row];
     for (int k = tid; k < K; k += blockDim.x) {
-      s_nbr[k] = nbr[row * K + k];
+      s_nbr[k] = ld_dep(nbr + row * K + k);
       // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
-      s_dt[k] = (float)(tq - (double)nbr_t[row * K + k]);
+      s_dt[k] = (float)(tq - (double)ld_dep(nbr_t + row * K + k));
     }
     __syncthreads();
     if (tid < t) {
@@ -45,7 +47,7 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
           float4 v[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
-            v[u] = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k + u] * d) + cv);
+            v[u] = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k + u] * d) + cv);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             acc.x += v[u].x;
@@ -55,7 +57,7 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
           }
         }
         for (; k < K; ++k) {
-          const float4 v = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k] * d) + cv);
+          const float4 v = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k] * d) + cv);
           acc.x += v.x;
           acc.y += v.y;
           acc.z += v.z;
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
         reinterpret_cast<float4*>(S + row * ldS)[cv] = acc;
       } else {
         float acc = 0.f;
-        for (int k = 0; k < K; ++k) acc += __ldg(pe + (int64_t)s_nbr[k] * d + cv);
+        for (int k = 0; k < K; ++k) acc += ld_dep(pe + (int64_t)s_nbr[k] * d + cv);
         S[row * ldS + cv] = acc;
       }
     }
@@ -103,9 +105,9 @@ int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* n
   if (smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
   const int64_t grid = n_rows < (int64_t)kNumSMs * 16 ? n_rows : (int64_t)kNumSMs * 16;
   if (v4)
-    nbr_aggregate_kernel<4><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period);
+    launch_k(nbr_aggregate_kernel<4>, dim3((unsigned)grid), dim3(threads), smem, st, pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period);
   else
-    nbr_aggregate_kernel<1><<<(unsigned)grid, threads, smem, st>>>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period);
+    launch_k(nbr_aggregate_kernel<1>, dim3((unsigned)grid), dim3(threads), smem, st, pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period);
   return check_launch("nbr_aggregate");
 }
 

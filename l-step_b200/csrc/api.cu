@@ -1,5 +1,6 @@
 // Status / error plumbing of the C ABI (include/lstep_b200.h).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -10,6 +11,11 @@ static thread_local char g_cuda_err[256] = "";
 
 void set_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
+}
+
+bool pdl_enabled() {
+  static const bool on = getenv("LSTEP_NO_PDL") == nullptr;
+  return on;
 }
 
 int check_launch(const char* where) {

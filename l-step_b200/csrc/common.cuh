@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <utility>
+
 #include "lstep_b200.h"
 
 namespace lstep {
@@ -20,17 +22,56 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// streaming 128-bit load that does not pollute L1 (history rows are read once)
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// The step is a chain of ~11 short, dependent kernels; a plain stream launch starts kernel n+1 only after
+// kernel n has drained (2-4 us of launch latency each, a fifth of the step). Every kernel of the chain
+// therefore (a) lets its successor be scheduled early (pdl_launch_dependents, first instruction) and
+// (b) calls pdl_wait() before its first access to global memory that a predecessor may have written or may
+// still read; griddepcontrol.wait returns when all preceding grids have completed and their writes are
+// visible, so the memory ordering is that of a plain launch. Launch with launch_k(); kernels that are
+// launched with <<<>>> execute both instructions as no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// A kernel launched this way is resident BEFORE its predecessor has finished, so it misses the L1
+// invalidation a kernel boundary normally gives: a line that a predecessor CTA on the same SM pulled into L1
+// (or the read-only path) and that was then rewritten from another SM would be read stale. Every load of data
+// that an earlier kernel of the step WRITES therefore goes through ld_dep() = ld.global.cg (served by L2,
+// the point of coherence). Plain / __ldg loads are kept for data no kernel of the step writes (CSR, packed
+// parameters, the batch arrays, query ids).
+__device__ __forceinline__ float ld_dep(const float* p) { return __ldcg(p); }
+__device__ __forceinline__ float4 ld_dep(const float4* p) { return __ldcg(p); }
+__device__ __forceinline__ int32_t ld_dep(const int32_t* p) { return __ldcg(p); }
+__device__ __forceinline__ int64_t ld_dep(const int64_t* p) { return (int64_t)__ldcg(reinterpret_cast<const long long*>(p)); }
+
+bool pdl_enabled();  // LSTEP_NO_PDL=1 turns the launch attribute off (A/B measurements)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(std::forward<Args>(args))...);
+}
+
+// streaming 128-bit load served by L2 (history rows are read once; also see ld_dep above)
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                : "l"(p));
   return v;
 }
 __device__ __forceinline__ float ld_stream_f(const float* p) {
   float v;
-  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 
@@ -46,6 +87,11 @@ struct RowIds {
   const int64_t* p[8];
   int64_t period;  // 0: single set, p[0][row]
   __device__ __forceinline__ int64_t at(int64_t row) const { return period ? p[row / period][row % period] : p[0][row]; }
+  // ids that an earlier kernel of the step wrote (update_pe phase B: the list of distinct destinations)
+  __device__ __forceinline__ int64_t at_dep(int64_t row) const {
+    return period ? __ldcg(reinterpret_cast<const long long*>(p[row / period]) + row % period)
+                  : __ldcg(reinterpret_cast<const long long*>(p[0]) + row);
+  }
   __device__ __forceinline__ int64_t time_index(int64_t row) const { return period ? row % period : row; }
 };
 inline RowIds single_ids(const int64_t* ids) {

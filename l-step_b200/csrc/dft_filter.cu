@@ -14,6 +14,8 @@
 // bytes of history, bound by HBM bandwidth. It reads each node's history once with 128-bit
 // loads that bypass L1, keeps G in L1/L2 (68.8 KB at T=100, d=172), and reduces the per-thread
 // partial sums over time through shared memory in a fixed order (deterministic).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lstep {
@@ -111,6 +113,8 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_kernel(const float* __
                                                                  const int64_t* __restrict__ ids, int64_t n_ids,
                                                                  const float* __restrict__ G, float* __restrict__ out,
                                                                  int64_t out_stride, const int64_t* __restrict__ out_ids) {
+  pdl_launch_dependents();
+  pdl_wait();
   using V = typename VecT<VEC>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V* red = reinterpret_cast<V*>(smem_raw);  // [groups][dvec]
@@ -154,6 +158,111 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_kernel(const float* __
       reinterpret_cast<V*>(out + (out_ids ? out_ids[n] : n) * out_stride)[cv] = tot;
     }
     __syncthreads();
+  }
+}
+
+
+// ---- node-major history (time_stride == d: the streaming ring, or a contiguous [V1,Th,d] tensor) ----------
+// A node's Th steps are one contiguous block (68.8 KB at T=100, d=172) apart from the ring wrap. One CTA per
+// node pulls the whole block into shared memory with a handful of cp.async.bulk copies (SASS UBLKCP), issued
+// up front, in LOGICAL time order (the wrap is resolved by the copy addresses), one mbarrier per chunk of
+// rows, and multiplies chunk c by G while chunks c+1.. are still in flight. With 3 CTAs resident per SM every
+// byte of the launch is requested within the first microsecond, so the kernel runs at the HBM rate instead of
+// paying one load latency per register-sized batch (the generic kernel above: 4 loads in flight per thread).
+constexpr int kDftChunks = 4;
+
+__device__ __forceinline__ uint32_t dft_s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const float* __restrict__ hist, int64_t node_stride, int s0,
+                                                                      int ring, int Th, int d, const int64_t* __restrict__ ids,
+                                                                      int64_t n_ids, const float* __restrict__ G,
+                                                                      float* __restrict__ out, int64_t out_stride,
+                                                                      const int64_t* __restrict__ out_ids) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bar[kDftChunks];
+  float4* xs = reinterpret_cast<float4*>(smem_raw);  // [Th][dvec] logical time order
+  const int dvec = d >> 2;
+  float4* red = xs + (size_t)Th * dvec;               // [groups][dvec]
+  const int groups = kDftThreads / dvec;
+  const int g = threadIdx.x / dvec, cv = threadIdx.x % dvec;
+  const bool active = g < groups;
+  const int rc = (Th + kDftChunks - 1) / kDftChunks;  // rows per chunk
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int c = 0; c < kDftChunks; ++c)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dft_s_u32(&bar[c])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  pdl_wait();
+  const float4* Gv = reinterpret_cast<const float4*>(G);
+  uint32_t it = 0;
+  for (int64_t n = blockIdx.x; n < n_ids; n += gridDim.x, ++it) {
+    if (threadIdx.x == 0) {
+      const float* base = hist + ids[n] * node_stride;
+      for (int c = 0; c < kDftChunks; ++c) {
+        const int a = c * rc, b = min(Th, a + rc);
+        if (a >= b) continue;
+        const uint32_t bytes = (uint32_t)(b - a) * (uint32_t)d * 4u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dft_s_u32(&bar[c])), "r"(bytes) : "memory");
+        int ps = s0 + a;
+        if (ps >= ring) ps -= ring;
+        const int first = min(b - a, ring - ps);  // rows before the ring wraps
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         dft_s_u32(xs + (size_t)a * dvec)),
+                     "l"(base + (int64_t)ps * d), "r"((uint32_t)first * (uint32_t)d * 4u), "r"(dft_s_u32(&bar[c]))
+                     : "memory");
+        if (first < b - a)
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           dft_s_u32(xs + (size_t)(a + first) * dvec)),
+                       "l"(base), "r"((uint32_t)(b - a - first) * (uint32_t)d * 4u), "r"(dft_s_u32(&bar[c]))
+                       : "memory");
+      }
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < kDftChunks; ++c) {
+      const int a = c * rc, b = min(Th, a + rc);
+      if (a >= b) break;
+      // this thread's rows of the chunk: a + g, a + g + groups, ...; fetch their filter rows before waiting
+      constexpr int kMaxRows = 8;
+      float4 w[kMaxRows];
+      if (active) {
+#pragma unroll
+        for (int u = 0; u < kMaxRows; ++u) {
+          const int s = a + g + u * groups;
+          if (s < b) w[u] = __ldg(Gv + (size_t)s * dvec + cv);
+        }
+      }
+      {  // wait for the chunk (parity flips once per node this CTA handles)
+        uint32_t done = 0, spins = 0;
+        while (!done) {
+          if (++spins > (1u << 24)) __trap();
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t"
+              "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+              "selp.u32 %0, 1, 0, p;\n\t}"
+              : "=r"(done)
+              : "r"(dft_s_u32(&bar[c])), "r"(it & 1u)
+              : "memory");
+        }
+      }
+      if (active) {
+#pragma unroll
+        for (int u = 0; u < kMaxRows; ++u) {
+          const int s = a + g + u * groups;
+          if (s < b) fma_acc(acc, w[u], xs[(size_t)s * dvec + cv]);
+        }
+        for (int s = a + g + kMaxRows * groups; s < b; s += groups) fma_acc(acc, __ldg(Gv + (size_t)s * dvec + cv), xs[(size_t)s * dvec + cv]);
+      }
+    }
+    if (active) red[g * dvec + cv] = acc;
+    __syncthreads();
+    if (active && g == 0) {
+      float4 tot = red[cv];
+      for (int gg = 1; gg < groups; ++gg) add_acc(tot, red[gg * dvec + cv]);
+      reinterpret_cast<float4*>(out + (out_ids ? out_ids[n] : n) * out_stride)[cv] = tot;
+    }
+    __syncthreads();  // xs / red are reused by the next node of this CTA
   }
 }
 
@@ -218,12 +327,33 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
   const int groups = kDftThreads / dvec;
   const size_t smem = (size_t)groups * dvec * (v4 ? 16 : 4);
   const int64_t grid = n_ids < (int64_t)kNumSMs * 6 ? n_ids : (int64_t)kNumSMs * 6;
+  cudaStream_t st = as_stream(stream);
+  {
+    // node-major history: bulk-async kernel (one CTA stages a node's whole block in shared memory)
+    static const bool no_bulk = getenv("LSTEP_DFT_GENERIC") != nullptr;
+    const size_t bulk_smem = ((size_t)Th * dvec + (size_t)groups * dvec) * 16;
+    if (v4 && !no_bulk && time_stride == d && Th > 0 && bulk_smem <= 74 * 1024) {  // <= 74 KB: 3 CTAs per SM
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(dft_filter_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 74 * 1024);
+        if (e != cudaSuccess) {
+          set_cuda_error(e, "dft_filter_bulk attr");
+          return LSTEP_ERR_CUDA;
+        }
+        attr_set = true;
+      }
+      const int64_t bgrid = n_ids < (int64_t)kNumSMs * 3 ? n_ids : (int64_t)kNumSMs * 3;
+      launch_k(dft_filter_bulk_kernel, dim3((unsigned)bgrid), dim3(kDftThreads), bulk_smem, st, hist, node_stride, s0, ring, Th, d, ids,
+               n_ids, G, out, out_stride, out_ids);
+      return check_launch("dft_filter_bulk");
+    }
+  }
   if (v4)
-    dft_filter_kernel<4><<<(unsigned)grid, kDftThreads, smem, as_stream(stream)>>>(
-        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids);
+    launch_k(dft_filter_kernel<4>, dim3((unsigned)grid), dim3(kDftThreads), smem, st, hist, node_stride, time_stride, s0, ring, Th, d,
+             ids, n_ids, G, out, out_stride, out_ids);
   else
-    dft_filter_kernel<1><<<(unsigned)grid, kDftThreads, smem, as_stream(stream)>>>(
-        hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids);
+    launch_k(dft_filter_kernel<1>, dim3((unsigned)grid), dim3(kDftThreads), smem, st, hist, node_stride, time_stride, s0, ring, Th, d,
+             ids, n_ids, G, out, out_stride, out_ids);
   return check_launch("dft_filter");
 }
 }  // namespace lstep

@@ -24,12 +24,14 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
 
 // res[row] = sum_c x[row][c]: one warp per row, lanes stride the columns, fixed-order shuffle tree
 __global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ x, int64_t n_rows, int d, float* __restrict__ res) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n_rows) return;
   const float* p = x + row * d;
   float acc = 0.f;
-  for (int c = lane; c < d; c += 32) acc += p[c];
+  for (int c = lane; c < d; c += 32) acc += ld_dep(p + c);
   acc = warp_sum(acc);
   if (lane == 0) res[row] = acc;
 }
@@ -170,7 +172,7 @@ extern "C" int lstep_pe_step_host(lstep_host_stepper* h, const lstep_pe_stream* 
   if (rc != LSTEP_OK) return rc;
   const int64_t rows = (int64_t)n_queries * n_edges;
   if (rows > 0) {
-    row_sum_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, st>>>(outp, rows, h->d, h->d_res[slot]);
+    launch_k(row_sum_kernel, dim3((unsigned)ceil_div(rows * 32, 256)), dim3(256), 0, st, outp, rows, h->d, h->d_res[slot]);
     if ((rc = check_launch("row_sum")) != LSTEP_OK) return rc;
     if ((e = cudaMemcpyAsync(h->h_res[slot], h->d_res[slot], sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
       return cuda_fail(e, "pe_step_host d2h");

@@ -35,6 +35,8 @@ __global__ void pack_linear_kernel(const float* __restrict__ w, const float* __r
     for (int c = threadIdx.x; c < ldo; c += blockDim.x) pb[c] = (b && c < out_f) ? b[c] : 0.f;
 }
 
+__global__ void stream_order_fence_kernel() {}
+
 // ---- mbarrier / bulk-copy primitives (PTX) ---------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -302,6 +304,9 @@ static int launch_mlp_r(const float* A, int64_t lda, const float* pe, RowIds bas
 int launch_pe_mlp_tc(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                      const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                      cudaStream_t st);
+int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
+                          const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
+                          cudaStream_t st);
 
 // n_rows is the host-side upper bound of rows; *n_rows_dev (optional) the device-side count.
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
@@ -309,6 +314,15 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
                   cudaStream_t st) {
   if (n_rows <= 0) return LSTEP_OK;
   if (!A || !pe || !base_ids.p[0] || !m || (!out && !pe_inplace)) return LSTEP_ERR_INVALID_ARG;
+  {
+    // default: the cluster split-K kernel (csrc/mlp_cluster.cu); LSTEP_MLP_RING=1 selects the all-columns
+    // weight-ring kernel below, which also serves shapes the cluster kernel does not cover
+    static const bool use_ring = getenv("LSTEP_MLP_RING") != nullptr || getenv("LSTEP_MLP_TC") != nullptr;
+    if (!use_ring) {
+      const int rc = launch_pe_mlp_cluster(A, lda, pe, base_ids, n_rows, expected_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
+      if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
+    }
+  }
   {
     // The 3xTF32 tensor-core variant (csrc/mlp_tc.cu) is opt-in: measured on B200 it is not faster than the
     // fp32 kernel at these sizes (both are bound by streaming the weights into each SM, and it streams twice
@@ -342,6 +356,10 @@ extern "C" int lstep_pack_linear(const float* weight, const float* bias, int out
   const int ldo = lstep_packed_ld(out_features);
   pack_linear_kernel<<<64, 256, 0, as_stream(stream)>>>(weight, bias, out_features, in_features,
                                                         lstep_packed_rows(in_features), ldo, packed_w, packed_b);
+  // The MLP kernels fetch the packed parameters BEFORE their programmatic-dependency wait (they are constants
+  // of the step). A plainly launched empty kernel behind the pack kernel is a full stream-order barrier: whatever
+  // is launched after it, early start or not, begins after the packed weights are complete and visible.
+  stream_order_fence_kernel<<<1, 32, 0, as_stream(stream)>>>();
   return check_launch("pack_linear");
 }
 

@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(256) sample_recent_kernel(const int64_t* __res
                                                             int64_t n_valid, int K, IdT* __restrict__ out_nbr,
                                                             IdT* __restrict__ out_eid, float* __restrict__ out_t,
                                                             uint32_t* err_flag, PhaseBHook hook) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   if (kHook && blockIdx.x == 0)
     for (int c = threadIdx.x; c < hook.d; c += blockDim.x) hook.pe0[c] = 0.f;
@@ -93,7 +95,7 @@ int launch_sample(const lstep_csr* csr, RowIds q_node, const double* q_time, int
   if (n_valid > n_rows) n_valid = n_rows;
   const int warps = 8;
   const int64_t blocks = ceil_div(n_rows, warps);
-  sample_recent_kernel<IdT, kWithEid, false><<<(unsigned)blocks, warps * 32, 0, as_stream(stream)>>>(
+  launch_k(sample_recent_kernel<IdT, kWithEid, false>, dim3((unsigned)blocks), dim3(warps * 32), 0, as_stream(stream), 
       csr->indptr, csr->nbr, csr->eid, csr->t, csr->num_rows, q_node, q_time, n_rows, n_valid, K, out_nbr, out_eid,
       out_t, err_flag, PhaseBHook{});
   return check_launch("sample_recent");
@@ -106,7 +108,7 @@ int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const doubl
   if (n_valid > n_rows) n_valid = n_rows;
   const int warps = 8;
   const int64_t blocks = ceil_div(n_rows, warps);
-  sample_recent_kernel<int32_t, false, true><<<(unsigned)blocks, warps * 32, 0, as_stream(stream)>>>(
+  launch_k(sample_recent_kernel<int32_t, false, true>, dim3((unsigned)blocks), dim3(warps * 32), 0, as_stream(stream), 
       csr->indptr, csr->nbr, csr->eid, csr->t, csr->num_rows, single_ids(q_node), q_time, n_rows, n_valid, K, out_nbr,
       nullptr, out_t, err_flag, hook);
   return check_launch("sample_recent+count");

@@ -30,13 +30,15 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
 // table row of ring row v is v*row_mul + row_add (1, 0 for a single GPU; G, rank for a node-id sharded ring)
 __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restrict__ cur, float* __restrict__ ring,
                                                           int64_t V1, int T, int d, int slot, int64_t row_mul, int64_t row_add) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int dvec = d >> 2;
   const int64_t total = V1 * dvec;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = i / dvec;
     const int c = (int)(i % dvec);
     reinterpret_cast<float4*>(ring + (v * T + slot) * (int64_t)d)[c] =
-        reinterpret_cast<const float4*>(cur + (v * row_mul + row_add) * (int64_t)d)[c];
+        ld_dep(reinterpret_cast<const float4*>(cur + (v * row_mul + row_add) * (int64_t)d) + c);
   }
 }
 
@@ -104,7 +106,7 @@ extern "C" int lstep_ring_copy_rows(float* ring, float* cur, int64_t ring_rows, 
     return LSTEP_ERR_INVALID_ARG;
   if (ring_rows == 0) return LSTEP_OK;
   if (to_ring)
-    ring_append_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(cur, ring, ring_rows, T, d, slot, row_mul, row_add);
+    launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, as_stream(stream), cur, ring, ring_rows, T, d, slot, row_mul, row_add);
   else
     ring_load_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(ring, cur, ring_rows, T, d, slot, row_mul, row_add);
   return check_launch("ring_copy_rows");
@@ -154,7 +156,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   rc = lstep_update_pe(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update,
                        w.update_bytes, err_flag, stream);
   if (rc != LSTEP_OK) return rc;
-  ring_append_kernel<<<kNumSMs * 8, 256, 0, st>>>(s->cur, s->ring, s->V1, T, d, append_slot, 1, 0);
+  launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0);
   return check_launch("ring_append");
 }
 }  // namespace lstep

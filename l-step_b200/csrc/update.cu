@@ -108,6 +108,8 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
                                                              const float* __restrict__ tw, int d, int t, int t_pad,
                                                              float* __restrict__ A, int64_t lda,
                                                              int32_t* __restrict__ counters) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int nthr = blockDim.x;
   const int seg = nthr * kSegPerThread;
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
           for (; j + 4 <= total; j += 4) {
             float4 v[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)s_other[j + u] * d) + cv);
+            for (int u = 0; u < 4; ++u) v[u] = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_other[j + u] * d) + cv);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               acc.x += v[u].x;
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
             }
           }
           for (; j < total; ++j) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(pe + (int64_t)s_other[j] * d) + cv);
+            const float4 v = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_other[j] * d) + cv);
             acc.x += v.x;
             acc.y += v.y;
             acc.z += v.z;
@@ -221,33 +223,35 @@ __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__
                                                            int fill_here, const float* __restrict__ pe,
                                                            const int64_t* __restrict__ ids, int64_t n_ids, int d,
                                                            float* __restrict__ row0_part) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (blockIdx.x > 0) {
     {  // accumulator rows of this call's long lists start from zero: at most min(M, N*K/(kHubLen+1)) lists are long
-      const int64_t cap = min((int64_t)counters[0], total / (kHubLen + 1) + 1) * in1;
+      const int64_t cap = min((int64_t)ld_dep(counters + 0), total / (kHubLen + 1) + 1) * in1;
       ulonglong2* z = reinterpret_cast<ulonglong2*>(hub_acc);
       for (int64_t i = (int64_t)(blockIdx.x - 1) * blockDim.x + threadIdx.x; i < (cap + 1) / 2; i += (int64_t)(gridDim.x - 1) * blockDim.x)
         z[i] = make_ulonglong2(0ull, 0ull);
     }
-    if (counters[1] == 0) return;
+    if (ld_dep(counters + 1) == 0) return;
     const int part = blockIdx.x - 1;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
       float acc = 0.f;
       for (int64_t n = part; n < n_ids; n += kRow0Parts) {
         int z = 0;
-        for (int k = 0; k < K; ++k) z += (nbrB[n * K + k] == 0);
-        if (z) acc = fmaf((float)z, pe[ids[n] * (int64_t)d + c], acc);
+        for (int k = 0; k < K; ++k) z += (ld_dep(nbrB + n * K + k) == 0);
+        if (z) acc = fmaf((float)z, ld_dep(pe + ids[n] * (int64_t)d + c), acc);
       }
       row0_part[part * d + c] = acc;
     }
     return;
   }
   __shared__ int s_warp[32];
-  const int M = counters[0];
+  const int M = ld_dep(counters + 0);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int chunk = (M + blockDim.x - 1) / blockDim.x;
   const int lo = min(M, tid * chunk), hi = min(M, lo + chunk);
   int sum = 0;
-  for (int s = lo; s < hi; ++s) sum += cnt_of[U[s]];
+  for (int s = lo; s < hi; ++s) sum += ld_dep(cnt_of + ld_dep(U + s));
   int incl = sum;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -269,8 +273,8 @@ __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__
   __syncthreads();
   int run = s_warp[wid] + incl - sum;
   for (int s = lo; s < hi; ++s) {
-    const int64_t u = U[s];
-    const int deg = cnt_of[u];
+    const int64_t u = ld_dep(U + s);
+    const int deg = ld_dep(cnt_of + u);
     off[s] = run;
     run += deg;
     cnt_of[u] = 0;  // restore the all-zero invariant
@@ -288,15 +292,15 @@ __global__ void __launch_bounds__(1024) phaseB_scan_kernel(int32_t* __restrict__
     }
   }
   if (tid == 0) {
-    const int hz = counters[1];
+    const int hz = ld_dep(counters + 1);
     counters[2] = M + hz;
     if (hz) U[M] = 0;
   }
   __syncthreads();  // off[] / slot_of[] / the hub list written above are visible to the whole CTA
   if (fill_here) {
     for (int64_t i = tid; i < total; i += blockDim.x) {
-      const int32_t u = nbrB[i];
-      if (u > 0) list[off[slot_of[u]] + rank[i]] = (int32_t)i;
+      const int32_t u = ld_dep(nbrB + i);
+      if (u > 0) list[off[slot_of[u]] + ld_dep(rank + i)] = (int32_t)i;  // off / slot_of: written by this CTA above
     }
   }
 }
@@ -306,10 +310,12 @@ __global__ void __launch_bounds__(256) phaseB_fill_kernel(const int32_t* __restr
                                                           const int32_t* __restrict__ slot_of,
                                                           const int32_t* __restrict__ off,
                                                           const int32_t* __restrict__ rank, int32_t* __restrict__ list) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i < total) {
-    const int32_t u = nbrB[i];
-    if (u > 0) list[off[slot_of[u]] + rank[i]] = (int32_t)i;
+    const int32_t u = ld_dep(nbrB + i);
+    if (u > 0) list[ld_dep(off + ld_dep(slot_of + u)) + ld_dep(rank + i)] = (int32_t)i;
   }
 }
 
@@ -334,7 +340,7 @@ __device__ __forceinline__ void accumulate_chunk(const float* my_row, float my_d
     for (int u = 0; u < 4; ++u)
 #pragma unroll
       for (int q = 0; q < DVPL; ++q)
-        if (lane + 32 * q < dvec) v[u][q] = __ldg(row[u] + lane + 32 * q);
+        if (lane + 32 * q < dvec) v[u][q] = ld_dep(row[u] + lane + 32 * q);
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       if (j0 + u < m) {
@@ -369,13 +375,15 @@ __global__ void __launch_bounds__(256, DVPL <= 2 ? 2 : 1) phaseB_gather_kernel(
     int32_t* __restrict__ hub_remaining, const int32_t* __restrict__ task_hub, const int32_t* __restrict__ task_chunk,
     unsigned long long* __restrict__ hub_acc, const int32_t* __restrict__ counters, float tc, const float* __restrict__ tw, int d,
     int t, const float* __restrict__ row0_part, float* __restrict__ A, int64_t lda, int warp_blocks, int hub_blocks) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int in1 = d + t;
-  const int M = counters[0];
+  const int M = ld_dep(counters + 0);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nw = blockDim.x >> 5;
   // the grid is sized for the worst case (every slot a distinct destination); surplus CTAs leave at once
   if ((int)blockIdx.x < warp_blocks && (int)blockIdx.x * nw >= M) return;
-  const int n_tasks = counters[4];
+  const int n_tasks = ld_dep(counters + 4);
   if ((int)blockIdx.x >= warp_blocks && (int)blockIdx.x < warp_blocks + hub_blocks && ((int)blockIdx.x - warp_blocks) * nw >= n_tasks) return;
   const int dvec = d >> 2;
   float w[TFPL];
@@ -383,11 +391,11 @@ __global__ void __launch_bounds__(256, DVPL <= 2 ? 2 : 1) phaseB_gather_kernel(
   for (int q = 0; q < TFPL; ++q) w[q] = (lane + 32 * q < t) ? tw[lane + 32 * q] : 0.f;
 
   if ((int)blockIdx.x == warp_blocks + hub_blocks) {  // ---- padding row
-    if (counters[1]) {
+    if (ld_dep(counters + 1)) {
       for (int c = threadIdx.x; c < in1; c += blockDim.x) {
         float acc = 0.f;
         if (c < d)
-          for (int p = 0; p < kRow0Parts; ++p) acc += row0_part[p * d + c];
+          for (int p = 0; p < kRow0Parts; ++p) acc += ld_dep(row0_part + p * d + c);
         A[(int64_t)M * lda + c] = acc;  // time features of padded slots are zeroed (LSTEP.py:316)
       }
     }
@@ -404,9 +412,9 @@ __global__ void __launch_bounds__(256, DVPL <= 2 ? 2 : 1) phaseB_gather_kernel(
   if ((int)blockIdx.x < warp_blocks) {  // ---- short lists
     const int s = blockIdx.x * nw + wid;
     if (s >= M) return;
-    const int o0 = off[s], len = off[s + 1] - o0;
+    const int o0 = ld_dep(off + s), len = ld_dep(off + s + 1) - o0;
     if (len > kHubLen) return;  // reduced by hub chunk tasks
-    int e = (lane < len) ? list[o0 + lane] : 0x7fffffff;
+    int e = (lane < len) ? ld_dep(list + o0 + lane) : 0x7fffffff;
     // bitonic sort ascending across the warp: restores flat-index (= reference add) order
 #pragma unroll
     for (int k = 2; k <= 32; k <<= 1) {
@@ -422,7 +430,7 @@ __global__ void __launch_bounds__(256, DVPL <= 2 ? 2 : 1) phaseB_gather_kernel(
     float my_dt = 0.f;
     if (lane < len) {
       my_row = pe + ids[e / K] * (int64_t)d;
-      my_dt = tc - ntB[e];  // fp32 - fp32 (LSTEP.py:314)
+      my_dt = tc - ld_dep(ntB + e);  // fp32 - fp32 (LSTEP.py:314)
     }
     accumulate_chunk<DVPL, TFPL>(my_row, my_dt, len, lane, dvec, t, w, acc, acc_tf);
     float* arow = A + (int64_t)s * lda;
@@ -439,16 +447,16 @@ __global__ void __launch_bounds__(256, DVPL <= 2 ? 2 : 1) phaseB_gather_kernel(
   constexpr float kScale = 4294967296.f;           // 2^32
   constexpr float kInv = 2.3283064365386963e-10f;  // 2^-32
   for (int task = ((int)blockIdx.x - warp_blocks) * nw + wid; task < n_tasks; task += hub_blocks * nw) {
-    const int h = task_hub[task], c0 = task_chunk[task] << kChunkLog2;
-    const int s = hubs[h];
-    const int o0 = off[s], len = off[s + 1] - o0;
+    const int h = ld_dep(task_hub + task), c0 = ld_dep(task_chunk + task) << kChunkLog2;
+    const int s = ld_dep(hubs + h);
+    const int o0 = ld_dep(off + s), len = ld_dep(off + s + 1) - o0;
     const int m = min(1 << kChunkLog2, len - c0);
     const float* my_row = pe;
     float my_dt = 0.f;
     if (lane < m) {
-      const int e = list[o0 + c0 + lane];
+      const int e = ld_dep(list + o0 + c0 + lane);
       my_row = pe + ids[e / K] * (int64_t)d;
-      my_dt = tc - ntB[e];
+      my_dt = tc - ld_dep(ntB + e);
     }
     long long facc[DVPL][4], ftf[TFPL];
 #pragma unroll
@@ -469,7 +477,7 @@ __global__ void __launch_bounds__(256, DVPL <= 2 ? 2 : 1) phaseB_gather_kernel(
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int q = 0; q < DVPL; ++q)
-          if (lane + 32 * q < dvec) v[u][q] = __ldg(row[u] + lane + 32 * q);
+          if (lane + 32 * q < dvec) v[u][q] = ld_dep(row[u] + lane + 32 * q);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         if (j0 + u < m) {
@@ -558,7 +566,7 @@ static int phase_a(float* pe, const UpdateWs& w, const int64_t* ids, int64_t n_i
   const int threads = (int)align_up((size_t)t_pad + dvec, 32);
   const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
   const int64_t grid = n_ids < (int64_t)kNumSMs * 16 ? n_ids : (int64_t)kNumSMs * 16;
-  edge_aggregate_kernel<<<(unsigned)grid, threads, smem, st>>>(pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d, t,
+  launch_k(edge_aggregate_kernel, dim3((unsigned)grid), dim3(threads), smem, st, pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d, t,
                                                                t_pad, w.A, w.lda, w.counters);
   int rc = check_launch("edge_aggregate");
   if (rc != LSTEP_OK) return rc;
@@ -583,12 +591,12 @@ static int phase_b_partial(float* pe, int64_t pe_rows, const UpdateWs& w, const 
   }
   {
     const int fill_here = total <= 16384 ? 1 : 0;
-    phaseB_scan_kernel<<<1 + kRow0Parts, 1024, 0, st>>>(w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.hub_remaining, w.task_hub,
+    launch_k(phaseB_scan_kernel, dim3(1 + kRow0Parts), dim3(1024), 0, st, w.cnt_of, w.slot_of, w.U, w.off, w.hubs, w.hub_remaining, w.task_hub,
                                                         w.task_chunk, w.hub_acc, d + t, w.counters, w.nbrB, total, K,
                                                         w.rank, w.list, fill_here, pe, row_ids, n_ids, d, w.row0_part);
     if ((rc = check_launch("phaseB_scan")) != LSTEP_OK) return rc;
     if (!fill_here) {
-      phaseB_fill_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(w.nbrB, total, w.slot_of, w.off, w.rank, w.list);
+      launch_k(phaseB_fill_kernel, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, st, w.nbrB, total, w.slot_of, w.off, w.rank, w.list);
       if ((rc = check_launch("phaseB_fill")) != LSTEP_OK) return rc;
     }
   }
@@ -598,11 +606,11 @@ static int phase_b_partial(float* pe, int64_t pe_rows, const UpdateWs& w, const 
   if (hub_blocks > 4 * kNumSMs) hub_blocks = 4 * kNumSMs;
   const unsigned blocks = (unsigned)(warp_blocks + hub_blocks + 1);
   if (dvec <= 64 && t <= 128)
-    phaseB_gather_kernel<2, 4><<<blocks, 256, 0, st>>>(pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.hub_remaining, w.task_hub,
+    launch_k(phaseB_gather_kernel<2, 4>, dim3(blocks), dim3(256), 0, st, pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.hub_remaining, w.task_hub,
                                                        w.task_chunk, w.hub_acc, w.counters, tc, mlp->tw, d, t, w.row0_part, w.A, w.lda,
                                                        warp_blocks, hub_blocks);
   else
-    phaseB_gather_kernel<8, 8><<<blocks, 256, 0, st>>>(pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.hub_remaining, w.task_hub,
+    launch_k(phaseB_gather_kernel<8, 8>, dim3(blocks), dim3(256), 0, st, pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.hub_remaining, w.task_hub,
                                                        w.task_chunk, w.hub_acc, w.counters, tc, mlp->tw, d, t, w.row0_part, w.A, w.lda,
                                                        warp_blocks, hub_blocks);
   return check_launch("phaseB_gather");
