@@ -306,7 +306,7 @@ int launch_pe_mlp_tc(const float* A, int64_t lda, const float* pe, RowIds base_i
                      cudaStream_t st);
 int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          cudaStream_t st);
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st);
 
 // n_rows is the host-side upper bound of rows; *n_rows_dev (optional) the device-side count.
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
@@ -319,7 +319,7 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
     // weight-ring kernel below, which also serves shapes the cluster kernel does not cover
     static const bool use_ring = getenv("LSTEP_MLP_RING") != nullptr || getenv("LSTEP_MLP_TC") != nullptr;
     if (!use_ring) {
-      const int rc = launch_pe_mlp_cluster(A, lda, pe, base_ids, n_rows, expected_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
+      const int rc = launch_pe_mlp_cluster(A, lda, pe, base_ids, n_rows, expected_rows, n_rows_dev, m, out, out_stride, pe_inplace, nullptr, nullptr, st);
       if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
     }
   }

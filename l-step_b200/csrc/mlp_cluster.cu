@@ -82,6 +82,14 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 
 constexpr int kCl = 4;  // CTAs per cluster = k slices
 
+// Optional fixed-point input (update_pe phase B, csrc/update_push.cu): row r of the aggregate is
+// acc[r][0 .. d+t) in 32.32 fixed point instead of A[r][:]; reset_map[node of row r] is cleared once the
+// row has been consumed (the claim map of the push kernel returns to all-zero).
+struct FixedRows {
+  const unsigned long long* acc;
+  int32_t* reset_map;
+};
+
 #ifdef LSTEP_MLP_TIMING
 __device__ long long g_mlp_clk[16];
 #define MLP_T(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_mlp_clk[i] = clock64(); } while (0)
@@ -150,7 +158,7 @@ template <int TR>
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
     pe_mlp_cluster_kernel(const float* __restrict__ A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows,
                           const int32_t* __restrict__ n_rows_dev, lstep_pe_mlp m, float* __restrict__ out, int64_t out_stride,
-                          float* pe_inplace) {
+                          float* pe_inplace, FixedRows fx) {
   constexpr int RB = 4 * TR, RBp = RB + 4;
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t wbar[2];  // weight slices landed (layer 1, layer 2)
@@ -264,6 +272,15 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
     }
     return v;
   };
+  auto load4_fixed = [&](const unsigned long long* p, int kg, int lim) {
+    constexpr float kInv = 2.3283064365386963e-10f;  // 2^-32
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kg + 0 < lim) v.x = (float)(long long)__ldcg(p + 0) * kInv;
+    if (kg + 1 < lim) v.y = (float)(long long)__ldcg(p + 1) * kInv;
+    if (kg + 2 < lim) v.z = (float)(long long)__ldcg(p + 2) * kInv;
+    if (kg + 3 < lim) v.w = (float)(long long)__ldcg(p + 3) * kInv;
+    return v;
+  };
   auto put4 = [&](float* dst, float4 v) {
     dst[0] = v.x;
     dst[RBp] = v.y;
@@ -295,7 +312,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
           const int r = idx % RB, q = idx / RB;
           const int64_t row = row0 + r;
           const int kg = kA0 + 4 * q;
-          if (row < n_rows) v[u] = load4(A + row * lda + kg, kg, in1, a_vec);
+          if (row < n_rows) v[u] = fx.acc ? load4_fixed(fx.acc + row * (int64_t)in1 + kg, kg, in1) : load4(A + row * lda + kg, kg, in1, a_vec);
         } else if (idx < nA + nB) {
           const int r = (idx - nA) % RB, q = (idx - nA) / RB;
           const int kg = kB0 + 4 * q;
@@ -415,6 +432,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
         }
       }
     }
+    if (fx.reset_map && j == 0 && tid < RB && row0 + tid < n_rows) fx.reset_map[s_node[tid]] = 0;
     MLP_T(12);
     __syncthreads();  // As / Hs / Bs / s_node are restaged by the next row tile; every reader is past Red2
     if (tid == 0) mb_expect_tx(&rbar[1], red_bytes);
@@ -423,7 +441,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
 
 template <int TR>
 int launch_cl(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, const int32_t* n_rows_dev,
-              const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace, cudaStream_t st) {
+              const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace, FixedRows fx, cudaStream_t st) {
   constexpr int RB = 4 * TR;
   const ClShape sh = cl_shape(m->d, m->t, m->ws != nullptr, RB);
   const size_t smem = sh.smem_floats * sizeof(float);
@@ -457,22 +475,32 @@ int launch_cl(const float* A, int64_t lda, const float* pe, RowIds base_ids, int
   }
   int64_t clusters = ceil_div(n_rows, RB);
   if (clusters > max_clusters) clusters = max_clusters;  // persistent: the cluster walks row tiles, weights stay resident
-  launch_k(kern, dim3((unsigned)(clusters * kCl)), dim3(sh.nthreads), smem, st, A, lda, pe, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace);
+  launch_k(kern, dim3((unsigned)(clusters * kCl)), dim3(sh.nthreads), smem, st, A, lda, pe, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace, fx);
   return check_launch("pe_mlp_cluster");
 }
 
 }  // namespace
 
-// expected_rows: the typical row count (n_rows is only an upper bound when n_rows_dev carries the real one)
+// expected_rows: the typical row count (n_rows is only an upper bound when n_rows_dev carries the real one).
+// acc_fixed / reset_map: see FixedRows (both NULL: the aggregate is the float matrix A).
 int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          cudaStream_t st) {
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st) {
+  const FixedRows fx{acc_fixed, reset_map};
   // rows per cluster tile: the smallest tile that covers the launch in one round of ~32 co-resident clusters
-  if (expected_rows <= 32 * 16) return launch_cl<4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
-  if (expected_rows <= 32 * 32) return launch_cl<8>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
-  const int rc = launch_cl<12>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
+  if (expected_rows <= 32 * 16) return launch_cl<4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
+  if (expected_rows <= 32 * 32) return launch_cl<8>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
+  const int rc = launch_cl<12>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
   if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
-  return launch_cl<8>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
+  return launch_cl<8>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
+}
+
+// true when the cluster kernel covers this MLP shape (the push form of update_pe phase B depends on it)
+bool pe_mlp_cluster_supports(const lstep_pe_mlp* m) {
+  static const bool off = getenv("LSTEP_MLP_RING") != nullptr || getenv("LSTEP_MLP_TC") != nullptr;
+  if (off || !m) return false;
+  const ClShape sh = cl_shape(m->d, m->t, m->ws != nullptr, 32);
+  return sh.smem_floats * sizeof(float) <= 226 * 1024 && sh.nthreads <= 512 && sh.ncg % kCl == 0;
 }
 
 #ifdef LSTEP_MLP_TIMING

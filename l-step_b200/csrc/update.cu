@@ -23,6 +23,8 @@
 //     serial chain.
 // All gathers of a phase finish (kernel boundary) before its rows are written, which is what
 // makes the in-place write-back safe for nodes that are both source and destination (Q6).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lstep {
@@ -32,6 +34,13 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
                   cudaStream_t st);
 int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int64_t n_valid,
                         int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag, PhaseBHook hook, void* stream);
+int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
+                          const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st);
+bool pe_mlp_cluster_supports(const lstep_pe_mlp* m);
+int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
+                       float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
+                       unsigned long long* acc, uint32_t* err_flag, cudaStream_t st);
 
 constexpr int kRow0Parts = 64;
 constexpr int kHubLen = 4;     // a warp reduces a destination's slot list serially (~430 dependent instructions per
@@ -41,6 +50,7 @@ constexpr int kChunkLog2 = 2;  // slots per chunk task = 4
 struct UpdateWs {
   int32_t* cnt_of;   // [pe_rows]  zero between calls
   int32_t* slot_of;  // [pe_rows]
+  int32_t* claim_of; // [pe_rows]  zero between calls (push form of phase B: 0 free, -1 being set up, j+1 = accumulator row j)
   unsigned long long* hub_acc;  // [#long lists][d+t] 32.32 fixed-point accumulators (zeroed per call by the scan kernel)
   int32_t* counters; // [8]: 0=M, 1=has_zero, 2=n_dest, 3=n_hubs, 4=n_hub_tasks
   int32_t* src32;    // [E]
@@ -58,6 +68,7 @@ struct UpdateWs {
   int32_t* task_chunk;     // [2*N*K/32+2] chunk index of a chunk task
   float* row0_part;  // [kRow0Parts*d]
   float* A;          // [max(N, N*K+1)][lda], lda = d+t rounded up to 4 floats
+  unsigned long long* push_acc;  // [N*K+1][d+t] 32.32 fixed-point accumulator rows of the push form; shares storage with A
   int64_t lda;
   size_t bytes;
 };
@@ -73,6 +84,7 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
   const size_t nk = (size_t)n_ids * K;
   w.cnt_of = (int32_t*)take(sizeof(int32_t) * pe_rows);
   w.slot_of = (int32_t*)take(sizeof(int32_t) * pe_rows);
+  w.claim_of = (int32_t*)take(sizeof(int32_t) * pe_rows);
   w.counters = (int32_t*)take(sizeof(int32_t) * 8);
   w.src32 = (int32_t*)take(sizeof(int32_t) * (n_edges + 4));
   w.dst32 = (int32_t*)take(sizeof(int32_t) * (n_edges + 4));
@@ -91,7 +103,11 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
   w.row0_part = (float*)take(sizeof(float) * kRow0Parts * d);
   const size_t rowsA = nk + 1 > (size_t)n_ids ? nk + 1 : (size_t)n_ids;
   w.lda = (int64_t)align_up((size_t)(d + t), 4);
-  w.A = (float*)take(sizeof(float) * rowsA * w.lda);
+  {
+    const size_t bytesA = sizeof(float) * rowsA * w.lda, bytesAcc = sizeof(unsigned long long) * (nk + 1) * (size_t)(d + t);
+    w.A = (float*)take(bytesA > bytesAcc ? bytesA : bytesAcc);
+    w.push_acc = reinterpret_cast<unsigned long long*>(w.A);  // phase A's rows are consumed before phase B accumulates
+  }
   w.bytes = o;
   return w;
 }
@@ -530,9 +546,11 @@ extern "C" size_t lstep_update_pe_workspace_bytes(int64_t n_ids, int64_t n_edges
 }
 
 extern "C" int lstep_update_pe_workspace_init(void* workspace, size_t workspace_bytes, int64_t pe_rows, void* stream) {
-  if (!workspace || pe_rows <= 0 || workspace_bytes < sizeof(int32_t) * (size_t)pe_rows) return LSTEP_ERR_INVALID_ARG;
-  // the per-node counter map must be zero on entry (every call leaves it zero)
-  cudaError_t e = cudaMemsetAsync(workspace, 0, sizeof(int32_t) * (size_t)pe_rows, as_stream(stream));
+  // the per-node maps at the head of the workspace (counter, slot, claim) must be zero on entry; every call
+  // leaves them zero
+  const size_t head = 3 * align_up(sizeof(int32_t) * (size_t)pe_rows, 256);
+  if (!workspace || pe_rows <= 0 || workspace_bytes < head) return LSTEP_ERR_INVALID_ARG;
+  cudaError_t e = cudaMemsetAsync(workspace, 0, head, as_stream(stream));
   if (e != cudaSuccess) {
     set_cuda_error(e, "workspace_init");
     return LSTEP_ERR_CUDA;
@@ -652,6 +670,24 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
   }
   if ((rc = phase_a(pe, w, ids, n_ids, src, dst, times, n_edges, tc, mlp, st)) != LSTEP_OK) return rc;
   const int64_t n_valid = n_ids < n_edges ? n_ids : n_edges;  // zip(node_ids, times) truncation (Q1)
+  {
+    // phase B, push form (csrc/update_push.cu): lookup + exact fixed-point accumulation where the contribution
+    // lands, then the MLP straight off the accumulator rows. LSTEP_PHASEB_PULL=1 selects the pull form below.
+    static const bool pull = getenv("LSTEP_PHASEB_PULL") != nullptr;
+    if (!pull && (d + t) % 2 == 0 && d <= 256 && t <= 256 && pe_mlp_cluster_supports(mlp)) {
+      rc = launch_phaseB_push(csr, ids, times, n_ids, n_valid, K, pe, d, t, mlp->tw, tc, w.claim_of, w.U, w.counters, w.push_acc,
+                              err_flag, st);
+      if (rc != LSTEP_OK) return rc;
+      const int64_t total = n_ids * (int64_t)K;
+      const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;
+      lstep_pe_mlp noself = *mlp;
+      noself.ws = nullptr;  // the self term is computed and discarded by the reference (LSTEP.py:334-335, Q3)
+      noself.bs = nullptr;
+      noself.ws_tc = nullptr;
+      return launch_pe_mlp_cluster(nullptr, 0, pe, single_ids(w.U), max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe,
+                                   w.push_acc, w.claim_of, st);
+    }
+  }
   if ((rc = phase_b_partial(pe, pe_rows, w, csr, ids, ids, n_ids, times, n_valid, tc, K, mlp, err_flag, stream)) != LSTEP_OK) return rc;
   return phase_b_apply(pe, pe_rows, w, n_ids, K, mlp, st);
 }

@@ -1,0 +1,228 @@
+// update_pe phase B, push form (LSTEP.update_pe, /root/reference/models/LSTEP.py:305-341) — ONE kernel for
+//   nbr, _, nt = sampler(ids, times, K)                       (:306-308, zip truncation Q1/Q1b)
+//   agg2[nbr[i,k]] += [ pe[ids[i]] || cos((tc - nt[i,k]) * w) ]   (:314-322, padded slots: time features zeroed,
+//                                                                  destination 0 collects pe[ids[i]] only)
+// followed by the MLP over the distinct destinations (csrc/mlp_cluster.cu reads the accumulators directly).
+//
+// The pull form in csrc/update.cu builds an inverse index (count -> scan -> fill) and then reduces every
+// destination's slot list in the reference's order: four launches and a single-CTA scan, 40 us of a 110 us
+// step for ~1 MB of useful traffic. Here every contribution is ADDED WHERE IT LANDS:
+//   * one CTA per batch node i: warp 0 does the most-recent-K lookup (same 32-ary search as csrc/sampler.cu);
+//   * each distinct destination u is given a compact accumulator row on first touch: atomicCAS on a per-node
+//     claim map (0 = free, -1 = being set up, j+1 = row j); the winner zeroes the row, fences, and publishes
+//     j+1; later arrivals (in any CTA) spin until the row is published — the winner never waits on anyone;
+//   * contributions are accumulated in 32.32 fixed point with 64-bit integer atomics (RED at L2): integer
+//     addition is associative, so the result is EXACT and independent of arrival order — bit-reproducible
+//     run to run, and one rounding (at the final conversion) instead of one per addition of the
+//     reference's sequential fp32 sum. The padding destination 0 receives z_i * pe[ids[i]] (z_i = number of
+//     padded slots of row i) as one contribution per row.
+// The claim map is returned to all-zero by the MLP kernel once a row has been consumed; U (row -> node id)
+// and the row count (counters[2]) are what the MLP launch reads. Accumulator rows need no invariant: a row
+// is zeroed by whoever claims it.
+#include "common.cuh"
+
+namespace lstep {
+
+constexpr float kFixScale = 4294967296.f;  // 2^32
+
+template <int DQ, int TQ>
+__global__ void __launch_bounds__(128) phaseB_push_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ c_nbr,
+                                                          const double* __restrict__ c_t, int64_t num_rows,
+                                                          const int64_t* __restrict__ ids, const double* __restrict__ q_time,
+                                                          int64_t n_ids, int64_t n_valid, int K, float* pe, int d, int t,
+                                                          const float* __restrict__ tw, float tc, int32_t* claim_of,
+                                                          int64_t* __restrict__ U, int32_t* counters,
+                                                          unsigned long long* acc, uint32_t* err_flag) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);  // [K]
+  float* s_dt = reinterpret_cast<float*>(s_nbr + K);      // [K]  tc - nt (fp32 - fp32, LSTEP.py:314)
+  int32_t* s_slot = reinterpret_cast<int32_t*>(s_dt + K); // [K]  accumulator row of the slot's destination, -1 = padding
+  __shared__ int s_z, s_j0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int in1 = d + t;
+  const int64_t row = blockIdx.x;
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // pe[0] = 0 (LSTEP.py:317); no batch row reads row 0 below
+
+  if (warp == 0) {
+    // ---- lookup: strictly-earlier count by warp-cooperative 32-ary search, last min(K, c) entries right-aligned
+    int64_t end = 0, cnt = 0;
+    if (row < n_valid) {
+      const int64_t node = ids[row];
+      if (node < 0 || node >= num_rows) {
+        if (lane == 0 && err_flag) atomicOr(err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
+      } else {
+        const int64_t lo = indptr[node];
+        int64_t a = lo, b = indptr[node + 1];
+        const double tq = q_time[row];
+        while (b - a > 32) {
+          const int64_t len = b - a;
+          const int64_t p = a + (len * (lane + 1)) / 33;
+          const int jj = __popc(__ballot_sync(kFull, c_t[p] < tq));
+          const int64_t pa = a + (len * jj) / 33, pb = a + (len * (jj + 1)) / 33;
+          if (jj < 32) b = pb;
+          if (jj > 0) a = pa + 1;
+        }
+        const int64_t p = a + lane;
+        const bool less = (p < b) && (c_t[p] < tq);
+        end = a + __popc(__ballot_sync(kFull, less));
+        cnt = end - lo;
+      }
+    }
+    const int take = (int)(cnt < K ? cnt : K);
+    const int pad = K - take;
+    const int64_t first = end - take;
+    // ---- claim an accumulator row per distinct destination
+    int z = 0;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+      const int k = k0 + lane;
+      int32_t u = 0;
+      float dt = 0.f;
+      if (k < K && k >= pad) {
+        const int64_t e = first + (k - pad);
+        u = c_nbr[e];
+        dt = tc - (float)c_t[e];  // neighbour times are returned as fp32 (utils.py:166,208), then fp32 - fp32
+      }
+      const bool active = k < K && u > 0;
+      z += __popc(__ballot_sync(kFull, k < K && u <= 0));
+      const unsigned grp = __match_any_sync(kFull, active ? u : -(lane + 1));
+      const int leader = __ffs(grp) - 1;
+      int j = -1;
+      bool won = false;
+      if (active && lane == leader) {
+        const int old = atomicCAS(claim_of + u, 0, -1);
+        if (old == 0) {
+          j = atomicAdd(counters + 2, 1);
+          U[j] = (int64_t)u;
+          won = true;
+        } else if (old > 0) {
+          j = old - 1;
+        }
+      }
+      // winners' rows are zeroed by the whole warp before they are published
+      unsigned wm = __ballot_sync(kFull, won);
+      while (wm) {
+        const int src = __ffs(wm) - 1;
+        wm &= wm - 1;
+        const int jj = __shfl_sync(kFull, j, src);
+        ulonglong2* zr = reinterpret_cast<ulonglong2*>(acc + (size_t)jj * in1);  // in1 even: 16-byte rows
+        for (int c = lane; c < in1 / 2; c += 32) zr[c] = make_ulonglong2(0ull, 0ull);
+      }
+      __threadfence();
+      __syncwarp();
+      if (won) atomicExch(claim_of + u, j + 1);
+      if (active && lane == leader && j < 0) {  // someone else is setting the row up: wait for its number
+        int v;
+        unsigned spins = 0;
+        do {
+          v = atomicAdd(claim_of + u, 0);
+          if (++spins > (1u << 26)) __trap();
+        } while (v <= 0);
+        j = v - 1;
+      }
+      j = __shfl_sync(kFull, j, leader);
+      if (k < K) {
+        s_nbr[k] = u;
+        s_dt[k] = dt;
+        s_slot[k] = active ? j : -1;
+      }
+    }
+    // ---- the padding destination: node 0 collects z * pe[ids[row]]
+    int j0 = -1;
+    if (z > 0) {
+      bool won = false;
+      if (lane == 0) {
+        const int old = atomicCAS(claim_of + 0, 0, -1);
+        if (old == 0) {
+          j0 = atomicAdd(counters + 2, 1);
+          U[j0] = 0;
+          won = true;
+        } else if (old > 0) {
+          j0 = old - 1;
+        }
+      }
+      won = __shfl_sync(kFull, (int)won, 0) != 0;
+      if (won) {
+        const int jj = __shfl_sync(kFull, j0, 0);
+        ulonglong2* zr = reinterpret_cast<ulonglong2*>(acc + (size_t)jj * in1);
+        for (int c = lane; c < in1 / 2; c += 32) zr[c] = make_ulonglong2(0ull, 0ull);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicExch(claim_of + 0, j0 + 1);
+      } else if (lane == 0 && j0 < 0) {
+        int v;
+        unsigned spins = 0;
+        do {
+          v = atomicAdd(claim_of + 0, 0);
+          if (++spins > (1u << 26)) __trap();
+        } while (v <= 0);
+        j0 = v - 1;
+      }
+    }
+    if (lane == 0) {
+      s_z = z;
+      s_j0 = j0;
+    }
+  }
+  __syncthreads();
+
+  // ---- this row's PE in fixed point (phase-A table), once per warp
+  const int64_t node = ids[row];
+  long long fx[DQ];
+#pragma unroll
+  for (int q = 0; q < DQ; ++q) {
+    const int c = lane + 32 * q;
+    fx[q] = (c < d && node > 0) ? __float2ll_rn(ld_dep(pe + node * (int64_t)d + c) * kFixScale) : 0ll;
+  }
+  float w[TQ];
+#pragma unroll
+  for (int q = 0; q < TQ; ++q) w[q] = (lane + 32 * q < t) ? tw[lane + 32 * q] : 0.f;
+
+  for (int k = warp; k < K; k += nwarps) {
+    const int j = s_slot[k];
+    if (j < 0) continue;
+    unsigned long long* rowp = acc + (size_t)j * in1;
+    const float dt = s_dt[k];
+#pragma unroll
+    for (int q = 0; q < DQ; ++q) {
+      const int c = lane + 32 * q;
+      if (c < d) atomicAdd(rowp + c, (unsigned long long)fx[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < TQ; ++q) {
+      const int jf = lane + 32 * q;
+      if (jf < t) atomicAdd(rowp + d + jf, (unsigned long long)__float2ll_rn(time_feature(dt, w[q]) * kFixScale));
+    }
+  }
+  if (s_z > 0 && warp == nwarps - 1) {
+    unsigned long long* rowp = acc + (size_t)s_j0 * in1;
+    const long long zz = s_z;
+#pragma unroll
+    for (int q = 0; q < DQ; ++q) {
+      const int c = lane + 32 * q;
+      if (c < d) atomicAdd(rowp + c, (unsigned long long)(zz * fx[q]));
+    }
+  }
+}
+
+// enqueue the push kernel; on return (stream order) acc rows [0, counters[2]) hold the aggregates of the
+// destinations U[0 .. counters[2])
+int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
+                       float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
+                       unsigned long long* acc, uint32_t* err_flag, cudaStream_t st) {
+  if (!csr || !ids || !q_time || n_ids <= 0 || K <= 0 || (d + t) % 2 != 0) return LSTEP_ERR_INVALID_ARG;
+  const size_t smem = (size_t)K * 12;
+  if (d <= 6 * 32 && t <= 4 * 32)
+    launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)n_ids), dim3(128), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, err_flag);
+  else if (d <= 8 * 32 && t <= 8 * 32)
+    launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)n_ids), dim3(128), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, err_flag);
+  else
+    return LSTEP_ERR_UNSUPPORTED;
+  return check_launch("phaseB_push");
+}
+
+}  // namespace lstep
