@@ -10,13 +10,24 @@
 
 namespace lstep {
 
-template <int VEC>
+// kLookup: the kernel does the most-recent-K lookup itself (warp 0, warp_recent_range) instead of reading the
+// sampler's output — the streaming step's form: one launch and no [rows, K] round trip through global memory.
+struct LookupArgs {
+  const int64_t* indptr;
+  const int32_t* c_nbr;
+  const double* c_t;
+  int64_t num_rows;
+  RowIds q_node;
+  uint32_t* err_flag;
+};
+
+template <int VEC, bool kLookup>
 __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restrict__ pe,
                                                             const double* __restrict__ q_time,
                                                             const int32_t* __restrict__ nbr,
                                                             const float* __restrict__ nbr_t, int64_t n_rows, int K,
                                                             const float* __restrict__ tw, int d, int t, int t_pad,
-                                                            float* __restrict__ S, int64_t ldS, int64_t period) {
+                                                            float* __restrict__ S, int64_t ldS, int64_t period, LookupArgs lk) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -26,10 +37,35 @@ __global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restr
   const int dvec = d / VEC;
   for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
     const double tq = q_time[period ? row % period : row];
-    for (int k = tid; k < K; k += blockDim.x) {
-      s_nbr[k] = ld_dep(nbr + row * K + k);
-      // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
-      s_dt[k] = (float)(tq - (double)ld_dep(nbr_t + row * K + k));
+    if (kLookup) {
+      if (tid < 32) {
+        const int64_t node = lk.q_node.at(row);
+        int64_t first = 0;
+        int take = 0;
+        if (node < 0 || node >= lk.num_rows) {
+          if (tid == 0 && lk.err_flag) atomicOr(lk.err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
+        } else {
+          warp_recent_range(lk.indptr, lk.c_t, node, tq, K, tid, first, take);
+        }
+        const int pad = K - take;
+        for (int k = tid; k < K; k += 32) {
+          int32_t n = 0;
+          float tt = 0.f;
+          if (k >= pad) {
+            const int64_t e = first + (k - pad);
+            n = lk.c_nbr[e];
+            tt = (float)lk.c_t[e];  // the sampler returns fp32 times (utils.py:166,208)
+          }
+          s_nbr[k] = n;
+          s_dt[k] = (float)(tq - (double)tt);  // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
+        }
+      }
+    } else {
+      for (int k = tid; k < K; k += blockDim.x) {
+        s_nbr[k] = ld_dep(nbr + row * K + k);
+        // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
+        s_dt[k] = (float)(tq - (double)ld_dep(nbr_t + row * K + k));
+      }
     }
     __syncthreads();
     if (tid < t) {
@@ -93,9 +129,9 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
 
 static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 
-int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* nbr, const float* nbr_t,
-                         int64_t n_rows, int K, const float* tw, int d, int t, float* S, int64_t ldS, int64_t period,
-                         cudaStream_t st) {
+template <bool kLookup>
+static int launch_nbr_aggregate_t(const float* pe, const double* q_time, const int32_t* nbr, const float* nbr_t, int64_t n_rows, int K,
+                                  const float* tw, int d, int t, float* S, int64_t ldS, int64_t period, LookupArgs lk, cudaStream_t st) {
   const bool v4 = d % 4 == 0 && ldS % 4 == 0 && aligned16(pe) && aligned16(S);
   const int dvec = v4 ? d / 4 : d;
   const int t_pad = (int)align_up((size_t)t, 32);
@@ -105,10 +141,26 @@ int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* n
   if (smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
   const int64_t grid = n_rows < (int64_t)kNumSMs * 16 ? n_rows : (int64_t)kNumSMs * 16;
   if (v4)
-    launch_k(nbr_aggregate_kernel<4>, dim3((unsigned)grid), dim3(threads), smem, st, pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period);
+    launch_k(nbr_aggregate_kernel<4, kLookup>, dim3((unsigned)grid), dim3(threads), smem, st, pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t,
+             t_pad, S, ldS, period, lk);
   else
-    launch_k(nbr_aggregate_kernel<1>, dim3((unsigned)grid), dim3(threads), smem, st, pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period);
+    launch_k(nbr_aggregate_kernel<1, kLookup>, dim3((unsigned)grid), dim3(threads), smem, st, pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t,
+             t_pad, S, ldS, period, lk);
   return check_launch("nbr_aggregate");
+}
+
+int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* nbr, const float* nbr_t,
+                         int64_t n_rows, int K, const float* tw, int d, int t, float* S, int64_t ldS, int64_t period,
+                         cudaStream_t st) {
+  return launch_nbr_aggregate_t<false>(pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, S, ldS, period, LookupArgs{}, st);
+}
+
+// lookup + aggregate in one launch (row r: node q_node.at(r), time q_time[q_node.time_index(r)])
+int launch_nbr_lookup_aggregate(const lstep_csr* csr, RowIds q_node, const float* pe, const double* q_time, int64_t n_rows, int K,
+                                const float* tw, int d, int t, float* S, int64_t ldS, uint32_t* err_flag, cudaStream_t st) {
+  if (!csr || K <= 0 || !q_node.p[0] || !q_time) return LSTEP_ERR_INVALID_ARG;
+  LookupArgs lk{csr->indptr, csr->nbr, csr->t, csr->num_rows, q_node, err_flag};
+  return launch_nbr_aggregate_t<true>(pe, q_time, nullptr, nullptr, n_rows, K, tw, d, t, S, ldS, q_node.period, lk, st);
 }
 
 }  // namespace lstep

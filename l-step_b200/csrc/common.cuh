@@ -101,6 +101,31 @@ inline RowIds single_ids(const int64_t* ids) {
   return r;
 }
 
+// Most-recent-K lookup of one (node, time) query by a full warp over the time-sorted CSR row of `node`
+// (utils/utils.py:129-146): c = #entries with t < tq (strict, fp64) by a 32-ary search — each step the 32
+// lanes probe 32 interior pivots and a ballot shrinks the range 33x — then the last take = min(K, c) entries
+// are [first, first + take). All 32 lanes must call it with the same arguments.
+__device__ __forceinline__ void warp_recent_range(const int64_t* __restrict__ indptr, const double* __restrict__ c_t, int64_t node,
+                                                  double tq, int K, int lane, int64_t& first, int& take) {
+  const int64_t lo = indptr[node];
+  int64_t a = lo, b = indptr[node + 1];
+  // invariant: entries < a are earlier than tq, entries >= b are not
+  while (b - a > 32) {
+    const int64_t len = b - a;
+    const int64_t p = a + (len * (lane + 1)) / 33;
+    const int j = __popc(__ballot_sync(kFull, c_t[p] < tq));
+    const int64_t pa = a + (len * j) / 33, pb = a + (len * (j + 1)) / 33;
+    if (j < 32) b = pb;
+    if (j > 0) a = pa + 1;
+  }
+  const int64_t p = a + lane;
+  const bool less = (p < b) && (c_t[p] < tq);
+  const int64_t end = a + __popc(__ballot_sync(kFull, less));
+  const int64_t cnt = end - lo;
+  take = (int)(cnt < K ? cnt : K);
+  first = end - take;
+}
+
 // Optional tail of the lookup kernel used by update_pe phase B: while a row's K neighbours are still in
 // registers, count them per destination (integer atomics on the per-node map), record the arrival rank
 // and the list of distinct destinations, flag padding; block 0 also zeroes pe[0] (LSTEP.py:317).

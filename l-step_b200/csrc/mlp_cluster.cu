@@ -275,10 +275,18 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   auto load4_fixed = [&](const unsigned long long* p, int kg, int lim) {
     constexpr float kInv = 2.3283064365386963e-10f;  // 2^-32
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (kg + 0 < lim) v.x = (float)(long long)__ldcg(p + 0) * kInv;
-    if (kg + 1 < lim) v.y = (float)(long long)__ldcg(p + 1) * kInv;
-    if (kg + 2 < lim) v.z = (float)(long long)__ldcg(p + 2) * kInv;
-    if (kg + 3 < lim) v.w = (float)(long long)__ldcg(p + 3) * kInv;
+    if (kg + 3 < lim && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+      const ulonglong2 a = __ldcg(reinterpret_cast<const ulonglong2*>(p)), b = __ldcg(reinterpret_cast<const ulonglong2*>(p) + 1);
+      v.x = (float)(long long)a.x * kInv;
+      v.y = (float)(long long)a.y * kInv;
+      v.z = (float)(long long)b.x * kInv;
+      v.w = (float)(long long)b.y * kInv;
+    } else {
+      if (kg + 0 < lim) v.x = (float)(long long)__ldcg(p + 0) * kInv;
+      if (kg + 1 < lim) v.y = (float)(long long)__ldcg(p + 1) * kInv;
+      if (kg + 2 < lim) v.z = (float)(long long)__ldcg(p + 2) * kInv;
+      if (kg + 3 < lim) v.w = (float)(long long)__ldcg(p + 3) * kInv;
+    }
     return v;
   };
   auto put4 = [&](float* dst, float4 v) {

@@ -17,8 +17,8 @@ namespace lstep {
 template <typename IdT, bool kWithEid>
 int launch_sample(const lstep_csr* csr, RowIds q_node, const double* q_time, int64_t n_rows, int64_t n_valid, int K,
                   IdT* out_nbr, IdT* out_eid, float* out_t, uint32_t* err_flag, void* stream);
-int launch_nbr_aggregate(const float* pe, const double* q_time, const int32_t* nbr, const float* nbr_t, int64_t n_rows,
-                         int K, const float* tw, int d, int t, float* S, int64_t ldS, int64_t period, cudaStream_t st);
+int launch_nbr_lookup_aggregate(const lstep_csr* csr, RowIds q_node, const float* pe, const double* q_time, int64_t n_rows, int K,
+                                const float* tw, int d, int t, float* S, int64_t ldS, uint32_t* err_flag, cudaStream_t st);
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st);
@@ -145,9 +145,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
       q.p[c] = query_ids_host[c];
     }
     q.period = n_edges;
-    rc = launch_sample<int32_t, false>(csr, q, tq, rows, rows, K, w.nbrQ, nullptr, w.ntQ, err_flag, stream);
-    if (rc != LSTEP_OK) return rc;
-    rc = launch_nbr_aggregate(s->cur, tq, w.nbrQ, w.ntQ, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, n_edges, st);
+    rc = launch_nbr_lookup_aggregate(csr, q, s->cur, tq, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, err_flag, st);
     if (rc != LSTEP_OK) return rc;
     rc = launch_pe_mlp(w.S, w.lda, s->cur, q, rows, rows, nullptr, mlp_nbr, nbr_out, d, nullptr, st);
     if (rc != LSTEP_OK) return rc;

@@ -7,7 +7,9 @@
 // The pull form in csrc/update.cu builds an inverse index (count -> scan -> fill) and then reduces every
 // destination's slot list in the reference's order: four launches and a single-CTA scan, 40 us of a 110 us
 // step for ~1 MB of useful traffic. Here every contribution is ADDED WHERE IT LANDS:
-//   * one CTA per batch node i: warp 0 does the most-recent-K lookup (same 32-ary search as csrc/sampler.cu);
+//   * kPushSplit small CTAs per batch node i, each owning a quarter of the K slots (the SM-side issue rate of
+//     64-bit reductions, ~1.3 cycles per lane, is what bounds the kernel: many small CTAs spread it evenly over
+//     the 148 SMs); warp 0 of each does the most-recent-K lookup (same 32-ary search as csrc/sampler.cu);
 //   * each distinct destination u is given a compact accumulator row on first touch: atomicCAS on a per-node
 //     claim map (0 = free, -1 = being set up, j+1 = row j); the winner zeroes the row, fences, and publishes
 //     j+1; later arrivals (in any CTA) spin until the row is published — the winner never waits on anyone;
@@ -24,9 +26,11 @@
 namespace lstep {
 
 constexpr float kFixScale = 4294967296.f;  // 2^32
+constexpr int kPushSplit = 4;              // CTAs per batch node
+constexpr int kPushThreads = 64;
 
 template <int DQ, int TQ>
-__global__ void __launch_bounds__(128) phaseB_push_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ c_nbr,
+__global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ c_nbr,
                                                           const double* __restrict__ c_t, int64_t num_rows,
                                                           const int64_t* __restrict__ ids, const double* __restrict__ q_time,
                                                           int64_t n_ids, int64_t n_valid, int K, float* pe, int d, int t,
@@ -36,13 +40,18 @@ __global__ void __launch_bounds__(128) phaseB_push_kernel(const int64_t* __restr
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);  // [K]
-  float* s_dt = reinterpret_cast<float*>(s_nbr + K);      // [K]  tc - nt (fp32 - fp32, LSTEP.py:314)
-  int32_t* s_slot = reinterpret_cast<int32_t*>(s_dt + K); // [K]  accumulator row of the slot's destination, -1 = padding
+  const int Kcap = (K + kPushSplit - 1) / kPushSplit;
+  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);     // [Kcap] this CTA's slots
+  float* s_dt = reinterpret_cast<float*>(s_nbr + Kcap);      // [Kcap]  tc - nt (fp32 - fp32, LSTEP.py:314)
+  int32_t* s_slot = reinterpret_cast<int32_t*>(s_dt + Kcap); // [Kcap]  accumulator row of the slot's destination, -1 = padding
   __shared__ int s_z, s_j0;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int in1 = d + t;
-  const int64_t row = blockIdx.x;
+  const int64_t row = blockIdx.x / kPushSplit;
+  const int part = blockIdx.x % kPushSplit;
+  const int Kp = (K + kPushSplit - 1) / kPushSplit;
+  const int k_lo = min(K, part * Kp), k_hi = min(K, k_lo + Kp);  // this CTA's slots
+  if (k_lo >= k_hi) return;
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // pe[0] = 0 (LSTEP.py:317); no batch row reads row 0 below
 
@@ -76,17 +85,17 @@ __global__ void __launch_bounds__(128) phaseB_push_kernel(const int64_t* __restr
     const int64_t first = end - take;
     // ---- claim an accumulator row per distinct destination
     int z = 0;
-    for (int k0 = 0; k0 < K; k0 += 32) {
+    for (int k0 = k_lo; k0 < k_hi; k0 += 32) {
       const int k = k0 + lane;
       int32_t u = 0;
       float dt = 0.f;
-      if (k < K && k >= pad) {
+      if (k < k_hi && k >= pad) {
         const int64_t e = first + (k - pad);
         u = c_nbr[e];
         dt = tc - (float)c_t[e];  // neighbour times are returned as fp32 (utils.py:166,208), then fp32 - fp32
       }
-      const bool active = k < K && u > 0;
-      z += __popc(__ballot_sync(kFull, k < K && u <= 0));
+      const bool active = k < k_hi && u > 0;
+      z += __popc(__ballot_sync(kFull, k < k_hi && u <= 0));
       const unsigned grp = __match_any_sync(kFull, active ? u : -(lane + 1));
       const int leader = __ffs(grp) - 1;
       int j = -1;
@@ -123,10 +132,10 @@ __global__ void __launch_bounds__(128) phaseB_push_kernel(const int64_t* __restr
         j = v - 1;
       }
       j = __shfl_sync(kFull, j, leader);
-      if (k < K) {
-        s_nbr[k] = u;
-        s_dt[k] = dt;
-        s_slot[k] = active ? j : -1;
+      if (k < k_hi) {
+        s_nbr[k - k_lo] = u;
+        s_dt[k - k_lo] = dt;
+        s_slot[k - k_lo] = active ? j : -1;
       }
     }
     // ---- the padding destination: node 0 collects z * pe[ids[row]]
@@ -180,7 +189,7 @@ __global__ void __launch_bounds__(128) phaseB_push_kernel(const int64_t* __restr
 #pragma unroll
   for (int q = 0; q < TQ; ++q) w[q] = (lane + 32 * q < t) ? tw[lane + 32 * q] : 0.f;
 
-  for (int k = warp; k < K; k += nwarps) {
+  for (int k = warp; k < k_hi - k_lo; k += nwarps) {
     const int j = s_slot[k];
     if (j < 0) continue;
     unsigned long long* rowp = acc + (size_t)j * in1;
@@ -213,12 +222,12 @@ int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
                        unsigned long long* acc, uint32_t* err_flag, cudaStream_t st) {
   if (!csr || !ids || !q_time || n_ids <= 0 || K <= 0 || (d + t) % 2 != 0) return LSTEP_ERR_INVALID_ARG;
-  const size_t smem = (size_t)K * 12;
+  const size_t smem = (size_t)((K + kPushSplit - 1) / kPushSplit) * 12;
   if (d <= 6 * 32 && t <= 4 * 32)
-    launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)n_ids), dim3(128), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
+    launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
              q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, err_flag);
   else if (d <= 8 * 32 && t <= 8 * 32)
-    launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)n_ids), dim3(128), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
+    launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
              q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, err_flag);
   else
     return LSTEP_ERR_UNSUPPORTED;
