@@ -125,6 +125,15 @@ __host__ __device__ inline ClShape cl_shape(int d, int t, bool has_self, int RB)
 template <int TR>
 __device__ __forceinline__ void k_run(const float* __restrict__ w, int ldo, const float* __restrict__ a, int RBp, int kn,
                                       float (&acc)[TR][4]) {
+  // Accumulators are kept as row PAIRS so that one packed FFMA2 (fma.rn.f32x2, sm_100: two IEEE fp32 FMAs per
+  // issue slot, each bit-identical to fmaf) updates rows 2p and 2p+1 of a column: the activation pair comes
+  // straight out of the 128-bit shared load, the weight is duplicated once per column and k step. The loop is
+  // issue bound (32 FMAs + 3 loads per k step and warp), so halving the FMA instructions is the lever.
+  float2 acc2[TR / 2][4];
+#pragma unroll
+  for (int p = 0; p < TR / 2; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc2[p][c] = make_float2(acc[2 * p][c], acc[2 * p + 1][c]);
   float4 wv = *reinterpret_cast<const float4*>(w);
   float4 av[TR / 4];
 #pragma unroll
@@ -137,21 +146,27 @@ __device__ __forceinline__ void k_run(const float* __restrict__ w, int ldo, cons
     float4 an[TR / 4];
 #pragma unroll
     for (int q = 0; q < TR / 4; ++q) an[q] = *reinterpret_cast<const float4*>(a + 4 * q);
+    const float2 wd[4] = {make_float2(wv.x, wv.x), make_float2(wv.y, wv.y), make_float2(wv.z, wv.z), make_float2(wv.w, wv.w)};
 #pragma unroll
     for (int q = 0; q < TR / 4; ++q) {
-      const float ar[4] = {av[q].x, av[q].y, av[q].z, av[q].w};
+      const float2 lo = make_float2(av[q].x, av[q].y), hi = make_float2(av[q].z, av[q].w);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc[4 * q + u][0] = fmaf(ar[u], wv.x, acc[4 * q + u][0]);
-        acc[4 * q + u][1] = fmaf(ar[u], wv.y, acc[4 * q + u][1]);
-        acc[4 * q + u][2] = fmaf(ar[u], wv.z, acc[4 * q + u][2]);
-        acc[4 * q + u][3] = fmaf(ar[u], wv.w, acc[4 * q + u][3]);
+      for (int c = 0; c < 4; ++c) {
+        acc2[2 * q][c] = __ffma2_rn(lo, wd[c], acc2[2 * q][c]);
+        acc2[2 * q + 1][c] = __ffma2_rn(hi, wd[c], acc2[2 * q + 1][c]);
       }
     }
     wv = wn;
 #pragma unroll
     for (int q = 0; q < TR / 4; ++q) av[q] = an[q];
   }
+#pragma unroll
+  for (int p = 0; p < TR / 2; ++p)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      acc[2 * p][c] = acc2[p][c].x;
+      acc[2 * p + 1][c] = acc2[p][c].y;
+    }
 }
 
 template <int TR>
