@@ -42,6 +42,13 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def clk_ghz(clk):
+    try:
+        return float(clk["sm_mhz"]) * 1e-3
+    except Exception:
+        return 1.965
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -194,15 +201,31 @@ def run_ours(args, rank, world):
     M_mean = float(np.mean(M_meas)) if M_meas else 0.0
     bm = bytes_model(B, N_mean, M_mean, K, V1=V1)
     hbm_peak, peak_src = peaks()
-    # dominant kernel: the one with the largest share of the step
-    dom = max((k for k in kern if not k.startswith("_")), key=lambda k: kern[k]["ms"])
-    alg = {"dft_filter": bm["F"], "nbr_aggregate": bm["P"], "sample_recent": bm["S"] * (C_CALLS * B / (C_CALLS * B + N_mean)),
-           "pe_mlp(nbr)": (C_CALLS * B * 4 * D * 3 + 4 * ((D + T_DIM) * D + 2 * D * D))}
-    roof = None
-    if dom in alg:
-        ach = alg[dom] / (kern[dom]["ms"] * 1e-3) / 1e9
-        roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom], "ms_per_launch": kern[dom]["ms"]}
+    # per-kernel algorithmic bytes (SURVEY §8(d) terms split by kernel; W/2 = the three packed matrices of one MLP)
+    CB = C_CALLS * B
+    alg = {"dft_filter": bm["F"],
+           "nbr_lookup_aggregate": CB * (16 + 16 * K) + CB * 4 * D * K + CB * 4 * (D + T_DIM),
+           "pe_mlp(nbr)": CB * 4 * (D + T_DIM) + 2 * CB * 4 * D + bm["W"] / 2,
+           "ring_append": bm["H"]}
+    ncu_full = {}
+    try:  # DRAM traffic per launch from the committed `ncu --set full` capture of this command (profiles/)
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_kernels.json")) as f:
+            ncu_full = {e["stage"]: e for e in json.load(f) if "stage" in e}
+    except Exception:
+        pass
+    roof_all = {}
+    for k in alg:
+        ach = alg[k] / (kern[k]["ms"] * 1e-3) / 1e9
+        roof_all[k] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                       "traffic": ncu_full.get(k, {}).get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": alg[k],
+                       "ms_per_launch": kern[k]["ms"]}
+    # dominant kernel: the single kernel with the largest share of the step
+    dom = max(alg, key=lambda k: kern[k]["ms"])
+    roof = dict(kernel=dom, peak_source=peak_src, **roof_all[dom])
+    if dom.startswith("pe_mlp"):  # an fp32 FMA kernel: its HBM fraction is not the binding roofline; also state the one that is
+        flops = 2.0 * CB * ((D + T_DIM) * D + 2 * D * D)
+        roof["fp32_fma"] = {"achieved_tflops": flops / (kern[dom]["ms"] * 1e-3) / 1e12, "peak_tflops": 148 * 128 * 2 * clk_ghz(clk),
+                            "note": "fp32 SIMT peak = 148 SMs x 128 FMA/clk x SM clock; 1e-5 parity rules out single-pass TF32/BF16 tensor math"}
     path_gbs = bm["bytes_path"] / (ms_total_max / Ksteps * 1e-3) / 1e9
 
     # ---- end to end through the host-facing API (numpy in, result out), same stream / model
@@ -228,6 +251,7 @@ def run_ours(args, rank, world):
             "e2e": e2e,
             "gpu_launches": int(kern["_launches_per_step"]["n"] * Ksteps),
             "roofline": roof,
+            "roofline_kernels": roof_all,
             "path_roofline": {"bytes_path_per_step": bm["bytes_path"], "bytes_breakdown": {k: bm[k] for k in ("F", "S", "P", "UA", "UB", "W", "H")},
                               "achieved_GBps": path_gbs, "peak_GBps": hbm_peak, "frac": path_gbs / hbm_peak, "peak_source": peak_src},
             "stages_ms": stages, "kernels_ms": {k: v for k, v in kern.items() if not k.startswith("_")},
@@ -358,15 +382,16 @@ def run_sharded(args, rank, world):
 
 
 def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, lib):
-    """Stand-alone CUDA-event times of the kernels of one step, each through its own C-ABI entry point
-    on the live state of the stream (the update runs on a scratch copy of the table); the stream is
-    then advanced by a normal step so the next measurement sees fresh data."""
+    """Stand-alone CUDA-event durations of the kernels of one step, each through its own C-ABI entry point on
+    the live state of the stream (the update runs on a scratch copy of the table). The GPU is kept busy by a
+    spin kernel while the measured launches are enqueued, so an event pair brackets the kernel itself and not
+    the host's launch latency; the stream is then advanced by a normal step so the next sample sees fresh data."""
     import torch
     from lstep_b200 import _lib
     m = model
     T, d, t = T_HIST, D, T_DIM
-    acc = {"dft_filter": 0.0, "sample_recent": 0.0, "nbr_aggregate": 0.0, "pe_mlp(nbr)": 0.0, "update_pe(4 kernels)": 0.0,
-           "ring_append": 0.0}
+    names = ["dft_filter", "nbr_lookup_aggregate", "pe_mlp(nbr)", "update_pe(4 kernels)", "ring_append"]
+    acc = {k: 0.0 for k in names}
     M_meas = []
 
     def timed(fn):
@@ -396,34 +421,32 @@ def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, l
             rows = qcat.shape[0]
             G = m._collapsed_filter(T if stream.len >= T else min(stream.batch_idx, T), False)
             fft = torch.empty((N, d), dtype=torch.float32, device=dev)
-            nbr = torch.empty((rows, K), dtype=torch.int32, device=dev)
-            nt = torch.empty((rows, K), dtype=torch.float32, device=dev)
             S = torch.empty((rows, d + t), dtype=torch.float32, device=dev)
             outb = torch.empty((rows, d), dtype=torch.float32, device=dev)
+            nxt = (stream.head + stream.len) % T if stream.len < T else stream.head  # the slot the coming step overwrites anyway
             scratch.copy_(stream.cur)
             torch.cuda.synchronize()
+            torch.cuda._sleep(400_000)  # ~0.2 ms of GPU spin: everything below is queued before it ends
             ev = {}
             ev["dft_filter"] = timed(lambda: _lib.check(lib.lstep_dft_filter(_lib.ptr(stream.ring), T * d, d, stream.head, T, stream.len, d,
                                                                             _lib.ptr(ids), N, _lib.ptr(G), _lib.ptr(fft), d, _lib.stream_ptr()), "dft"))
-            ev["sample_recent"] = timed(lambda: _lib.check(lib.lstep_sample_recent_compact(sampler.csr_ref, _lib.ptr(qcat), _lib.ptr(tcat), rows, rows, K,
-                                                                                          _lib.ptr(nbr), _lib.ptr(nt), _lib.ptr(sampler._err),
-                                                                                          _lib.stream_ptr()), "k1"))
-            ev["nbr_aggregate"] = timed(lambda: _lib.check(lib.lstep_nbr_aggregate(_lib.ptr(stream.cur), stream.V1, _lib.ptr(tcat), _lib.ptr(nbr), _lib.ptr(nt),
-                                                                                  rows, K, _lib.ptr(tw), d, t, _lib.ptr(S), _lib.stream_ptr()), "agg"))
+            ev["nbr_lookup_aggregate"] = timed(lambda: _lib.check(lib.lstep_nbr_lookup_aggregate(
+                sampler.csr_ref, _lib.ptr(qcat), _lib.ptr(tcat), rows, K, _lib.ptr(stream.cur), stream.V1, _lib.ptr(tw), d, t, _lib.ptr(S),
+                _lib.ptr(sampler._err), _lib.stream_ptr()), "agg"))
             ev["pe_mlp(nbr)"] = timed(lambda: _lib.check(lib.lstep_pe_mlp_apply(_lib.ptr(S), _lib.ptr(stream.cur), _lib.ptr(qcat), rows, m._mlp_ref("nbr"),
                                                                                _lib.ptr(outb), d, None, _lib.stream_ptr()), "mlp"))
             ev["update_pe(4 kernels)"] = timed(lambda: m.update_pe_device(scratch, ids, src, dst, tt, stream.batch_tmax[b], K))
-            nxt = (stream.head + stream.len) % T if stream.len < T else stream.head  # the slot the coming step overwrites anyway
-            ev["ring_append"] = timed(lambda: stream.ring[:, nxt, :].copy_(stream.cur))
+            ev["ring_append"] = timed(lambda: _lib.check(lib.lstep_ring_copy_rows(_lib.ptr(stream.ring), _lib.ptr(stream.cur), stream.V1, T, d, nxt, 1, 0, 1,
+                                                                                 _lib.stream_ptr()), "append"))
             torch.cuda.synchronize()
             stream.step(b, qs)  # advance the recurrence (untimed here; the main loop times whole steps)
             for k2, (a, bb, _) in ev.items():
                 acc[k2] += a.elapsed_time(bb)
     stages = {k2: v / n for k2, v in acc.items()}
     kern = {"dft_filter": {"ms": stages["dft_filter"], "launches_per_step": 1},
-            "sample_recent": {"ms": stages["sample_recent"], "launches_per_step": 2},
-            "nbr_aggregate": {"ms": stages["nbr_aggregate"], "launches_per_step": 1},
+            "nbr_lookup_aggregate": {"ms": stages["nbr_lookup_aggregate"], "launches_per_step": 1},
             "pe_mlp(nbr)": {"ms": stages["pe_mlp(nbr)"], "launches_per_step": 1},
+            "ring_append": {"ms": stages["ring_append"], "launches_per_step": 1},
             # own kernels per step (csrc/step.cu): DFT filter 1; a6 2 (lookup + aggregate, MLP; all C query sets per
             # launch); update_pe 4 (phase A edge aggregate, MLP; phase B push, MLP); ring append 1
             "_launches_per_step": {"n": 1 + 2 + 4 + 1, "ms": 0.0, "launches_per_step": 0}}

@@ -160,6 +160,11 @@ typedef struct lstep_pe_mlp {
 int lstep_nbr_aggregate(const float* pe, int64_t pe_rows, const double* q_time, const int32_t* nbr,
                         const float* nbr_t, int64_t n_rows, int K, const float* tw, int d, int t, float* S,
                         void* stream);
+/* Lookup + aggregate in one launch (the streaming step's form): row i looks up the K most recent neighbours of
+ * (q_node[i], q_time[i]) itself, as lstep_sample_recent would, and writes S[i] (row pitch d + t). */
+int lstep_nbr_lookup_aggregate(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int K,
+                               const float* pe, int64_t pe_rows, const float* tw, int d, int t, float* S,
+                               uint32_t* err_flag, void* stream);
 int lstep_nbr_aggregate_bwd(const float* dS, const int32_t* nbr, int64_t n_rows, int K, int d, int t, float* dpe,
                             int64_t pe_rows, void* stream);
 int lstep_neighborhood_pe(const float* pe, int64_t pe_rows, const int64_t* q_node, const double* q_time,

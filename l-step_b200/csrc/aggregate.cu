@@ -201,3 +201,12 @@ extern "C" int lstep_neighborhood_pe(const float* pe, int64_t pe_rows, const int
   if (rc != LSTEP_OK) return rc;
   return launch_pe_mlp(S, ldS, pe, single_ids(q_node), n_rows, n_rows, nullptr, mlp, out, mlp->d, nullptr, as_stream(stream));
 }
+
+extern "C" int lstep_nbr_lookup_aggregate(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int K,
+                                          const float* pe, int64_t pe_rows, const float* tw, int d, int t, float* S,
+                                          uint32_t* err_flag, void* stream) {
+  if (n_rows < 0 || K <= 0 || d <= 0 || t < 0 || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
+  if (n_rows == 0) return LSTEP_OK;
+  if (!csr || !pe || !q_node || !q_time || !S || (t > 0 && !tw)) return LSTEP_ERR_INVALID_ARG;
+  return launch_nbr_lookup_aggregate(csr, single_ids(q_node), pe, q_time, n_rows, K, tw, d, t, S, d + t, err_flag, as_stream(stream));
+}
