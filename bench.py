@@ -519,8 +519,8 @@ def e2e_pass(stream, g, e0, neg_all, step_no, nb, n, B, world, dev):
     return {"value": float(et.item()) / (float(tm.item()) * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d / n,
             "d2h_bytes_per_step": d2h / n, "steps": n, "ms_per_step": float(tm.item()) / n,
             "unpipelined_ms_per_step": sync_ms, "unpipelined_value": B / (sync_ms * 1e-3),
-            "api": "PEStream.step_host_async + result (numpy batch in -> pinned slot -> one H2D copy; per-query row sums -> pinned D2H; "
-                   "results read one step behind)"}
+            "api": "PEStream.step_host_async + result (numpy batch in -> pinned slot -> one copy-in kernel reading the pinned slot on a "
+                   "side stream; per-query row sums written to the pinned result slot by the result kernel; results read one step behind)"}
 
 
 # ------------------------------------------------------------------------------------------------

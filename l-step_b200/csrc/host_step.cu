@@ -9,8 +9,10 @@
 // synchronising. lstep_host_step_result waits for a ticket's event and hands out the pinned result, so a
 // loop can keep `slots - 1` steps in flight (results read one step behind hide the host's own time).
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "common.cuh"
 
@@ -21,6 +23,17 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
                  const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
                  const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
                  uint32_t* err_flag, void* stream);
+
+// The batch moves in and the result moves out through KERNELS that read / write the pinned slots directly
+// (pinned host memory is device-addressable under unified virtual addressing): a copy-engine transfer between
+// two kernels costs a stream hand-over in each direction (~6-8 us each for these 14 KB / 3 KB payloads) and
+// is slower than a 4-CTA copy kernel. The copy-in runs on a side stream (it overlaps the previous step; the
+// compute stream waits on its event), the result kernel on another (the next step does not queue behind it).
+// LSTEP_HOST_MEMCPY=1 selects cudaMemcpyAsync instead (A/B).
+__global__ void __launch_bounds__(256) stage_in_kernel(const uint4* __restrict__ host_slot, uint4* __restrict__ dev_slot, int64_t n16) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n16; i += (int64_t)gridDim.x * blockDim.x)
+    dev_slot[i] = __ldcv(host_slot + i);  // the host rewrites the pinned slot between launches: never cached
+}
 
 // res[row] = sum_c x[row][c]: one warp per row, lanes stride the columns, fixed-order shuffle tree
 __global__ void __launch_bounds__(256) row_sum_kernel(const float* __restrict__ x, int64_t n_rows, int d, float* __restrict__ res) {
@@ -53,13 +66,55 @@ struct lstep_host_stepper {
   char* d_in[kMaxSlots];
   float* h_res[kMaxSlots];
   float* d_res[kMaxSlots];
-  cudaEvent_t done[kMaxSlots];
+  cudaEvent_t done[kMaxSlots];       // result of the slot's step is in the pinned result slot
+  cudaEvent_t in_ready[kMaxSlots];   // the slot's batch is on the device
+  cudaEvent_t step_done[kMaxSlots];  // the slot's step has written nbr_out
+  float* d_nbr[kMaxSlots];           // [max_queries][max_edges][d] per slot: the result kernel of step i reads it while step i+1 runs
+  cudaStream_t in_stream, out_stream;  // side streams: copy-in overlaps the previous step, the result path leaves the critical path
   int64_t res_n[kMaxSlots];
   int64_t ticket_of[kMaxSlots];  // ticket currently held by the slot, -1 = none
   float* d_nbr_out;              // [max_queries][max_edges][d] when the caller keeps no copy of its own
   int64_t next_ticket;
   uint64_t h2d_bytes, d2h_bytes;
 };
+
+// sorted unique ids of src[0..n) U dst[0..n) -> out[<= 2n]. Small id spaces: a bitmap over [0, V1) scanned in
+// order (1 us for 11 k nodes); otherwise (or when an id is out of range, which the device lookup reports) sort.
+static int64_t unique_sorted_ids(const int64_t* src, const int64_t* dst, size_t n, int64_t V1, int64_t* out) {
+  static thread_local std::vector<uint64_t> bits;
+  if (V1 > 0 && V1 <= (1 << 18)) {
+    const size_t words = (size_t)(V1 + 63) / 64;
+    if (bits.size() < words) bits.assign(words, 0);
+    bool ok = true;
+    for (size_t i = 0; i < n && ok; ++i) {
+      const int64_t a = src[i], b = dst[i];
+      if (a < 0 || a >= V1 || b < 0 || b >= V1) {
+        ok = false;
+        break;
+      }
+      bits[(size_t)a >> 6] |= 1ull << (a & 63);
+      bits[(size_t)b >> 6] |= 1ull << (b & 63);
+    }
+    if (ok) {
+      int64_t m = 0;
+      for (size_t w = 0; w < words; ++w) {
+        uint64_t x = bits[w];
+        if (!x) continue;
+        bits[w] = 0;
+        while (x) {
+          out[m++] = (int64_t)(w * 64 + (size_t)__builtin_ctzll(x));
+          x &= x - 1;
+        }
+      }
+      return m;
+    }
+    std::fill(bits.begin(), bits.begin() + words, 0);
+  }
+  memcpy(out, src, 8 * n);
+  memcpy(out + n, dst, 8 * n);
+  std::sort(out, out + 2 * n);
+  return std::unique(out, out + 2 * n) - out;
+}
 
 static int cuda_fail(cudaError_t e, const char* where) {
   set_cuda_error(e, where);
@@ -70,12 +125,17 @@ extern "C" void lstep_host_stepper_destroy(lstep_host_stepper* h) {
   if (!h) return;
   for (int i = 0; i < h->slots; ++i) {
     if (h->done[i]) cudaEventDestroy(h->done[i]);
+    if (h->in_ready[i]) cudaEventDestroy(h->in_ready[i]);
+    if (h->step_done[i]) cudaEventDestroy(h->step_done[i]);
+    if (h->d_nbr[i]) cudaFree(h->d_nbr[i]);
     if (h->h_in[i]) cudaFreeHost(h->h_in[i]);
     if (h->h_res[i]) cudaFreeHost(h->h_res[i]);
     if (h->d_in[i]) cudaFree(h->d_in[i]);
     if (h->d_res[i]) cudaFree(h->d_res[i]);
   }
   if (h->d_nbr_out) cudaFree(h->d_nbr_out);
+  if (h->in_stream) cudaStreamDestroy(h->in_stream);
+  if (h->out_stream) cudaStreamDestroy(h->out_stream);
   delete h;
 }
 
@@ -89,15 +149,17 @@ extern "C" int lstep_host_stepper_create(int slots, int64_t max_edges, int max_q
   h->max_queries = max_queries;
   h->d = d;
   // src | dst | t | ids (<= 2n) | C query sets, 8 bytes each
-  h->in_bytes = sizeof(int64_t) * (size_t)max_edges * (size_t)(5 + max_queries);
+  h->in_bytes = align_up(sizeof(int64_t) * (size_t)max_edges * (size_t)(5 + max_queries), 16);
   h->res_floats = (size_t)std::max(1, max_queries) * (size_t)max_edges;
   h->next_ticket = 0;
   h->h2d_bytes = h->d2h_bytes = 0;
   h->d_nbr_out = nullptr;
+  h->in_stream = h->out_stream = nullptr;
   for (int i = 0; i < kMaxSlots; ++i) {
     h->h_in[i] = h->d_in[i] = nullptr;
     h->h_res[i] = h->d_res[i] = nullptr;
-    h->done[i] = nullptr;
+    h->done[i] = h->in_ready[i] = h->step_done[i] = nullptr;
+    h->d_nbr[i] = nullptr;
     h->ticket_of[i] = -1;
     h->res_n[i] = 0;
   }
@@ -108,8 +170,12 @@ extern "C" int lstep_host_stepper_create(int slots, int64_t max_edges, int max_q
     if ((e = cudaMalloc((void**)&h->d_in[i], h->in_bytes)) != cudaSuccess) break;
     if ((e = cudaMalloc((void**)&h->d_res[i], sizeof(float) * h->res_floats)) != cudaSuccess) break;
     if ((e = cudaEventCreateWithFlags(&h->done[i], cudaEventDisableTiming)) != cudaSuccess) break;
+    if ((e = cudaEventCreateWithFlags(&h->in_ready[i], cudaEventDisableTiming)) != cudaSuccess) break;
+    if ((e = cudaEventCreateWithFlags(&h->step_done[i], cudaEventDisableTiming)) != cudaSuccess) break;
+    if ((e = cudaMalloc((void**)&h->d_nbr[i], sizeof(float) * h->res_floats * (size_t)d)) != cudaSuccess) break;
   }
-  if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_nbr_out, sizeof(float) * h->res_floats * (size_t)d);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->in_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->out_stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     lstep_host_stepper_destroy(h);
     return cuda_fail(e, "host_stepper_create");
@@ -152,33 +218,51 @@ extern "C" int lstep_pe_step_host(lstep_host_stepper* h, const lstep_pe_stream* 
   if (ids_host) {
     memcpy(h_ids, ids_host, 8 * (size_t)n_ids);
   } else {  // sorted unique endpoints (evaluate_model_utils.py:54-55 does this with torch.unique on the host)
-    memcpy(h_ids, src_host, 8 * n);
-    memcpy(h_ids + n, dst_host, 8 * n);
-    std::sort(h_ids, h_ids + 2 * n);
-    n_ids = std::unique(h_ids, h_ids + 2 * n) - h_ids;
+    n_ids = unique_sorted_ids(src_host, dst_host, n, s->V1, h_ids);
   }
   for (int c = 0; c < n_queries; ++c) memcpy(h_q + (size_t)c * n, query_ids_host_arrays[c], 8 * n);
   const size_t bytes = 8 * n * (size_t)(5 + n_queries);
-  if ((e = cudaMemcpyAsync(h->d_in[slot], h->h_in[slot], bytes, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-    return cuda_fail(e, "pe_step_host h2d");
+  static const bool use_memcpy = getenv("LSTEP_HOST_MEMCPY") != nullptr;
+  // copy-in on its own stream: it only has to wait for the slot's previous use (synchronised above), so it runs
+  // while the previous step is still computing; the compute stream picks it up through an event
+  if (use_memcpy) {
+    if ((e = cudaMemcpyAsync(h->d_in[slot], h->h_in[slot], bytes, cudaMemcpyHostToDevice, h->in_stream)) != cudaSuccess)
+      return cuda_fail(e, "pe_step_host h2d");
+  } else {
+    stage_in_kernel<<<4, 256, 0, h->in_stream>>>(reinterpret_cast<const uint4*>(h->h_in[slot]), reinterpret_cast<uint4*>(h->d_in[slot]),
+                                                 (int64_t)((bytes + 15) / 16));
+    int rc0 = check_launch("stage_in");
+    if (rc0 != LSTEP_OK) return rc0;
+  }
+  if ((e = cudaEventRecord(h->in_ready[slot], h->in_stream)) != cudaSuccess) return cuda_fail(e, "pe_step_host event");
+  if ((e = cudaStreamWaitEvent(st, h->in_ready[slot], 0)) != cudaSuccess) return cuda_fail(e, "pe_step_host wait");
   h->h2d_bytes += bytes;
   const int64_t* dp = reinterpret_cast<const int64_t*>(h->d_in[slot]);
   const int64_t* qdev[8];
   for (int c = 0; c < n_queries; ++c) qdev[c] = dp + 5 * n + (size_t)c * n;
-  float* outp = nbr_out ? nbr_out : h->d_nbr_out;
+  float* outp = nbr_out ? nbr_out : h->d_nbr[slot];
   int rc = pe_step_core(s, csr, dp, dp + n, reinterpret_cast<const double*>(dp + 2 * n), n_edges, dp + 3 * n, n_ids, tmax, head,
                         len, append_slot, G, qdev, n_queries, outp, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag,
                         stream);
   if (rc != LSTEP_OK) return rc;
   const int64_t rows = (int64_t)n_queries * n_edges;
+  // result path on its own stream, behind the step: the next step does not queue behind it. (A caller-owned
+  // nbr_out is reused by the caller's next step, so in that case the result kernel stays on the compute stream.)
+  cudaStream_t rs = nbr_out ? st : h->out_stream;
+  if (!nbr_out) {
+    if ((e = cudaEventRecord(h->step_done[slot], st)) != cudaSuccess) return cuda_fail(e, "pe_step_host event");
+    if ((e = cudaStreamWaitEvent(rs, h->step_done[slot], 0)) != cudaSuccess) return cuda_fail(e, "pe_step_host wait");
+  }
   if (rows > 0) {
-    launch_k(row_sum_kernel, dim3((unsigned)ceil_div(rows * 32, 256)), dim3(256), 0, st, outp, rows, h->d, h->d_res[slot]);
+    // the row sums go straight into the pinned result slot (visible to the host once the event below has fired)
+    row_sum_kernel<<<(unsigned)ceil_div(rows * 32, 256), 256, 0, rs>>>(outp, rows, h->d, use_memcpy ? h->d_res[slot] : h->h_res[slot]);
     if ((rc = check_launch("row_sum")) != LSTEP_OK) return rc;
-    if ((e = cudaMemcpyAsync(h->h_res[slot], h->d_res[slot], sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+    if (use_memcpy &&
+        (e = cudaMemcpyAsync(h->h_res[slot], h->d_res[slot], sizeof(float) * (size_t)rows, cudaMemcpyDeviceToHost, rs)) != cudaSuccess)
       return cuda_fail(e, "pe_step_host d2h");
     h->d2h_bytes += sizeof(float) * (size_t)rows;
   }
-  if ((e = cudaEventRecord(h->done[slot], st)) != cudaSuccess) return cuda_fail(e, "pe_step_host event");
+  if ((e = cudaEventRecord(h->done[slot], rs)) != cudaSuccess) return cuda_fail(e, "pe_step_host event");
   h->res_n[slot] = rows;
   h->ticket_of[slot] = h->next_ticket;
   *ticket = h->next_ticket++;

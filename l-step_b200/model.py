@@ -137,6 +137,7 @@ class LSTEP(nn.Module):
         self.out_node_emb = nn.Linear(pe_dim + node_feat_dim, node_feat_dim)
 
         self._pack_cache = {}
+        self._pack_fast = {}
         self._filter_cache = {}
         self._twiddle = {}
         self._stager = None
@@ -221,8 +222,20 @@ class LSTEP(nn.Module):
         return st
 
     def _mlp_ref(self, which: str):
+        # fast path (one call per step on the streaming API): the parameter tensors are remembered, and a packed
+        # copy is reused while none of them has been modified in place (_version) or replaced (data_ptr)
+        fast = self._pack_fast.get(which)
+        if fast is not None:
+            params, key, ref = fast
+            if all(p._version == v and p.data_ptr() == q for p, (q, v) in zip(params, key)):
+                return ref
         self._packed_mlp(which)
-        return self._pack_cache[which][3]
+        names = {"update": ("pe_mlp_1", "pe_mlp_2", "self_update_pe"),
+                 "nbr": ("pe_neighbor_mlp_1", "pe_neighbor_mlp_2", "self_update_neighbor_pe")}[which]
+        params = [p for n in names for p in (getattr(self, n).weight, getattr(self, n).bias)] + [self.time_encoder.w.weight]
+        entry = self._pack_cache[which]
+        self._pack_fast[which] = (params, entry[0], entry[3])
+        return entry[3]
 
     # ---- a3: DFT filter ---------------------------------------------------------------------
     def _twiddles(self, T: int, dev):
