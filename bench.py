@@ -447,9 +447,9 @@ def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, l
             "nbr_lookup_aggregate": {"ms": stages["nbr_lookup_aggregate"], "launches_per_step": 1},
             "pe_mlp(nbr)": {"ms": stages["pe_mlp(nbr)"], "launches_per_step": 1},
             "ring_append": {"ms": stages["ring_append"], "launches_per_step": 1},
-            # own kernels per step (csrc/step.cu): DFT filter 1; a6 2 (lookup + aggregate, MLP; all C query sets per
-            # launch); update_pe 4 (phase A edge aggregate, MLP; phase B push, MLP); ring append 1
-            "_launches_per_step": {"n": 1 + 2 + 4 + 1, "ms": 0.0, "launches_per_step": 0}}
+            # own kernels per step (csrc/step.cu): DFT filter 1; fused gather (a6 lookup + aggregate of all C query sets
+            # || a7 edge aggregate) 1; MLP(nbr) 1; update_pe 3 (MLP phase A, phase B push, MLP phase B); ring append 1
+            "_launches_per_step": {"n": 1 + 1 + 1 + 3 + 1, "ms": 0.0, "launches_per_step": 0}}
     # measured M: distinct sampled neighbours per batch
     for i in range(min(n, 20)):
         b = (step_no + i) % nb

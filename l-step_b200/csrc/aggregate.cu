@@ -7,110 +7,20 @@
 // k = 0..K-1 (the PE table is L2 resident: 7.6 MB at Reddit size). Padded slots (id 0) read
 // pe[0] like any other row — it is non-zero after an update.
 #include "common.cuh"
+#include "gather_bodies.cuh"
 
 namespace lstep {
 
-// kLookup: the kernel does the most-recent-K lookup itself (warp 0, warp_recent_range) instead of reading the
-// sampler's output — the streaming step's form: one launch and no [rows, K] round trip through global memory.
-struct LookupArgs {
-  const int64_t* indptr;
-  const int32_t* c_nbr;
-  const double* c_t;
-  int64_t num_rows;
-  RowIds q_node;
-  uint32_t* err_flag;
-};
-
 template <int VEC, bool kLookup>
-__global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restrict__ pe,
-                                                            const double* __restrict__ q_time,
-                                                            const int32_t* __restrict__ nbr,
-                                                            const float* __restrict__ nbr_t, int64_t n_rows, int K,
-                                                            const float* __restrict__ tw, int d, int t, int t_pad,
+__global__ void __launch_bounds__(512) nbr_aggregate_kernel(const float* __restrict__ pe, const double* __restrict__ q_time,
+                                                            const int32_t* __restrict__ nbr, const float* __restrict__ nbr_t,
+                                                            int64_t n_rows, int K, const float* __restrict__ tw, int d, int t, int t_pad,
                                                             float* __restrict__ S, int64_t ldS, int64_t period, LookupArgs lk) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);
-  float* s_dt = reinterpret_cast<float*>(s_nbr + K);
-  const int tid = threadIdx.x;
-  const int dvec = d / VEC;
-  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
-    const double tq = q_time[period ? row % period : row];
-    if (kLookup) {
-      if (tid < 32) {
-        const int64_t node = lk.q_node.at(row);
-        int64_t first = 0;
-        int take = 0;
-        if (node < 0 || node >= lk.num_rows) {
-          if (tid == 0 && lk.err_flag) atomicOr(lk.err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
-        } else {
-          warp_recent_range(lk.indptr, lk.c_t, node, tq, K, tid, first, take);
-        }
-        const int pad = K - take;
-        for (int k = tid; k < K; k += 32) {
-          int32_t n = 0;
-          float tt = 0.f;
-          if (k >= pad) {
-            const int64_t e = first + (k - pad);
-            n = lk.c_nbr[e];
-            tt = (float)lk.c_t[e];  // the sampler returns fp32 times (utils.py:166,208)
-          }
-          s_nbr[k] = n;
-          s_dt[k] = (float)(tq - (double)tt);  // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
-        }
-      }
-    } else {
-      for (int k = tid; k < K; k += blockDim.x) {
-        s_nbr[k] = ld_dep(nbr + row * K + k);
-        // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
-        s_dt[k] = (float)(tq - (double)ld_dep(nbr_t + row * K + k));
-      }
-    }
-    __syncthreads();
-    if (tid < t) {
-      const float w = tw[tid];
-      float acc = 0.f;
-      for (int k = 0; k < K; ++k)
-        if (s_nbr[k] != 0) acc += time_feature(s_dt[k], w);
-      S[row * ldS + d + tid] = acc;
-    } else if (tid >= t_pad && tid - t_pad < dvec) {
-      const int cv = tid - t_pad;
-      if (VEC == 4) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int k = 0;
-        for (; k + 4 <= K; k += 4) {
-          float4 v[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            v[u] = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k + u] * d) + cv);
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            acc.x += v[u].x;
-            acc.y += v[u].y;
-            acc.z += v[u].z;
-            acc.w += v[u].w;
-          }
-        }
-        for (; k < K; ++k) {
-          const float4 v = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k] * d) + cv);
-          acc.x += v.x;
-          acc.y += v.y;
-          acc.z += v.z;
-          acc.w += v.w;
-        }
-        reinterpret_cast<float4*>(S + row * ldS)[cv] = acc;
-      } else {
-        float acc = 0.f;
-        for (int k = 0; k < K; ++k) acc += ld_dep(pe + (int64_t)s_nbr[k] * d + cv);
-        S[row * ldS + cv] = acc;
-      }
-    }
-    __syncthreads();
-  }
+  nbr_aggregate_rows<VEC, kLookup>(blockIdx.x, gridDim.x, pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t, t_pad, S, ldS, period, lk);
 }
 
-// dpe[nbr[i,k], :] += dS[i, :d]   (training only; fp32 atomics)
 __global__ void __launch_bounds__(256) nbr_aggregate_bwd_kernel(const float* __restrict__ dS,
                                                                 const int32_t* __restrict__ nbr, int64_t n_rows, int K,
                                                                 int d, int t, float* __restrict__ dpe) {

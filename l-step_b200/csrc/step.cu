@@ -10,7 +10,11 @@
 // `cur` always equals the newest ring slot between steps, so the loops' clone(hist[:, -1]) disappears,
 // and the history is never trimmed or concatenated: one [V1, d] table copy per step remains (the H term
 // of SURVEY §8(d)) instead of ~3 GB of clone + cat at Reddit size.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
+#include "gather_bodies.cuh"
 
 namespace lstep {
 
@@ -19,6 +23,31 @@ int launch_sample(const lstep_csr* csr, RowIds q_node, const double* q_time, int
                   IdT* out_nbr, IdT* out_eid, float* out_t, uint32_t* err_flag, void* stream);
 int launch_nbr_lookup_aggregate(const lstep_csr* csr, RowIds q_node, const float* pe, const double* q_time, int64_t n_rows, int K,
                                 const float* tw, int d, int t, float* S, int64_t ldS, uint32_t* err_flag, cudaStream_t st);
+void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows, float** A, int64_t* lda,
+                       int32_t** counters);
+int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
+                   const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
+                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done);
+
+// a6's neighbourhood aggregate (blocks [0, grid_q)) and a7's edge aggregate (the rest) in ONE launch: both only
+// read the current table and neither depends on the other, so the short edge kernel (and its hub chain) hides
+// behind the cosine-bound neighbourhood rows instead of being a link of the step's dependency chain.
+__global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict__ pe, const double* __restrict__ q_time, int64_t n_rows,
+                                                        int K, const float* __restrict__ tw_q, int d, int t, int t_pad,
+                                                        float* __restrict__ S, int64_t ldS, int64_t period, LookupArgs lk, int grid_q,
+                                                        const int64_t* __restrict__ ids, int64_t n_ids,
+                                                        const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
+                                                        const double* __restrict__ times, int64_t n_edges, float tc,
+                                                        const float* __restrict__ tw_u, float* __restrict__ A, int64_t lda,
+                                                        int32_t* __restrict__ counters) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if ((int)blockIdx.x < grid_q)
+    nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk);
+  else
+    edge_aggregate_rows((int64_t)blockIdx.x - grid_q, (int64_t)gridDim.x - grid_q, (int)blockIdx.x == grid_q, pe, ids, n_ids, src, dst,
+                        times, n_edges, tc, tw_u, d, t, t_pad, A, lda, counters);
+}
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                   cudaStream_t st);
@@ -136,23 +165,46 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
     rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, ids, stream);
     if (rc != LSTEP_OK) return rc;
   }
-  // a6: all query sets in one pass
+  // a6 gather + a7 edge aggregate: one heterogeneous launch when both exist and the 128-bit paths apply
   const int64_t rows = (int64_t)n_queries * n_edges;
-  if (rows > 0) {
-    RowIds q{};
-    for (int c = 0; c < n_queries; ++c) {
-      if (!query_ids_host[c]) return LSTEP_ERR_INVALID_ARG;
-      q.p[c] = query_ids_host[c];
+  RowIds q{};
+  for (int c = 0; c < n_queries; ++c) {
+    if (!query_ids_host[c]) return LSTEP_ERR_INVALID_ARG;
+    q.p[c] = query_ids_host[c];
+  }
+  q.period = n_edges;
+  bool edges_done = false;
+  static const bool no_fuse = getenv("LSTEP_NO_GATHER_FUSE") != nullptr;
+  const int t_pad = (int)align_up((size_t)t, 32);
+  const int threads = (int)align_up((size_t)t_pad + d / 4, 32);
+  const bool vec_ok = d % 4 == 0 && w.lda % 4 == 0 && reinterpret_cast<uintptr_t>(s->cur) % 16 == 0 && threads <= 512;
+  if (!no_fuse && rows > 0 && n_ids > 0 && n_edges > 0 && vec_ok && t == mlp_upd->t && d == mlp_upd->d) {
+    float* A = nullptr;
+    int64_t ldA = 0;
+    int32_t* counters = nullptr;
+    update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters);
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    const int grid_q = (int)(rows < cap ? rows : cap), grid_e = (int)(n_ids < cap ? n_ids : cap);
+    const size_t smem = std::max((size_t)K * 8, (size_t)threads * kSegPerThread * 8 + 32 * 4);
+    if (smem <= 48 * 1024) {
+      LookupArgs lk{csr->indptr, csr->nbr, csr->t, csr->num_rows, q, err_flag};
+      launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads), smem, st, s->cur, tq, rows, K, mlp_nbr->tw, d, t, t_pad,
+               w.S, w.lda, n_edges, lk, grid_q, ids, n_ids, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
+      if ((rc = check_launch("gather_ab")) != LSTEP_OK) return rc;
+      edges_done = true;
     }
-    q.period = n_edges;
-    rc = launch_nbr_lookup_aggregate(csr, q, s->cur, tq, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, err_flag, st);
-    if (rc != LSTEP_OK) return rc;
+  }
+  if (rows > 0) {
+    if (!edges_done) {
+      rc = launch_nbr_lookup_aggregate(csr, q, s->cur, tq, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, err_flag, st);
+      if (rc != LSTEP_OK) return rc;
+    }
     rc = launch_pe_mlp(w.S, w.lda, s->cur, q, rows, rows, nullptr, mlp_nbr, nbr_out, d, nullptr, st);
     if (rc != LSTEP_OK) return rc;
   }
   // a7 + a8
-  rc = lstep_update_pe(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update,
-                       w.update_bytes, err_flag, stream);
+  rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,
+                      err_flag, stream, edges_done);
   if (rc != LSTEP_OK) return rc;
   launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0);
   return check_launch("ring_append");

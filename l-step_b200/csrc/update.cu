@@ -26,6 +26,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "gather_bodies.cuh"
 
 namespace lstep {
 
@@ -113,114 +114,15 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase A: one CTA per batch node. Threads [0,t): time frequencies; [t_pad, t_pad+d/4): PE columns.
-constexpr int kSegPerThread = 4;
-
-__global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __restrict__ pe,
-                                                             const int64_t* __restrict__ ids, int64_t n_ids,
-                                                             const int64_t* __restrict__ src,
-                                                             const int64_t* __restrict__ dst,
+// phase A edge aggregate (body: edge_aggregate_rows, csrc/gather_bodies.cuh)
+__global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __restrict__ pe, const int64_t* __restrict__ ids, int64_t n_ids,
+                                                             const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                                              const double* __restrict__ times, int64_t n_edges, float tc,
                                                              const float* __restrict__ tw, int d, int t, int t_pad,
-                                                             float* __restrict__ A, int64_t lda,
-                                                             int32_t* __restrict__ counters) {
+                                                             float* __restrict__ A, int64_t lda, int32_t* __restrict__ counters) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int nthr = blockDim.x;
-  const int seg = nthr * kSegPerThread;
-  int32_t* s_other = reinterpret_cast<int32_t*>(smem_raw);  // [seg]
-  float* s_dt = reinterpret_cast<float*>(s_other + seg);    // [seg]
-  int32_t* s_warp = reinterpret_cast<int32_t*>(s_dt + seg); // [32] warp totals
-  __shared__ int s_total;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int dvec = d / 4;
-  const bool is_tf = tid < t;
-  const bool is_pe = tid >= t_pad && tid - t_pad < dvec;
-  const int cv = tid - t_pad;
-  if (blockIdx.x == 0 && tid < 8) counters[tid] = 0;  // phase-B counters, consumed by later launches
-
-  for (int64_t n = blockIdx.x; n < n_ids; n += gridDim.x) {
-    const int64_t node = ids[n];
-    float acc_tf = 0.f;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float w = is_tf ? tw[tid] : 0.f;
-    for (int side = 0; side < 2; ++side) {
-      const int64_t* match = side == 0 ? src : dst;  // scatter #1 indexes by src (LSTEP.py:283-286), #2 by dst
-      const int64_t* other = side == 0 ? dst : src;
-      for (int64_t lo = 0; lo < n_edges; lo += seg) {
-        // ordered compaction of the matches in [lo, lo+seg)
-        const int64_t e0 = lo + (int64_t)tid * kSegPerThread;
-        int64_t mv[kSegPerThread];
-        int cnt = 0;
-#pragma unroll
-        for (int u = 0; u < kSegPerThread; ++u) {
-          mv[u] = (e0 + u < n_edges) ? match[e0 + u] : -1;
-          cnt += (mv[u] == node);
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int v = __shfl_up_sync(kFull, incl, o);
-          if (lane >= o) incl += v;
-        }
-        if (lane == 31) s_warp[wid] = incl;
-        __syncthreads();
-        if (wid == 0) {
-          const int nw = nthr >> 5;
-          int v = lane < nw ? s_warp[lane] : 0;
-          int iv = v;
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int x = __shfl_up_sync(kFull, iv, o);
-            if (lane >= o) iv += x;
-          }
-          if (lane < nw) s_warp[lane] = iv - v;  // exclusive
-          if (lane == 31) s_total = iv;
-        }
-        __syncthreads();
-        int pos = s_warp[wid] + incl - cnt;
-#pragma unroll
-        for (int u = 0; u < kSegPerThread; ++u) {
-          if (mv[u] == node) {
-            s_other[pos] = (int32_t)other[e0 + u];
-            // torch.Tensor([current_time]) is fp32; fp32 - fp64 promotes to fp64; then .float() (LSTEP.py:277, Q4)
-            s_dt[pos] = (float)((double)tc - times[e0 + u]);
-            ++pos;
-          }
-        }
-        __syncthreads();
-        const int total = s_total;
-        if (is_tf) {
-          for (int j = 0; j < total; ++j) acc_tf += time_feature(s_dt[j], w);
-        } else if (is_pe) {
-          int j = 0;
-          for (; j + 4 <= total; j += 4) {
-            float4 v[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[u] = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_other[j + u] * d) + cv);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              acc.x += v[u].x;
-              acc.y += v[u].y;
-              acc.z += v[u].z;
-              acc.w += v[u].w;
-            }
-          }
-          for (; j < total; ++j) {
-            const float4 v = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_other[j] * d) + cv);
-            acc.x += v.x;
-            acc.y += v.y;
-            acc.z += v.z;
-            acc.w += v.w;
-          }
-        }
-        __syncthreads();
-      }
-    }
-    if (is_tf) A[n * lda + d + tid] = acc_tf;
-    if (is_pe) reinterpret_cast<float4*>(A + n * lda)[cv] = acc;
-  }
+  edge_aggregate_rows(blockIdx.x, gridDim.x, blockIdx.x == 0, pe, ids, n_ids, src, dst, times, n_edges, tc, tw, d, t, t_pad, A, lda, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -577,17 +479,20 @@ static int check_update_args(const float* pe, int64_t pe_rows, const lstep_pe_ml
 // phase A: aggregate over the batch edges for the rows `ids`, MLP with self term, in place. Also resets
 // the phase-B counters.
 static int phase_a(float* pe, const UpdateWs& w, const int64_t* ids, int64_t n_ids, const int64_t* src, const int64_t* dst,
-                   const double* times, int64_t n_edges, float tc, const lstep_pe_mlp* mlp, cudaStream_t st) {
+                   const double* times, int64_t n_edges, float tc, const lstep_pe_mlp* mlp, cudaStream_t st,
+                   bool edges_done = false) {
   const int d = mlp->d, t = mlp->t;
   const int dvec = d / 4;
   const int t_pad = (int)align_up((size_t)t, 32);
   const int threads = (int)align_up((size_t)t_pad + dvec, 32);
   const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
   const int64_t grid = n_ids < (int64_t)kNumSMs * 16 ? n_ids : (int64_t)kNumSMs * 16;
-  launch_k(edge_aggregate_kernel, dim3((unsigned)grid), dim3(threads), smem, st, pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d, t,
-                                                               t_pad, w.A, w.lda, w.counters);
-  int rc = check_launch("edge_aggregate");
-  if (rc != LSTEP_OK) return rc;
+  if (!edges_done) {  // (the streaming step forms the aggregate rows in its fused gather launch, csrc/step.cu)
+    launch_k(edge_aggregate_kernel, dim3((unsigned)grid), dim3(threads), smem, st, pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d,
+             t, t_pad, w.A, w.lda, w.counters);
+    const int rc = check_launch("edge_aggregate");
+    if (rc != LSTEP_OK) return rc;
+  }
   return launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st);
 }
 
@@ -648,10 +553,34 @@ static int phase_b_apply(float* pe, int64_t pe_rows, const UpdateWs& w, int64_t 
 
 }  // namespace lstep
 
+namespace lstep {
+// where phase A's aggregate rows and the phase-B counters live inside an update workspace
+void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows, float** A, int64_t* lda,
+                       int32_t** counters) {
+  UpdateWs w = carve(workspace, n_ids, n_edges, K, d, t, pe_rows);
+  *A = w.A;
+  *lda = w.lda;
+  *counters = w.counters;
+}
+
+int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
+                   const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
+                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done);
+}  // namespace lstep
+
 extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids,
                                const int64_t* src, const int64_t* dst, const double* times, int64_t n_edges,
                                double current_time, int K, const lstep_pe_mlp* mlp, void* workspace,
                                size_t workspace_bytes, uint32_t* err_flag, void* stream) {
+  return update_pe_impl(pe, pe_rows, csr, ids, n_ids, src, dst, times, n_edges, current_time, K, mlp, workspace, workspace_bytes,
+                        err_flag, stream, false);
+}
+
+// edges_done: phase A's aggregate rows (and the zeroed counters) are already in the workspace
+int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
+                          const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K,
+                          const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream,
+                          bool edges_done) {
   int rc = check_update_args(pe, pe_rows, mlp, n_ids, n_edges, K, workspace, workspace_bytes);
   if (rc != LSTEP_OK) return rc;
   if (!csr || (n_ids > 0 && !ids) || (n_edges > 0 && (!src || !dst || !times))) return LSTEP_ERR_INVALID_ARG;
@@ -668,7 +597,7 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
     }
     return LSTEP_OK;
   }
-  if ((rc = phase_a(pe, w, ids, n_ids, src, dst, times, n_edges, tc, mlp, st)) != LSTEP_OK) return rc;
+  if ((rc = phase_a(pe, w, ids, n_ids, src, dst, times, n_edges, tc, mlp, st, edges_done)) != LSTEP_OK) return rc;
   const int64_t n_valid = n_ids < n_edges ? n_ids : n_edges;  // zip(node_ids, times) truncation (Q1)
   {
     // phase B, push form (csrc/update_push.cu): lookup + exact fixed-point accumulation where the contribution
