@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(256) nbr_aggregate_bwd_kernel(const float* __r
 
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                  cudaStream_t st);
+                  cudaStream_t st, bool late_trigger = false);
 
 static bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
 

@@ -306,12 +306,12 @@ int launch_pe_mlp_tc(const float* A, int64_t lda, const float* pe, RowIds base_i
                      cudaStream_t st);
 int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st);
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger = false);
 
 // n_rows is the host-side upper bound of rows; *n_rows_dev (optional) the device-side count.
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                  cudaStream_t st) {
+                  cudaStream_t st, bool late_trigger) {
   if (n_rows <= 0) return LSTEP_OK;
   if (!A || !pe || !base_ids.p[0] || !m || (!out && !pe_inplace)) return LSTEP_ERR_INVALID_ARG;
   {
@@ -319,7 +319,7 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
     // weight-ring kernel below, which also serves shapes the cluster kernel does not cover
     static const bool use_ring = getenv("LSTEP_MLP_RING") != nullptr || getenv("LSTEP_MLP_TC") != nullptr;
     if (!use_ring) {
-      const int rc = launch_pe_mlp_cluster(A, lda, pe, base_ids, n_rows, expected_rows, n_rows_dev, m, out, out_stride, pe_inplace, nullptr, nullptr, st);
+      const int rc = launch_pe_mlp_cluster(A, lda, pe, base_ids, n_rows, expected_rows, n_rows_dev, m, out, out_stride, pe_inplace, nullptr, nullptr, st, late_trigger);
       if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
     }
   }
@@ -369,5 +369,5 @@ extern "C" int lstep_pe_mlp_apply(const float* A, const float* pe, const int64_t
   if (n_rows < 0) return LSTEP_ERR_INVALID_ARG;
   if (!mlp) return LSTEP_ERR_INVALID_ARG;
   return launch_pe_mlp(A, mlp->d + mlp->t, pe, single_ids(base_ids), n_rows, n_rows, nullptr, mlp, out, out_stride, pe_inplace,
-                       as_stream(stream));
+                       as_stream(stream), false);
 }

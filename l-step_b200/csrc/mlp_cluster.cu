@@ -88,6 +88,10 @@ constexpr int kCl = 4;  // CTAs per cluster = k slices
 struct FixedRows {
   const unsigned long long* acc;
   int32_t* reset_map;
+  // late_trigger: let the NEXT kernel of the chain become resident only once this kernel's CTAs are past their
+  // dependency wait, i.e. once everything BEFORE this kernel is complete. update_pe's phase-B push kernel relies on
+  // it: its lookup / claim phase runs before its own wait, concurrently with the phase-A MLP and with nothing else.
+  int late_trigger;
 };
 
 #ifdef LSTEP_MLP_TIMING
@@ -201,7 +205,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   // ---- everything that does not depend on the preceding kernel: barriers, the weight slices (parameters),
   // the bias slices, the cluster rendezvous. With programmatic dependent launch this overlaps the tail of
   // the kernel in front.
-  pdl_launch_dependents();
+  if (!fx.late_trigger) pdl_launch_dependents();
   if (tid == 0) {
     mb_init(&wbar[0], 1);
     mb_init(&wbar[1], 1);
@@ -228,6 +232,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   // arrive now, wait right before the first remote store (the staging and layer 1 run in between)
   cluster_arrive();
   pdl_wait();  // from here on the kernel reads what the preceding kernels wrote
+  if (fx.late_trigger) pdl_launch_dependents();
   MLP_T(0);
   if (n_rows_dev) {
     const int64_t nd = ld_dep(n_rows_dev);
@@ -508,8 +513,8 @@ int launch_cl(const float* A, int64_t lda, const float* pe, RowIds base_ids, int
 // acc_fixed / reset_map: see FixedRows (both NULL: the aggregate is the float matrix A).
 int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st) {
-  const FixedRows fx{acc_fixed, reset_map};
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger) {
+  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0};
   // rows per cluster tile: the smallest tile that covers the launch in one round of ~32 co-resident clusters
   if (expected_rows <= 32 * 16) return launch_cl<4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
   if (expected_rows <= 32 * 32) return launch_cl<8>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict_
 }
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                  cudaStream_t st);
+                  cudaStream_t st, bool late_trigger = false);
 int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
                       const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride,
                       const int64_t* out_ids, void* stream);

@@ -32,12 +32,12 @@ namespace lstep {
 
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                  cudaStream_t st);
+                  cudaStream_t st, bool late_trigger = false);
 int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int64_t n_valid,
                         int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag, PhaseBHook hook, void* stream);
 int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st);
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger = false);
 bool pe_mlp_cluster_supports(const lstep_pe_mlp* m);
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
@@ -69,7 +69,7 @@ struct UpdateWs {
   int32_t* task_chunk;     // [2*N*K/32+2] chunk index of a chunk task
   float* row0_part;  // [kRow0Parts*d]
   float* A;          // [max(N, N*K+1)][lda], lda = d+t rounded up to 4 floats
-  unsigned long long* push_acc;  // [N*K+1][d+t] 32.32 fixed-point accumulator rows of the push form; shares storage with A
+  unsigned long long* push_acc;  // [N*K+1][d+t] 32.32 fixed-point accumulator rows of the push form
   int64_t lda;
   size_t bytes;
 };
@@ -104,11 +104,9 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
   w.row0_part = (float*)take(sizeof(float) * kRow0Parts * d);
   const size_t rowsA = nk + 1 > (size_t)n_ids ? nk + 1 : (size_t)n_ids;
   w.lda = (int64_t)align_up((size_t)(d + t), 4);
-  {
-    const size_t bytesA = sizeof(float) * rowsA * w.lda, bytesAcc = sizeof(unsigned long long) * (nk + 1) * (size_t)(d + t);
-    w.A = (float*)take(bytesA > bytesAcc ? bytesA : bytesAcc);
-    w.push_acc = reinterpret_cast<unsigned long long*>(w.A);  // phase A's rows are consumed before phase B accumulates
-  }
+  w.A = (float*)take(sizeof(float) * rowsA * w.lda);
+  // own storage: the push kernel sets accumulator rows up while the phase-A MLP is still reading A
+  w.push_acc = (unsigned long long*)take(sizeof(unsigned long long) * (nk + 1) * (size_t)(d + t));
   w.bytes = o;
   return w;
 }
@@ -493,7 +491,8 @@ static int phase_a(float* pe, const UpdateWs& w, const int64_t* ids, int64_t n_i
     const int rc = check_launch("edge_aggregate");
     if (rc != LSTEP_OK) return rc;
   }
-  return launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st);
+  // late trigger: the kernel behind this one (phase B's push) may run its pre-wait part next to it, not earlier
+  return launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st, true);
 }
 
 // phase B, aggregation half: lookup of (csr_ids[i], q_times[i]) for i < n_valid, inverse index, per

@@ -37,8 +37,12 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
                                                           const float* __restrict__ tw, float tc, int32_t* claim_of,
                                                           int64_t* __restrict__ U, int32_t* counters,
                                                           unsigned long long* acc, uint32_t* err_flag) {
+  // Dependency structure (programmatic dependent launch): the kernel in front is the phase-A MLP, launched with
+  // a LATE trigger, so this kernel is resident only after everything before that MLP has completed. The lookup
+  // and the claim phase touch nothing the phase-A MLP reads or writes (CSR, ids, claim map, counters, U, the
+  // accumulator rows), so they run BEFORE the wait, next to the MLP; the wait sits in front of the first access
+  // to the table (pe[0] = 0 and the phase-A rows).
   pdl_launch_dependents();
-  pdl_wait();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Kcap = (K + kPushSplit - 1) / kPushSplit;
   int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);     // [Kcap] this CTA's slots
@@ -52,8 +56,6 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
   const int Kp = (K + kPushSplit - 1) / kPushSplit;
   const int k_lo = min(K, part * Kp), k_hi = min(K, k_lo + Kp);  // this CTA's slots
   if (k_lo >= k_hi) return;
-  if (blockIdx.x == 0)
-    for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // pe[0] = 0 (LSTEP.py:317); no batch row reads row 0 below
 
   if (warp == 0) {
     // ---- lookup: strictly-earlier count by warp-cooperative 32-ary search, last min(K, c) entries right-aligned
@@ -176,6 +178,9 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
     }
   }
   __syncthreads();
+  pdl_wait();  // phase A has written the table
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // pe[0] = 0 (LSTEP.py:317); no batch row reads row 0 below
 
   // ---- this row's PE in fixed point (phase-A table), once per warp
   const int64_t node = ids[row];
