@@ -113,8 +113,8 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_kernel(const float* __
                                                                  const int64_t* __restrict__ ids, int64_t n_ids,
                                                                  const float* __restrict__ G, float* __restrict__ out,
                                                                  int64_t out_stride, const int64_t* __restrict__ out_ids) {
-  pdl_launch_dependents();
   pdl_wait();
+  pdl_launch_dependents();  // late trigger (see dft_filter_bulk_kernel)
   using V = typename VecT<VEC>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   V* red = reinterpret_cast<V*>(smem_raw);  // [groups][dvec]
@@ -187,7 +187,6 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
   const int g = threadIdx.x / dvec, cv = threadIdx.x % dvec;
   const bool active = g < groups;
   const int rc = (Th + kDftChunks - 1) / kDftChunks;  // rows per chunk
-  pdl_launch_dependents();
   if (threadIdx.x == 0) {
     for (int c = 0; c < kDftChunks; ++c)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dft_s_u32(&bar[c])), "r"(1));
@@ -195,6 +194,9 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
   }
   __syncthreads();
   pdl_wait();
+  // late trigger: the next kernel of the step (the fused gather) does its lookups and cosines before its own wait;
+  // it may only become resident once everything before this filter has completed
+  pdl_launch_dependents();
   const float4* Gv = reinterpret_cast<const float4*>(G);
   uint32_t it = 0;
   for (int64_t n = blockIdx.x; n < n_ids; n += gridDim.x, ++it) {

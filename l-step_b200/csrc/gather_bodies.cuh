@@ -19,7 +19,7 @@ struct LookupArgs {
 };
 
 template <int VEC, bool kLookup>
-__device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t row_stride, const float* __restrict__ pe,
+__device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t row_stride, bool late_wait, const float* __restrict__ pe,
                                                             const double* __restrict__ q_time,
                                                             const int32_t* __restrict__ nbr,
                                                             const float* __restrict__ nbr_t, int64_t n_rows, int K,
@@ -70,6 +70,9 @@ __device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t ro
         if (s_nbr[k] != 0) acc += time_feature(s_dt[k], w);
       S[row * ldS + d + tid] = acc;
     } else if (tid >= t_pad && tid - t_pad < dvec) {
+      // late_wait (fused launch of the streaming step): lookups and cosines depend on nothing the kernel in front
+      // writes, so only the threads that read the table wait for it
+      if (late_wait) pdl_wait();
       const int cv = tid - t_pad;
       if (VEC == 4) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -110,7 +113,7 @@ __device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t ro
 // phase A: one CTA per batch node. Threads [0,t): time frequencies; [t_pad, t_pad+d/4): PE columns.
 constexpr int kSegPerThread = 4;
 
-__device__ __forceinline__ void edge_aggregate_rows(int64_t first_node, int64_t node_stride, bool zero_counters,
+__device__ __forceinline__ void edge_aggregate_rows(int64_t first_node, int64_t node_stride, bool zero_counters, bool late_wait,
                                                     const float* __restrict__ pe,
                                                              const int64_t* __restrict__ ids, int64_t n_ids,
                                                              const int64_t* __restrict__ src,
@@ -187,6 +190,7 @@ __device__ __forceinline__ void edge_aggregate_rows(int64_t first_node, int64_t 
         if (is_tf) {
           for (int j = 0; j < total; ++j) acc_tf += time_feature(s_dt[j], w);
         } else if (is_pe) {
+          if (late_wait) pdl_wait();
           int j = 0;
           for (; j + 4 <= total; j += 4) {
             float4 v[4];

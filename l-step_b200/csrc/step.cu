@@ -40,12 +40,15 @@ __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict_
                                                         const double* __restrict__ times, int64_t n_edges, float tc,
                                                         const float* __restrict__ tw_u, float* __restrict__ A, int64_t lda,
                                                         int32_t* __restrict__ counters) {
+  // The kernel in front (the DFT filter, launched with a late trigger: this kernel is resident only after
+  // everything before the filter has completed) writes the table and nothing else this kernel touches. Lookups,
+  // edge scans and all cosines therefore run BEFORE the dependency wait, next to the HBM-bound filter; only the
+  // threads that gather table rows wait (inside the bodies).
   pdl_launch_dependents();
-  pdl_wait();
   if ((int)blockIdx.x < grid_q)
-    nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk);
+    nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, true, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk);
   else
-    edge_aggregate_rows((int64_t)blockIdx.x - grid_q, (int64_t)gridDim.x - grid_q, (int)blockIdx.x == grid_q, pe, ids, n_ids, src, dst,
+    edge_aggregate_rows((int64_t)blockIdx.x - grid_q, (int64_t)gridDim.x - grid_q, (int)blockIdx.x == grid_q, true, pe, ids, n_ids, src, dst,
                         times, n_edges, tc, tw_u, d, t, t_pad, A, lda, counters);
 }
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(512) edge_aggregate_kernel(const float* __rest
                                                              float* __restrict__ A, int64_t lda, int32_t* __restrict__ counters) {
   pdl_launch_dependents();
   pdl_wait();
-  edge_aggregate_rows(blockIdx.x, gridDim.x, blockIdx.x == 0, pe, ids, n_ids, src, dst, times, n_edges, tc, tw, d, t, t_pad, A, lda, counters);
+  edge_aggregate_rows(blockIdx.x, gridDim.x, blockIdx.x == 0, false, pe, ids, n_ids, src, dst, times, n_edges, tc, tw, d, t, t_pad, A, lda, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
