@@ -178,6 +178,23 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
     }
   }
   __syncthreads();
+  // ---- time features of this CTA's slots: they depend on the lookup only, so they are accumulated BEFORE the
+  // wait as well (the accumulator rows are private to this kernel)
+  float w[TQ];
+#pragma unroll
+  for (int q = 0; q < TQ; ++q) w[q] = (lane + 32 * q < t) ? tw[lane + 32 * q] : 0.f;
+  for (int k = warp; k < k_hi - k_lo; k += nwarps) {
+    const int j = s_slot[k];
+    if (j < 0) continue;
+    unsigned long long* rowp = acc + (size_t)j * in1 + d;
+    const float dt = s_dt[k];
+#pragma unroll
+    for (int q = 0; q < TQ; ++q) {
+      const int jf = lane + 32 * q;
+      if (jf < t) atomicAdd(rowp + jf, (unsigned long long)__float2ll_rn(time_feature(dt, w[q]) * kFixScale));
+    }
+  }
+
   pdl_wait();  // phase A has written the table
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // pe[0] = 0 (LSTEP.py:317); no batch row reads row 0 below
@@ -190,24 +207,14 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
     const int c = lane + 32 * q;
     fx[q] = (c < d && node > 0) ? __float2ll_rn(ld_dep(pe + node * (int64_t)d + c) * kFixScale) : 0ll;
   }
-  float w[TQ];
-#pragma unroll
-  for (int q = 0; q < TQ; ++q) w[q] = (lane + 32 * q < t) ? tw[lane + 32 * q] : 0.f;
-
   for (int k = warp; k < k_hi - k_lo; k += nwarps) {
     const int j = s_slot[k];
     if (j < 0) continue;
     unsigned long long* rowp = acc + (size_t)j * in1;
-    const float dt = s_dt[k];
 #pragma unroll
     for (int q = 0; q < DQ; ++q) {
       const int c = lane + 32 * q;
       if (c < d) atomicAdd(rowp + c, (unsigned long long)fx[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < TQ; ++q) {
-      const int jf = lane + 32 * q;
-      if (jf < t) atomicAdd(rowp + d + jf, (unsigned long long)__float2ll_rn(time_feature(dt, w[q]) * kFixScale));
     }
   }
   if (s_z > 0 && warp == nwarps - 1) {
