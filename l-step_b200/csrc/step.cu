@@ -11,6 +11,7 @@
 // and the history is never trimmed or concatenated: one [V1, d] table copy per step remains (the H term
 // of SURVEY §8(d)) instead of ~3 GB of clone + cat at Reddit size.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -27,7 +28,7 @@ void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, i
                        int32_t** counters);
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
-                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done);
+                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp);
 
 // a6's neighbourhood aggregate (blocks [0, grid_q)) and a7's edge aggregate (the rest) in ONE launch: both only
 // read the current table and neither depends on the other, so the short edge kernel (and its hub chain) hides
@@ -60,12 +61,33 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
 
 // ring[v][slot][:] = cur[v][:]  (node-major ring: 688-byte rows at a 68.8 KB pitch)
 // table row of ring row v is v*row_mul + row_add (1, 0 for a single GPU; G, rank for a node-id sharded ring)
+// dirty != NULL (streaming step, push form of phase B): the kernel in front is the phase-B MLP, launched with a late
+// trigger, so this kernel is resident only after the push kernel has completed: the set of rows the MLP is changing
+// (dirty[v] == stamp) is final, and all other rows of `cur` are. Every thread copies its elements BEFORE the
+// dependency wait, next to the MLP, and copies the elements of the changed rows again after it (same thread, same
+// address: program order). 14 of the 15.1 MB move off the step's critical path.
 __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restrict__ cur, float* __restrict__ ring,
-                                                          int64_t V1, int T, int d, int slot, int64_t row_mul, int64_t row_add) {
+                                                          int64_t V1, int T, int d, int slot, int64_t row_mul, int64_t row_add,
+                                                          const int32_t* dirty, int stamp) {
   pdl_launch_dependents();
-  pdl_wait();
   const int dvec = d >> 2;
   const int64_t total = V1 * dvec;
+  if (dirty) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t v = i / dvec;
+      const int c = (int)(i % dvec);
+      reinterpret_cast<float4*>(ring + (v * T + slot) * (int64_t)d)[c] = ld_dep(reinterpret_cast<const float4*>(cur + v * (int64_t)d) + c);
+    }
+    pdl_wait();
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t v = i / dvec;
+      const int c = (int)(i % dvec);
+      if (ld_dep(dirty + v) == stamp)
+        reinterpret_cast<float4*>(ring + (v * T + slot) * (int64_t)d)[c] = ld_dep(reinterpret_cast<const float4*>(cur + v * (int64_t)d) + c);
+    }
+    return;
+  }
+  pdl_wait();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t v = i / dvec;
     const int c = (int)(i % dvec);
@@ -138,7 +160,8 @@ extern "C" int lstep_ring_copy_rows(float* ring, float* cur, int64_t ring_rows, 
     return LSTEP_ERR_INVALID_ARG;
   if (ring_rows == 0) return LSTEP_OK;
   if (to_ring)
-    launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, as_stream(stream), cur, ring, ring_rows, T, d, slot, row_mul, row_add);
+    launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, as_stream(stream), cur, ring, ring_rows, T, d, slot, row_mul, row_add,
+             nullptr, 0);
   else
     ring_load_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(ring, cur, ring_rows, T, d, slot, row_mul, row_add);
   return check_launch("ring_copy_rows");
@@ -206,10 +229,18 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
     if (rc != LSTEP_OK) return rc;
   }
   // a7 + a8
+  static std::atomic<int> g_stamp{0};
+  int stamp = ++g_stamp;
+  if (stamp <= 0) {  // wrapped: restart (a stale equal value only costs a redundant row copy)
+    g_stamp = 1;
+    stamp = 1;
+  }
+  int32_t* dirty = nullptr;
+  static const bool no_early_append = getenv("LSTEP_NO_EARLY_APPEND") != nullptr;
   rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,
-                      err_flag, stream, edges_done);
+                      err_flag, stream, edges_done, no_early_append ? nullptr : &dirty, stamp);
   if (rc != LSTEP_OK) return rc;
-  launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0);
+  launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0, dirty, stamp);
   return check_launch("ring_append");
 }
 }  // namespace lstep

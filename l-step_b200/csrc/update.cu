@@ -41,7 +41,7 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
 bool pe_mlp_cluster_supports(const lstep_pe_mlp* m);
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
-                       unsigned long long* acc, uint32_t* err_flag, cudaStream_t st);
+                       unsigned long long* acc, int32_t* dirty, int stamp, uint32_t* err_flag, cudaStream_t st);
 
 constexpr int kRow0Parts = 64;
 constexpr int kHubLen = 4;     // a warp reduces a destination's slot list serially (~430 dependent instructions per
@@ -50,7 +50,7 @@ constexpr int kChunkLog2 = 2;  // slots per chunk task = 4
 
 struct UpdateWs {
   int32_t* cnt_of;   // [pe_rows]  zero between calls
-  int32_t* slot_of;  // [pe_rows]
+  int32_t* slot_of;  // [pe_rows]  pull form: slot index of a destination; push form: stamp of the last step whose phase B changed the row
   int32_t* claim_of; // [pe_rows]  zero between calls (push form of phase B: 0 free, -1 being set up, j+1 = accumulator row j)
   unsigned long long* hub_acc;  // [#long lists][d+t] 32.32 fixed-point accumulators (zeroed per call by the scan kernel)
   int32_t* counters; // [8]: 0=M, 1=has_zero, 2=n_dest, 3=n_hubs, 4=n_hub_tasks
@@ -564,7 +564,7 @@ void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, i
 
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
-                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done);
+                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp);
 }  // namespace lstep
 
 extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids,
@@ -572,14 +572,18 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
                                double current_time, int K, const lstep_pe_mlp* mlp, void* workspace,
                                size_t workspace_bytes, uint32_t* err_flag, void* stream) {
   return update_pe_impl(pe, pe_rows, csr, ids, n_ids, src, dst, times, n_edges, current_time, K, mlp, workspace, workspace_bytes,
-                        err_flag, stream, false);
+                        err_flag, stream, false, nullptr, 0);
 }
 
 // edges_done: phase A's aggregate rows (and the zeroed counters) are already in the workspace
 int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                           const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K,
                           const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream,
-                          bool edges_done) {
+                          bool edges_done, int32_t** dirty_out, int stamp) {
+  // dirty_out (streaming step): when the push form runs, *dirty_out = per-node map in which the rows phase B changes
+  // carry `stamp` (unique per step; no clearing, stale values never match), which the caller's ring append reads;
+  // the phase-B MLP is then launched with a late trigger so that the append may copy the unchanged rows next to it.
+  if (dirty_out) *dirty_out = nullptr;
   int rc = check_update_args(pe, pe_rows, mlp, n_ids, n_edges, K, workspace, workspace_bytes);
   if (rc != LSTEP_OK) return rc;
   if (!csr || (n_ids > 0 && !ids) || (n_edges > 0 && (!src || !dst || !times))) return LSTEP_ERR_INVALID_ARG;
@@ -604,7 +608,7 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
     static const bool pull = getenv("LSTEP_PHASEB_PULL") != nullptr;
     if (!pull && (d + t) % 2 == 0 && d <= 256 && t <= 256 && pe_mlp_cluster_supports(mlp)) {
       rc = launch_phaseB_push(csr, ids, times, n_ids, n_valid, K, pe, d, t, mlp->tw, tc, w.claim_of, w.U, w.counters, w.push_acc,
-                              err_flag, st);
+                              w.slot_of, stamp, err_flag, st);
       if (rc != LSTEP_OK) return rc;
       const int64_t total = n_ids * (int64_t)K;
       const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;
@@ -612,8 +616,10 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
       noself.ws = nullptr;  // the self term is computed and discarded by the reference (LSTEP.py:334-335, Q3)
       noself.bs = nullptr;
       noself.ws_tc = nullptr;
-      return launch_pe_mlp_cluster(nullptr, 0, pe, single_ids(w.U), max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe,
-                                   w.push_acc, w.claim_of, st);
+      if (dirty_out) *dirty_out = w.slot_of;
+      rc = launch_pe_mlp_cluster(nullptr, 0, pe, single_ids(w.U), max_dest + 1, n_ids * 6, w.counters + 2, &noself, nullptr, 0, pe,
+                                 w.push_acc, w.claim_of, st, dirty_out != nullptr);
+      return rc;
     }
   }
   if ((rc = phase_b_partial(pe, pe_rows, w, csr, ids, ids, n_ids, times, n_valid, tc, K, mlp, err_flag, stream)) != LSTEP_OK) return rc;

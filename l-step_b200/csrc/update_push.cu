@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
                                                           int64_t n_ids, int64_t n_valid, int K, float* pe, int d, int t,
                                                           const float* __restrict__ tw, float tc, int32_t* claim_of,
                                                           int64_t* __restrict__ U, int32_t* counters,
-                                                          unsigned long long* acc, uint32_t* err_flag) {
+                                                          unsigned long long* acc, int32_t* dirty, int stamp, uint32_t* err_flag) {
   // Dependency structure (programmatic dependent launch): the kernel in front is the phase-A MLP, launched with
   // a LATE trigger, so this kernel is resident only after everything before that MLP has completed. The lookup
   // and the claim phase touch nothing the phase-A MLP reads or writes (CSR, ids, claim map, counters, U, the
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
         if (old == 0) {
           j = atomicAdd(counters + 2, 1);
           U[j] = (int64_t)u;
+          dirty[u] = stamp;  // this table row changes in phase B of step `stamp` (read by the step's ring append)
           won = true;
         } else if (old > 0) {
           j = old - 1;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
         if (old == 0) {
           j0 = atomicAdd(counters + 2, 1);
           U[j0] = 0;
+          dirty[0] = stamp;
           won = true;
         } else if (old > 0) {
           j0 = old - 1;
@@ -232,15 +234,15 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
 // destinations U[0 .. counters[2])
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
-                       unsigned long long* acc, uint32_t* err_flag, cudaStream_t st) {
-  if (!csr || !ids || !q_time || n_ids <= 0 || K <= 0 || (d + t) % 2 != 0) return LSTEP_ERR_INVALID_ARG;
+                       unsigned long long* acc, int32_t* dirty, int stamp, uint32_t* err_flag, cudaStream_t st) {
+  if (!csr || !ids || !q_time || !dirty || n_ids <= 0 || K <= 0 || (d + t) % 2 != 0) return LSTEP_ERR_INVALID_ARG;
   const size_t smem = (size_t)((K + kPushSplit - 1) / kPushSplit) * 12;
   if (d <= 6 * 32 && t <= 4 * 32)
     launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, err_flag);
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, err_flag);
   else if (d <= 8 * 32 && t <= 8 * 32)
     launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, err_flag);
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, err_flag);
   else
     return LSTEP_ERR_UNSUPPORTED;
   return check_launch("phaseB_push");
