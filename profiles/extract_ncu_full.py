@@ -8,7 +8,7 @@ import json
 import subprocess
 import sys
 
-STAGE = [("dft_filter_bulk_kernel", "dft_filter"), ("dft_filter_kernel", "dft_filter(generic)"), ("nbr_aggregate_kernel", "nbr_lookup_aggregate"),
+STAGE = [("dft_filter_bulk_kernel", "dft_filter"), ("dft_filter_kernel", "dft_filter(generic)"), ("gather_ab_kernel", "gather_ab"), ("nbr_aggregate_kernel", "nbr_lookup_aggregate"),
          ("pe_mlp_cluster_kernel<(int)8>", "pe_mlp(nbr)"), ("pe_mlp_cluster_kernel<(int)4>", "pe_mlp(update A)"),
          ("pe_mlp_cluster_kernel<(int)12>", "pe_mlp(update B)"), ("pe_mlp_cluster_kernel<8>", "pe_mlp(nbr)"),
          ("pe_mlp_cluster_kernel<4>", "pe_mlp(update A)"), ("pe_mlp_cluster_kernel<12>", "pe_mlp(update B)"),
