@@ -125,7 +125,9 @@ def make_params_model(graph, sampler, device):
     return m.to(device).eval()
 
 
-def run_ours(args, rank, world):
+def run_ours(args, rank, world, own_pg=True):
+    """The headline workload on every rank (N > 1: independent replicas, weak scaling — the path does not shard at
+    this size). Returns the result line on rank 0; emits it when it owns the process group."""
     import torch
     import torch.distributed as dist
     from lstep_b200 import NeighborSampler, PEStream, _lib
@@ -133,7 +135,7 @@ def run_ours(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and own_pg:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     assert lib.lstep_device_ok() == 1
@@ -162,7 +164,10 @@ def run_ours(args, rank, world):
     W, Ksteps = args.warmup, args.steps
     W = max(W, 3)
     step_no = 0
-    for _ in range(W):
+    # the measured regime is the steady state with a FULL history (T steps per node: the DFT filter reads all of
+    # them); if fewer warm-up steps were asked for, the ring is filled first (untimed, reported in config)
+    fill = max(0, T_HIST + 10 - W)
+    for _ in range(fill + W):
         stream.step(step_no % nb, queries(step_no % nb), outs)
         step_no += 1
     torch.cuda.synchronize()
@@ -236,7 +241,7 @@ def run_ours(args, rank, world):
         e2e = e2e_pass(stream, g, e0, neg_all, step_no, nb, min(Ksteps, 300), B, world, dev)
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
         cpu = cpu_baseline(args.workload, B, K, args.cpu_batches)
 
     if rank == 0:
@@ -248,7 +253,7 @@ def run_ours(args, rank, world):
                                    f"T={T_HIST}, d={D}, t={T_DIM}, C={C_CALLS} neighbourhood calls/batch (eval loop)",
                        "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (path does not shard at this size)",
                        "l2_policy": f"inputs larger than L2: PE history ring {V1 * T_HIST * D * 4 / 1e6:.0f} MB, a different node set is read each step",
-                       "N_mean": N_mean, "M_mean": M_mean, "csr_build_s": t_csr},
+                       "N_mean": N_mean, "M_mean": M_mean, "csr_build_s": t_csr, "history_fill_steps_before_warmup": fill},
             "clocks": clk,
             "e2e": e2e,
             "gpu_launches": int(kern["_launches_per_step"]["n"] * Ksteps),
@@ -259,12 +264,18 @@ def run_ours(args, rank, world):
             "stages_ms": stages, "kernels_ms": {k: v for k, v in kern.items() if not k.startswith("_")},
             "cpu_baseline": cpu,
         }
-        emit(out)
-    if world > 1:
+        if own_pg:
+            emit(out)
+    else:
+        out = None
+    if world > 1 and own_pg:
         dist.destroy_process_group()
+    del stream, model, sampler
+    torch.cuda.empty_cache()
+    return out
 
 
-def run_sharded(args, rank, world):
+def run_sharded(args, rank, world, own_pg=True):
     """BASELINE config 5: scale-out graph (10 M nodes), node-id sharded PE history / CSR, NCCL all-to-all row
     exchanges (l-step_b200/shard.py). The batch is replicated, so the total work is fixed as N grows
     (strong scaling). T = 20 history steps so that the ring (137.6 GB in total) fits from N = 1 upwards."""
@@ -275,7 +286,9 @@ def run_sharded(args, rank, world):
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if not own_pg:
+        pass
+    elif world > 1:
         dist.init_process_group("nccl", device_id=dev)
     else:  # degenerate group of one: same code path, no peers
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -311,6 +324,9 @@ def run_sharded(args, rank, world):
         return [g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.src_node_ids[lo:hi], rng.choice(dst_pool, hi - lo)]
 
     W, Ksteps = max(args.warmup, 3), args.steps
+    if not own_pg:  # riding along with the replica run: a bounded sample
+        W, Ksteps = min(W, 30), min(Ksteps, 100)
+    W = max(W, T + 5)  # full history before the clock starts
     step_no = 0
     for _ in range(W):
         sh.step(step_no % nb, queries(step_no % nb))
@@ -379,8 +395,13 @@ def run_sharded(args, rank, world):
             "gpu_launches": int(Ksteps * 12 * world),
             "roofline": None, "cpu_baseline": None,
         }
-        emit(out)
-    dist.destroy_process_group()
+        if own_pg:
+            emit(out)
+    else:
+        out = None
+    if own_pg:
+        dist.destroy_process_group()
+    return out
 
 
 def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, lib):
@@ -582,7 +603,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     global T_HIST
-    if args.workload == "scaleout" or (world > 1 and not args.replicas):
+    if args.workload == "scaleout":
         # the sharded arm's config: batch shape of the Flights config (B=2000, K=20), T = --scaleout-T
         args.workload, T_HIST = "flights", args.scaleout_T
     B, K = WORKLOADS[args.workload]
@@ -635,7 +656,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS) + ["scaleout"])
-    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas of the single-GPU workload instead of the sharded scale-out graph")
+    ap.add_argument("--replicas", action="store_true", help="N > 1: only the replicas of the single-GPU workload (skip the sharded scale-out sample)")
     ap.add_argument("--scaleout-nodes", type=int, default=10_000_000)
     ap.add_argument("--scaleout-edges", type=int, default=40_000_000)
     ap.add_argument("--scaleout-T", type=int, default=20)
@@ -643,16 +664,40 @@ def main():
     ap.add_argument("--cpu-batches", type=int, default=40)
     args = ap.parse_args()
     if args.steps is None:
-        args.steps = 1000 if (int(os.environ.get("WORLD_SIZE", 1)) == 1 and args.workload != "scaleout") else 100
+        args.steps = 1000 if args.workload != "scaleout" else 100
     if args.warmup is None:
-        args.warmup = 120 if (int(os.environ.get("WORLD_SIZE", 1)) == 1 and args.workload != "scaleout") else 30
+        args.warmup = 120 if args.workload != "scaleout" else 30
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
-    elif args.workload == "scaleout" or (world > 1 and not args.replicas):
+    elif args.workload == "scaleout":
         run_sharded(args, rank, world)
+    elif world > 1:
+        # N > 1: the headline workload does not shard at this size (7 MB table, strictly sequential 200-edge batches), so
+        # the main line is N independent replicas of it (weak scaling, comparable with the N = 1 line). The sharded
+        # scale-out graph of BASELINE config 5 (node-id sharded PE table, NCCL all-to-all) is measured in the same
+        # run and reported under "scaleout" (strong scaling: the batch is replicated, the state is split).
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", 0))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        out = run_ours(args, rank, world, own_pg=False)
+        extra = None
+        if not args.replicas:
+            try:
+                extra = run_sharded(args, rank, world, own_pg=False)
+            except Exception as e:  # the main line must survive a failure of the extra arm
+                log("scale-out arm failed:", repr(e))
+                extra = {"error": repr(e)[:300]}
+        if rank == 0:
+            if extra is not None:
+                out["scaleout"] = {k: extra[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "e2e", "error")
+                                   if k in extra}
+            emit(out)
+        dist.destroy_process_group()
     else:
         run_ours(args, rank, world)
 

@@ -30,33 +30,51 @@ def _nvcc() -> str:
 
 
 def _digest() -> str:
+    """Content hash of the sources and flags. File NAMES enter relative to the repo (the snapshot on the GPU box lives
+    under another path; an absolute path here would force a rebuild there, by every rank at once)."""
     h = hashlib.sha256()
     files = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "lstep_b200.h")]
     for f in files:
         with open(f, "rb") as fh:
-            h.update(f.encode())
+            h.update(os.path.basename(f).encode())
             h.update(fh.read())
     h.update((" ".join(NVCC_FLAGS) + os.environ.get("LSTEP_NVCC_EXTRA", "")).encode())
     return h.hexdigest()
 
 
+def _up_to_date(dig: str) -> bool:
+    return os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
+    if not force and _up_to_date(dig):
         return LIB
-    extra = os.environ.get("LSTEP_NVCC_EXTRA", "").split()  # e.g. -DLSTEP_PROFILE_GATHER for instrumented builds
-    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
-    with open(os.path.join(PKG, ".build.log"), "w") as fh:
-        fh.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + log[-6000:])
-    if verbose:
-        print(log)
-    with open(STAMP, "w") as fh:
-        fh.write(dig)
+    import fcntl
+    with open(os.path.join(PKG, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)  # one builder at a time (torchrun starts one process per GPU)
+        try:
+            if not force and _up_to_date(dig):  # another process built it while this one waited
+                return LIB
+            extra = os.environ.get("LSTEP_NVCC_EXTRA", "").split()  # e.g. -DLSTEP_MLP_TIMING for instrumented builds
+            tmp = LIB + f".tmp{os.getpid()}"
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", tmp] + \
+                  [os.path.join(CSRC, s) for s in SOURCES]
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            log = res.stdout + res.stderr
+            with open(os.path.join(PKG, ".build.log"), "w") as fh:
+                fh.write(" ".join(cmd) + "\n" + log)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + log[-6000:])
+            if verbose:
+                print(log)
+            os.replace(tmp, LIB)  # atomic: a concurrent loader sees the old or the new library, never a partial file
+            with open(STAMP, "w") as fh:
+                fh.write(dig)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
