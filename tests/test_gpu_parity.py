@@ -443,6 +443,65 @@ def test_host_fed_step_matches_device_resident_step(torch_cuda):
     s.check_errors()
 
 
+def test_lookup_fused_aggregate_matches_sampler_plus_aggregate(torch_cuda):
+    """lstep_nbr_lookup_aggregate (lookup inside the gather kernel) == lstep_sample_recent_compact + lstep_nbr_aggregate,
+    bit for bit, including ties, empty histories and K larger than a warp."""
+    torch = torch_cuda
+    from lstep_b200 import NeighborSampler, _lib
+    lib = _lib.load()
+    g = synth.make_graph("tiny_ties", seed=3)
+    V1, d, t = g.num_nodes + 1, 172, 100
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V1)
+    rng = np.random.default_rng(1)
+    pe = torch.from_numpy(seeded_normal(8, (V1, d), 0.3)).cuda()
+    tw = torch.from_numpy((1.0 / 10 ** np.linspace(0, 9, t, dtype=np.float32)).astype(np.float32)).cuda()
+    n = 333
+    q = torch.from_numpy(rng.integers(0, V1, n).astype(np.int64)).cuda()  # includes the padding node 0
+    qt = torch.from_numpy(rng.choice(g.node_interact_times, n).astype(np.float64) + rng.integers(0, 2, n)).cuda()
+    for K in (1, 20, 70):
+        nbr = torch.empty((n, K), dtype=torch.int32, device="cuda")
+        nt = torch.empty((n, K), dtype=torch.float32, device="cuda")
+        S0 = torch.empty((n, d + t), dtype=torch.float32, device="cuda")
+        S1 = torch.empty_like(S0)
+        _lib.check(lib.lstep_sample_recent_compact(s.csr_ref, _lib.ptr(q), _lib.ptr(qt), n, n, K, _lib.ptr(nbr), _lib.ptr(nt),
+                                                   _lib.ptr(s._err), _lib.stream_ptr()), "k1")
+        _lib.check(lib.lstep_nbr_aggregate(_lib.ptr(pe), V1, _lib.ptr(qt), _lib.ptr(nbr), _lib.ptr(nt), n, K, _lib.ptr(tw), d, t,
+                                           _lib.ptr(S0), _lib.stream_ptr()), "agg")
+        _lib.check(lib.lstep_nbr_lookup_aggregate(s.csr_ref, _lib.ptr(q), _lib.ptr(qt), n, K, _lib.ptr(pe), V1, _lib.ptr(tw), d, t,
+                                                  _lib.ptr(S1), _lib.ptr(s._err), _lib.stream_ptr()), "fused")
+        assert torch.equal(S0, S1), K
+    s.check_errors()
+
+
+def test_stream_is_bit_reproducible(torch_cuda):
+    """Two streams fed the same batches end with bit-identical tables and histories: the programmatic-dependent-launch
+    chain (kernels resident before their predecessors finish, work done before the dependency wait) and the atomic
+    fixed-point accumulation leave no run-to-run freedom."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream
+    g = synth.make_graph("tiny_bip", seed=9)
+    V, d, T, K, B = g.num_nodes, 172, 100, 20, 40
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin("full", g, s, 172, d, 100, T, K)[0].eval()
+    init = seeded_normal(12, (V + 1, d), 0.3)
+    init[0] = 0
+    e0 = g.num_edges - 30 * B
+    rng = np.random.default_rng(4)
+    negs = [torch.from_numpy(rng.integers(1, V + 1, B).astype(np.int64)).cuda() for _ in range(30)]
+    tables = []
+    for rep in range(2):
+        st = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=torch.from_numpy(init).cuda(), start=e0)
+        outs = []
+        for b in range(st.num_batches):
+            lo, hi, _, _ = st.batch_arrays(b)
+            outs.append(st.step(b, [st.src[lo:hi], st.dst[lo:hi], negs[b][:hi - lo]]).clone())
+        tables.append((st.cur.clone(), st.export_history(), torch.cat([o.reshape(-1) for o in outs])))
+    for a, b in zip(tables[0], tables[1]):
+        assert torch.equal(a, b)
+    s.check_errors()
+
+
 # ------------------------------------------------------------------------------------------ (e) sharded table
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_ranks_match_single_gpu_stream(torch_cuda, world):
