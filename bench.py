@@ -413,7 +413,7 @@ def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, l
     from lstep_b200 import _lib
     m = model
     T, d, t = T_HIST, D, T_DIM
-    names = ["dft_filter", "nbr_lookup_aggregate", "pe_mlp(nbr)", "update_pe(4 kernels)", "ring_append"]
+    names = ["dft_filter", "nbr_lookup_aggregate", "pe_mlp(nbr)", "update_pe(drop-in, 4 kernels)", "ring_append"]
     acc = {k: 0.0 for k in names}
     M_meas = []
 
@@ -458,7 +458,7 @@ def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, l
                 _lib.ptr(sampler._err), _lib.stream_ptr()), "agg"))
             ev["pe_mlp(nbr)"] = timed(lambda: _lib.check(lib.lstep_pe_mlp_apply(_lib.ptr(S), _lib.ptr(stream.cur), _lib.ptr(qcat), rows, m._mlp_ref("nbr"),
                                                                                _lib.ptr(outb), d, None, _lib.stream_ptr()), "mlp"))
-            ev["update_pe(4 kernels)"] = timed(lambda: m.update_pe_device(scratch, ids, src, dst, tt, stream.batch_tmax[b], K))
+            ev["update_pe(drop-in, 4 kernels)"] = timed(lambda: m.update_pe_device(scratch, ids, src, dst, tt, stream.batch_tmax[b], K))
             ev["ring_append"] = timed(lambda: _lib.check(lib.lstep_ring_copy_rows(_lib.ptr(stream.ring), _lib.ptr(stream.cur), stream.V1, T, d, nxt, 1, 0, 1,
                                                                                  _lib.stream_ptr()), "append"))
             torch.cuda.synchronize()
@@ -471,8 +471,9 @@ def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, l
             "pe_mlp(nbr)": {"ms": stages["pe_mlp(nbr)"], "launches_per_step": 1},
             "ring_append": {"ms": stages["ring_append"], "launches_per_step": 1},
             # own kernels per step (csrc/step.cu): DFT filter 1; fused gather (a6 lookup + aggregate of all C query sets
-            # || a7 edge aggregate) 1; MLP(nbr) 1; update_pe 3 (MLP phase A, phase B push, MLP phase B); ring append 1
-            "_launches_per_step": {"n": 1 + 1 + 1 + 3 + 1, "ms": 0.0, "launches_per_step": 0}}
+            # || a7 edge aggregate) 1; paired MLP (neighbourhood MLP || phase-A MLP) 1; phase-B push 1; phase-B MLP 1;
+            # ring append 1
+            "_launches_per_step": {"n": 6, "ms": 0.0, "launches_per_step": 0}}
     # measured M: distinct sampled neighbours per batch
     for i in range(min(n, 20)):
         b = (step_no + i) % nb

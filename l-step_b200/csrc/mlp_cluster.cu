@@ -173,12 +173,39 @@ __device__ __forceinline__ void k_run(const float* __restrict__ w, int ldo, cons
     }
 }
 
+// One launch can carry TWO independent MLP jobs (different rows, weights and outputs) on disjoint sets of clusters:
+// clusters [0, split) run job 0, the rest job 1. The streaming step uses it for the neighbourhood MLP of the C query
+// sets and the phase-A MLP of update_pe, which both only read the table (phase A then writes its rows to a side
+// buffer that the push kernel applies): one launch, one set of fixed costs, instead of two links of the chain.
+struct MlpJob {
+  const float* A;
+  int64_t lda;
+  RowIds base_ids;
+  int64_t n_rows;
+  const int32_t* n_rows_dev;
+  lstep_pe_mlp m;
+  float* out;
+  int64_t out_stride;
+  float* pe_inplace;
+};
+
 template <int TR>
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
-    pe_mlp_cluster_kernel(const float* __restrict__ A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows,
-                          const int32_t* __restrict__ n_rows_dev, lstep_pe_mlp m, float* __restrict__ out, int64_t out_stride,
-                          float* pe_inplace, FixedRows fx) {
+    pe_mlp_cluster_kernel(const __grid_constant__ MlpJob job0, const __grid_constant__ MlpJob job1, int split, const float* pe,
+                          FixedRows fx) {
   constexpr int RB = 4 * TR, RBp = RB + 4;
+  const int64_t cluster_raw = blockIdx.x / kCl;
+  const bool second = cluster_raw >= split;
+  const MlpJob& jb = second ? job1 : job0;
+  const float* __restrict__ A = jb.A;
+  const int64_t lda = jb.lda;
+  const RowIds& base_ids = jb.base_ids;
+  int64_t n_rows = jb.n_rows;
+  const int32_t* __restrict__ n_rows_dev = jb.n_rows_dev;
+  const lstep_pe_mlp& m = jb.m;
+  float* __restrict__ out = jb.out;
+  const int64_t out_stride = jb.out_stride;
+  float* pe_inplace = jb.pe_inplace;
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t wbar[2];  // weight slices landed (layer 1, layer 2)
   __shared__ __align__(8) uint64_t rbar[2];  // reduce-scatter 1 / 2 of the current row tile landed
@@ -239,7 +266,8 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
     n_rows = nd < n_rows ? nd : n_rows;
   }
   const int64_t n_tiles = (n_rows + RB - 1) / RB;
-  const int64_t cluster_id = blockIdx.x / kCl, n_clusters = gridDim.x / kCl;
+  const int64_t cluster_id = second ? cluster_raw - split : cluster_raw;
+  const int64_t n_clusters = second ? (int64_t)(gridDim.x / kCl) - split : (int64_t)split;
   const bool idle = cluster_id >= n_tiles;  // a cluster without a row tile still completes the rendezvous and drains its copies
   if (tid < RB) {  // first dependent load chain of the kernel (id -> base row)
     const int64_t row = cluster_id * RB + tid;
@@ -468,12 +496,13 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
 }
 
 template <int TR>
-int launch_cl(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, const int32_t* n_rows_dev,
-              const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace, FixedRows fx, cudaStream_t st) {
+int launch_cl(const MlpJob& j0, const MlpJob* j1, const float* pe, FixedRows fx, cudaStream_t st) {
   constexpr int RB = 4 * TR;
+  const lstep_pe_mlp* m = &j0.m;
   const ClShape sh = cl_shape(m->d, m->t, m->ws != nullptr, RB);
   const size_t smem = sh.smem_floats * sizeof(float);
   if (smem > 226 * 1024 || sh.nthreads > 512 || sh.ncg % kCl != 0) return LSTEP_ERR_UNSUPPORTED;
+  if (j1 && (j1->m.d != m->d || j1->m.t != m->t || (j1->m.ws != nullptr) != (m->ws != nullptr))) return LSTEP_ERR_UNSUPPORTED;
   auto kern = pe_mlp_cluster_kernel<TR>;
   static int max_clusters = 0;  // co-resident clusters of 4 (B200: 33 — some GPCs strand SMs), queried once
   if (max_clusters == 0) {
@@ -501,9 +530,13 @@ int launch_cl(const float* A, int64_t lda, const float* pe, RowIds base_ids, int
     }
     max_clusters = n;
   }
-  int64_t clusters = ceil_div(n_rows, RB);
-  if (clusters > max_clusters) clusters = max_clusters;  // persistent: the cluster walks row tiles, weights stay resident
-  launch_k(kern, dim3((unsigned)(clusters * kCl)), dim3(sh.nthreads), smem, st, A, lda, pe, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace, fx);
+  int64_t c0 = ceil_div(j0.n_rows, RB), c1 = j1 ? ceil_div(j1->n_rows, RB) : 0;
+  if (j1) {
+    if (c0 + c1 > max_clusters) return LSTEP_ERR_UNSUPPORTED;  // a pair must fit one round (the caller picks a larger tile or splits)
+  } else if (c0 > max_clusters) {
+    c0 = max_clusters;  // persistent: the cluster walks row tiles, weights stay resident
+  }
+  launch_k(kern, dim3((unsigned)((c0 + c1) * kCl)), dim3(sh.nthreads), smem, st, j0, j1 ? *j1 : j0, (int)c0, pe, fx);
   return check_launch("pe_mlp_cluster");
 }
 
@@ -515,12 +548,27 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                           const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger) {
   const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0};
+  const MlpJob j{A, lda, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace};
   // rows per cluster tile: the smallest tile that covers the launch in one round of ~32 co-resident clusters
-  if (expected_rows <= 32 * 16) return launch_cl<4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
-  if (expected_rows <= 32 * 32) return launch_cl<8>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
-  const int rc = launch_cl<12>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
+  if (expected_rows <= 32 * 16) return launch_cl<4>(j, nullptr, pe, fx, st);
+  if (expected_rows <= 32 * 32) return launch_cl<8>(j, nullptr, pe, fx, st);
+  const int rc = launch_cl<12>(j, nullptr, pe, fx, st);
   if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
-  return launch_cl<8>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, fx, st);
+  return launch_cl<8>(j, nullptr, pe, fx, st);
+}
+
+// Two float-input jobs in one launch (see MlpJob); LSTEP_ERR_UNSUPPORTED when they do not fit one round of clusters.
+int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, RowIds ids0, int64_t rows0, const lstep_pe_mlp* m0,
+                               float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
+                               const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger) {
+  if (rows0 <= 0 || rows1 <= 0 || !out0 || !out1) return LSTEP_ERR_UNSUPPORTED;
+  const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0};
+  const MlpJob j0{A0, lda0, ids0, rows0, nullptr, *m0, out0, out_stride0, nullptr};
+  const MlpJob j1{A1, lda1, ids1, rows1, nullptr, *m1, out1, out_stride1, nullptr};
+  int rc = launch_cl<4>(j0, &j1, pe, fx, st);
+  if (rc == LSTEP_ERR_UNSUPPORTED) rc = launch_cl<8>(j0, &j1, pe, fx, st);
+  if (rc == LSTEP_ERR_UNSUPPORTED) rc = launch_cl<12>(j0, &j1, pe, fx, st);
+  return rc;
 }
 
 // true when the cluster kernel covers this MLP shape (the push form of update_pe phase B depends on it)

@@ -25,10 +25,14 @@ int launch_sample(const lstep_csr* csr, RowIds q_node, const double* q_time, int
 int launch_nbr_lookup_aggregate(const lstep_csr* csr, RowIds q_node, const float* pe, const double* q_time, int64_t n_rows, int K,
                                 const float* tw, int d, int t, float* S, int64_t ldS, uint32_t* err_flag, cudaStream_t st);
 void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows, float** A, int64_t* lda,
-                       int32_t** counters);
+                       int32_t** counters, float** new_rows);
+bool update_push_available(const lstep_pe_mlp* mlp);
+int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, RowIds ids0, int64_t rows0, const lstep_pe_mlp* m0,
+                               float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
+                               const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger);
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
-                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp);
+                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows);
 
 // a6's neighbourhood aggregate (blocks [0, grid_q)) and a7's edge aggregate (the rest) in ONE launch: both only
 // read the current table and neither depends on the other, so the short edge kernel (and its hub chain) hides
@@ -199,16 +203,17 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
     q.p[c] = query_ids_host[c];
   }
   q.period = n_edges;
-  bool edges_done = false;
+  bool edges_done = false, phase_a_done = false;
+  float* A = nullptr;      // phase A's aggregate rows / result rows inside the update workspace
+  float* new_rows = nullptr;
+  int64_t ldA = 0;
+  int32_t* counters = nullptr;
   static const bool no_fuse = getenv("LSTEP_NO_GATHER_FUSE") != nullptr;
   const int t_pad = (int)align_up((size_t)t, 32);
   const int threads = (int)align_up((size_t)t_pad + d / 4, 32);
   const bool vec_ok = d % 4 == 0 && w.lda % 4 == 0 && reinterpret_cast<uintptr_t>(s->cur) % 16 == 0 && threads <= 512;
   if (!no_fuse && rows > 0 && n_ids > 0 && n_edges > 0 && vec_ok && t == mlp_upd->t && d == mlp_upd->d) {
-    float* A = nullptr;
-    int64_t ldA = 0;
-    int32_t* counters = nullptr;
-    update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters);
+    update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters, &new_rows);
     const int64_t cap = (int64_t)kNumSMs * 16;
     const int grid_q = (int)(rows < cap ? rows : cap), grid_e = (int)(n_ids < cap ? n_ids : cap);
     const size_t smem = std::max((size_t)K * 8, (size_t)threads * kSegPerThread * 8 + 32 * 4);
@@ -225,8 +230,24 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
       rc = launch_nbr_lookup_aggregate(csr, q, s->cur, tq, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, err_flag, st);
       if (rc != LSTEP_OK) return rc;
     }
-    rc = launch_pe_mlp(w.S, w.lda, s->cur, q, rows, rows, nullptr, mlp_nbr, nbr_out, d, nullptr, st);
-    if (rc != LSTEP_OK) return rc;
+    // the neighbourhood MLP and phase A's MLP in ONE launch when they fit one round of clusters: neither writes the
+    // table then (phase A's rows go to new_rows and are applied by the push kernel), so they need no order
+    static const bool no_pair = getenv("LSTEP_NO_MLP_PAIR") != nullptr;
+    if (edges_done && !no_pair && mlp_nbr->ws && mlp_upd->ws && update_push_available(mlp_upd)) {
+      RowIds ida{};
+      ida.p[0] = ids;
+      ida.period = 0;
+      rc = launch_pe_mlp_cluster_pair(s->cur, w.S, w.lda, q, rows, mlp_nbr, nbr_out, d, A, ldA, ida, n_ids, mlp_upd, new_rows, d, st,
+                                      /*late_trigger=*/true);
+      if (rc == LSTEP_OK)
+        phase_a_done = true;
+      else if (rc != LSTEP_ERR_UNSUPPORTED)
+        return rc;
+    }
+    if (!phase_a_done) {
+      rc = launch_pe_mlp(w.S, w.lda, s->cur, q, rows, rows, nullptr, mlp_nbr, nbr_out, d, nullptr, st);
+      if (rc != LSTEP_OK) return rc;
+    }
   }
   // a7 + a8
   static std::atomic<int> g_stamp{0};
@@ -238,7 +259,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   int32_t* dirty = nullptr;
   static const bool no_early_append = getenv("LSTEP_NO_EARLY_APPEND") != nullptr;
   rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,
-                      err_flag, stream, edges_done, no_early_append ? nullptr : &dirty, stamp);
+                      err_flag, stream, edges_done, no_early_append ? nullptr : &dirty, stamp, phase_a_done);
   if (rc != LSTEP_OK) return rc;
   launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0, dirty, stamp);
   return check_launch("ring_append");

@@ -41,7 +41,7 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
 bool pe_mlp_cluster_supports(const lstep_pe_mlp* m);
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
-                       unsigned long long* acc, int32_t* dirty, int stamp, uint32_t* err_flag, cudaStream_t st);
+                       unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st);
 
 constexpr int kRow0Parts = 64;
 constexpr int kHubLen = 4;     // a warp reduces a destination's slot list serially (~430 dependent instructions per
@@ -70,6 +70,7 @@ struct UpdateWs {
   float* row0_part;  // [kRow0Parts*d]
   float* A;          // [max(N, N*K+1)][lda], lda = d+t rounded up to 4 floats
   unsigned long long* push_acc;  // [N*K+1][d+t] 32.32 fixed-point accumulator rows of the push form
+  float* new_rows;   // [N][d] phase A's result rows when its MLP does not write the table itself (streaming step)
   int64_t lda;
   size_t bytes;
 };
@@ -107,6 +108,7 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
   w.A = (float*)take(sizeof(float) * rowsA * w.lda);
   // own storage: the push kernel sets accumulator rows up while the phase-A MLP is still reading A
   w.push_acc = (unsigned long long*)take(sizeof(unsigned long long) * (nk + 1) * (size_t)(d + t));
+  w.new_rows = (float*)take(sizeof(float) * (size_t)n_ids * d);
   w.bytes = o;
   return w;
 }
@@ -555,16 +557,23 @@ static int phase_b_apply(float* pe, int64_t pe_rows, const UpdateWs& w, int64_t 
 namespace lstep {
 // where phase A's aggregate rows and the phase-B counters live inside an update workspace
 void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows, float** A, int64_t* lda,
-                       int32_t** counters) {
+                       int32_t** counters, float** new_rows) {
   UpdateWs w = carve(workspace, n_ids, n_edges, K, d, t, pe_rows);
   *A = w.A;
   *lda = w.lda;
   *counters = w.counters;
+  *new_rows = w.new_rows;
+}
+
+// the push form of phase B (and with it the side-buffer form of phase A) is available for this shape
+bool update_push_available(const lstep_pe_mlp* mlp) {
+  static const bool pull = getenv("LSTEP_PHASEB_PULL") != nullptr;
+  return !pull && mlp && (mlp->d + mlp->t) % 2 == 0 && mlp->d <= 256 && mlp->t <= 256 && pe_mlp_cluster_supports(mlp);
 }
 
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
-                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp);
+                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows);
 }  // namespace lstep
 
 extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids,
@@ -572,14 +581,16 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
                                double current_time, int K, const lstep_pe_mlp* mlp, void* workspace,
                                size_t workspace_bytes, uint32_t* err_flag, void* stream) {
   return update_pe_impl(pe, pe_rows, csr, ids, n_ids, src, dst, times, n_edges, current_time, K, mlp, workspace, workspace_bytes,
-                        err_flag, stream, false, nullptr, 0);
+                        err_flag, stream, false, nullptr, 0, false);
 }
 
 // edges_done: phase A's aggregate rows (and the zeroed counters) are already in the workspace
 int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                           const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K,
                           const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream,
-                          bool edges_done, int32_t** dirty_out, int stamp) {
+                          bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows) {
+  // phase_a_in_new_rows (streaming step): phase A's MLP has already run (in the caller's paired launch) and left its
+  // rows in the workspace's new_rows buffer; the push kernel applies them. Requires update_push_available().
   // dirty_out (streaming step): when the push form runs, *dirty_out = per-node map in which the rows phase B changes
   // carry `stamp` (unique per step; no clearing, stale values never match), which the caller's ring append reads;
   // the phase-B MLP is then launched with a late trigger so that the append may copy the unchanged rows next to it.
@@ -600,15 +611,15 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
     }
     return LSTEP_OK;
   }
-  if ((rc = phase_a(pe, w, ids, n_ids, src, dst, times, n_edges, tc, mlp, st, edges_done)) != LSTEP_OK) return rc;
+  if (phase_a_in_new_rows && !update_push_available(mlp)) return LSTEP_ERR_INVALID_ARG;
+  if (!phase_a_in_new_rows && (rc = phase_a(pe, w, ids, n_ids, src, dst, times, n_edges, tc, mlp, st, edges_done)) != LSTEP_OK) return rc;
   const int64_t n_valid = n_ids < n_edges ? n_ids : n_edges;  // zip(node_ids, times) truncation (Q1)
   {
     // phase B, push form (csrc/update_push.cu): lookup + exact fixed-point accumulation where the contribution
     // lands, then the MLP straight off the accumulator rows. LSTEP_PHASEB_PULL=1 selects the pull form below.
-    static const bool pull = getenv("LSTEP_PHASEB_PULL") != nullptr;
-    if (!pull && (d + t) % 2 == 0 && d <= 256 && t <= 256 && pe_mlp_cluster_supports(mlp)) {
+    if (update_push_available(mlp)) {
       rc = launch_phaseB_push(csr, ids, times, n_ids, n_valid, K, pe, d, t, mlp->tw, tc, w.claim_of, w.U, w.counters, w.push_acc,
-                              w.slot_of, stamp, err_flag, st);
+                              w.slot_of, stamp, phase_a_in_new_rows ? w.new_rows : nullptr, err_flag, st);
       if (rc != LSTEP_OK) return rc;
       const int64_t total = n_ids * (int64_t)K;
       const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
                                                           int64_t n_ids, int64_t n_valid, int K, float* pe, int d, int t,
                                                           const float* __restrict__ tw, float tc, int32_t* claim_of,
                                                           int64_t* __restrict__ U, int32_t* counters,
-                                                          unsigned long long* acc, int32_t* dirty, int stamp, uint32_t* err_flag) {
+                                                          unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag) {
   // Dependency structure (programmatic dependent launch): the kernel in front is the phase-A MLP, launched with
   // a LATE trigger, so this kernel is resident only after everything before that MLP has completed. The lookup
   // and the claim phase touch nothing the phase-A MLP reads or writes (CSR, ids, claim map, counters, U, the
@@ -201,14 +201,19 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // pe[0] = 0 (LSTEP.py:317); no batch row reads row 0 below
 
-  // ---- this row's PE in fixed point (phase-A table), once per warp
+  // ---- this row's PE in fixed point (phase-A table), once per warp. new_rows != NULL (streaming step): phase A
+  // wrote its result rows to a side buffer (its MLP ran in the same launch as the neighbourhood MLP, which still
+  // read the old table); this kernel both uses them and applies them to the table (one CTA per row).
   const int64_t node = ids[row];
+  const float* src_row = new_rows ? new_rows + row * (int64_t)d : pe + node * (int64_t)d;
   long long fx[DQ];
 #pragma unroll
   for (int q = 0; q < DQ; ++q) {
     const int c = lane + 32 * q;
-    fx[q] = (c < d && node > 0) ? __float2ll_rn(ld_dep(pe + node * (int64_t)d + c) * kFixScale) : 0ll;
+    fx[q] = (c < d && node > 0) ? __float2ll_rn(ld_dep(src_row + c) * kFixScale) : 0ll;
   }
+  if (new_rows && part == 0 && node > 0)  // row 0 is zeroed above (LSTEP.py:317 follows the phase-A write)
+    for (int c = threadIdx.x; c < d; c += blockDim.x) pe[node * (int64_t)d + c] = ld_dep(src_row + c);
   for (int k = warp; k < k_hi - k_lo; k += nwarps) {
     const int j = s_slot[k];
     if (j < 0) continue;
@@ -234,15 +239,15 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
 // destinations U[0 .. counters[2])
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
-                       unsigned long long* acc, int32_t* dirty, int stamp, uint32_t* err_flag, cudaStream_t st) {
+                       unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st) {
   if (!csr || !ids || !q_time || !dirty || n_ids <= 0 || K <= 0 || (d + t) % 2 != 0) return LSTEP_ERR_INVALID_ARG;
   const size_t smem = (size_t)((K + kPushSplit - 1) / kPushSplit) * 12;
   if (d <= 6 * 32 && t <= 4 * 32)
     launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, err_flag);
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag);
   else if (d <= 8 * 32 && t <= 8 * 32)
     launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, err_flag);
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag);
   else
     return LSTEP_ERR_UNSUPPORTED;
   return check_launch("phaseB_push");
