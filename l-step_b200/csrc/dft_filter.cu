@@ -173,11 +173,16 @@ constexpr int kDftChunks = 4;
 
 __device__ __forceinline__ uint32_t dft_s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// prefetch (streaming step): the kernel in front is the previous step's ring append, and everything before THAT has
+// completed by the time this kernel is resident (late triggers, see csrc/common.cuh), so the only rows of the ring
+// still being written are those of the NEWEST slot. The first kDftChunks-1 chunks then cover the Th-1 older rows and
+// are requested BEFORE the dependency wait — 99 % of the kernel's HBM traffic overlaps the tail of the previous
+// step — and the last chunk is the newest row alone, requested after the wait.
 __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const float* __restrict__ hist, int64_t node_stride, int s0,
                                                                       int ring, int Th, int d, const int64_t* __restrict__ ids,
                                                                       int64_t n_ids, const float* __restrict__ G,
                                                                       float* __restrict__ out, int64_t out_stride,
-                                                                      const int64_t* __restrict__ out_ids) {
+                                                                      const int64_t* __restrict__ out_ids, int prefetch) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar[kDftChunks];
   float4* xs = reinterpret_cast<float4*>(smem_raw);  // [Th][dvec] logical time order
@@ -186,11 +191,45 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
   const int groups = kDftThreads / dvec;
   const int g = threadIdx.x / dvec, cv = threadIdx.x % dvec;
   const bool active = g < groups;
-  const int rc = (Th + kDftChunks - 1) / kDftChunks;  // rows per chunk
+  // chunks 0 .. kDftChunks-2: the Th-1 older rows; last chunk: the newest row alone (the same partition with and
+  // without prefetch, so both forms add in the same order and agree bit for bit)
+  const int rc = (Th - 1 + kDftChunks - 2) / (kDftChunks - 1);  // rows per chunk
+  auto bounds = [&](int c, int& a, int& b) {
+    if (c == kDftChunks - 1) {
+      a = Th - 1;
+      b = Th;
+    } else {
+      a = c * rc;
+      b = min(Th - 1, a + rc);
+    }
+  };
+  auto request = [&](const float* base, int c) {  // one elected thread: bulk copies of chunk c, logical order in smem
+    int a, b;
+    bounds(c, a, b);
+    if (a >= b) return;
+    const uint32_t bytes = (uint32_t)(b - a) * (uint32_t)d * 4u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dft_s_u32(&bar[c])), "r"(bytes) : "memory");
+    int ps = s0 + a;
+    if (ps >= ring) ps -= ring;
+    const int first = min(b - a, ring - ps);  // rows before the ring wraps
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dft_s_u32(xs + (size_t)a * dvec)),
+                 "l"(base + (int64_t)ps * d), "r"((uint32_t)first * (uint32_t)d * 4u), "r"(dft_s_u32(&bar[c]))
+                 : "memory");
+    if (first < b - a)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       dft_s_u32(xs + (size_t)(a + first) * dvec)),
+                   "l"(base), "r"((uint32_t)(b - a - first) * (uint32_t)d * 4u), "r"(dft_s_u32(&bar[c]))
+                   : "memory");
+  };
   if (threadIdx.x == 0) {
     for (int c = 0; c < kDftChunks; ++c)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(dft_s_u32(&bar[c])), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    if (prefetch && (int64_t)blockIdx.x < n_ids) {  // ids: the batch's node list, not written by any kernel of the chain
+      const float* base = hist + ids[blockIdx.x] * node_stride;
+      for (int c = 0; c < kDftChunks - 1; ++c) request(base, c);
+    }
   }
   __syncthreads();
   pdl_wait();
@@ -202,29 +241,13 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
   for (int64_t n = blockIdx.x; n < n_ids; n += gridDim.x, ++it) {
     if (threadIdx.x == 0) {
       const float* base = hist + ids[n] * node_stride;
-      for (int c = 0; c < kDftChunks; ++c) {
-        const int a = c * rc, b = min(Th, a + rc);
-        if (a >= b) continue;
-        const uint32_t bytes = (uint32_t)(b - a) * (uint32_t)d * 4u;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(dft_s_u32(&bar[c])), "r"(bytes) : "memory");
-        int ps = s0 + a;
-        if (ps >= ring) ps -= ring;
-        const int first = min(b - a, ring - ps);  // rows before the ring wraps
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         dft_s_u32(xs + (size_t)a * dvec)),
-                     "l"(base + (int64_t)ps * d), "r"((uint32_t)first * (uint32_t)d * 4u), "r"(dft_s_u32(&bar[c]))
-                     : "memory");
-        if (first < b - a)
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           dft_s_u32(xs + (size_t)(a + first) * dvec)),
-                       "l"(base), "r"((uint32_t)(b - a - first) * (uint32_t)d * 4u), "r"(dft_s_u32(&bar[c]))
-                       : "memory");
-      }
+      for (int c = (prefetch && it == 0) ? kDftChunks - 1 : 0; c < kDftChunks; ++c) request(base, c);
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = 0; c < kDftChunks; ++c) {
-      const int a = c * rc, b = min(Th, a + rc);
-      if (a >= b) break;
+      int a, b;
+      bounds(c, a, b);
+      if (a >= b) continue;
       // this thread's rows of the chunk: a + g, a + g + groups, ...; fetch their filter rows before waiting
       constexpr int kMaxRows = 8;
       float4 w[kMaxRows];
@@ -319,7 +342,7 @@ extern "C" int lstep_dft_collapse(const float* W_c64, const float* a, int T, int
 namespace lstep {
 int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
                       const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride,
-                      const int64_t* out_ids, void* stream) {
+                      const int64_t* out_ids, void* stream, bool prefetch_old_rows) {
   if (n_ids < 0 || Th < 0 || d <= 0 || ring < Th || s0 < 0 || (ring > 0 && s0 >= ring)) return LSTEP_ERR_INVALID_ARG;
   if (n_ids == 0) return LSTEP_OK;
   if (!ids || !out || !G || (Th > 0 && !hist)) return LSTEP_ERR_INVALID_ARG;
@@ -346,7 +369,7 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
       }
       const int64_t bgrid = n_ids < (int64_t)kNumSMs * 3 ? n_ids : (int64_t)kNumSMs * 3;
       launch_k(dft_filter_bulk_kernel, dim3((unsigned)bgrid), dim3(kDftThreads), bulk_smem, st, hist, node_stride, s0, ring, Th, d, ids,
-               n_ids, G, out, out_stride, out_ids);
+               n_ids, G, out, out_stride, out_ids, prefetch_old_rows ? 1 : 0);
       return check_launch("dft_filter_bulk");
     }
   }
@@ -363,7 +386,7 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
 extern "C" int lstep_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th,
                                 int d, const int64_t* ids, int64_t n_ids, const float* G, float* out,
                                 int64_t out_stride, void* stream) {
-  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, nullptr, stream);
+  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, nullptr, stream, false);
 }
 
 /* Same filter with the result row n written to out + out_ids[n]*out_stride (history rows and table rows
@@ -372,7 +395,7 @@ extern "C" int lstep_dft_filter_scatter(const float* hist, int64_t node_stride, 
                                         int d, const int64_t* ids, const int64_t* out_ids, int64_t n_ids, const float* G,
                                         float* out, int64_t out_stride, void* stream) {
   if (!out_ids && n_ids > 0) return LSTEP_ERR_INVALID_ARG;
-  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids, stream);
+  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids, stream, false);
 }
 
 extern "C" int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring,

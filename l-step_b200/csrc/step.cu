@@ -61,7 +61,7 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
                   cudaStream_t st, bool late_trigger = false);
 int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
                       const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride,
-                      const int64_t* out_ids, void* stream);
+                      const int64_t* out_ids, void* stream, bool prefetch_old_rows);
 
 // ring[v][slot][:] = cur[v][:]  (node-major ring: 688-byte rows at a 68.8 KB pitch)
 // table row of ring row v is v*row_mul + row_add (1, 0 for a single GPU; G, rank for a node-id sharded ring)
@@ -192,7 +192,8 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   int rc;
   // a3: filtered history of the batch nodes straight into the current table
   if (n_ids > 0) {
-    rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, ids, stream);
+    static const bool no_prefetch = getenv("LSTEP_NO_DFT_PREFETCH") != nullptr;
+    rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, ids, stream, !no_prefetch);
     if (rc != LSTEP_OK) return rc;
   }
   // a6 gather + a7 edge aggregate: one heterogeneous launch when both exist and the 128-bit paths apply
@@ -261,7 +262,9 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,
                       err_flag, stream, edges_done, no_early_append ? nullptr : &dirty, stamp, phase_a_done);
   if (rc != LSTEP_OK) return rc;
-  launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0, dirty, stamp);
+  // 2 CTAs per SM: the append is resident (copying, then waiting for the phase-B MLP) while the NEXT step's DFT filter
+  // wants to become resident and prefetch — it must leave thread slots and shared memory for it
+  launch_k(ring_append_kernel, dim3(kNumSMs * 2), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0, dirty, stamp);
   return check_launch("ring_append");
 }
 }  // namespace lstep
