@@ -222,8 +222,8 @@ def run_ours(args, rank, world, own_pg=True):
     for k in alg:
         ach = alg[k] / (kern[k]["ms"] * 1e-3) / 1e9
         roof_all[k] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                       # (the step launches the gather fused with phase A's edge aggregate: its capture stands in here)
-                       "traffic": (ncu_full.get(k) or ncu_full.get({"nbr_lookup_aggregate": "gather_ab"}.get(k, ""), {})).get("dram_bytes_per_launch"),
+                       # (the step launches the gather fused with phase A's edge aggregate and the two MLPs as a pair: those captures stand in)
+                       "traffic": (ncu_full.get(k) or ncu_full.get({"nbr_lookup_aggregate": "gather_ab", "pe_mlp(nbr)": "pe_mlp(pair: nbr || update A)"}.get(k, ""), {})).get("dram_bytes_per_launch"),
                        "algorithmic_bytes_per_launch": alg[k],
                        "ms_per_launch": kern[k]["ms"]}
     # dominant kernel: the single kernel with the largest share of the step

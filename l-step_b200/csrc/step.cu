@@ -77,17 +77,41 @@ __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restric
   const int dvec = d >> 2;
   const int64_t total = V1 * dvec;
   if (dirty) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t v = i / dvec;
-      const int c = (int)(i % dvec);
-      reinterpret_cast<float4*>(ring + (v * T + slot) * (int64_t)d)[c] = ld_dep(reinterpret_cast<const float4*>(cur + v * (int64_t)d) + c);
+    // every thread owns up to kPer elements per sweep; loads of a sweep are issued together (one latency, not kPer)
+    constexpr int kPer = 8;
+    const int64_t nthr = (int64_t)gridDim.x * blockDim.x, gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t base = 0; base < total; base += nthr * kPer) {
+      float4 val[kPer];
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        const int64_t i = base + gtid + e * nthr;
+        if (i < total) val[e] = ld_dep(reinterpret_cast<const float4*>(cur + (i / dvec) * (int64_t)d) + (int)(i % dvec));
+      }
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        const int64_t i = base + gtid + e * nthr;
+        if (i < total) reinterpret_cast<float4*>(ring + ((i / dvec) * T + slot) * (int64_t)d)[i % dvec] = val[e];
+      }
     }
     pdl_wait();
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t v = i / dvec;
-      const int c = (int)(i % dvec);
-      if (ld_dep(dirty + v) == stamp)
-        reinterpret_cast<float4*>(ring + (v * T + slot) * (int64_t)d)[c] = ld_dep(reinterpret_cast<const float4*>(cur + v * (int64_t)d) + c);
+    for (int64_t base = 0; base < total; base += nthr * kPer) {
+      int flag[kPer];
+      float4 val[kPer];
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        const int64_t i = base + gtid + e * nthr;
+        flag[e] = i < total ? ld_dep(dirty + i / dvec) : stamp - 1;
+      }
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        const int64_t i = base + gtid + e * nthr;
+        if (flag[e] == stamp) val[e] = ld_dep(reinterpret_cast<const float4*>(cur + (i / dvec) * (int64_t)d) + (int)(i % dvec));
+      }
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        const int64_t i = base + gtid + e * nthr;
+        if (flag[e] == stamp) reinterpret_cast<float4*>(ring + ((i / dvec) * T + slot) * (int64_t)d)[i % dvec] = val[e];
+      }
     }
     return;
   }
