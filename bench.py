@@ -661,6 +661,7 @@ def main():
     ap.add_argument("--scaleout-nodes", type=int, default=10_000_000)
     ap.add_argument("--scaleout-edges", type=int, default=40_000_000)
     ap.add_argument("--scaleout-T", type=int, default=20)
+    ap.add_argument("--scaleout-timeout", type=float, default=420.0, help="seconds the scale-out sample may take at N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batches", type=int, default=40)
     args = ap.parse_args()
@@ -688,17 +689,32 @@ def main():
         out = run_ours(args, rank, world, own_pg=False)
         extra = None
         if not args.replicas:
+            # the main line must survive the extra arm: an exception is caught, and a hang (a collective that never
+            # completes) is cut by a watchdog that prints the main line and leaves
+            def bail():
+                log(f"scale-out arm exceeded {args.scaleout_timeout:.0f} s: reporting the replica line only")
+                if rank == 0:
+                    out["scaleout"] = {"error": f"timed out after {args.scaleout_timeout:.0f} s"}
+                    emit(out)
+                os._exit(0)
+            dog = threading.Timer(args.scaleout_timeout, bail)
+            dog.daemon = True
+            dog.start()
             try:
                 extra = run_sharded(args, rank, world, own_pg=False)
-            except Exception as e:  # the main line must survive a failure of the extra arm
+            except Exception as e:
                 log("scale-out arm failed:", repr(e))
                 extra = {"error": repr(e)[:300]}
+            dog.cancel()
         if rank == 0:
             if extra is not None:
                 out["scaleout"] = {k: extra[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "e2e", "error")
                                    if k in extra}
             emit(out)
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
     else:
         run_ours(args, rank, world)
 
