@@ -106,6 +106,11 @@ struct ClShape {
   size_t smem_floats;
 };
 
+// rows per thread TR need not be a multiple of 4: in the k-major activation rows every row group owns a segment of
+// TRP = TR rounded up to 4 floats, so the 128-bit loads of a thread stay aligned (TR = 10: 40-row tiles, which
+// cover ~1200 rows in 30 of the 33 co-resident clusters and save a sixth of the inner loop against TR = 12)
+__host__ __device__ constexpr int cl_trp(int TR) { return (TR + 3) / 4 * 4; }
+
 __host__ __device__ inline ClShape cl_shape(int d, int t, bool has_self, int RB) {
   ClShape s;
   s.ldo = (int)align_up((size_t)d, 32);
@@ -116,7 +121,7 @@ __host__ __device__ inline ClShape cl_shape(int d, int t, bool has_self, int RB)
   s.kc = d_pad / kCl;      // output columns owned by one CTA == its k slice of the hidden row
   s.wpr = (s.ncg + 15) / 16;  // warps per row group: 16 column groups x 2 k halves per warp
   s.nthreads = 4 * s.wpr * 32;
-  const int RBp = RB + 4;
+  const int RBp = 4 * cl_trp(RB / 4) + 4;
   s.smem_floats = (size_t)(s.k1 + s.k2 + (has_self ? s.k2 : 0)) * s.ldo + (size_t)(s.k1 + 2 * s.k2) * RBp + (size_t)2 * kCl * RB * s.kc +
                   (size_t)2 * s.kc;  // + the owned slices of b1 and b2 (+ bs)
   return s;
@@ -139,30 +144,31 @@ __device__ __forceinline__ void k_run(const float* __restrict__ w, int ldo, cons
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc2[p][c] = make_float2(acc[2 * p][c], acc[2 * p + 1][c]);
   float4 wv = *reinterpret_cast<const float4*>(w);
-  float4 av[TR / 4];
+  constexpr int NQ = cl_trp(TR) / 4;  // 128-bit activation loads per k step (the last may carry unused padding)
+  float4 av[NQ];
 #pragma unroll
-  for (int q = 0; q < TR / 4; ++q) av[q] = *reinterpret_cast<const float4*>(a + 4 * q);
+  for (int q = 0; q < NQ; ++q) av[q] = *reinterpret_cast<const float4*>(a + 4 * q);
 #pragma unroll 2
   for (int k = 0; k < kn; ++k) {
     w += ldo;
     a += RBp;
     const float4 wn = *reinterpret_cast<const float4*>(w);
-    float4 an[TR / 4];
+    float4 an[NQ];
 #pragma unroll
-    for (int q = 0; q < TR / 4; ++q) an[q] = *reinterpret_cast<const float4*>(a + 4 * q);
+    for (int q = 0; q < NQ; ++q) an[q] = *reinterpret_cast<const float4*>(a + 4 * q);
     const float2 wd[4] = {make_float2(wv.x, wv.x), make_float2(wv.y, wv.y), make_float2(wv.z, wv.z), make_float2(wv.w, wv.w)};
 #pragma unroll
-    for (int q = 0; q < TR / 4; ++q) {
+    for (int q = 0; q < NQ; ++q) {
       const float2 lo = make_float2(av[q].x, av[q].y), hi = make_float2(av[q].z, av[q].w);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        acc2[2 * q][c] = __ffma2_rn(lo, wd[c], acc2[2 * q][c]);
-        acc2[2 * q + 1][c] = __ffma2_rn(hi, wd[c], acc2[2 * q + 1][c]);
+        if (2 * q < TR / 2) acc2[2 * q][c] = __ffma2_rn(lo, wd[c], acc2[2 * q][c]);
+        if (2 * q + 1 < TR / 2) acc2[2 * q + 1][c] = __ffma2_rn(hi, wd[c], acc2[2 * q + 1][c]);
       }
     }
     wv = wn;
 #pragma unroll
-    for (int q = 0; q < TR / 4; ++q) av[q] = an[q];
+    for (int q = 0; q < NQ; ++q) av[q] = an[q];
   }
 #pragma unroll
   for (int p = 0; p < TR / 2; ++p)
@@ -193,7 +199,8 @@ template <int TR>
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
     pe_mlp_cluster_kernel(const __grid_constant__ MlpJob job0, const __grid_constant__ MlpJob job1, int split, const float* pe,
                           FixedRows fx) {
-  constexpr int RB = 4 * TR, RBp = RB + 4;
+  constexpr int RB = 4 * TR, TRP = cl_trp(TR), RBp = 4 * TRP + 4;
+  auto col_of = [](int r) { return (r / TR) * TRP + r % TR; };  // position of tile row r in a k-major activation row
   const int64_t cluster_raw = blockIdx.x / kCl;
   const bool second = cluster_raw >= split;
   const MlpJob& jb = second ? job1 : job0;
@@ -380,9 +387,9 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
       for (int u = 0; u < 4; ++u) {
         const int idx = base + u * nthr + tid;
         if (idx < nA) {
-          put4(As + (size_t)(4 * (idx / RB)) * RBp + idx % RB, v[u]);
+          put4(As + (size_t)(4 * (idx / RB)) * RBp + col_of(idx % RB), v[u]);
         } else if (idx < nA + nB) {
-          put4(Bs + (size_t)(4 * ((idx - nA) / RB)) * RBp + (idx - nA) % RB, v[u]);
+          put4(Bs + (size_t)(4 * ((idx - nA) / RB)) * RBp + col_of((idx - nA) % RB), v[u]);
         }
       }
     }
@@ -397,7 +404,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
     for (int r = 0; r < TR; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
     {
       const int kh = k1 / 2;
-      k_run<TR>(W1s + (size_t)(ks * kh) * ldo + 4 * cg, ldo, As + (size_t)(ks * kh) * RBp + rg * TR, RBp, kh, acc);
+      k_run<TR>(W1s + (size_t)(ks * kh) * ldo + 4 * cg, ldo, As + (size_t)(ks * kh) * RBp + rg * TRP, RBp, kh, acc);
     }
 #pragma unroll
     for (int r = 0; r < TR; ++r)
@@ -425,7 +432,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
       }
       const float4 b = *reinterpret_cast<const float4*>(bias1 + c);
       const int col = (int)j * kc + c;
-      float* dst = Hs + (size_t)c * RBp + r;
+      float* dst = Hs + (size_t)c * RBp + col_of(r);
       dst[0] = col + 0 < d ? fmaxf(v.x + b.x, 0.f) : 0.f;
       dst[RBp] = col + 1 < d ? fmaxf(v.y + b.y, 0.f) : 0.f;
       dst[2 * RBp] = col + 2 < d ? fmaxf(v.z + b.z, 0.f) : 0.f;
@@ -443,7 +450,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
     {
       const int kn = has_self ? 2 * k2 : k2;  // Hs and Bs are adjacent, so are the two weight slices
       const int kh = kn / 2;
-      k_run<TR>(W2s + (size_t)(ks * kh) * ldo + 4 * cg, ldo, Hs + (size_t)(ks * kh) * RBp + rg * TR, RBp, kh, acc);
+      k_run<TR>(W2s + (size_t)(ks * kh) * ldo + 4 * cg, ldo, Hs + (size_t)(ks * kh) * RBp + rg * TRP, RBp, kh, acc);
     }
 #pragma unroll
     for (int r = 0; r < TR; ++r)
@@ -471,7 +478,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
           z.z += p.z;
           z.w += p.w;
         }
-        const float* bp = Bs + (size_t)c * RBp + r;
+        const float* bp = Bs + (size_t)c * RBp + col_of(r);
         float4 o;
         o.x = bp[0] + tanhf(z.x);
         o.y = bp[RBp] + tanhf(z.y);
@@ -552,6 +559,10 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
   // rows per cluster tile: the smallest tile that covers the launch in one round of ~32 co-resident clusters
   if (expected_rows <= 32 * 16) return launch_cl<4>(j, nullptr, pe, fx, st);
   if (expected_rows <= 32 * 32) return launch_cl<8>(j, nullptr, pe, fx, st);
+  if (expected_rows <= 33 * 40) {
+    const int rc10 = launch_cl<10>(j, nullptr, pe, fx, st);
+    if (rc10 != LSTEP_ERR_UNSUPPORTED) return rc10;
+  }
   const int rc = launch_cl<12>(j, nullptr, pe, fx, st);
   if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
   return launch_cl<8>(j, nullptr, pe, fx, st);
@@ -567,6 +578,7 @@ int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, R
   const MlpJob j1{A1, lda1, ids1, rows1, nullptr, *m1, out1, out_stride1, nullptr};
   int rc = launch_cl<4>(j0, &j1, pe, fx, st);
   if (rc == LSTEP_ERR_UNSUPPORTED) rc = launch_cl<8>(j0, &j1, pe, fx, st);
+  if (rc == LSTEP_ERR_UNSUPPORTED) rc = launch_cl<10>(j0, &j1, pe, fx, st);
   if (rc == LSTEP_ERR_UNSUPPORTED) rc = launch_cl<12>(j0, &j1, pe, fx, st);
   return rc;
 }
