@@ -33,6 +33,35 @@ __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a -
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// ---- opt-in timeline instrumentation (-DLSTEP_TIMELINE): first CTA entry, first return from the dependency wait and
+// last CTA exit of every kernel of a step on the global nanosecond timer, read back with lstep_debug_timeline().
+#ifdef LSTEP_TIMELINE
+static __device__ unsigned long long g_timeline[64];  // one copy per translation unit (no relocatable device code)
+// defines the reader of this translation unit's copy: mode 0 resets (min slots to ~0, max slots to 0), mode 1 reads
+#define LSTEP_TIMELINE_DEFINE(name)                                                                   \
+  extern "C" int lstep_debug_timeline_##name(int mode, unsigned long long* out64) {                   \
+    unsigned long long h[64];                                                                         \
+    if (mode == 0) {                                                                                  \
+      for (int i = 0; i < 64; ++i) h[i] = (i % 4 == 2) ? 0ull : ~0ull;                                \
+      return cudaMemcpyToSymbol(lstep::g_timeline, h, sizeof(h)) == cudaSuccess ? 0 : 4;              \
+    }                                                                                                 \
+    return cudaMemcpyFromSymbol(out64, lstep::g_timeline, sizeof(h)) == cudaSuccess ? 0 : 4;          \
+  }
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TL_ENTRY(k) do { if (threadIdx.x == 0) atomicMin(&g_timeline[(k) * 4 + 0], gtimer()); } while (0)
+#define TL_WAITED(k) do { if (threadIdx.x == 0) atomicMin(&g_timeline[(k) * 4 + 1], gtimer()); } while (0)
+#define TL_EXIT(k) do { if (threadIdx.x == 0) atomicMax(&g_timeline[(k) * 4 + 2], gtimer()); } while (0)
+#else
+#define LSTEP_TIMELINE_DEFINE(name)
+#define TL_ENTRY(k)
+#define TL_WAITED(k)
+#define TL_EXIT(k)
+#endif
+
 // A kernel launched this way is resident BEFORE its predecessor has finished, so it misses the L1
 // invalidation a kernel boundary normally gives: a line that a predecessor CTA on the same SM pulled into L1
 // (or the read-only path) and that was then rewritten from another SM would be read stale. Every load of data

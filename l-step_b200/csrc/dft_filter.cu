@@ -193,6 +193,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
   const bool active = g < groups;
   // chunks 0 .. kDftChunks-2: the Th-1 older rows; last chunk: the newest row alone (the same partition with and
   // without prefetch, so both forms add in the same order and agree bit for bit)
+  TL_ENTRY(0);
   const int rc = (Th - 1 + kDftChunks - 2) / (kDftChunks - 1);  // rows per chunk
   auto bounds = [&](int c, int& a, int& b) {
     if (c == kDftChunks - 1) {
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
   }
   __syncthreads();
   pdl_wait();
+  TL_WAITED(0);
   // late trigger: the next kernel of the step (the fused gather) does its lookups and cosines before its own wait;
   // it may only become resident once everything before this filter has completed
   pdl_launch_dependents();
@@ -289,6 +291,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
     }
     __syncthreads();  // xs / red are reused by the next node of this CTA
   }
+  TL_EXIT(0);
 }
 
 // dG[s,c] += sum_{n in slice} x[n,s,c] * dout[n,c]; grid = (time groups, node slices)
@@ -420,3 +423,5 @@ extern "C" int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int6
                                                                           d, ids, n_ids, dout, dG);
   return check_launch("dft_filter_bwd");
 }
+
+LSTEP_TIMELINE_DEFINE(dft)

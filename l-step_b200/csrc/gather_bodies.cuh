@@ -72,11 +72,31 @@ __device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t ro
     } else if (tid >= t_pad && tid - t_pad < dvec) {
       // late_wait (fused launch of the streaming step): lookups and cosines depend on nothing the kernel in front
       // writes, so only the threads that read the table wait for it
-      if (late_wait) pdl_wait();
+      if (late_wait) {
+        pdl_wait();
+#ifdef LSTEP_TIMELINE
+        if (tid == t_pad) atomicMin(&g_timeline[1 * 4 + 1], gtimer());
+#endif
+      }
       const int cv = tid - t_pad;
       if (VEC == 4) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         int k = 0;
+        // the K row loads sit on the step's critical path (they wait for the kernel in front): 10 in flight per thread
+        // (one L2 round trip per 10 rows), added in order k = 0..K-1
+        for (; k + 10 <= K; k += 10) {
+          float4 v[10];
+#pragma unroll
+          for (int u = 0; u < 10; ++u)
+            v[u] = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k + u] * d) + cv);
+#pragma unroll
+          for (int u = 0; u < 10; ++u) {
+            acc.x += v[u].x;
+            acc.y += v[u].y;
+            acc.z += v[u].z;
+            acc.w += v[u].w;
+          }
+        }
         for (; k + 4 <= K; k += 4) {
           float4 v[4];
 #pragma unroll

@@ -239,6 +239,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   // ---- everything that does not depend on the preceding kernel: barriers, the weight slices (parameters),
   // the bias slices, the cluster rendezvous. With programmatic dependent launch this overlaps the tail of
   // the kernel in front.
+  TL_ENTRY(fx.acc ? 4 : 2);
   if (!fx.late_trigger) pdl_launch_dependents();
   if (tid == 0) {
     mb_init(&wbar[0], 1);
@@ -266,6 +267,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   // arrive now, wait right before the first remote store (the staging and layer 1 run in between)
   cluster_arrive();
   pdl_wait();  // from here on the kernel reads what the preceding kernels wrote
+  TL_WAITED(fx.acc ? 4 : 2);
   if (fx.late_trigger) pdl_launch_dependents();
   MLP_T(0);
   if (n_rows_dev) {
@@ -500,6 +502,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
     __syncthreads();  // As / Hs / Bs / s_node are restaged by the next row tile; every reader is past Red2
     if (tid == 0) mb_expect_tx(&rbar[1], red_bytes);
   }
+  TL_EXIT(fx.acc ? 4 : 2);
 }
 
 template <int TR>
@@ -590,6 +593,8 @@ bool pe_mlp_cluster_supports(const lstep_pe_mlp* m) {
   const ClShape sh = cl_shape(m->d, m->t, m->ws != nullptr, 32);
   return sh.smem_floats * sizeof(float) <= 226 * 1024 && sh.nthreads <= 512 && sh.ncg % kCl == 0;
 }
+
+LSTEP_TIMELINE_DEFINE(mlp)
 
 #ifdef LSTEP_MLP_TIMING
 extern "C" int lstep_debug_mlp_clocks(long long* out16) {

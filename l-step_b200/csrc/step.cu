@@ -49,12 +49,14 @@ __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict_
   // everything before the filter has completed) writes the table and nothing else this kernel touches. Lookups,
   // edge scans and all cosines therefore run BEFORE the dependency wait, next to the HBM-bound filter; only the
   // threads that gather table rows wait (inside the bodies).
+  TL_ENTRY(1);
   pdl_launch_dependents();
   if ((int)blockIdx.x < grid_q)
     nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, true, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk);
   else
     edge_aggregate_rows((int64_t)blockIdx.x - grid_q, (int64_t)gridDim.x - grid_q, (int)blockIdx.x == grid_q, true, pe, ids, n_ids, src, dst,
                         times, n_edges, tc, tw_u, d, t, t_pad, A, lda, counters);
+  TL_EXIT(1);
 }
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                   const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
@@ -73,6 +75,7 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
 __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restrict__ cur, float* __restrict__ ring,
                                                           int64_t V1, int T, int d, int slot, int64_t row_mul, int64_t row_add,
                                                           const int32_t* dirty, int stamp) {
+  TL_ENTRY(5);
   pdl_launch_dependents();
   const int dvec = d >> 2;
   const int64_t total = V1 * dvec;
@@ -80,6 +83,14 @@ __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restric
     // every thread owns up to kPer elements per sweep; loads of a sweep are issued together (one latency, not kPer)
     constexpr int kPer = 8;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x, gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // (the flags of the rows phase B changes are final — the push kernel has completed — so the first sweep's flags are
+    // fetched here, before the wait, and kept in registers: one L2 round trip less on the critical path)
+    int flag0[kPer];
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const int64_t i = gtid + e * nthr;
+      flag0[e] = i < total ? ld_dep(dirty + i / dvec) : stamp - 1;
+    }
     for (int64_t base = 0; base < total; base += nthr * kPer) {
       float4 val[kPer];
 #pragma unroll
@@ -94,13 +105,14 @@ __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restric
       }
     }
     pdl_wait();
+    TL_WAITED(5);
     for (int64_t base = 0; base < total; base += nthr * kPer) {
       int flag[kPer];
       float4 val[kPer];
 #pragma unroll
       for (int e = 0; e < kPer; ++e) {
         const int64_t i = base + gtid + e * nthr;
-        flag[e] = i < total ? ld_dep(dirty + i / dvec) : stamp - 1;
+        flag[e] = base == 0 ? flag0[e] : (i < total ? ld_dep(dirty + i / dvec) : stamp - 1);
       }
 #pragma unroll
       for (int e = 0; e < kPer; ++e) {
@@ -113,6 +125,7 @@ __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restric
         if (flag[e] == stamp) reinterpret_cast<float4*>(ring + ((i / dvec) * T + slot) * (int64_t)d)[i % dvec] = val[e];
       }
     }
+    TL_EXIT(5);
     return;
   }
   pdl_wait();
@@ -302,3 +315,5 @@ extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int
   return pe_step_core(s, csr, s->src + lo, s->dst + lo, s->t + lo, n_edges, ids, n_ids, current_time, head, len, append_slot, G,
                       query_ids_host, n_queries, nbr_out, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag, stream);
 }
+
+LSTEP_TIMELINE_DEFINE(step)

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
   // and the claim phase touch nothing the phase-A MLP reads or writes (CSR, ids, claim map, counters, U, the
   // accumulator rows), so they run BEFORE the wait, next to the MLP; the wait sits in front of the first access
   // to the table (pe[0] = 0 and the phase-A rows).
+  TL_ENTRY(3);
   pdl_launch_dependents();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int Kcap = (K + kPushSplit - 1) / kPushSplit;
@@ -198,6 +199,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
   }
 
   pdl_wait();  // phase A has written the table
+  TL_WAITED(3);
   if (blockIdx.x == 0)
     for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // pe[0] = 0 (LSTEP.py:317); no batch row reads row 0 below
 
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
       if (c < d) atomicAdd(rowp + c, (unsigned long long)(zz * fx[q]));
     }
   }
+  TL_EXIT(3);
 }
 
 // enqueue the push kernel; on return (stream order) acc rows [0, counters[2]) hold the aggregates of the
@@ -254,3 +257,5 @@ int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q
 }
 
 }  // namespace lstep
+
+LSTEP_TIMELINE_DEFINE(push)
