@@ -370,7 +370,8 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
         }
         attr_set = true;
       }
-      const int64_t bgrid = n_ids < (int64_t)kNumSMs * 3 ? n_ids : (int64_t)kNumSMs * 3;
+      static const int per_sm = getenv("LSTEP_DFT_CTAS_PER_SM") ? atoi(getenv("LSTEP_DFT_CTAS_PER_SM")) : 3;
+      const int64_t bgrid = n_ids < (int64_t)kNumSMs * per_sm ? n_ids : (int64_t)kNumSMs * per_sm;
       launch_k(dft_filter_bulk_kernel, dim3((unsigned)bgrid), dim3(kDftThreads), bulk_smem, st, hist, node_stride, s0, ring, Th, d, ids,
                n_ids, G, out, out_stride, out_ids, prefetch_old_rows ? 1 : 0);
       return check_launch("dft_filter_bulk");
