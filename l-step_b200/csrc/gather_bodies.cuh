@@ -69,7 +69,10 @@ __device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t ro
       for (int k = 0; k < K; ++k)
         if (s_nbr[k] != 0) acc += time_feature(s_dt[k], w);
       S[row * ldS + d + tid] = acc;
-    } else if (tid >= t_pad && tid - t_pad < dvec) {
+    }
+    // (two independent tests: with t_pad = 0 — the streaming step's 128-thread CTAs — the same threads first do a time
+    // frequency and then a table column group; with t_pad >= t the two roles are disjoint threads working side by side)
+    if (tid >= t_pad && tid - t_pad < dvec) {
       // late_wait (fused launch of the streaming step): lookups and cosines depend on nothing the kernel in front
       // writes, so only the threads that read the table wait for it
       if (late_wait) {
@@ -209,7 +212,8 @@ __device__ __forceinline__ void edge_aggregate_rows(int64_t first_node, int64_t 
         const int total = s_total;
         if (is_tf) {
           for (int j = 0; j < total; ++j) acc_tf += time_feature(s_dt[j], w);
-        } else if (is_pe) {
+        }
+        if (is_pe) {
           if (late_wait) pdl_wait();
           int j = 0;
           for (; j + 4 <= total; j += 4) {

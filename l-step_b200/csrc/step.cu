@@ -247,8 +247,12 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   int64_t ldA = 0;
   int32_t* counters = nullptr;
   static const bool no_fuse = getenv("LSTEP_NO_GATHER_FUSE") != nullptr;
-  const int t_pad = (int)align_up((size_t)t, 32);
-  const int threads = (int)align_up((size_t)t_pad + d / 4, 32);
+  // LSTEP_GATHER_PACKED=1: 128-thread CTAs in which the same threads are first time-frequency threads and then table
+  // threads (t_pad = 0). Tried to get all 1 107 CTAs resident beside the DFT filter in one wave; measured slower (the
+  // merged roles need 54 registers, so no more CTAs fit) — the disjoint 192-thread form stays the default.
+  static const bool packed = getenv("LSTEP_GATHER_PACKED") != nullptr;
+  const int t_pad = packed ? 0 : (int)align_up((size_t)t, 32);
+  const int threads = (int)align_up((size_t)std::max(t_pad + d / 4, t), 32);
   const bool vec_ok = d % 4 == 0 && w.lda % 4 == 0 && reinterpret_cast<uintptr_t>(s->cur) % 16 == 0 && threads <= 512;
   if (!no_fuse && rows > 0 && n_ids > 0 && n_edges > 0 && vec_ok && t == mlp_upd->t && d == mlp_upd->d) {
     update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters, &new_rows);
