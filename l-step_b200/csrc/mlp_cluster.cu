@@ -92,6 +92,11 @@ struct FixedRows {
   // dependency wait, i.e. once everything BEFORE this kernel is complete. update_pe's phase-B push kernel relies on
   // it: its lookup / claim phase runs before its own wait, concurrently with the phase-A MLP and with nothing else.
   int late_trigger;
+  // ring_slot != NULL (streaming step): every result row is also written into the history ring's new slot,
+  // ring_slot + node * ring_stride — the step's ring append then only copies the rows this kernel does not write and
+  // has nothing left to do after its dependency wait.
+  float* ring_slot;
+  int64_t ring_stride;
 };
 
 #ifdef LSTEP_MLP_TIMING
@@ -487,6 +492,9 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
         o.z = bp[2 * RBp] + tanhf(z.z);
         o.w = bp[3 * RBp] + tanhf(z.w);
         float* dst = (out ? out + row * out_stride : pe_inplace + s_node[r] * (int64_t)d) + col;
+        if (fx.ring_slot) {  // (d % 4 == 0 and 16-byte rows are preconditions of the streaming step)
+          *reinterpret_cast<float4*>(fx.ring_slot + s_node[r] * fx.ring_stride + col) = o;
+        }
         if (o_vec && col + 3 < d) {
           *reinterpret_cast<float4*>(dst) = o;
         } else {
@@ -556,8 +564,9 @@ int launch_cl(const MlpJob& j0, const MlpJob* j1, const float* pe, FixedRows fx,
 // acc_fixed / reset_map: see FixedRows (both NULL: the aggregate is the float matrix A).
 int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger) {
-  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0};
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger,
+                          float* ring_slot, int64_t ring_stride) {
+  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0, ring_slot, ring_stride};
   const MlpJob j{A, lda, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace};
   // rows per cluster tile: the smallest tile that covers the launch in one round of ~32 co-resident clusters
   if (expected_rows <= 32 * 16) return launch_cl<4>(j, nullptr, pe, fx, st);
@@ -576,7 +585,7 @@ int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, R
                                float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
                                const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger) {
   if (rows0 <= 0 || rows1 <= 0 || !out0 || !out1) return LSTEP_ERR_UNSUPPORTED;
-  const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0};
+  const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0, nullptr, 0};
   const MlpJob j0{A0, lda0, ids0, rows0, nullptr, *m0, out0, out_stride0, nullptr};
   const MlpJob j1{A1, lda1, ids1, rows1, nullptr, *m1, out1, out_stride1, nullptr};
   int rc = launch_cl<4>(j0, &j1, pe, fx, st);

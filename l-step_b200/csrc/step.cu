@@ -32,7 +32,8 @@ int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, R
                                const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger);
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
-                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows);
+                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows,
+                   float* ring_slot, int64_t ring_stride);
 
 // a6's neighbourhood aggregate (blocks [0, grid_q)) and a7's edge aggregate (the rest) in ONE launch: both only
 // read the current table and neither depends on the other, so the short edge kernel (and its hub chain) hides
@@ -80,51 +81,28 @@ __global__ void __launch_bounds__(256) ring_append_kernel(const float* __restric
   const int dvec = d >> 2;
   const int64_t total = V1 * dvec;
   if (dirty) {
-    // every thread owns up to kPer elements per sweep; loads of a sweep are issued together (one latency, not kPer)
+    // Rows carrying `stamp` are being rewritten by the phase-B MLP, which writes them into the ring slot itself; this
+    // kernel copies all other rows, all of it before the dependency wait (the flags are final: the push kernel has
+    // completed). kPer loads in flight per thread and sweep.
     constexpr int kPer = 8;
     const int64_t nthr = (int64_t)gridDim.x * blockDim.x, gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    // (the flags of the rows phase B changes are final — the push kernel has completed — so the first sweep's flags are
-    // fetched here, before the wait, and kept in registers: one L2 round trip less on the critical path)
-    int flag0[kPer];
-#pragma unroll
-    for (int e = 0; e < kPer; ++e) {
-      const int64_t i = gtid + e * nthr;
-      flag0[e] = i < total ? ld_dep(dirty + i / dvec) : stamp - 1;
-    }
-    for (int64_t base = 0; base < total; base += nthr * kPer) {
-      float4 val[kPer];
-#pragma unroll
-      for (int e = 0; e < kPer; ++e) {
-        const int64_t i = base + gtid + e * nthr;
-        if (i < total) val[e] = ld_dep(reinterpret_cast<const float4*>(cur + (i / dvec) * (int64_t)d) + (int)(i % dvec));
-      }
-#pragma unroll
-      for (int e = 0; e < kPer; ++e) {
-        const int64_t i = base + gtid + e * nthr;
-        if (i < total) reinterpret_cast<float4*>(ring + ((i / dvec) * T + slot) * (int64_t)d)[i % dvec] = val[e];
-      }
-    }
-    pdl_wait();
-    TL_WAITED(5);
     for (int64_t base = 0; base < total; base += nthr * kPer) {
       int flag[kPer];
       float4 val[kPer];
 #pragma unroll
       for (int e = 0; e < kPer; ++e) {
         const int64_t i = base + gtid + e * nthr;
-        flag[e] = base == 0 ? flag0[e] : (i < total ? ld_dep(dirty + i / dvec) : stamp - 1);
+        flag[e] = i < total ? ld_dep(dirty + i / dvec) : stamp;
+        if (i < total) val[e] = ld_dep(reinterpret_cast<const float4*>(cur + (i / dvec) * (int64_t)d) + (int)(i % dvec));
       }
 #pragma unroll
       for (int e = 0; e < kPer; ++e) {
         const int64_t i = base + gtid + e * nthr;
-        if (flag[e] == stamp) val[e] = ld_dep(reinterpret_cast<const float4*>(cur + (i / dvec) * (int64_t)d) + (int)(i % dvec));
-      }
-#pragma unroll
-      for (int e = 0; e < kPer; ++e) {
-        const int64_t i = base + gtid + e * nthr;
-        if (flag[e] == stamp) reinterpret_cast<float4*>(ring + ((i / dvec) * T + slot) * (int64_t)d)[i % dvec] = val[e];
+        if (flag[e] != stamp) reinterpret_cast<float4*>(ring + ((i / dvec) * T + slot) * (int64_t)d)[i % dvec] = val[e];
       }
     }
+    pdl_wait();  // (completion order only: the kernel must not finish before its predecessor)
+    TL_WAITED(5);
     TL_EXIT(5);
     return;
   }
@@ -301,7 +279,8 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   int32_t* dirty = nullptr;
   static const bool no_early_append = getenv("LSTEP_NO_EARLY_APPEND") != nullptr;
   rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,
-                      err_flag, stream, edges_done, no_early_append ? nullptr : &dirty, stamp, phase_a_done);
+                      err_flag, stream, edges_done, no_early_append ? nullptr : &dirty, stamp, phase_a_done,
+                      s->ring + (int64_t)append_slot * d, (int64_t)T * d);
   if (rc != LSTEP_OK) return rc;
   // 2 CTAs per SM: the append is resident (copying, then waiting for the phase-B MLP) while the NEXT step's DFT filter
   // wants to become resident and prefetch — it must leave thread slots and shared memory for it

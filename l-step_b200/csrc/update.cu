@@ -37,7 +37,8 @@ int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const doubl
                         int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag, PhaseBHook hook, void* stream);
 int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger = false);
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger = false,
+                          float* ring_slot = nullptr, int64_t ring_stride = 0);
 bool pe_mlp_cluster_supports(const lstep_pe_mlp* m);
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
@@ -573,7 +574,8 @@ bool update_push_available(const lstep_pe_mlp* mlp) {
 
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
-                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows);
+                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows,
+                   float* ring_slot, int64_t ring_stride);
 }  // namespace lstep
 
 extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids,
@@ -581,14 +583,17 @@ extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr,
                                double current_time, int K, const lstep_pe_mlp* mlp, void* workspace,
                                size_t workspace_bytes, uint32_t* err_flag, void* stream) {
   return update_pe_impl(pe, pe_rows, csr, ids, n_ids, src, dst, times, n_edges, current_time, K, mlp, workspace, workspace_bytes,
-                        err_flag, stream, false, nullptr, 0, false);
+                        err_flag, stream, false, nullptr, 0, false, nullptr, 0);
 }
 
 // edges_done: phase A's aggregate rows (and the zeroed counters) are already in the workspace
 int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                           const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K,
                           const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream,
-                          bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows) {
+                          bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows, float* ring_slot,
+                          int64_t ring_stride) {
+  // ring_slot / ring_stride (streaming step, with dirty_out): the phase-B MLP also writes its rows into the history
+  // ring's new slot, so the caller's ring append only has to copy the rows NOT carrying `stamp`.
   // phase_a_in_new_rows (streaming step): phase A's MLP has already run (in the caller's paired launch) and left its
   // rows in the workspace's new_rows buffer; the push kernel applies them. Requires update_push_available().
   // dirty_out (streaming step): when the push form runs, *dirty_out = per-node map in which the rows phase B changes
@@ -631,7 +636,7 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
       // expected rows: ~4 distinct sampled neighbours per batch node on the benchmark graphs (measured 3.9); a launch
       // with more rows than the chosen tile covers in one round of clusters just walks a second round
       rc = launch_pe_mlp_cluster(nullptr, 0, pe, single_ids(w.U), max_dest + 1, n_ids * 4, w.counters + 2, &noself, nullptr, 0, pe,
-                                 w.push_acc, w.claim_of, st, dirty_out != nullptr);
+                                 w.push_acc, w.claim_of, st, dirty_out != nullptr, dirty_out ? ring_slot : nullptr, ring_stride);
       return rc;
     }
   }
