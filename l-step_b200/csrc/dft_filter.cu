@@ -178,11 +178,11 @@ __device__ __forceinline__ uint32_t dft_s_u32(const void* p) { return (uint32_t)
 // still being written are those of the NEWEST slot. The first kDftChunks-1 chunks then cover the Th-1 older rows and
 // are requested BEFORE the dependency wait — 99 % of the kernel's HBM traffic overlaps the tail of the previous
 // step — and the last chunk is the newest row alone, requested after the wait.
-__global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const float* __restrict__ hist, int64_t node_stride, int s0,
+__global__ void __launch_bounds__(kDftThreads, 5) dft_filter_bulk_kernel(const float* __restrict__ hist, int64_t node_stride, int s0,
                                                                       int ring, int Th, int d, const int64_t* __restrict__ ids,
                                                                       int64_t n_ids, const float* __restrict__ G,
                                                                       float* __restrict__ out, int64_t out_stride,
-                                                                      const int64_t* __restrict__ out_ids, int prefetch) {
+                                                                      const int64_t* __restrict__ out_ids, int prefetch, int early_trigger) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t bar[kDftChunks];
   float4* xs = reinterpret_cast<float4*>(smem_raw);  // [Th][dvec] logical time order
@@ -194,6 +194,11 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
   // chunks 0 .. kDftChunks-2: the Th-1 older rows; last chunk: the newest row alone (the same partition with and
   // without prefetch, so both forms add in the same order and agree bit for bit)
   TL_ENTRY(0);
+  // early_trigger (streaming step, push form): the previous step ended with "phase-B MLP (late trigger) -> ring append",
+  // so this kernel being resident already means everything before that MLP has completed and the MLP has read its row
+  // counter — nothing the next kernel (the fused gather) writes before ITS wait is still in use. Triggering at once
+  // lets the gather start its lookups ~3 us earlier. Otherwise the trigger follows this kernel's own wait.
+  if (early_trigger) pdl_launch_dependents();
   const int rc = (Th - 1 + kDftChunks - 2) / (kDftChunks - 1);  // rows per chunk
   auto bounds = [&](int c, int& a, int& b) {
     if (c == kDftChunks - 1) {
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
   TL_WAITED(0);
   // late trigger: the next kernel of the step (the fused gather) does its lookups and cosines before its own wait;
   // it may only become resident once everything before this filter has completed
-  pdl_launch_dependents();
+  if (!early_trigger) pdl_launch_dependents();
   const float4* Gv = reinterpret_cast<const float4*>(G);
   uint32_t it = 0;
   for (int64_t n = blockIdx.x; n < n_ids; n += gridDim.x, ++it) {
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kDftThreads) dft_filter_bulk_kernel(const floa
       bounds(c, a, b);
       if (a >= b) continue;
       // this thread's rows of the chunk: a + g, a + g + groups, ...; fetch their filter rows before waiting
-      constexpr int kMaxRows = 8;
+      constexpr int kMaxRows = 5;  // (25-row chunks over 5 time groups; 48 registers: the step's next kernel shares the SM)
       float4 w[kMaxRows];
       if (active) {
 #pragma unroll
@@ -345,7 +350,7 @@ extern "C" int lstep_dft_collapse(const float* W_c64, const float* a, int T, int
 namespace lstep {
 int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
                       const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride,
-                      const int64_t* out_ids, void* stream, bool prefetch_old_rows) {
+                      const int64_t* out_ids, void* stream, bool prefetch_old_rows, bool early_trigger) {
   if (n_ids < 0 || Th < 0 || d <= 0 || ring < Th || s0 < 0 || (ring > 0 && s0 >= ring)) return LSTEP_ERR_INVALID_ARG;
   if (n_ids == 0) return LSTEP_OK;
   if (!ids || !out || !G || (Th > 0 && !hist)) return LSTEP_ERR_INVALID_ARG;
@@ -373,7 +378,7 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
       static const int per_sm = getenv("LSTEP_DFT_CTAS_PER_SM") ? atoi(getenv("LSTEP_DFT_CTAS_PER_SM")) : 3;
       const int64_t bgrid = n_ids < (int64_t)kNumSMs * per_sm ? n_ids : (int64_t)kNumSMs * per_sm;
       launch_k(dft_filter_bulk_kernel, dim3((unsigned)bgrid), dim3(kDftThreads), bulk_smem, st, hist, node_stride, s0, ring, Th, d, ids,
-               n_ids, G, out, out_stride, out_ids, prefetch_old_rows ? 1 : 0);
+               n_ids, G, out, out_stride, out_ids, prefetch_old_rows ? 1 : 0, early_trigger ? 1 : 0);
       return check_launch("dft_filter_bulk");
     }
   }
@@ -390,7 +395,7 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
 extern "C" int lstep_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th,
                                 int d, const int64_t* ids, int64_t n_ids, const float* G, float* out,
                                 int64_t out_stride, void* stream) {
-  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, nullptr, stream, false);
+  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, nullptr, stream, false, false);
 }
 
 /* Same filter with the result row n written to out + out_ids[n]*out_stride (history rows and table rows
@@ -399,7 +404,7 @@ extern "C" int lstep_dft_filter_scatter(const float* hist, int64_t node_stride, 
                                         int d, const int64_t* ids, const int64_t* out_ids, int64_t n_ids, const float* G,
                                         float* out, int64_t out_stride, void* stream) {
   if (!out_ids && n_ids > 0) return LSTEP_ERR_INVALID_ARG;
-  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids, stream, false);
+  return lstep::launch_dft_filter(hist, node_stride, time_stride, s0, ring, Th, d, ids, n_ids, G, out, out_stride, out_ids, stream, false, false);
 }
 
 extern "C" int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring,

@@ -24,7 +24,9 @@ __device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t ro
                                                             const int32_t* __restrict__ nbr,
                                                             const float* __restrict__ nbr_t, int64_t n_rows, int K,
                                                             const float* __restrict__ tw, int d, int t, int t_pad,
-                                                            float* __restrict__ S, int64_t ldS, int64_t period, LookupArgs lk) {
+                                                            float* __restrict__ S, int64_t ldS, int64_t period, LookupArgs lk,
+                                                            int tf_threads) {
+  // tf_threads: how many threads (tid < tf_threads) share the t time frequencies; thread i takes i, i + tf_threads, ...
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);
   float* s_dt = reinterpret_cast<float*>(s_nbr + K);
@@ -63,12 +65,20 @@ __device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t ro
       }
     }
     __syncthreads();
-    if (tid < t) {
-      const float w = tw[tid];
-      float acc = 0.f;
-      for (int k = 0; k < K; ++k)
-        if (s_nbr[k] != 0) acc += time_feature(s_dt[k], w);
-      S[row * ldS + d + tid] = acc;
+#ifdef LSTEP_TIMELINE
+    if (late_wait && tid == 0) atomicMax(&g_timeline[6 * 4 + 2], gtimer());  // last lookup done
+#endif
+    if (tid < tf_threads) {
+      for (int f = tid; f < t; f += tf_threads) {
+        const float w = tw[f];
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k)
+          if (s_nbr[k] != 0) acc += time_feature(s_dt[k], w);
+        S[row * ldS + d + f] = acc;
+      }
+#ifdef LSTEP_TIMELINE
+      if (late_wait && tid == 0) atomicMax(&g_timeline[7 * 4 + 2], gtimer());  // last cosine block done
+#endif
     }
     // (two independent tests: with t_pad = 0 — the streaming step's 128-thread CTAs — the same threads first do a time
     // frequency and then a table column group; with t_pad >= t the two roles are disjoint threads working side by side)
@@ -79,6 +89,7 @@ __device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t ro
         pdl_wait();
 #ifdef LSTEP_TIMELINE
         if (tid == t_pad) atomicMin(&g_timeline[1 * 4 + 1], gtimer());
+        if (tid == t_pad) atomicMax(&g_timeline[8 * 4 + 2], gtimer());  // last wait return (nbr rows)
 #endif
       }
       const int cv = tid - t_pad;

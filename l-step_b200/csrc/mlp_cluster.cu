@@ -273,12 +273,13 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   cluster_arrive();
   pdl_wait();  // from here on the kernel reads what the preceding kernels wrote
   TL_WAITED(fx.acc ? 4 : 2);
-  if (fx.late_trigger) pdl_launch_dependents();
   MLP_T(0);
   if (n_rows_dev) {
     const int64_t nd = ld_dep(n_rows_dev);
     n_rows = nd < n_rows ? nd : n_rows;
   }
+  // (after the row-count read: a kernel that becomes resident on this trigger may reset the counter)
+  if (fx.late_trigger) pdl_launch_dependents();
   const int64_t n_tiles = (n_rows + RB - 1) / RB;
   const int64_t cluster_id = second ? cluster_raw - split : cluster_raw;
   const int64_t n_clusters = second ? (int64_t)(gridDim.x / kCl) - split : (int64_t)split;

@@ -39,7 +39,7 @@ int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64
 // read the current table and neither depends on the other, so the short edge kernel (and its hub chain) hides
 // behind the cosine-bound neighbourhood rows instead of being a link of the step's dependency chain.
 __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict__ pe, const double* __restrict__ q_time, int64_t n_rows,
-                                                        int K, const float* __restrict__ tw_q, int d, int t, int t_pad,
+                                                        int K, const float* __restrict__ tw_q, int d, int t, int t_pad, int t_pad_e,
                                                         float* __restrict__ S, int64_t ldS, int64_t period, LookupArgs lk, int grid_q,
                                                         const int64_t* __restrict__ ids, int64_t n_ids,
                                                         const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
@@ -52,11 +52,18 @@ __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict_
   // threads that gather table rows wait (inside the bodies).
   TL_ENTRY(1);
   pdl_launch_dependents();
+#ifdef LSTEP_TIMELINE
+  if (threadIdx.x == 0) atomicMax(&g_timeline[((int)blockIdx.x < grid_q ? 9 : 10) * 4 + 2], gtimer());  // last CTA START (nbr / edge)
+#endif
   if ((int)blockIdx.x < grid_q)
-    nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, true, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk);
+    nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, true, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk,
+                                t_pad < t ? t_pad : t);
   else
     edge_aggregate_rows((int64_t)blockIdx.x - grid_q, (int64_t)gridDim.x - grid_q, (int)blockIdx.x == grid_q, true, pe, ids, n_ids, src, dst,
-                        times, n_edges, tc, tw_u, d, t, t_pad, A, lda, counters);
+                        times, n_edges, tc, tw_u, d, t, t_pad_e, A, lda, counters);
+#ifdef LSTEP_TIMELINE
+  if (threadIdx.x == 0) atomicMax(&g_timeline[((int)blockIdx.x < grid_q ? 11 : 12) * 4 + 2], gtimer());  // last CTA EXIT (nbr / edge)
+#endif
   TL_EXIT(1);
 }
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
@@ -64,7 +71,7 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
                   cudaStream_t st, bool late_trigger = false);
 int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_stride, int s0, int ring, int Th, int d,
                       const int64_t* ids, int64_t n_ids, const float* G, float* out, int64_t out_stride,
-                      const int64_t* out_ids, void* stream, bool prefetch_old_rows);
+                      const int64_t* out_ids, void* stream, bool prefetch_old_rows, bool early_trigger);
 
 // ring[v][slot][:] = cur[v][:]  (node-major ring: 688-byte rows at a 68.8 KB pitch)
 // table row of ring row v is v*row_mul + row_add (1, 0 for a single GPU; G, rank for a node-id sharded ring)
@@ -208,7 +215,13 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   // a3: filtered history of the batch nodes straight into the current table
   if (n_ids > 0) {
     static const bool no_prefetch = getenv("LSTEP_NO_DFT_PREFETCH") != nullptr;
-    rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, ids, stream, !no_prefetch);
+    // every step of this stream ends with "phase-B MLP (late trigger) -> ring append" when the push form and the early
+    // append are in use: only then may the filter let the gather in at once (see dft_filter_bulk_kernel)
+    // (LSTEP_DFT_EARLY_TRIGGER=1; measured within noise of the late trigger — 65.9 vs 64.9 us resident, 70.4 vs 72.3 us end
+    // to end — so it stays opt-in)
+    static const bool want_early = getenv("LSTEP_DFT_EARLY_TRIGGER") != nullptr && getenv("LSTEP_NO_EARLY_APPEND") == nullptr;
+    const bool early_trigger = want_early && n_queries > 0 && n_edges > 0 && update_push_available(mlp_upd);
+    rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, ids, stream, !no_prefetch, early_trigger);
     if (rc != LSTEP_OK) return rc;
   }
   // a6 gather + a7 edge aggregate: one heterogeneous launch when both exist and the 128-bit paths apply
@@ -225,12 +238,19 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   int64_t ldA = 0;
   int32_t* counters = nullptr;
   static const bool no_fuse = getenv("LSTEP_NO_GATHER_FUSE") != nullptr;
-  // LSTEP_GATHER_PACKED=1: 128-thread CTAs in which the same threads are first time-frequency threads and then table
-  // threads (t_pad = 0). Tried to get all 1 107 CTAs resident beside the DFT filter in one wave; measured slower (the
-  // merged roles need 54 registers, so no more CTAs fit) — the disjoint 192-thread form stays the default.
-  static const bool packed = getenv("LSTEP_GATHER_PACKED") != nullptr;
-  const int t_pad = packed ? 0 : (int)align_up((size_t)t, 32);
-  const int threads = (int)align_up((size_t)std::max(t_pad + d / 4, t), 32);
+  // CTA shape of the fused gather: the stand-alone kernels' 192 threads (t time-frequency threads + d/4 table threads).
+  // LSTEP_GATHER_NARROW=1: 128 threads — in a neighbourhood row 64 threads share the t time frequencies (two each) and
+  // d/4 threads gather table rows; in an edge row the same threads are first time-frequency and then table threads
+  // (t_pad_e = 0). It makes every CTA resident beside the DFT filter at once, but the instrumented timeline shows
+  // the gather is not bound by residency: all its CTAs start within 4 us, lookups end 5 us later and the 1.6 M
+  // cosines take ~9 us of issue-bound work either way.
+  static const bool wide = getenv("LSTEP_GATHER_NARROW") == nullptr;  // measured: no gain from the narrow shape (the cosine phase is issue bound)
+  const int t_al = (int)align_up((size_t)t, 32);
+  const int t_half = (int)align_up((size_t)(t + 1) / 2, 32);
+  const bool narrow = !wide && t_half + d / 4 <= 128 && t <= 128 && d / 4 <= 128;
+  const int t_pad = narrow ? t_half : t_al;
+  const int t_pad_e = narrow ? 0 : t_al;
+  const int threads = narrow ? 128 : (int)align_up((size_t)t_al + d / 4, 32);
   const bool vec_ok = d % 4 == 0 && w.lda % 4 == 0 && reinterpret_cast<uintptr_t>(s->cur) % 16 == 0 && threads <= 512;
   if (!no_fuse && rows > 0 && n_ids > 0 && n_edges > 0 && vec_ok && t == mlp_upd->t && d == mlp_upd->d) {
     update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters, &new_rows);
@@ -240,7 +260,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
     if (smem <= 48 * 1024) {
       LookupArgs lk{csr->indptr, csr->nbr, csr->t, csr->num_rows, q, err_flag};
       launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads), smem, st, s->cur, tq, rows, K, mlp_nbr->tw, d, t, t_pad,
-               w.S, w.lda, n_edges, lk, grid_q, ids, n_ids, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
+               t_pad_e, w.S, w.lda, n_edges, lk, grid_q, ids, n_ids, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
       if ((rc = check_launch("gather_ab")) != LSTEP_OK) return rc;
       edges_done = true;
     }

@@ -23,7 +23,7 @@ for b in range(130): st.step(b, q(b), outs)
 torch.cuda.synchronize()
 tus = ["dft", "step", "mlp", "push"]
 fns = {t: getattr(lib, "lstep_debug_timeline_" + t) for t in tus}
-names = {0: "dft", 1: "gather", 2: "mlp_pair", 3: "push", 4: "mlp_B", 5: "append"}
+names = {0: "dft", 1: "gather", 2: "mlp_pair", 3: "push", 4: "mlp_B", 5: "append", 6: "g:lookup", 7: "g:cos", 8: "g:waitret", 9: "g:start_q", 10: "g:start_e", 11: "g:exit_q", 12: "g:exit_e"}
 def reset():
     for f in fns.values(): f(0, None)
 def read():
@@ -31,7 +31,7 @@ def read():
     for t, f in fns.items():
         buf = (ctypes.c_ulonglong * 64)()
         f(1, buf)
-        for k in range(6):
+        for k in range(13):
             a, w, e = buf[4 * k], buf[4 * k + 1], buf[4 * k + 2]
             if e != 0: tl[k] = (a, w, e)
     return tl
@@ -44,8 +44,8 @@ for trial in range(12):
     st.step(b, q(b), outs); b += 1
     torch.cuda.synchronize()
     tl = read()
-    t0 = min(v[0] for v in tl.values())
-    rows.append({k: tuple((x - t0) / 1e3 for x in v) for k, v in tl.items()})
+    t0 = min(v[0] for k, v in tl.items() if k < 6)
+    rows.append({k: tuple(((x - t0) / 1e3 if 0 < x < 2**63 else float('nan')) for x in v) for k, v in tl.items()})
 med = {k: tuple(float(np.median([r[k][i] for r in rows if k in r])) for i in range(3)) for k in names}
 print("kernel      entry   waited     exit   (us since first entry; single isolated step)")
 for k in sorted(med): print(f"{names[k]:9s} {med[k][0]:8.1f} {med[k][1]:8.1f} {med[k][2]:8.1f}")
