@@ -177,7 +177,8 @@ struct PhaseBHook {
 // W is the 64-bit window of the bits of 2/pi that starts E+62 bits after the binary point (bits further
 // left only contribute multiples of 4 quadrants). The top two bits are the quadrant, the rest the
 // fraction of a quadrant (error < 2^-38), folded to [-1/2, 1/2), scaled by pi/2 and fed to the Cephes
-// single-precision minimax polynomials: ~35 integer / fp32 instructions, absolute error <= 1.1e-7
+// single-precision minimax polynomials: ~35 integer / fp32 instructions, absolute error <= 1.1e-7. (That general form
+// now serves |x| >= 2^32 only; below it the window selection is replaced by two fixed multiplies, see accurate_cos.)
 // (checked against libm on 15 000 arguments up to 2e9). Arguments below 2^14 — 72 % of the (dt, w_j)
 // pairs, all of them for j >= 28 — take a 3-term Cody-Waite reduction in fp32 FMAs instead (6 instructions).
 __device__ __forceinline__ float cos_poly(float rf, int q) {
@@ -198,6 +199,25 @@ __device__ __forceinline__ float accurate_cos(float x) {
     r = fmaf(-k, 4.837512969970703125e-4f, r);
     r = fmaf(-k, 7.549789954891882e-8f, r);
     return cos_poly(r, (int)k);
+  }
+  const float ax = fabsf(x);
+  if (ax < 4294967296.f) {
+    // 2^14 <= |x| < 2^32 — every large argument a timestamp difference produces: |x| = xi + xf with xi an exact 32-bit
+    // integer and xf an exact multiple of 2^-9 in [0, 1), so (|x| * 2/pi) mod 4 in 2.62 fixed point is
+    // xi * C + (xf * 2^9) * (C >> 9) mod 2^64 with C = floor(2/pi * 2^62): two integer multiplies instead of selecting a
+    // window of 2/pi by the exponent (error < 2^-30 of a quadrant). The top 32 bits of the folded fraction are all the
+    // fp32 polynomial can use.
+    const uint32_t xi = __float2uint_rz(ax);
+    const uint32_t xfi = __float2uint_rz((ax - __uint2float_rn(xi)) * 512.f);
+    const unsigned long long C = 0x28be60db9391054aull;
+    const unsigned long long R = (unsigned long long)xi * C + (unsigned long long)xfi * (C >> 9);
+    int q = (int)(R >> 62);
+    long long f = (long long)(R & 0x3fffffffffffffffull);
+    if (f >= (1ll << 61)) {
+      f -= (1ll << 62);
+      q += 1;
+    }
+    return cos_poly((float)(int)(f >> 30) * 3.6572951981678992e-10f /* (pi/2) * 2^-32 */, q);
   }
   const uint32_t bits = __float_as_uint(x);
   int e = (int)((bits >> 23) & 0xffu);
