@@ -2,20 +2,20 @@
 // The arithmetic of models/LSTEP.py:240-247 (neighbourhood), :294-301 (update phase A, with the
 // self term) and :329-336 (update phase B, where the self term is computed and discarded — Q3).
 //
-// fp32 FMA throughout: the parity bar (1e-5) rules out single-pass TF32/BF16 tensor-core math.
+// launch_pe_mlp() dispatches to the cluster split-K kernel (csrc/mlp_cluster.cu, the default). This file holds the
+// weight packing and the ALL-COLUMNS ring kernel it replaced, kept as the fallback for shapes the cluster kernel does
+// not cover (LSTEP_MLP_RING=1 forces it):
 //
-// Layout / schedule (sm_100a):
+// fp32 FMA throughout: the parity bar (1e-5) rules out single-pass TF32/BF16 tensor-core math.
 //   * weights are pre-packed (lstep_pack_linear) as [in_pad][ldo] row-major, in_pad = in rounded up
 //     to 16, ldo = out rounded up to 32, zero filled — so a k-tile of 16 input rows is one contiguous
 //     16*ldo*4-byte block (12 KB at d=172);
 //   * one CTA owns R = 2*RT rows and all output columns. The three GEMM segments (W1 over the
 //     aggregate, W2 over the hidden row, Ws over the base row) are walked as one flat sequence of
-//     k-tiles that a single elected thread streams into a 4-stage shared-memory ring with
-//     cp.async.bulk (the TMA 1-D bulk copy, completion on an mbarrier) — weights (0.85 MB total) stay
-//     L2 resident and their latency is hidden behind the FMAs of the previous tiles;
+//     k-tiles that a single elected thread streams into a shared-memory ring with cp.async.bulk
+//     (completion on an mbarrier);
 //   * activations sit in shared memory k-major ([k][R]) so one 128-bit broadcast load feeds RT rows;
-//     thread (rg, cp) keeps an RT x 2 register tile: rows rg*RT.., columns 2cp, 2cp+1 (one 64-bit
-//     conflict-free weight load per k).
+//     thread (rg, cp) keeps an RT x 2 register tile.
 #include <cstdlib>
 
 #include "common.cuh"

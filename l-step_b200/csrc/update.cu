@@ -8,19 +8,20 @@
 //             agg2[u] = sum over slots (i,k) with nbr[i,k]==u of [pe[ids[i]] || tf]  (phase-A table)
 //             pe[U] <- pe[U] + tanh(mlp(agg2[U])),  U = distinct sampled ids (0 included if padded)
 //
-// The reference scatters into two zeroed [V1, d+t] buffers (10.9 GB at 10 M nodes). Here both
-// phases are pull-based segmented reductions over batch-local indices, so no V1-sized float
-// buffer exists and every destination row is reduced in a fixed order without float atomics:
-//   * phase A: one CTA per batch node scans the 2B endpoint ids (int32, L2 resident), compacts
-//     its matches in edge order (source side first, as the two scatter calls do) and adds the
-//     rows in exactly the reference's order;
-//   * phase B: an inverse index (destination -> slots) is built with integer atomics on a
-//     per-node counter map (count / scan / fill), one warp per destination sorts its slot list
-//     (<= 32 entries: ascending flat index = the reference's add order) and reduces it; longer
-//     lists (hubs) are summed in 32.32 fixed point, which is exact and hence order independent. The
-//     padding row 0 collects every empty slot — thousands of contributions at B=200 — so it is
-//     reduced by a two-level tree (z_i * pe[ids[i]] per row, then over rows) instead of a
-//     serial chain.
+// The reference scatters into two zeroed [V1, d+t] buffers (10.9 GB at 10 M nodes). Here no V1-sized float
+// buffer exists and every destination row is reduced without float atomics:
+//   * phase A (pull): one CTA per batch node scans the 2B endpoint ids (L2 resident), compacts its matches in
+//     edge order (source side first, as the two scatter calls do) and adds the rows in exactly the reference's
+//     order (body: csrc/gather_bodies.cuh);
+//   * phase B, push form (default, csrc/update_push.cu): lookup + claim of a compact accumulator row per distinct
+//     destination + exact 32.32 fixed-point integer atomics where a contribution lands, in one kernel; the MLP
+//     (csrc/mlp_cluster.cu) reads the accumulator rows;
+//   * phase B, pull form (this file; used by the node-id sharded path, which ships float partial rows between
+//     ranks, and when the cluster MLP does not cover the shape; LSTEP_PHASEB_PULL=1): an inverse index
+//     (destination -> slots) is built with integer atomics on a per-node counter map (count / scan / fill), one
+//     warp per destination sorts its slot list (ascending flat index = the reference's add order) and reduces it;
+//     longer lists (hubs) are summed in 32.32 fixed point. The padding row 0 collects every empty slot —
+//     thousands of contributions at B=200 — and is reduced by a two-level tree.
 // All gathers of a phase finish (kernel boundary) before its rows are written, which is what
 // makes the in-place write-back safe for nodes that are both source and destination (Q6).
 #include <cstdlib>
