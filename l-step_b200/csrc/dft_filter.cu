@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kDftThreads, 5) dft_filter_bulk_kernel(const f
                                                                       int64_t n_ids, const float* __restrict__ G,
                                                                       float* __restrict__ out, int64_t out_stride,
                                                                       const int64_t* __restrict__ out_ids, int prefetch, int early_trigger) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // (bulk-copy destinations need 16-byte alignment)
   __shared__ __align__(8) uint64_t bar[kDftChunks];
   float4* xs = reinterpret_cast<float4*>(smem_raw);  // [Th][dvec] logical time order
   const int dvec = d >> 2;

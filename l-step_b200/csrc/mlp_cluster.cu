@@ -62,9 +62,6 @@ __device__ __forceinline__ uint32_t cluster_rank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-}
 // address of the same shared-memory offset in CTA `rank` of the cluster
 __device__ __forceinline__ uint32_t map_to_rank(uint32_t local_addr, uint32_t rank) {
   uint32_t r;
