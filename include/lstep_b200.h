@@ -283,6 +283,15 @@ int lstep_pe_step_host(lstep_host_stepper* h, const lstep_pe_stream* s, const ls
                        uint32_t* err_flag, void* stream, int64_t* ticket);
 int lstep_host_step_result(lstep_host_stepper* h, int64_t ticket, const float** result_host, int64_t* n_floats);
 void lstep_host_stepper_bytes(const lstep_host_stepper* h, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* A run of consecutive batches in one call (an evaluation split, evaluate_model_utils.py:38-142): the loop over
+ * lstep_pe_step_host / lstep_host_step_result is done natively, results read one step behind. Full history ring only
+ * (*len_io == T, one collapsed filter G); batch b = edges [b*batch_size, min((b+1)*batch_size, n_total)) of the host
+ * arrays; results_host [n_batches][n_queries][batch_size]; *head_io is advanced. Synchronous on return. */
+int lstep_pe_steps_host(lstep_host_stepper* h, const lstep_pe_stream* s, const lstep_csr* csr, int64_t n_total,
+                        int64_t batch_size, const int64_t* src_host, const int64_t* dst_host, const double* t_host,
+                        const int64_t* const* query_ids_host_arrays, int n_queries, int* head_io, int* len_io,
+                        const float* G, int K, const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace,
+                        size_t workspace_bytes, uint32_t* err_flag, void* stream, float* results_host);
 
 #ifdef __cplusplus
 }

@@ -285,3 +285,54 @@ extern "C" void lstep_host_stepper_bytes(const lstep_host_stepper* h, uint64_t* 
   if (h2d_bytes) *h2d_bytes = h->h2d_bytes;
   if (d2h_bytes) *d2h_bytes = h->d2h_bytes;
 }
+
+// A whole run of consecutive batches in one call (an evaluation split: evaluate_model_utils.py:38-142 loops over
+// batches of the split): the loop of lstep_pe_step_host + lstep_host_step_result lives here, results read one step
+// behind, so the host cost per batch is the CUDA launches alone. Steady-state regime only (the history ring is full:
+// *len_io == T, one collapsed filter G for every step); batch b is edges [b*batch_size, min((b+1)*batch_size, n_total)).
+// results_host: [n_batches][n_queries][batch_size] floats (the tail of a ragged last batch is left untouched).
+// Synchronous: every result has been read when the call returns.
+extern "C" int lstep_pe_steps_host(lstep_host_stepper* h, const lstep_pe_stream* s, const lstep_csr* csr, int64_t n_total,
+                                   int64_t batch_size, const int64_t* src_host, const int64_t* dst_host, const double* t_host,
+                                   const int64_t* const* query_ids_host_arrays, int n_queries, int* head_io, int* len_io,
+                                   const float* G, int K, const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd,
+                                   void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream,
+                                   float* results_host) {
+  if (!h || !s || !head_io || !len_io || !results_host || n_total < 0 || batch_size <= 0 || batch_size > h->max_edges)
+    return LSTEP_ERR_INVALID_ARG;
+  if (n_queries < 0 || n_queries > 8 || (n_queries > 0 && !query_ids_host_arrays)) return LSTEP_ERR_INVALID_ARG;
+  if (*len_io != s->T) return LSTEP_ERR_UNSUPPORTED;  // masked regime: the filter changes every step, use the per-step call
+  int head = *head_io;
+  int64_t pending = -1, pending_b = -1, pending_n = 0;
+  auto collect = [&](int64_t ticket, int64_t b, int64_t n) -> int {
+    const float* r = nullptr;
+    int64_t nf = 0;
+    const int rc = lstep_host_step_result(h, ticket, &r, &nf);
+    if (rc != LSTEP_OK) return rc;
+    float* dst = results_host + (size_t)b * n_queries * batch_size;
+    for (int c = 0; c < n_queries; ++c) memcpy(dst + (size_t)c * batch_size, r + (size_t)c * n, sizeof(float) * (size_t)n);
+    return LSTEP_OK;
+  };
+  int64_t b = 0;
+  for (int64_t lo = 0; lo < n_total; lo += batch_size, ++b) {
+    const int64_t n = n_total - lo < batch_size ? n_total - lo : batch_size;
+    const int64_t* q[8];
+    for (int c = 0; c < n_queries; ++c) q[c] = query_ids_host_arrays[c] + lo;
+    int64_t ticket = -1;
+    // full ring: the oldest slot (head) is overwritten, then becomes the newest
+    int rc = lstep_pe_step_host(h, s, csr, n, src_host + lo, dst_host + lo, t_host + lo, nullptr, 0, head, s->T, head, G, q, n_queries,
+                                nullptr, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag, stream, &ticket);
+    if (rc != LSTEP_OK) return rc;
+    head = (head + 1) % s->T;
+    if (pending >= 0 && (rc = collect(pending, pending_b, pending_n)) != LSTEP_OK) return rc;
+    pending = ticket;
+    pending_b = b;
+    pending_n = n;
+  }
+  if (pending >= 0) {
+    const int rc = collect(pending, pending_b, pending_n);
+    if (rc != LSTEP_OK) return rc;
+  }
+  *head_io = head;
+  return LSTEP_OK;
+}

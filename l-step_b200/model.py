@@ -138,6 +138,7 @@ class LSTEP(nn.Module):
 
         self._pack_cache = {}
         self._pack_fast = {}
+        self._pack_calls = 0
         self._filter_cache = {}
         self._twiddle = {}
         self._stager = None
@@ -222,19 +223,21 @@ class LSTEP(nn.Module):
         return st
 
     def _mlp_ref(self, which: str):
-        # fast path (one call per step on the streaming API): the parameter tensors are remembered, and a packed
-        # copy is reused while none of them has been modified in place (_version) or replaced (data_ptr)
+        # fast path (two calls per step on the streaming API): the parameter tensors are remembered, and a packed copy is
+        # reused while none of them has been modified in place (the tuple of _version counters is unchanged). Every
+        # 64th call also compares the storage addresses (a parameter moved by .to() / .data assignment keeps its version).
         fast = self._pack_fast.get(which)
         if fast is not None:
-            params, key, ref = fast
-            if all(p._version == v and p.data_ptr() == q for p, (q, v) in zip(params, key)):
+            params, key, ref, vers = fast
+            self._pack_calls += 1
+            if tuple(p._version for p in params) == vers and (self._pack_calls & 63 or all(p.data_ptr() == q for p, (q, _) in zip(params, key))):
                 return ref
         self._packed_mlp(which)
         names = {"update": ("pe_mlp_1", "pe_mlp_2", "self_update_pe"),
                  "nbr": ("pe_neighbor_mlp_1", "pe_neighbor_mlp_2", "self_update_neighbor_pe")}[which]
         params = [p for n in names for p in (getattr(self, n).weight, getattr(self, n).bias)] + [self.time_encoder.w.weight]
         entry = self._pack_cache[which]
-        self._pack_fast[which] = (params, entry[0], entry[3])
+        self._pack_fast[which] = (params, entry[0], entry[3], tuple(v for _, v in entry[0]))
         return entry[3]
 
     # ---- a3: DFT filter ---------------------------------------------------------------------
@@ -260,13 +263,20 @@ class LSTEP(nn.Module):
             G = G + a[:, None]
         return G.to(torch.float32)
 
+    def _parameters_ref(self, name: str):
+        """The weight Parameter of submodule `name` without nn.Module.__getattr__'s fallback chain."""
+        return self._modules[name]._parameters["weight"]
+
     def _collapsed_filter(self, b: int, residual: bool) -> torch.Tensor:
         """G[T,d] from the collapse kernel, cached until the parameters change."""
+        hit = self._filter_cache.get((b, residual))
+        if hit is not None:  # (parameters fetched through the cached references: nn.Module.__getattr__ is slow)
+            Wc, ac = hit[2], hit[3]
+            if (Wc.data_ptr(), Wc._version, ac.data_ptr(), ac._version, b, residual) == hit[0] and Wc is self._parameters_ref("fft_filter") \
+                    and ac is self._parameters_ref("fft_agg"):
+                return hit[1]
         W, a = self.fft_filter.weight, self.fft_agg.weight
         key = (W.data_ptr(), W._version, a.data_ptr(), a._version, b, residual)
-        hit = self._filter_cache.get((b, residual))
-        if hit is not None and hit[0] == key:
-            return hit[1]
         lib = _lib.load()
         T, d = self.num_fft_batches, self.pe_dim
         G = torch.empty((T, d), dtype=torch.float32, device=self._dev())
@@ -277,7 +287,7 @@ class LSTEP(nn.Module):
             G += ac[:, None]
         if len(self._filter_cache) > 8:
             self._filter_cache.clear()
-        self._filter_cache[(b, residual)] = (key, G)
+        self._filter_cache[(b, residual)] = (key, G, W, a)
         return G
 
     def fourier_transform_pe(self, node_ids, pe, batch_idx, use_dropout=False, use_mixer=False):

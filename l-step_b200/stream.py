@@ -260,6 +260,57 @@ class PEStream:
         m.h2d_bytes += 8 * n * (5 + C)  # what lstep_pe_step_host copies: src, dst, t, <= 2n ids, C query sets
         return tk
 
+    def run_host(self, src: np.ndarray, dst: np.ndarray, times: np.ndarray, query_ids) -> np.ndarray:
+        """A run of consecutive batches fed from HOST arrays in ONE native call (an evaluation split): batch b is edges
+        [b*B, (b+1)*B) of the given arrays; every step copies its own inputs in and its own per-query row sums out
+        (read one step behind inside the call). Returns [n_batches, C, B] float32 (tail of a ragged last batch zero).
+        While the history ring is still filling (the filter changes with every step) the batches go through
+        step_host_async one by one."""
+        n_total, B, C = len(src), self.B, len(query_ids)
+        src = np.ascontiguousarray(src, dtype=_I64)
+        dst = np.ascontiguousarray(dst, dtype=_I64)
+        times = np.ascontiguousarray(times, dtype=_F64)
+        qs = [np.ascontiguousarray(q, dtype=_I64) for q in query_ids]
+        if len(dst) != n_total or len(times) != n_total or any(len(q) != n_total for q in qs):
+            raise ValueError("run_host: src, dst, times and every query set must have the same length")
+        nb = (n_total + B - 1) // B
+        res = np.zeros((nb, C, B), dtype=np.float32)
+        lo = 0
+        pend = []
+        while lo < n_total and self.len < self.T:  # masked regime: per-step calls
+            hi = min(lo + B, n_total)
+            pend.append((lo // B, hi - lo, self.step_host_async(src[lo:hi], dst[lo:hi], times[lo:hi], [q[lo:hi] for q in qs])))
+            if len(pend) > 1:
+                b, n, tk = pend.pop(0)
+                res[b, :, :n] = self.result(tk)
+            lo = hi
+        for b, n, tk in pend:
+            res[b, :, :n] = self.result(tk)
+        if lo >= n_total:
+            return res
+        m, lib = self.model, self._libc
+        if torch.cuda.current_device() != self.dev.index:
+            torch.cuda.set_device(self.dev)
+        h = self._stepper(B, C)
+        G = m._collapsed_filter(self.T, False)
+        ws = self._workspace(2 * B, B, C)
+        qptrs = (C_void_p * max(C, 1))(*[q[lo:].ctypes.data for q in qs])
+        head, ln = ctypes.c_int(self.head), ctypes.c_int(self.len)
+        sub = res[lo // B:]
+        samp = m.neighbor_sampler
+        rc = lib.lstep_pe_steps_host(h, self._desc_ref, samp.csr_ref, n_total - lo, B, src[lo:].ctypes.data, dst[lo:].ctypes.data,
+                                     times[lo:].ctypes.data, qptrs, C, C_byref(head), C_byref(ln), G.data_ptr(), self.K,
+                                     m._mlp_ref("nbr"), m._mlp_ref("update"), ws.data_ptr(), ws.numel(), samp._err.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream, sub.ctypes.data)
+        if rc != 0:
+            _lib.check(rc, "lstep_pe_steps_host")
+        steps = (n_total - lo + B - 1) // B
+        self.head = head.value
+        self.batch_idx += steps
+        self.steps_done += steps
+        m.h2d_bytes += 8 * (n_total - lo) * (5 + C)
+        return res
+
     def result(self, ticket: int) -> np.ndarray:
         """Per-query row sums [C, n] of step `ticket` (waits for that step's device-to-host copy)."""
         p = ctypes.POINTER(ctypes.c_float)()

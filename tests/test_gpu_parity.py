@@ -443,6 +443,37 @@ def test_host_fed_step_matches_device_resident_step(torch_cuda):
     s.check_errors()
 
 
+def test_run_host_matches_device_resident_steps(torch_cuda):
+    """PEStream.run_host (a whole run of batches in one native call, both while the ring is filling — per-step calls —
+    and in the steady state — lstep_pe_steps_host) against PEStream.step on a twin stream."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream
+    g = synth.make_graph("tiny_bip", seed=6)
+    V, d, T, K, B = g.num_nodes, 172, 100, 20, 16
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin("full", g, s, 172, d, 100, T, K)[0].eval()
+    init = seeded_normal(13, (V + 1, d), 0.3)
+    init[0] = 0
+    e0 = g.num_edges - 118 * B - 5  # 119 batches, the last one ragged: the ring (T = 100) fills after 99 of them
+    a = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=torch.from_numpy(init).cuda(), start=e0)
+    b = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=torch.from_numpy(init).cuda(), start=e0)
+    rng = np.random.default_rng(0)
+    neg = rng.integers(1, V + 1, g.num_edges - e0).astype(np.int64)
+    want = np.zeros((a.num_batches, 3, B), np.float32)
+    for i in range(a.num_batches):
+        lo, hi, _, _ = a.batch_arrays(i)
+        out = a.step(i, [a.src[lo:hi], a.dst[lo:hi], torch.from_numpy(neg[lo - e0:hi - e0]).cuda()])
+        want[i, :, :hi - lo] = out.sum(dim=2).cpu().numpy()
+    got = b.run_host(g.src_node_ids[e0:], g.dst_node_ids[e0:], g.node_interact_times[e0:],
+                     [g.src_node_ids[e0:], g.dst_node_ids[e0:], neg])
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+    assert torch.equal(a.cur, b.cur) and torch.equal(a.export_history(), b.export_history())
+    assert (b.head, b.len, b.batch_idx) == (a.head, a.len, a.batch_idx)
+    s.check_errors()
+
+
 def test_lookup_fused_aggregate_matches_sampler_plus_aggregate(torch_cuda):
     """lstep_nbr_lookup_aggregate (lookup inside the gather kernel) == lstep_sample_recent_compact + lstep_nbr_aggregate,
     bit for bit, including ties, empty histories and K larger than a warp."""
