@@ -94,6 +94,10 @@ struct FixedRows {
   // has nothing left to do after its dependency wait.
   float* ring_slot;
   int64_t ring_stride;
+  // ids_stable: the base-id arrays of the launch are not written by any kernel of the stream (the streaming step's
+  // query / batch node lists): the first link of the kernel's dependent load chain, id -> base row, is then taken
+  // before the dependency wait.
+  int ids_stable;
 };
 
 #ifdef LSTEP_MLP_TIMING
@@ -268,6 +272,12 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   // every CTA of the cluster must be running, with its barriers initialised, before a peer stores into it:
   // arrive now, wait right before the first remote store (the staging and layer 1 run in between)
   cluster_arrive();
+  const bool ids_early = fx.ids_stable && !n_rows_dev;
+  if (ids_early && tid < RB) {
+    const int64_t cl = second ? cluster_raw - split : cluster_raw;
+    const int64_t row = cl * RB + tid;
+    s_node[tid] = row < n_rows ? base_ids.at(row) : 0;
+  }
   pdl_wait();  // from here on the kernel reads what the preceding kernels wrote
   TL_WAITED(fx.acc ? 4 : 2);
   MLP_T(0);
@@ -281,7 +291,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   const int64_t cluster_id = second ? cluster_raw - split : cluster_raw;
   const int64_t n_clusters = second ? (int64_t)(gridDim.x / kCl) - split : (int64_t)split;
   const bool idle = cluster_id >= n_tiles;  // a cluster without a row tile still completes the rendezvous and drains its copies
-  if (tid < RB) {  // first dependent load chain of the kernel (id -> base row)
+  if (!ids_early && tid < RB) {  // first dependent load chain of the kernel (id -> base row)
     const int64_t row = cluster_id * RB + tid;
     s_node[tid] = (!idle && row < n_rows) ? base_ids.at_dep(row) : 0;
   }
@@ -564,7 +574,7 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                           const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger,
                           float* ring_slot, int64_t ring_stride) {
-  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0, ring_slot, ring_stride};
+  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0, ring_slot, ring_stride, 0};
   const MlpJob j{A, lda, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace};
   // rows per cluster tile: the smallest tile that covers the launch in one round of ~32 co-resident clusters
   if (expected_rows <= 32 * 16) return launch_cl<4>(j, nullptr, pe, fx, st);
@@ -583,7 +593,7 @@ int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, R
                                float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
                                const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger) {
   if (rows0 <= 0 || rows1 <= 0 || !out0 || !out1) return LSTEP_ERR_UNSUPPORTED;
-  const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0, nullptr, 0};
+  const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0, nullptr, 0, 1};  // (the step's id lists are stable)
   const MlpJob j0{A0, lda0, ids0, rows0, nullptr, *m0, out0, out_stride0, nullptr};
   const MlpJob j1{A1, lda1, ids1, rows1, nullptr, *m1, out1, out_stride1, nullptr};
   int rc = launch_cl<4>(j0, &j1, pe, fx, st);
