@@ -35,7 +35,7 @@ typedef enum lstep_status {
   LSTEP_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels were built for */
   LSTEP_ERR_WORKSPACE = 3,     /* workspace too small */
   LSTEP_ERR_CUDA = 4,          /* a CUDA runtime call failed; see lstep_last_cuda_error() */
-  LSTEP_ERR_ID_RANGE = 5       /* id does not fit the int32 device encoding */
+  LSTEP_ERR_ID_RANGE = 5       /* id outside the table, or not representable in the int32 device encoding */
 } lstep_status;
 
 /* bits set in the device `err_flag` word by kernels */

@@ -133,6 +133,8 @@ def check(status: int, what: str = ""):
         msg += ": " + lib.lstep_last_cuda_error().decode()
     if status == 1:
         raise ValueError(f"{what}: {msg}")
+    if status == 5:  # the reference raises IndexError for a node id outside its tables
+        raise IndexError(f"{what}: index out of range ({msg})")
     raise LstepError(f"{what}: {msg}")
 
 

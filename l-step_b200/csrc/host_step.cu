@@ -221,6 +221,17 @@ extern "C" int lstep_pe_step_host(lstep_host_stepper* h, const lstep_pe_stream* 
     n_ids = unique_sorted_ids(src_host, dst_host, n, s->V1, h_ids);
   }
   for (int c = 0; c < n_queries; ++c) memcpy(h_q + (size_t)c * n, query_ids_host_arrays[c], 8 * n);
+  {
+    // every id indexes the [V1, d] table and the ring on the device: reject out-of-range ids here (the reference
+    // raises IndexError on them, utils.py:140 / LSTEP.py:303; the Python host maps this status to IndexError)
+    const int64_t V1 = s->V1;
+    bool ok = n_ids == 0 || (h_ids[0] >= 0 && h_ids[n_ids - 1] < V1);  // sorted
+    if (ids_host)
+      for (int64_t i = 0; i < n_ids && ok; ++i) ok = h_ids[i] >= 0 && h_ids[i] < V1;
+    for (size_t i = 0; i < n && ok; ++i) ok = src_host[i] >= 0 && src_host[i] < V1 && dst_host[i] >= 0 && dst_host[i] < V1;
+    for (size_t i = 0; i < (size_t)n_queries * n && ok; ++i) ok = h_q[i] >= 0 && h_q[i] < V1;
+    if (!ok) return LSTEP_ERR_ID_RANGE;
+  }
   const size_t bytes = 8 * n * (size_t)(5 + n_queries);
   static const bool use_memcpy = getenv("LSTEP_HOST_MEMCPY") != nullptr;
   // copy-in on its own stream: it only has to wait for the slot's previous use (synchronised above), so it runs

@@ -440,6 +440,16 @@ def test_host_fed_step_matches_device_resident_step(torch_cuda):
     assert torch.equal(a.export_history(), b.export_history())
     with pytest.raises(ValueError):
         b.step_host_async(g.src_node_ids[:4], g.dst_node_ids[:3], g.node_interact_times[:4], [])
+    # ids outside the table are rejected on the host side of the native call, before anything is enqueued
+    head, ln, bidx = b.head, b.len, b.batch_idx
+    bad = g.src_node_ids[:4].copy()
+    bad[2] = V + 7
+    with pytest.raises(IndexError):
+        b.step_host_async(bad, g.dst_node_ids[:4], g.node_interact_times[:4], [g.dst_node_ids[:4]])
+    with pytest.raises(IndexError):
+        b.step_host_async(g.src_node_ids[:4], g.dst_node_ids[:4], g.node_interact_times[:4], [bad])
+    assert (b.head, b.len, b.batch_idx) == (head, ln, bidx)
+    assert torch.equal(a.cur, b.cur)
     s.check_errors()
 
 
