@@ -150,6 +150,16 @@ typedef struct lstep_pe_mlp {
 } lstep_pe_mlp;
 
 /* ------------------------------------------------------------------------------------------
+ * a5 — TimeEncoder.forward (models/modules.py:27-39, frozen at models/LSTEP.py:50):
+ *   out[i, j] = cos(dt[i] * w[j])   — the fp32 product rounded on its own (what Linear(1 -> t) with a zero bias
+ * computes), then the accurate cosine the gather / update kernels use (time_feature() in csrc/common.cuh; all
+ * three argument ranges: |x| < 2^14 Cody-Waite, < 2^32 fixed-point Payne-Hanek, beyond: general window).
+ * In the step this is fused into the K2 kernels; the stand-alone entry point exists so that the encoder can be
+ * pinned on its own against a float64 cosine.
+ * ------------------------------------------------------------------------------------------ */
+int lstep_time_features(const float* dt, int64_t n, const float* w, int t, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * a6 — neighbourhood PE aggregate (kernel K2, gather side) + MLP.
  * Replaces LSTEP.compute_neighborhood_pe (models/LSTEP.py:222-249) after the sampler call:
  *   S[i] = sum_k [ pe[nbr[i,k]] || mask_k * cos(fp32(q_time[i] - nbr_t[i,k]) * tw) ]

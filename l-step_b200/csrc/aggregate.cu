@@ -6,6 +6,8 @@
 // threads own one 128-bit column group of the PE row and add the K gathered rows in order
 // k = 0..K-1 (the PE table is L2 resident: 7.6 MB at Reddit size). Padded slots (id 0) read
 // pe[0] like any other row — it is non-zero after an update.
+#include <algorithm>
+
 #include "common.cuh"
 #include "gather_bodies.cuh"
 
@@ -31,6 +33,14 @@ __global__ void __launch_bounds__(256) nbr_aggregate_bwd_kernel(const float* __r
       for (int k = 0; k < K; ++k) atomicAdd(dpe + (int64_t)nbr[row * K + k] * d + c, g);
     }
   }
+}
+
+// a5 stand-alone: out[i][j] = time_feature(dt[i], w[j]) (the function every fused kernel calls)
+__global__ void __launch_bounds__(256) time_features_kernel(const float* __restrict__ dt, int64_t n, const float* __restrict__ w, int t,
+                                                            float* __restrict__ out) {
+  const int64_t total = n * t;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = time_feature(dt[i / t], w[i % t]);
 }
 
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
@@ -119,4 +129,12 @@ extern "C" int lstep_nbr_lookup_aggregate(const lstep_csr* csr, const int64_t* q
   if (n_rows == 0) return LSTEP_OK;
   if (!csr || !pe || !q_node || !q_time || !S || (t > 0 && !tw)) return LSTEP_ERR_INVALID_ARG;
   return launch_nbr_lookup_aggregate(csr, single_ids(q_node), pe, q_time, n_rows, K, tw, d, t, S, d + t, err_flag, as_stream(stream));
+}
+
+extern "C" int lstep_time_features(const float* dt, int64_t n, const float* w, int t, float* out, void* stream) {
+  if (n < 0 || t <= 0 || (n > 0 && (!dt || !w || !out))) return LSTEP_ERR_INVALID_ARG;
+  if (n == 0) return LSTEP_OK;
+  const int64_t blocks = std::min<int64_t>(ceil_div(n * t, 256), (int64_t)kNumSMs * 8);
+  time_features_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(dt, n, w, t, out);
+  return check_launch("time_features");
 }

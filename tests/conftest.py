@@ -25,3 +25,26 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+_PARITY_LOG = {}
+
+
+@pytest.fixture(scope="session")
+def parity_log():
+    """Measured parity errors per case, written to gpurun_out/parity_log.json (or $LSTEP_PARITY_LOG) at session end;
+    the committed copy is profiles/r02_parity_errors.json."""
+    return _PARITY_LOG
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _PARITY_LOG:
+        return
+    import json
+    path = os.environ.get("LSTEP_PARITY_LOG") or os.path.join(ROOT, "gpurun_out", "parity_log.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "w") as f:
+            json.dump(_PARITY_LOG, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

@@ -64,26 +64,47 @@ def rel_err(a: np.ndarray, b: np.ndarray, scale_from: np.ndarray = None) -> np.n
     return np.abs(a - b) / np.maximum(np.abs(b), max(rms, 1e-30))
 
 
-def check_updated_table(got, want, what, truth=None):
-    """Parity bar for a PE table after update_pe.
-
-    update_pe pushes sums of up to thousands of rows through a 2-layer MLP whose pre-activations
-    reach |z| ~ 50, twice for nodes that are both batch nodes and sampled neighbours (Q6), and the
-    padding row 0 collects every empty slot. fp32 summation order alone therefore moves a handful of
-    elements by a few 1e-5 between two CPU BLAS libraries (numpy/OpenBLAS vs torch/MKL: 2.5e-5 on row 0;
-    measured against a float64 evaluation, the reference-style fp32 path itself is off by up to 1.6e-4
-    on row 0 and 7e-5 on twice-updated rows of the Flights-shaped batch). The bar is:
-      * 99.9 % of the elements within 1e-5 * max(|want|, rms(want))   (the north-star tolerance),
-      * when a float64 evaluation `truth` of the same function is given: the worst error of `got`
-        against it no larger than twice the worst error of the fp32 reference-style result (the CUDA
-        path is at least as close to the exact answer as the reference is — its hub sums are exact
-        fixed-point sums, so on hub rows it is the reference that is further from the truth),
-      * otherwise (golden vectors without a float64 twin): every element within 2e-4."""
+def update_error_report(got, want, truth=None, factor=1.0) -> dict:
+    """Elementwise error statistics of a PE table `got` against the reference-produced `want` (and, when given, a float64
+    evaluation `truth` of the same function on the same inputs). Errors are |a-b| / max(|want|, rms(want)).
+    An element is `explained` when it is (a) within 1e-5 of the reference, or (b) within 1e-5 of the exact value, or
+    (c) no further from the exact value than `factor` x the reference's own worst element of the same row."""
     e = rel_err(got, want)
-    q = float(np.quantile(e, 0.999)) if e.size else 0.0
-    assert q <= 1e-5, (what, "p99.9", q)
-    if truth is not None:
-        eg, er = rel_err(got, truth), rel_err(want, truth)
-        assert float(eg.max()) <= 2.0 * max(float(er.max()), 1e-5), (what, "vs float64", float(eg.max()), float(er.max()))
+    rep = {"max": float(e.max()) if e.size else 0.0, "n_gt_1e-5": int((e > 1e-5).sum()), "n": int(e.size)}
+    if truth is not None and e.size:
+        eg, er = rel_err(got, truth, want), rel_err(want, truth, want)
+        over = e > 1e-5
+        row_ref = er.reshape(er.shape[0], -1).max(axis=1).reshape((-1,) + (1,) * (er.ndim - 1))
+        bad = over & (eg > np.maximum(1e-5, factor * row_ref))
+        ill = np.nonzero(row_ref.reshape(-1) > 1e-5)[0]
+        rep.update({"max_vs_f64": float(eg.max()), "ref_max_vs_f64": float(er.max()),
+                    "rows_where_reference_is_gt_1e-5_from_f64": ill.tolist()[:24], "n_such_rows": int(len(ill)),
+                    "rows_over_1e-5_vs_reference": np.unique(np.nonzero(over)[0]).tolist()[:24],
+                    "n_unexplained": int(bad.sum()), "worst_unexplained": float(eg[bad].max()) if bad.any() else 0.0})
+    return rep
+
+
+def check_updated_table(got, want, what, truth=None, strict=False, factor=1.0, log=None):
+    """Parity bar for fp32 PE values that went through update_pe (BASELINE.json north_star: within 1e-5 relative).
+
+    Every element must be within 1e-5 * max(|want|, rms(want)) of the reference's value (`want`), with ONE exception
+    that needs a float64 evaluation `truth` of the same function on the same inputs: rows on which the fp32 reference
+    itself is not defined to 1e-5. Those exist — row 0 collects every padded neighbour slot of the batch (hundreds to
+    tens of thousands of rows summed sequentially in fp32, then pushed through the MLP), hub rows and rows updated
+    twice (batch node AND sampled neighbour, Q6) likewise: the reference's own value is 1.5e-5 .. 4.7e-5 away from
+    the exact result on such rows of the golden cases (3.1e-4 on the Flights shape), and two faithful fp32 CPU
+    evaluations (torch/MKL vs numpy/OpenBLAS, same summation order) already differ by 1.4e-5 there
+    (profiles/r02_parity_errors.json names the rows per case). An element further than 1e-5 from the reference passes
+    only if it is within 1e-5 of the EXACT value, or no further from it than `factor` x the reference's own worst element
+    of that row (factor 1 for the CUDA path: at least as accurate as the reference, row by row; 2 for the numpy oracle,
+    whose sequential fp32 sums err like the reference's). A localised bug (row 0 only, one hub row) cannot hide behind
+    this: its row error would exceed the reference's by orders of magnitude.
+    strict=True or no `truth`: no exception, every element within 1e-5."""
+    rep = update_error_report(got, want, truth, factor)
+    if log is not None:
+        log[str(what)] = rep
+    if strict or truth is None:
+        assert rep["max"] <= 1e-5, (what, "max rel err vs reference", rep)
     else:
-        assert float(e.max()) <= 2e-4, (what, "max", float(e.max()))
+        assert rep["n_unexplained"] == 0, (what, rep)
+    return rep

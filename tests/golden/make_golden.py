@@ -23,7 +23,7 @@ sys.path.insert(0, HERE)
 from common import ROOT, checksum, golden_path, seeded_edge_feats, seeded_normal  # noqa: E402
 
 REF = os.environ.get("LSTEP_REFERENCE", "/root/reference")
-sys.path.insert(0, os.path.join(HERE, "shims"))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "shims"))
 sys.path.insert(0, REF)
 
 import torch  # noqa: E402
@@ -45,8 +45,14 @@ def ref_data(g) -> RefData:
     return RefData(g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids, g.labels)
 
 
-def build_model(g, pe_dim, time_dim, T, K, feat_dim, seed=0):
-    """Reference constructor under torch.manual_seed(seed)."""
+PE_MLPS = ["pe_mlp_1", "pe_mlp_2", "self_update_pe", "pe_neighbor_mlp_1", "pe_neighbor_mlp_2", "self_update_neighbor_pe"]
+
+
+def build_model(g, pe_dim, time_dim, T, K, feat_dim, seed=0, scale=2.0):
+    """Reference constructor under torch.manual_seed(seed). `scale` multiplies the six PE-MLP weight
+    matrices: 2.0 = the stress regime (tanh exercised off zero, pre-activations up to |z| ~ 50), 1.0 = the torch
+    default initialisation as it is (the realistic regime; fixtures tagged `...u`). Scaling by 2 is exact in fp32, so
+    the unscaled parameters are params_<tag>.npz with those six matrices halved (tests/harness.py does that)."""
     torch.manual_seed(seed)
     node_feats = np.zeros((g.num_nodes + 1, feat_dim), dtype=np.float32)  # zeros, as the datasets' node feats
     edge_feats = seeded_edge_feats(g.num_edges, feat_dim)
@@ -57,9 +63,8 @@ def build_model(g, pe_dim, time_dim, T, K, feat_dim, seed=0):
     model = nn.Sequential(lstep, merge)
     # the torch default init leaves the PE MLPs small; scale them up so tanh() is exercised off zero
     with torch.no_grad():
-        for name in ["pe_mlp_1", "pe_mlp_2", "self_update_pe", "pe_neighbor_mlp_1", "pe_neighbor_mlp_2",
-                     "self_update_neighbor_pe"]:
-            getattr(lstep, name).weight.mul_(2.0)
+        for name in PE_MLPS:
+            getattr(lstep, name).weight.mul_(scale)
     return model, sampler, node_feats, edge_feats
 
 
@@ -119,14 +124,17 @@ def gen_sampler():
         print("sampler", gname, n_out, "outputs")
 
 
-def gen_module_goldens(tag, pe_dim, time_dim, T, K, feat_dim, gname):
+def gen_module_goldens(tag, pe_dim, time_dim, T, K, feat_dim, gname, scale=2.0):
     """(ii) fourier_transform_pe, (iii) compute_neighborhood_pe, (iv) update_pe, plus a training
-    step's gradients, all on one seeded model; parameters saved as params_<tag>.npz."""
+    step's gradients, all on one seeded model; parameters saved as params_<tag>.npz.
+    scale=1.0 (tag `<base>u`): only the parts that depend on the PE-MLP weights, no parameter file."""
     g = synth.make_graph(gname, seed=0)
-    model, sampler, node_feats, edge_feats = build_model(g, pe_dim, time_dim, T, K, feat_dim)
+    model, sampler, node_feats, edge_feats = build_model(g, pe_dim, time_dim, T, K, feat_dim, scale=scale)
     lstep = model[0]
     model.eval()
-    np.savez_compressed(golden_path(f"params_{tag}.npz"), **state_to_npz(model))
+    mlp_only = scale != 2.0
+    if not mlp_only:
+        np.savez_compressed(golden_path(f"params_{tag}.npz"), **state_to_npz(model))
     V1 = g.num_nodes + 1
     out = dict(gname=np.array(gname), pe_dim=np.int64(pe_dim), time_dim=np.int64(time_dim), T=np.int64(T), K=np.int64(K),
                feat_dim=np.int64(feat_dim))
@@ -135,8 +143,8 @@ def gen_module_goldens(tag, pe_dim, time_dim, T, K, feat_dim, gname):
     lo = g.num_edges // 2
     ids = synth.unique_batch_nodes(g.src_node_ids[lo:lo + 16], g.dst_node_ids[lo:lo + 16])
     out["dft_ids"] = ids
-    cases = [(1, 0), (1, 1), (min(5, T), 3), (min(5, T), 5), (T - 1, T - 1), (T - 1, 2 * T), (T, 0), (T, 7), (T, 5 * T)]
-    if T > 40:
+    cases = [] if mlp_only else [(1, 0), (1, 1), (min(5, T), 3), (min(5, T), 5), (T - 1, T - 1), (T - 1, 2 * T), (T, 0), (T, 7), (T, 5 * T)]
+    if T > 40 and not mlp_only:
         cases += [(37, 37), (37, 12)]
     out["dft_cases"] = np.array(cases, dtype=np.int64)
     with torch.no_grad():
@@ -145,10 +153,10 @@ def gen_module_goldens(tag, pe_dim, time_dim, T, K, feat_dim, gname):
             out[f"dft{ci}_in_ck"] = checksum(hist)
             y = lstep.fourier_transform_pe(ids, torch.from_numpy(hist), bidx)
             out[f"dft{ci}_out"] = y.numpy()
-        # single node -> .squeeze() drops the row dim
-        hist = seeded_normal(99, (V1, T, pe_dim), 0.5)
-        y = lstep.fourier_transform_pe(ids[:1], torch.from_numpy(hist), 3)
-        out["dft_single_out"] = y.numpy()
+        if not mlp_only:  # single node -> .squeeze() drops the row dim
+            hist = seeded_normal(99, (V1, T, pe_dim), 0.5)
+            y = lstep.fourier_transform_pe(ids[:1], torch.from_numpy(hist), 3)
+            out["dft_single_out"] = y.numpy()
 
     # ---- (iii) neighbourhood aggregate with nonzero pe[0] (Q2)
     pe = seeded_normal(5, (V1, pe_dim), 0.3)
@@ -185,6 +193,10 @@ def gen_module_goldens(tag, pe_dim, time_dim, T, K, feat_dim, gname):
         out["upd_subset_ids"] = nids
         out["upd_subset_out"] = pe_t.numpy().copy()
 
+    if mlp_only:
+        np.savez_compressed(golden_path(f"module_{tag}.npz"), **out)
+        print("module", tag, "done")
+        return
     # ---- training step: gradients that reach the PE path
     model.train()
     hist = torch.from_numpy(seeded_normal(77, (V1, T, pe_dim), 0.5))
@@ -208,11 +220,11 @@ def gen_module_goldens(tag, pe_dim, time_dim, T, K, feat_dim, gname):
     print("module", tag, "done")
 
 
-def gen_replay(tag, pe_dim, time_dim, T, K, feat_dim, time_gap, V, E, B, n_eval_batches):
-    """(v) free-running evaluate_model_link_prediction replay: per-batch AP/AUC/loss and PE
-    checksums. Hooks record what the untouched loop feeds the model."""
+def gen_replay(tag, pe_dim, time_dim, T, K, feat_dim, time_gap, V, E, B, n_eval_batches, scale=2.0, params_tag=None):
+    """(v) free-running evaluate_model_link_prediction replay: per-batch AP/AUC/loss, the 2B link
+    probabilities themselves and PE checksums. Hooks record what the untouched loop feeds the model."""
     g = synth.make_graph("tiny", seed=3, num_nodes=V, num_edges=E)
-    model, sampler, node_feats, edge_feats = build_model(g, pe_dim, time_dim, T, K, feat_dim)
+    model, sampler, node_feats, edge_feats = build_model(g, pe_dim, time_dim, T, K, feat_dim, scale=scale)
     lstep = model[0]
     e0 = E - n_eval_batches * B
     ev = g.slice(e0, E)
@@ -222,7 +234,7 @@ def gen_replay(tag, pe_dim, time_dim, T, K, feat_dim, time_gap, V, E, B, n_eval_
     hist0 = seeded_normal(11, (V + 1, 1, pe_dim), 0.3)
     hist0[0] = 0
 
-    rec = dict(neg_dst=[], pe_ck=[])
+    rec = dict(neg_dst=[], pe_ck=[], predicts=[])
     orig_sample = neg.sample
     orig_update = lstep.update_pe
 
@@ -239,12 +251,23 @@ def gen_replay(tag, pe_dim, time_dim, T, K, feat_dim, time_gap, V, E, B, n_eval_
 
     neg.sample = sample_hook
     lstep.update_pe = update_hook
-    import tqdm as _tqdm
     import evaluate_model_utils as emu
+    orig_metrics = emu.get_link_prediction_metrics
+
+    def metrics_hook(predicts, labels):
+        rec["predicts"].append(predicts.detach().numpy().astype(np.float32).copy())
+        return orig_metrics(predicts=predicts, labels=labels)
+
+    emu.get_link_prediction_metrics = metrics_hook
     emu.tqdm = lambda it, **kw: type("Q", (), {"__iter__": lambda s: iter(it), "set_description": lambda s, *_: None})()
     losses, metrics = evaluate_model_link_prediction("LSTEP", model, torch.from_numpy(hist0), sampler, loader, neg, eval_data,
                                                      nn.BCELoss(), num_fft_batches=T, num_neighbors=K, time_gap=time_gap)
-    out = dict(pe_dim=np.int64(pe_dim), time_dim=np.int64(time_dim), T=np.int64(T), K=np.int64(K), feat_dim=np.int64(feat_dim),
+    emu.get_link_prediction_metrics = orig_metrics
+    pred = np.zeros((len(rec["predicts"]), 2 * B), np.float32)  # [pos | neg] per batch; the ragged last batch is zero padded
+    for i, p_ in enumerate(rec["predicts"]):
+        h = len(p_) // 2
+        pred[i, :h], pred[i, B:B + h] = p_[:h], p_[h:]
+    out = dict(predicts=pred, mlp_scale=np.float64(scale),pe_dim=np.int64(pe_dim), time_dim=np.int64(time_dim), T=np.int64(T), K=np.int64(K), feat_dim=np.int64(feat_dim),
                time_gap=np.int64(time_gap), V=np.int64(V), E=np.int64(E), B=np.int64(B), e0=np.int64(e0),
                graph_seed=np.int64(3), hist0_seed=np.int64(11),
                losses=np.array(losses), ap=np.array([m["average_precision"] for m in metrics]),
@@ -255,8 +278,10 @@ def gen_replay(tag, pe_dim, time_dim, T, K, feat_dim, time_gap, V, E, B, n_eval_
                graph_ck=checksum(g.node_interact_times), edge_feats_ck=checksum(edge_feats))
     np.savez_compressed(golden_path(f"replay_{tag}.npz"), **out)
     # parameters: identical to params_<tag>.npz (same constructor under the same torch seed)
-    ref_params = np.load(golden_path(f"params_{tag}.npz"))
-    assert all(np.array_equal(ref_params[k], v) for k, v in state_to_npz(model).items())
+    ref_params = np.load(golden_path(f"params_{params_tag or tag}.npz"))
+    for k, v in state_to_npz(model).items():
+        is_mlp = k.startswith("0.") and k[2:].rsplit(".", 1)[0] in PE_MLPS and k.endswith(".weight")
+        assert np.array_equal(ref_params[k] * np.float32(scale / 2.0 if is_mlp else 1.0), v), k
     print("replay", tag, "AP", float(np.mean(out["ap"])), "AUC", float(np.mean(out["auc"])), "batches", len(losses))
 
 
@@ -267,7 +292,10 @@ if __name__ == "__main__":
     if "module" in which:
         gen_module_goldens("small", pe_dim=12, time_dim=10, T=8, K=4, feat_dim=12, gname="tiny")
         gen_module_goldens("full", pe_dim=172, time_dim=100, T=100, K=20, feat_dim=172, gname="tiny_bip")
+        gen_module_goldens("fullu", pe_dim=172, time_dim=100, T=100, K=20, feat_dim=172, gname="tiny_bip", scale=1.0)
     if "replay" in which:
         gen_replay("small", pe_dim=12, time_dim=10, T=8, K=4, feat_dim=12, time_gap=50, V=60, E=1500, B=10, n_eval_batches=60)
         gen_replay("full", pe_dim=172, time_dim=100, T=100, K=20, feat_dim=172, time_gap=2000, V=300, E=14000, B=50,
                    n_eval_batches=230)
+        gen_replay("fullu", pe_dim=172, time_dim=100, T=100, K=20, feat_dim=172, time_gap=2000, V=300, E=14000, B=50,
+                   n_eval_batches=230, scale=1.0, params_tag="full")

@@ -1,13 +1,17 @@
 """Parity of the CUDA path (through the C ABI and the drop-in Python API) against
  (a) golden vectors produced by the unmodified reference, and
  (b) the CPU oracle on seeded inputs at sizes the oracle finishes in seconds.
-Bars: indices / CSR bit-exact; fp32 PE values |a-b| <= 1e-5 * max(|b|, rms(b)) for the DFT filter
-and the neighbourhood aggregate; tables after update_pe: tests/golden/common.py::check_updated_table
-(99.9 % within 1e-5, all within 2e-4, and no further from a float64 evaluation than the reference)."""
+Bars: indices / CSR bit-exact; fp32 PE values |a-b| <= 1e-5 * max(|b|, rms(b)), every element, for the time encoder,
+the DFT filter, the neighbourhood aggregate and the tables after update_pe; the single exception (rows on which
+the fp32 reference itself is further than 1e-5 from a float64 evaluation: row 0, hub rows, twice-updated rows) is
+stated in tests/golden/common.py::check_updated_table and the rows are named per case in
+profiles/r02_parity_errors.json (written from the `parity_log` fixture). Two weight regimes: `full` = PE-MLP weights
+x2 (stress), `fullu` = the torch initialisation as it is (realistic). AP / AUC: equal unless the reference's own
+positive / negative scores tie within the fp32 noise (tests/harness.py::check_rank_metrics)."""
 import numpy as np
 import pytest
 
-from common import check_updated_table, checksum, golden_path, pe_close, seeded_edge_feats, seeded_normal
+from common import check_updated_table, checksum, golden_path, pe_close, seeded_edge_feats, seeded_normal, update_error_report
 from lstep_b200 import synth
 from oracle import lstep_oracle as orc
 
@@ -115,6 +119,50 @@ def test_sampler_vs_oracle_dataset_shapes(torch_cuda, gname, n_edges):
             assert a.dtype == b.dtype and np.array_equal(a, b), (gname, K)
 
 
+# ------------------------------------------------------------------------------------------ a5
+def test_time_encoder_all_cosine_branches(torch_cuda, parity_log):
+    """TimeEncoder.forward (models/modules.py:27-39) on its own: cos(fp32(dt) * w_j), through lstep_time_features, against
+    the oracle's float64 cosine of the same fp32 product. Covers the three argument ranges of accurate_cos (|x| < 2^14,
+    2^14 <= |x| < 2^32, |x| >= 2^32 incl. the e >= 214 cosf fallback), negative arguments, zero, denormals and the
+    products a timestamp difference actually yields. Bar: 1.2e-7 absolute (one fp32 ulp of values near 1)."""
+    torch = torch_cuda
+    from lstep_b200 import _lib
+    lib = _lib.load()
+    w = orc.time_encoder_weights(100)
+    rng = np.random.default_rng(0)
+    mags = np.concatenate([
+        rng.random(4000) * 16384.0,                       # Cody-Waite branch
+        2.0 ** (14 + 18 * rng.random(6000)),              # fixed-point Payne-Hanek branch (2^14 .. 2^32)
+        2.0 ** (32 + 60 * rng.random(3000)),              # general window (2^32 .. 2^92)
+        2.0 ** (92 + 35 * rng.random(500)),               # up to 2^127: e >= 214 takes cosf
+        np.array([0.0, 1e-42, 16383.999, 16384.0, 16384.001, 4294967040.0, 4294967296.0, 4294967808.0, 1.1e8, 2.68e6, 3.0e38]),
+        np.abs(rng.standard_normal(2000)) * 1e6,          # typical dt in seconds
+    ]).astype(np.float32)
+    dt = np.concatenate([mags, -mags[::3]]).astype(np.float32)
+    dt_d = torch.from_numpy(dt).cuda()
+    w_d = torch.from_numpy(w).cuda()
+    out = torch.empty((len(dt), len(w)), dtype=torch.float32, device="cuda")
+    _lib.check(lib.lstep_time_features(_lib.ptr(dt_d), len(dt), _lib.ptr(w_d), len(w), _lib.ptr(out), _lib.stream_ptr()), "time_features")
+    got = out.cpu().numpy()
+    want = orc.time_encode(dt, w)  # float64 cosine of the fp32 product, rounded to fp32
+    arg = np.abs(dt[:, None] * w[None, :])
+    err = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    rep = {}
+    for name, lo, hi in (("lt_2^14", 0.0, 16384.0), ("2^14..2^32", 16384.0, 4294967296.0), ("ge_2^32", 4294967296.0, np.inf)):
+        m = (arg >= lo) & (arg < hi)
+        assert m.sum() > 1000, name
+        rep[name] = {"n": int(m.sum()), "max_abs_err": float(err[m].max())}
+        assert err[m].max() <= 1.2e-7, (name, float(err[m].max()))
+    parity_log["a5/time_encoder"] = rep
+    # with w = 1 (j = 0) directly on the branch boundaries: every element of dt is its own argument
+    one = torch.ones(1, device="cuda")
+    out1 = torch.empty((len(dt), 1), dtype=torch.float32, device="cuda")
+    _lib.check(lib.lstep_time_features(_lib.ptr(dt_d), len(dt), _lib.ptr(one), 1, _lib.ptr(out1), _lib.stream_ptr()), "time_features")
+    e1 = np.abs(out1.cpu().numpy()[:, 0].astype(np.float64) - np.cos(dt.astype(np.float64)))
+    assert e1.max() <= 1.2e-7, float(e1.max())
+    assert (np.abs(dt) >= 2.0 ** 92).sum() > 100  # the cosf fallback was reached
+
+
 # ------------------------------------------------------------------------------------------ a3
 @pytest.mark.parametrize("tag", ["small", "full"])
 def test_dft_filter_vs_reference_golden(torch_cuda, tag):
@@ -180,8 +228,8 @@ def test_dft_filter_linearity_full_size(torch_cuda):
 
 
 # ------------------------------------------------------------------------------------------ a6/a7/a8
-@pytest.mark.parametrize("tag", ["small", "full"])
-def test_neighborhood_and_update_vs_reference_golden(torch_cuda, tag):
+@pytest.mark.parametrize("tag", ["small", "full", "fullu"])
+def test_neighborhood_and_update_vs_reference_golden(torch_cuda, tag, parity_log):
     torch = torch_cuda
     from harness import build_dropin
     from lstep_b200 import NeighborSampler
@@ -199,6 +247,7 @@ def test_neighborhood_and_update_vs_reference_golden(torch_cuda, tag):
         for KK in (K, 3):
             y = lstep.compute_neighborhood_pe(pe, z["nbr_q_ids"], z["nbr_q_t"], num_neighbors=KK)
             ok, worst = pe_close(y.cpu().numpy(), z[f"nbr_out_K{KK}"])
+            parity_log[f"golden/{tag}/nbr_K{KK}"] = {"max": worst}
             assert ok, (KK, worst)
         for ci, (st, B) in enumerate(z["upd_cases"]):
             st, B = int(st), int(B)
@@ -211,13 +260,16 @@ def test_neighborhood_and_update_vs_reference_golden(torch_cuda, tag):
             with orc.high_precision():
                 truth = orc.update_pe(p_np, adj, seeded_normal(40 + ci, (V1, d), 0.3).astype(np.float64), ids, src, dst, tt,
                                       tt.max(), K)
-            check_updated_table(pe_t.cpu().numpy(), z[f"upd{ci}_out"], (tag, ci), truth)
+            check_updated_table(pe_t.cpu().numpy(), z[f"upd{ci}_out"], f"golden/{tag}/upd{ci}", truth, log=parity_log)
         st, B = [int(x) for x in z["upd_cases"][0]]
         src, dst = g.src_node_ids[st:st + B], g.dst_node_ids[st:st + B]
         tt, ee = g.node_interact_times[st:st + B], g.edge_ids[st:st + B]
         pe_t = torch.from_numpy(seeded_normal(49, (V1, d), 0.3)).cuda()
         lstep.update_pe(pe_t, z["upd_subset_ids"], ee, src, dst, tt, tt.max(), num_neighbors=K)
-        check_updated_table(pe_t.cpu().numpy(), z["upd_subset_out"], (tag, "subset"))
+        with orc.high_precision():
+            truth = orc.update_pe(p_np, adj, seeded_normal(49, (V1, d), 0.3).astype(np.float64), z["upd_subset_ids"], src, dst, tt,
+                                  tt.max(), K)
+        check_updated_table(pe_t.cpu().numpy(), z["upd_subset_out"], f"golden/{tag}/upd_subset", truth, log=parity_log)
         # running the same update twice from the same input gives the same bits (workspace invariants hold)
         a = torch.from_numpy(seeded_normal(40, (V1, d), 0.3)).cuda()
         b = a.clone()
@@ -232,43 +284,59 @@ def test_neighborhood_and_update_vs_reference_golden(torch_cuda, tag):
             lstep.update_pe(a, np.array([V1 + 1]), ee, src, dst, tt, tt.max(), num_neighbors=K)
 
 
-@pytest.mark.parametrize("gname,B,K", [("enron", 200, 20), ("reddit", 200, 20), ("flights", 2000, 20)])
-def test_pe_step_vs_oracle_dataset_shapes(torch_cuda, gname, B, K):
-    """One teacher-forced module-boundary step (a3 + 4 x a6 + a7/a8) at the BASELINE config sizes
-    (graph truncated to keep the oracle's python adjacency build short) against the oracle."""
+@pytest.mark.parametrize("gname,B,K", [("enron", 200, 20), ("wikipedia", 200, 20), ("reddit", 200, 20), ("flights", 2000, 20)])
+def test_pe_step_vs_oracle_dataset_shapes(torch_cuda, gname, B, K, parity_log):
+    """One teacher-forced module-boundary step (a3 + 4 x a6 + a7/a8) on every BASELINE dataset shape at its FULL edge
+    count and a full history (T = 100 steps per node), against the oracle, in both weight regimes."""
     torch = torch_cuda
     from harness import build_dropin, lstep_params_np
     from lstep_b200 import NeighborSampler
-    n_edges = {"enron": 60_000, "reddit": 120_000, "flights": 150_000}[gname]
-    g = synth.make_graph(gname, seed=0, num_edges=n_edges)
+    g = synth.make_graph(gname, seed=0)
+    assert g.num_edges == synth.SHAPES[gname]["num_edges"]
     d, T, t_dim = 172, 100, 100
-    adj = orc.build_adjacency(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times)
+    adj = orc.build_adjacency_fast(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, num_rows=g.num_nodes + 1)
     s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent",
                                    num_rows=g.num_nodes + 1)
-    lstep = build_dropin("full", g, s, 172, d, t_dim, T, K)[0].eval()
-    p = lstep_params_np("full")
     V1 = g.num_nodes + 1
-    Th = 12  # short history keeps the host copy small; the filter itself is covered at T=100 above
-    hist = seeded_normal(3, (V1, Th, d), 0.3)
-    lo = n_edges - B
+    lo = g.num_edges - B
     src, dst, tt, ee = (a[lo:lo + B] for a in (g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids))
+    ids = synth.unique_batch_nodes(src, dst)
     rng = np.random.default_rng(5)
     neg = rng.choice(g.dst_node_ids, B)
     queries = [(src, tt), (dst, tt), (src, tt), (neg, tt)]
-    hist_o, outs_o, cur_o = orc.pe_step(p, adj, hist.copy(), 50, src, dst, tt, queries, T, K)
-    with orc.high_precision():
-        _, outs_truth, cur_truth = orc.pe_step(p, adj, hist.copy(), 50, src, dst, tt, queries, T, K)
-    with torch.no_grad():
-        pe_h = torch.from_numpy(hist).cuda()
-        ids = synth.unique_batch_nodes(src, dst)
-        fft = lstep.fourier_transform_pe(ids, pe_h, 50)
-        cur = pe_h[:, -1, :].clone()
-        cur[torch.from_numpy(ids).cuda()] = fft
-        for (qi, qt), want, truth in zip(queries, outs_o, outs_truth):
-            got = lstep.compute_neighborhood_pe(cur, qi, qt, num_neighbors=K)
-            check_updated_table(got.cpu().numpy(), want, (gname, "neighbourhood"), truth)
-        lstep.update_pe(cur, ids, ee, src, dst, tt, tt.max(), num_neighbors=K)
-    check_updated_table(cur.cpu().numpy(), cur_o, gname, cur_truth)
+    # the oracle only reads the history rows of the batch nodes: keep the host copy to those (the device gets all V1 rows)
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    pe_h = torch.randn((V1, T, d), device="cuda", generator=gen) * 0.3
+    hist_ids = pe_h[torch.from_numpy(ids).cuda()].cpu().numpy()
+    last = pe_h[:, -1, :].cpu().numpy()
+    for tag in ("fullu", "full"):
+        lstep = build_dropin(tag, g, s, 172, d, t_dim, T, K)[0].eval()
+        p = lstep_params_np(tag)
+
+        def oracle_step():
+            fft = orc.fourier_transform_pe(p, np.arange(len(ids)), hist_ids, 50, T)
+            cur = last.astype(fft.dtype)
+            cur[ids] = fft
+            outs = [orc.compute_neighborhood_pe(p, adj, cur, qi, qt, K) for qi, qt in queries]
+            return fft, outs, orc.update_pe(p, adj, cur, ids, src, dst, tt, tt.max(), K)
+
+        fft_o, outs_o, cur_o = oracle_step()
+        with orc.high_precision():
+            _, outs_truth, cur_truth = oracle_step()
+        with torch.no_grad():
+            fft = lstep.fourier_transform_pe(ids, pe_h, 50)
+            ok, worst = pe_close(fft.cpu().numpy(), fft_o)
+            parity_log[f"shape/{gname}/{tag}/dft"] = {"max": worst, "N": int(len(ids))}
+            assert ok, (gname, tag, "dft", worst)
+            cur = pe_h[:, -1, :].clone()
+            cur[torch.from_numpy(ids).cuda()] = fft
+            for c, ((qi, qt), want, truth) in enumerate(zip(queries, outs_o, outs_truth)):
+                got = lstep.compute_neighborhood_pe(cur, qi, qt, num_neighbors=K)
+                check_updated_table(got.cpu().numpy(), want, f"shape/{gname}/{tag}/nbr{c}", truth, log=parity_log)
+            lstep.update_pe(cur, ids, ee, src, dst, tt, tt.max(), num_neighbors=K)
+        check_updated_table(cur.cpu().numpy(), cur_o, f"shape/{gname}/{tag}/update", cur_truth, log=parity_log)
+    del pe_h
+    torch.cuda.empty_cache()
 
 
 # ------------------------------------------------------------------------------------------ training
@@ -315,12 +383,12 @@ def test_training_step_gradients_vs_reference_golden(torch_cuda, tag):
 
 
 # ------------------------------------------------------------------------------------------ replay
-@pytest.mark.parametrize("tag", ["small", "full"])
-def test_free_running_replay_ap_auc(torch_cuda, tag):
+@pytest.mark.parametrize("tag", ["small", "full", "fullu"])
+def test_free_running_replay_ap_auc(torch_cuda, tag, parity_log):
     """>= 200-step free-running eval replay (evaluate_model_utils.py:38-142) against the reference's
-    per-batch PE checksums, AP, AUC and final table."""
+    per-batch PE checksums, link probabilities, AP, AUC and final table."""
     torch = torch_cuda
-    from harness import build_dropin, replay_eval
+    from harness import build_dropin, check_rank_metrics, oracle_replay_f64, replay_eval
     from lstep_b200 import NeighborSampler
     z = np.load(golden_path(f"replay_{tag}.npz"))
     d, T, K, t_dim, F, tg, B = (int(z[k]) for k in ("pe_dim", "T", "K", "time_dim", "feat_dim", "time_gap", "B"))
@@ -339,27 +407,22 @@ def test_free_running_replay_ap_auc(torch_cuda, tag):
     cks = np.stack(cks)
     rel = np.abs(cks[:, 1] - z["pe_ck"][:, 1]) / z["pe_ck"][:, 1]
     assert rel.max() < 1e-5, rel.max()
-    check_updated_table(cur.cpu().numpy(), z["last_pe"], "final table")
-    assert len(aps) == len(z["ap"]) >= (200 if tag == "full" else 50)
-    # AP / AUC are rank statistics over 2B scores: equal unless two scores closer than the fp32 noise swap ranks.
-    # One adjacent swap moves a batch's AP/AUC by up to ~1e-3 at B=50; allow that in at most 3 % of the batches
-    # and require the means to agree to 2e-5.
-    for got, want, name in ((aps, z["ap"], "AP"), (aucs, z["auc"], "AUC")):
-        diff = np.abs(got - want)
-        assert diff.max() < 2e-3, (name, diff.max())
-        assert np.count_nonzero(diff > 1e-9) <= max(1, int(0.03 * len(diff))), (name, np.count_nonzero(diff > 1e-9))
-        assert abs(got.mean() - want.mean()) < 2e-5, (name, got.mean(), want.mean())
+    # final table after the whole free-running recurrence (errors of every step compound): factor 2 of the rule
+    check_updated_table(cur.cpu().numpy(), z["last_pe"], f"replay/{tag}/final_table", oracle_replay_f64(tag), factor=2.0, log=parity_log)
+    assert len(aps) == len(z["ap"]) >= (200 if tag != "small" else 50)
+    rep = check_rank_metrics(replay_eval.last_predicts, z["predicts"], B, aps, aucs, z["ap"], z["auc"], f"replay/{tag}/ap_auc", parity_log)
+    assert rep["mean_ap_diff"] < 2e-5 and rep["mean_auc_diff"] < 2e-5, rep
     assert np.abs(losses - z["losses"]).max() < 1e-4
 
 
 # ------------------------------------------------------------------------------------------ f1 streaming API
-@pytest.mark.parametrize("tag", ["small", "full"])
-def test_stream_api_matches_reference_replay(torch_cuda, tag):
+@pytest.mark.parametrize("tag", ["small", "full", "fullu"])
+def test_stream_api_matches_reference_replay(torch_cuda, tag, parity_log):
     """PEStream (device-resident edge stream + history ring, one C call per batch) against the
     reference's free-running replay: per-batch PE checksums, final table, exported history layout,
     and the neighbourhood outputs against the drop-in method on the same table."""
     torch = torch_cuda
-    from harness import build_dropin
+    from harness import build_dropin, oracle_replay_f64
     from lstep_b200 import NeighborSampler, PEStream
     z = np.load(golden_path(f"replay_{tag}.npz"))
     d, T, K, t_dim, F, B = (int(z[k]) for k in ("pe_dim", "T", "K", "time_dim", "feat_dim", "B"))
@@ -394,7 +457,7 @@ def test_stream_api_matches_reference_replay(torch_cuda, tag):
         ck = checksum(st.cur.cpu().numpy())
         worst = max(worst, abs(ck[1] - z["pe_ck"][b][1]) / z["pe_ck"][b][1])
     assert worst < 1e-5, worst
-    check_updated_table(st.cur.cpu().numpy(), z["last_pe"], "final table (stream)")
+    check_updated_table(st.cur.cpu().numpy(), z["last_pe"], f"stream/{tag}/final_table", oracle_replay_f64(tag), factor=2.0, log=parity_log)
     h = st.export_history()
     assert tuple(h.shape) == (V + 1, min(T, st.num_batches + 1), d)
     assert torch.equal(h[:, -1, :], st.cur)
@@ -545,7 +608,7 @@ def test_stream_is_bit_reproducible(torch_cuda):
 
 # ------------------------------------------------------------------------------------------ (e) sharded table
 @pytest.mark.parametrize("world", [2, 3])
-def test_sharded_ranks_match_single_gpu_stream(torch_cuda, world):
+def test_sharded_ranks_match_single_gpu_stream(torch_cuda, world, parity_log):
     """The node-id sharded algorithm (owner-computes, two row exchanges per step) with all ranks of the
     group emulated in one process on one GPU (LocalGroup) against the single-GPU PEStream and the
     reference's replay checksums: neighbourhood outputs bit-identical (same kernels per row), tables within
@@ -586,10 +649,37 @@ def test_sharded_ranks_match_single_gpu_stream(torch_cuda, world):
         ck = checksum(grp.gather_table().cpu().numpy())
         worst = max(worst, abs(ck[1] - z["pe_ck"][b][1]) / z["pe_ck"][b][1])
     assert worst < 1e-5, worst
-    check_updated_table(grp.gather_table().cpu().numpy(), st.cur.cpu().numpy(), f"sharded G={world} vs single GPU")
+    from harness import oracle_replay_f64
+    truth = oracle_replay_f64(tag) if n_steps == len(z["ap"]) else None
+    rep = update_error_report(grp.gather_table().cpu().numpy(), st.cur.cpu().numpy(), truth)
+    parity_log[f"sharded/G{world}/table_vs_single_gpu"] = rep
+    # float partial rows are summed per rank and then in rank order: same terms, other grouping than the single-GPU
+    # exact fixed-point sum -> a few 1e-5 on row 0 / hub rows over 120 free-running steps
+    assert rep["max"] <= 1e-4, rep
     # the sharded rings hold exactly the owners' rows of the single-GPU ring
     h = st.export_history()
     for rk in ranks:
         idx = (rk.head + torch.arange(rk.len, device="cuda")) % rk.T
         mine = rk.ring.index_select(1, idx)[:rk.rows_local]
-        check_updated_table(mine.cpu().numpy(), h[rk.rank::world].cpu().numpy(), f"ring of rank {rk.rank}")
+        r2 = update_error_report(mine.cpu().numpy(), h[rk.rank::world].cpu().numpy())
+        assert r2["max"] <= 1e-4, (rk.rank, r2)
+
+
+@pytest.mark.parametrize("world", [2])
+def test_sharded_ranks_over_nccl(torch_cuda, world):
+    """The same comparison with REAL ranks: one process per GPU under torchrun, NCCL all-to-all row exchanges
+    (tests/run_sharded_nccl_check.py: every rank's owned rows and the neighbourhood outputs against the single-GPU
+    stream). Needs `world` GPUs on the box; skipped otherwise (the emulated-ranks test above always runs)."""
+    import os
+    import subprocess
+    import sys
+    torch = torch_cuda
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + os.getpid() % 300
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "run_sharded_nccl_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.stdout.count("sharded == single GPU") == world, res.stdout[-2000:]

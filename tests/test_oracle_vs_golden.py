@@ -4,14 +4,10 @@ on the GPU box alike (no /root/reference access)."""
 import numpy as np
 import pytest
 
-from common import check_updated_table, checksum, golden_path, load_params, pe_close, seeded_normal
+from common import check_updated_table, checksum, golden_path, pe_close, seeded_normal
+from harness import lstep_params_np as lstep_params
 from lstep_b200 import synth
 from oracle import lstep_oracle as orc
-
-
-def lstep_params(tag):
-    p = load_params(f"params_{tag}.npz")
-    return {k[2:]: v for k, v in p.items() if k.startswith("0.")}
 
 
 @pytest.mark.parametrize("gname", ["tiny", "tiny_bip", "tiny_ties"])
@@ -40,6 +36,17 @@ def test_sampler_errors():
         orc.sample_recent(adj, np.array([10 ** 6]), np.array([1.0]), 3)
 
 
+@pytest.mark.parametrize("gname", ["tiny", "tiny_bip", "tiny_ties"])
+def test_fast_adjacency_builder_matches_literal_one(gname):
+    z = np.load(golden_path(f"sampler_{gname}.npz"))
+    a = orc.build_adjacency(z["src"], z["dst"], z["eid"], z["t"])
+    b = orc.build_adjacency_fast(z["src"], z["dst"], z["eid"], z["t"])
+    assert a.num_rows == b.num_rows
+    for x, y in zip(a.to_csr(), b.to_csr()):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+    assert np.array_equal(z["csr_nbr"], b.to_csr()[1])
+
+
 @pytest.mark.parametrize("tag", ["small", "full"])
 def test_dft_filter(tag):
     z = np.load(golden_path(f"module_{tag}.npz"))
@@ -59,8 +66,11 @@ def test_dft_filter(tag):
     assert pe_close(y, z["dft_single_out"])[0]
 
 
-@pytest.mark.parametrize("tag", ["small", "full"])
+@pytest.mark.parametrize("tag", ["small", "full", "fullu"])
 def test_neighborhood_and_update(tag):
+    """Bar: tests/golden/common.py::check_updated_table with factor 2 (the oracle's fp32 sums run in the reference's
+    order but through another BLAS: on rows where the reference itself is > 1e-5 from the float64 result — row 0 in
+    these cases — it may be up to twice as far from it; everywhere else every element is within 1e-5)."""
     z = np.load(golden_path(f"module_{tag}.npz"))
     p = lstep_params(tag)
     d, K = int(z["pe_dim"]), int(z["K"])
@@ -81,15 +91,19 @@ def test_neighborhood_and_update(tag):
         pe_t = seeded_normal(40 + ci, (V1, d), 0.3)
         ret = orc.update_pe(p, adj, pe_t, ids, src, dst, tt, tt.max(), K)
         assert ret is pe_t
-        check_updated_table(pe_t, z[f"upd{ci}_out"], ci)
+        with orc.high_precision():
+            truth = orc.update_pe(p, adj, seeded_normal(40 + ci, (V1, d), 0.3).astype(np.float64), ids, src, dst, tt, tt.max(), K)
+        check_updated_table(pe_t, z[f"upd{ci}_out"], (tag, ci), truth, factor=2.0)
     s, B = [int(x) for x in z["upd_cases"][0]]
     src, dst, tt = g.src_node_ids[s:s + B], g.dst_node_ids[s:s + B], g.node_interact_times[s:s + B]
     pe_t = seeded_normal(49, (V1, d), 0.3)
     orc.update_pe(p, adj, pe_t, z["upd_subset_ids"], src, dst, tt, tt.max(), K)
-    check_updated_table(pe_t, z["upd_subset_out"], "subset")
+    with orc.high_precision():
+        truth = orc.update_pe(p, adj, seeded_normal(49, (V1, d), 0.3).astype(np.float64), z["upd_subset_ids"], src, dst, tt, tt.max(), K)
+    check_updated_table(pe_t, z["upd_subset_out"], (tag, "subset"), truth, factor=2.0)
 
 
-@pytest.mark.parametrize("tag", ["small", "full"])
+@pytest.mark.parametrize("tag", ["small", "full", "fullu"])
 def test_free_running_replay_pe_checksums(tag):
     """The PE recurrence of evaluate_model_link_prediction (evaluate_model_utils.py:54-135) does not
     depend on the feature branch or the negatives, so the oracle can replay it alone: per-batch
@@ -104,7 +118,7 @@ def test_free_running_replay_pe_checksums(tag):
     hist = seeded_normal(int(z["hist0_seed"]), (V + 1, 1, d), 0.3)
     hist[0] = 0
     n_batches = len(z["ap"])
-    if tag == "full":
+    if tag.startswith("full"):
         n_batches = 40  # keep the CPU suite short; the GPU replay covers all 230
     worst_ck = 0.0
     for b in range(n_batches):
@@ -115,4 +129,4 @@ def test_free_running_replay_pe_checksums(tag):
         worst_ck = max(worst_ck, abs(ck[1] - z["pe_ck"][b][1]) / z["pe_ck"][b][1])
     assert worst_ck < 1e-5, worst_ck
     if n_batches == len(z["ap"]):
-        check_updated_table(cur, z["last_pe"], "final table")
+        check_updated_table(cur, z["last_pe"], "final table", strict=True)  # (tag small: 60 steps of the small model)
