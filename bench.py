@@ -9,10 +9,13 @@ A step is one pass of the module-boundary PE path over one batch of the syntheti
 pos dst, neg src, neg dst — the eval loop's four calls), update_pe (a7+a8), plus the history
 bookkeeping the streaming API does instead of the loops' clone/cat (one table copy in, one out).
 
-    value   edges/s with the edge stream, negatives and PE history resident in HBM
-    e2e     edges/s through PEStream.step_host(): numpy batch in (pinned H2D), per-query row sums out (D2H)
-    roofline  the dominant kernel's algorithmic bytes / its CUDA-event time vs the measured HBM peak
-    cpu_baseline  the oracle (numpy port of the reference path) on this box's host cores, bounded sample
+    value   edges/s with the edge stream, negatives and PE history resident in HBM: the K timed steps are ONE native call
+            (PEStream.run -> lstep_pe_steps) queued behind a short spin kernel, so the region is device-bound at any K
+    e2e     edges/s through PEStream.run_host(): numpy batches in (pinned H2D), per-query row sums out (D2H)
+    roofline  the step's dominant kernel (largest median duration of its six launches, CUDA events around each kernel of the
+              real step on live data): algorithmic bytes (or flops) / duration vs the measured peak
+    cpu_baseline  the UNMODIFIED reference (oracle/_ref, torch CPU) on this box's host cores, bounded sample of the same
+              workload with the same weights; the numpy oracle port when oracle/_ref is absent
 
 One JSON line on stdout (rank 0).
 """
@@ -125,6 +128,14 @@ def make_params_model(graph, sampler, device):
     return m.to(device).eval()
 
 
+def workload_config(workload, g, B, K, world=1):
+    """The `config` both arms print (same string for the CUDA arm and the reference arm: the driver compares them)."""
+    return {"workload": f"{workload}-shaped synthetic temporal graph, V={g.num_nodes}, E={g.num_edges}, B={B}, K={K}, "
+                        f"T={T_HIST}, d={D}, t={T_DIM}, C={C_CALLS} neighbourhood calls/batch (eval loop)",
+            "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (path does not shard at this size)",
+            "l2_policy": f"inputs larger than L2: PE history {(g.num_nodes + 1) * T_HIST * D * 4 / 1e6:.0f} MB, a different node set is read each step"}
+
+
 def run_ours(args, rank, world, own_pg=True):
     """The headline workload on every rank (N > 1: independent replicas, weak scaling — the path does not shard at
     this size). Returns the result line on rank 0; emits it when it owns the process group."""
@@ -152,6 +163,8 @@ def run_ours(args, rank, world, own_pg=True):
     e0 = int(g.num_edges * 0.7) // B * B
     stream = PEStream(model, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=init, start=e0)
     nb = stream.num_batches
+    if stream.batch_lo[-1] + B > g.num_edges:
+        nb -= 1  # full batches only (a ragged tail would change the per-step work)
     rng = np.random.default_rng(2)
     neg_all = rng.choice(np.unique(g.dst_node_ids), size=g.num_edges - e0).astype(np.int64)
     neg_dev = torch.from_numpy(neg_all).to(dev)
@@ -160,6 +173,17 @@ def run_ours(args, rank, world, own_pg=True):
         lo, hi, _, _ = stream.batch_arrays(b)
         return [stream.src[lo:hi], stream.dst[lo:hi], stream.src[lo:hi], neg_dev[lo - e0:hi - e0]]
 
+    def run_steps(first, n):
+        """n consecutive steps starting at step number `first` (wrapping over the evaluation split): one native call per
+        contiguous run of batches."""
+        done = 0
+        while done < n:
+            b0 = (first + done) % nb
+            cnt = min(n - done, nb - b0)
+            lo0 = stream.batch_lo[b0]
+            stream.run(b0, cnt, [stream.src[lo0:], stream.dst[lo0:], stream.src[lo0:], neg_dev[lo0 - e0:]])
+            done += cnt
+
     outs = torch.empty((C_CALLS, B, D), dtype=torch.float32, device=dev)
     W, Ksteps = args.warmup, args.steps
     W = max(W, 3)
@@ -167,27 +191,34 @@ def run_ours(args, rank, world, own_pg=True):
     # the measured regime is the steady state with a FULL history (T steps per node: the DFT filter reads all of
     # them); if fewer warm-up steps were asked for, the ring is filled first (untimed, reported in config)
     fill = max(0, T_HIST + 10 - W)
-    for _ in range(fill + W):
+    for _ in range(min(fill + W, T_HIST + 2)):  # per-step calls while the ring fills (the filter changes every step)
         stream.step(step_no % nb, queries(step_no % nb), outs)
         step_no += 1
+    rest = fill + W - step_no
+    if rest > 0:
+        run_steps(step_no, rest)
+        step_no += rest
     torch.cuda.synchronize()
+    sampler.check_errors()
     if world > 1:
         dist.barrier()
     clocks = ClockSampler(local)
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    Ns, Ms_est, edges = [], [], 0
-    ev0.record()
-    for _ in range(Ksteps):
-        b = step_no % nb
-        stream.step(b, queries(b), outs)
-        lo, hi, io, ie = stream.batch_arrays(b)
+    Ns, edges = [], 0
+    for i in range(Ksteps):
+        lo, hi, io, ie = stream.batch_arrays((step_no + i) % nb)
         edges += hi - lo
         Ns.append(ie - io)
-        step_no += 1
+    torch.cuda.synchronize()
+    # a short spin keeps the GPU busy while the host enqueues the first steps: the clock starts when the spin ends, with
+    # launches already queued behind it, so the timed region is the device's own chain of kernels at any K
+    torch.cuda._sleep(int(1.0e6))
+    ev0.record()
+    run_steps(step_no, Ksteps)
     ev1.record()
     torch.cuda.synchronize()
+    step_no += Ksteps
     ms_total = ev0.elapsed_time(ev1)
     clk = clocks.stop()
     t_max = torch.tensor([ms_total], device=dev)
@@ -198,70 +229,61 @@ def run_ours(args, rank, world, own_pg=True):
         dist.all_reduce(edges_t, op=dist.ReduceOp.SUM)
     ms_total_max = float(t_max.item())
     value = float(edges_t.item()) / (ms_total_max * 1e-3)
+    # the same steps through one Python call per step (what a loop calling PEStream.step pays), for reference
+    n_py = min(Ksteps, 200)
+    torch.cuda.synchronize()
+    t_py = time.perf_counter()
+    for _ in range(n_py):
+        stream.step(step_no % nb, queries(step_no % nb), outs)
+        step_no += 1
+    torch.cuda.synchronize()
+    py_ms = (time.perf_counter() - t_py) * 1e3 / n_py
 
-    # ---- per-stage / per-kernel instrumented pass (CUDA events on the launching stream)
-    stages, kern, M_meas = instrumented_pass(stream, model, sampler, queries, step_no, nb, min(Ksteps, 100), K, dev, lib)
-    step_no += min(Ksteps, 100)
+    # ---- per-kernel durations of the step's OWN six launches (CUDA events around every kernel of the real step)
+    n_prof = max(20, min(Ksteps, 100))
+    kern, M_meas = profile_pass(stream, sampler, queries, step_no, nb, n_prof, K, lib, outs)
+    step_no += n_prof
     N_mean = float(np.mean(Ns))
     M_mean = float(np.mean(M_meas)) if M_meas else 0.0
     bm = bytes_model(B, N_mean, M_mean, K, V1=V1)
     hbm_peak, peak_src = peaks()
-    # per-kernel algorithmic bytes (SURVEY §8(d) terms split by kernel; W/2 = the three packed matrices of one MLP)
-    CB = C_CALLS * B
-    alg = {"dft_filter": bm["F"],
-           "nbr_lookup_aggregate": CB * (16 + 16 * K) + CB * 4 * D * K + CB * 4 * (D + T_DIM),
-           "pe_mlp(nbr)": CB * 4 * (D + T_DIM) + 2 * CB * 4 * D + bm["W"] / 2,
-           "ring_append": bm["H"]}
-    ncu_full = {}
-    try:  # DRAM traffic per launch from the committed `ncu --set full` capture of this command (profiles/)
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_full_kernels.json")) as f:
-            ncu_full = {e["stage"]: e for e in json.load(f) if "stage" in e}
-    except Exception:
-        pass
-    roof_all = {}
-    for k in alg:
-        ach = alg[k] / (kern[k]["ms"] * 1e-3) / 1e9
-        roof_all[k] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                       # (the step launches the gather fused with phase A's edge aggregate and the two MLPs as a pair: those captures stand in)
-                       "traffic": (ncu_full.get(k) or ncu_full.get({"nbr_lookup_aggregate": "gather_ab", "pe_mlp(nbr)": "pe_mlp(pair: nbr || update A)"}.get(k, ""), {})).get("dram_bytes_per_launch"),
-                       "algorithmic_bytes_per_launch": alg[k],
-                       "ms_per_launch": kern[k]["ms"]}
-    # dominant kernel: the single kernel with the largest share of the step
-    dom = max(alg, key=lambda k: kern[k]["ms"])
+    roof_all = kernel_rooflines(kern, bm, B, N_mean, M_mean, K, V1, hbm_peak, clk)
+    dom = max(roof_all, key=lambda k: roof_all[k]["ms_per_launch"])
     roof = dict(kernel=dom, peak_source=peak_src, **roof_all[dom])
-    if dom.startswith("pe_mlp"):  # an fp32 FMA kernel: its HBM fraction is not the binding roofline; also state the one that is
-        flops = 2.0 * CB * ((D + T_DIM) * D + 2 * D * D)
-        roof["fp32_fma"] = {"achieved_tflops": flops / (kern[dom]["ms"] * 1e-3) / 1e12, "peak_tflops": 148 * 128 * 2 * clk_ghz(clk),
-                            "note": "fp32 SIMT peak = 148 SMs x 128 FMA/clk x SM clock; 1e-5 parity rules out single-pass TF32/BF16 tensor math"}
+    serial_ms = sum(v["ms_per_launch"] for v in roof_all.values())
     path_gbs = bm["bytes_path"] / (ms_total_max / Ksteps * 1e-3) / 1e9
 
     # ---- end to end through the host-facing API (numpy in, result out), same stream / model
     e2e = None
     if rank == 0 or world > 1:
-        e2e = e2e_pass(stream, g, e0, neg_all, step_no, nb, min(Ksteps, 300), B, world, dev)
+        e2e = e2e_pass(stream, g, e0, neg_all, step_no, nb, min(max(Ksteps, 100), 300), B, world, dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
         cpu = cpu_baseline(args.workload, B, K, args.cpu_batches)
 
     if rank == 0:
+        cfg = workload_config(args.workload, g, B, K, world)
+        info = {"timed_region": "K steps in one native call (PEStream.run -> lstep_pe_steps) queued behind a spin kernel; CUDA events on the launch stream",
+                "N_mean": N_mean, "M_mean": M_mean, "csr_build_s": t_csr, "history_fill_steps_before_warmup": fill}
         out = {
             "metric": "temporal edges/sec through PE update+aggregation; % HBM roofline", "value": value, "unit": "edges/s",
             "n_gpus": world, "steps": Ksteps, "warmup": W, "ms_per_step": ms_total_max / Ksteps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}-shaped synthetic temporal graph, V={g.num_nodes}, E={g.num_edges}, B={B}, K={K}, "
-                                   f"T={T_HIST}, d={D}, t={T_DIM}, C={C_CALLS} neighbourhood calls/batch (eval loop)",
-                       "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (path does not shard at this size)",
-                       "l2_policy": f"inputs larger than L2: PE history ring {V1 * T_HIST * D * 4 / 1e6:.0f} MB, a different node set is read each step",
-                       "N_mean": N_mean, "M_mean": M_mean, "csr_build_s": t_csr, "history_fill_steps_before_warmup": fill},
+            "config": cfg,
+            "run_info": info,
             "clocks": clk,
             "e2e": e2e,
-            "gpu_launches": int(kern["_launches_per_step"]["n"] * Ksteps),
+            "gpu_launches": int(6 * Ksteps),
             "roofline": roof,
             "roofline_kernels": roof_all,
             "path_roofline": {"bytes_path_per_step": bm["bytes_path"], "bytes_breakdown": {k: bm[k] for k in ("F", "S", "P", "UA", "UB", "W", "H")},
-                              "achieved_GBps": path_gbs, "peak_GBps": hbm_peak, "frac": path_gbs / hbm_peak, "peak_source": peak_src},
-            "stages_ms": stages, "kernels_ms": {k: v for k, v in kern.items() if not k.startswith("_")},
+                              "achieved_GBps": path_gbs, "peak_GBps": hbm_peak, "frac": path_gbs / hbm_peak, "peak_source": peak_src,
+                              "with_H": {"bytes_step": bm["bytes_path"] + bm["H"],
+                                         "frac": (bm["bytes_path"] + bm["H"]) / (ms_total_max / Ksteps * 1e-3) / 1e9 / hbm_peak}},
+            "step_ms": {"device_chain": ms_total_max / Ksteps, "python_call_per_step": py_ms, "sum_of_serialised_kernels": serial_ms,
+                        "note": "device_chain < sum_of_serialised_kernels: programmatic dependent launch overlaps each kernel's "
+                                "pre-wait work with its predecessor"},
             "cpu_baseline": cpu,
         }
         if own_pg:
@@ -404,85 +426,77 @@ def run_sharded(args, rank, world, own_pg=True):
     return out
 
 
-def instrumented_pass(stream, model, sampler, queries, step_no, nb, n, K, dev, lib):
-    """Stand-alone CUDA-event durations of the kernels of one step, each through its own C-ABI entry point on
-    the live state of the stream (the update runs on a scratch copy of the table). The GPU is kept busy by a
-    spin kernel while the measured launches are enqueued, so an event pair brackets the kernel itself and not
-    the host's launch latency; the stream is then advanced by a normal step so the next sample sees fresh data."""
+KERNELS = ["dft_filter", "gather_ab (a6 lookup+aggregate || a7 edge aggregate)", "pe_mlp pair (neighbourhood MLP || phase-A MLP)",
+           "phaseB_push", "pe_mlp (phase B)", "ring_append"]
+
+
+def profile_pass(stream, sampler, queries, step_no, nb, n, K, lib, outs):
+    """Durations of the six kernels of the REAL step on live data: lstep_step_profile(1) makes the step record a CUDA
+    event on its launch stream before its first kernel and after each kernel (csrc/step.cu); an event between two
+    kernels also removes their programmatic overlap, so these are the kernels run back to back. Medians over n steps
+    after 3 warm steps. Also measures M (distinct sampled neighbours per batch) for the byte model."""
+    import ctypes
     import torch
     from lstep_b200 import _lib
-    m = model
-    T, d, t = T_HIST, D, T_DIM
-    names = ["dft_filter", "nbr_lookup_aggregate", "pe_mlp(nbr)", "update_pe(drop-in, 4 kernels)", "ring_append"]
-    acc = {k: 0.0 for k in names}
-    M_meas = []
-
-    def timed(fn):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        r = fn()
-        b.record()
-        return a, b, r
-
-    tw = m.time_encoder.w.weight.detach().reshape(-1)
-    scratch = torch.empty_like(stream.cur)
-    with torch.no_grad():
-        # one untimed call: the drop-in update allocates its own workspace on first use
-        lo, hi, io, ie = stream.batch_arrays(step_no % nb)
-        scratch.copy_(stream.cur)
-        m.update_pe_device(scratch, stream.ids[io:ie], stream.src[lo:hi], stream.dst[lo:hi], stream.t[lo:hi], stream.batch_tmax[step_no % nb], K)
-        torch.cuda.synchronize()
-        for i in range(n):
+    ms = (ctypes.c_float * 6)()
+    rows = []
+    _lib.check(lib.lstep_step_profile(1), "profile on")
+    try:
+        for i in range(n + 3):
             b = (step_no + i) % nb
-            lo, hi, io, ie = stream.batch_arrays(b)
-            nB, N = hi - lo, ie - io
-            ids = stream.ids[io:ie]
-            src, dst, tt = stream.src[lo:hi], stream.dst[lo:hi], stream.t[lo:hi]
-            qs = queries(b)
-            qcat = torch.cat(qs)
-            tcat = tt.repeat(len(qs))
-            rows = qcat.shape[0]
-            G = m._collapsed_filter(T if stream.len >= T else min(stream.batch_idx, T), False)
-            fft = torch.empty((N, d), dtype=torch.float32, device=dev)
-            S = torch.empty((rows, d + t), dtype=torch.float32, device=dev)
-            outb = torch.empty((rows, d), dtype=torch.float32, device=dev)
-            nxt = (stream.head + stream.len) % T if stream.len < T else stream.head  # the slot the coming step overwrites anyway
-            scratch.copy_(stream.cur)
-            torch.cuda.synchronize()
-            torch.cuda._sleep(400_000)  # ~0.2 ms of GPU spin: everything below is queued before it ends
-            ev = {}
-            ev["dft_filter"] = timed(lambda: _lib.check(lib.lstep_dft_filter(_lib.ptr(stream.ring), T * d, d, stream.head, T, stream.len, d,
-                                                                            _lib.ptr(ids), N, _lib.ptr(G), _lib.ptr(fft), d, _lib.stream_ptr()), "dft"))
-            ev["nbr_lookup_aggregate"] = timed(lambda: _lib.check(lib.lstep_nbr_lookup_aggregate(
-                sampler.csr_ref, _lib.ptr(qcat), _lib.ptr(tcat), rows, K, _lib.ptr(stream.cur), stream.V1, _lib.ptr(tw), d, t, _lib.ptr(S),
-                _lib.ptr(sampler._err), _lib.stream_ptr()), "agg"))
-            ev["pe_mlp(nbr)"] = timed(lambda: _lib.check(lib.lstep_pe_mlp_apply(_lib.ptr(S), _lib.ptr(stream.cur), _lib.ptr(qcat), rows, m._mlp_ref("nbr"),
-                                                                               _lib.ptr(outb), d, None, _lib.stream_ptr()), "mlp"))
-            ev["update_pe(drop-in, 4 kernels)"] = timed(lambda: m.update_pe_device(scratch, ids, src, dst, tt, stream.batch_tmax[b], K))
-            ev["ring_append"] = timed(lambda: _lib.check(lib.lstep_ring_copy_rows(_lib.ptr(stream.ring), _lib.ptr(stream.cur), stream.V1, T, d, nxt, 1, 0, 1,
-                                                                                 _lib.stream_ptr()), "append"))
-            torch.cuda.synchronize()
-            stream.step(b, qs)  # advance the recurrence (untimed here; the main loop times whole steps)
-            for k2, (a, bb, _) in ev.items():
-                acc[k2] += a.elapsed_time(bb)
-    stages = {k2: v / n for k2, v in acc.items()}
-    kern = {"dft_filter": {"ms": stages["dft_filter"], "launches_per_step": 1},
-            "nbr_lookup_aggregate": {"ms": stages["nbr_lookup_aggregate"], "launches_per_step": 1},
-            "pe_mlp(nbr)": {"ms": stages["pe_mlp(nbr)"], "launches_per_step": 1},
-            "ring_append": {"ms": stages["ring_append"], "launches_per_step": 1},
-            # own kernels per step (csrc/step.cu): DFT filter 1; fused gather (a6 lookup + aggregate of all C query sets
-            # || a7 edge aggregate) 1; paired MLP (neighbourhood MLP || phase-A MLP) 1; phase-B push 1; phase-B MLP 1;
-            # ring append 1
-            "_launches_per_step": {"n": 6, "ms": 0.0, "launches_per_step": 0}}
-    # measured M: distinct sampled neighbours per batch
+            stream.step(b, queries(b), outs)
+            _lib.check(lib.lstep_step_profile_read(ms), "profile read")
+            if i >= 3:
+                rows.append([float(x) for x in ms])
+    finally:
+        lib.lstep_step_profile(0)
+    arr = np.array(rows)
+    kern = {name: {"ms": float(np.median(arr[:, k])), "ms_min": float(arr[:, k].min()), "ms_p90": float(np.quantile(arr[:, k], 0.9)),
+                   "launches_per_step": 1} for k, name in enumerate(KERNELS)}
+    M_meas = []
     for i in range(min(n, 20)):
         b = (step_no + i) % nb
         lo, hi, io, ie = stream.batch_arrays(b)
-        ids = stream.ids[io:ie]
         nv = min(ie - io, hi - lo)
-        nbr, _ = sampler.sample_device(ids, stream.t[lo:hi], ie - io, nv, K)
+        nbr, _ = sampler.sample_device(stream.ids[io:ie], stream.t[lo:hi], ie - io, nv, K)
         M_meas.append(int(torch.unique(nbr).numel()))
-    return stages, kern, M_meas
+    return kern, M_meas
+
+
+def kernel_rooflines(kern, bm, B, N, M, K, V1, hbm_peak, clk, d=D, t=T_DIM, C=C_CALLS):
+    """Algorithmic bytes / flops of each of the step's six launches (SURVEY §8(d) terms split by kernel; every distinct
+    tensor a kernel touches counted once) against its measured duration. Memory kernels: bound 'hbm' vs the measured copy
+    peak. The two MLP launches are fp32 FMA work (1e-5 parity rules out single-pass TF32 / BF16): bound 'fp32_fma' vs
+    148 SMs x 128 FMA/clk x SM clock."""
+    CB, W = C * B, bm["W"]
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_full_kernels.json")) as f:
+            ncu_full = {e["kernel"]: e for e in json.load(f) if "kernel" in e}
+    except Exception:
+        ncu_full = {}
+    alg = {
+        KERNELS[0]: bm["F"],
+        KERNELS[1]: CB * (16 + 16 * K) + CB * 4 * d * K + CB * 4 * (d + t) + 4 * d * 2 * B + 24 * B + 4 * (d + t) * N,
+        KERNELS[2]: (CB + N) * (4 * (d + t) + 8 * d) + W,
+        KERNELS[3]: N * (16 + 16 * K) + 8 * d * N + 8 * (d + t) * M + 12 * N * K,
+        KERNELS[4]: M * (8 * (d + t) + 12 * d) + W / 2,
+        KERNELS[5]: bm["H"],
+    }
+    flops = {KERNELS[2]: 2.0 * (CB + N) * ((d + t) * d + 2 * d * d), KERNELS[4]: 2.0 * M * ((d + t) * d + d * d)}
+    fma_peak = 148 * 128 * 2 * clk_ghz(clk)  # GFLOP/s * 1e-3 = TFLOP/s
+    out = {}
+    for name in KERNELS:
+        ms = kern[name]["ms"]
+        gbs = alg[name] / (ms * 1e-3) / 1e9
+        e = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+             "traffic": (ncu_full.get(name) or {}).get("dram_bytes_per_launch"), "algorithmic_bytes_per_launch": alg[name],
+             "ms_per_launch": ms, "ms_min": kern[name]["ms_min"], "ms_p90": kern[name]["ms_p90"]}
+        if name in flops:
+            tf = flops[name] / (ms * 1e-3) / 1e12
+            e.update({"bound": "fp32_fma", "achieved": tf, "peak": fma_peak * 1e-3, "unit": "TFLOP/s", "frac": tf / (fma_peak * 1e-3),
+                      "flops_per_launch": flops[name], "hbm_GBps": gbs, "hbm_frac": gbs / hbm_peak})
+        out[name] = e
+    return out
 
 
 def e2e_pass(stream, g, e0, neg_all, step_no, nb, n, B, world, dev):
@@ -577,8 +591,8 @@ def e2e_pass(stream, g, e0, neg_all, step_no, nb, n, B, world, dev):
 
 # ------------------------------------------------------------------------------------------------
 def oracle_setup(workload, B, K, n_batches, seed=0):
-    """Bounded sample of the workload for the CPU legs: the first 15 % of the stream builds the
-    adjacency (python loops dominate beyond that), batches are taken from its tail."""
+    """(fallback when oracle/_ref is absent) bounded sample of the workload for the numpy port: the first 15 % of the
+    stream builds the adjacency (python loops dominate beyond that), batches are taken from its tail."""
     from oracle import lstep_oracle as orc
     full = synth.SHAPES[workload]["num_edges"]
     n_edges = min(full, max(40_000, (n_batches + 4) * B * 4))
@@ -609,10 +623,90 @@ def oracle_batch(orc, g, adj, p, hist, lo, B, K, neg):
     return (t1 - t0) + (t3 - t2)
 
 
+class ReferenceArm:
+    """The UNMODIFIED reference's own CPU implementation of the path (oracle/_ref: models/LSTEP.py + utils/utils.py as they
+    lie in /root/reference, imported through oracle/refload.py) on the SAME workload as the CUDA arm: the full synthetic
+    graph, the reference's own NeighborSampler built over all its edges, the same weights (the drop-in's constructor under
+    torch.manual_seed(0) — identical state_dict keys — loaded into the reference module), T = 100 history steps per node,
+    torch CPU kernels on all host threads. A step = the module-boundary functions of one batch: fourier_transform_pe,
+    C x compute_neighborhood_pe, update_pe (the loop's own clone / index_put between them is outside the timer)."""
+
+    def __init__(self, workload, B, K):
+        import torch
+        from oracle import refload
+        self.ref = refload.load()
+        if self.ref is None:
+            raise RuntimeError("oracle/_ref not materialised")
+        ref = self.ref
+        torch.set_num_threads(os.cpu_count())
+        self.torch, self.B, self.K = torch, B, K
+        self.g = g = synth.make_graph(workload, seed=0)
+        V1 = g.num_nodes + 1
+        t0 = time.time()
+        self.sampler = ref.get_neighbor_sampler(ref.Data(g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids, g.labels),
+                                                "recent", seed=1)
+        self.t_sampler = time.time() - t0
+        node_feats = np.zeros((V1, 172), dtype=np.float32)
+        edge_feats = np.zeros((1, 172), dtype=np.float32)
+        from lstep_b200 import LSTEP as DropIn
+        torch.manual_seed(0)  # make_params_model(): the CUDA arm's weights
+        ours = DropIn(node_feats, edge_feats, None, None, pe_dim=D, num_neighbors=20, time_feat_dim=T_DIM, num_fft_batches=T_HIST, device="cpu")
+        self.model = ref.LSTEP(node_feats, edge_feats, self.sampler, self.sampler, pe_dim=D, num_neighbors=20, time_feat_dim=T_DIM,
+                               num_fft_batches=T_HIST, device="cpu")
+        self.model.load_state_dict(ours.state_dict())
+        self.model.eval()
+        gen = torch.Generator().manual_seed(1)
+        self.hist = torch.randn((V1, T_HIST, D), generator=gen) * 0.1
+        self.e0 = int(g.num_edges * 0.7) // B * B
+        self.rng = np.random.default_rng(3)
+        self.dst_pool = np.unique(g.dst_node_ids)
+
+    def batch(self, i):
+        """Batch i of the evaluation split; returns seconds spent in the module-boundary functions."""
+        torch, g, B, K, m = self.torch, self.g, self.B, self.K, self.model
+        lo = self.e0 + (i * B) % ((g.num_edges - self.e0) // B * B)
+        src, dst, tt, ee = (a[lo:lo + B] for a in (g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids))
+        neg = self.rng.choice(self.dst_pool, len(src))
+        ids = torch.from_numpy(np.array(src.tolist() + dst.tolist())).unique().numpy()  # evaluate_model_utils.py:54-55
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            fft = m.fourier_transform_pe(ids, self.hist, 10 ** 6)
+            t1 = time.perf_counter()
+            cur = torch.clone(self.hist[:, -1, :])
+            cur[torch.from_numpy(ids)] = fft
+            t2 = time.perf_counter()
+            for q in (src, dst, src, neg):
+                m.compute_neighborhood_pe(cur, q, tt, num_neighbors=K)
+            m.update_pe(cur, ids, ee, src, dst, tt, tt.max(), num_neighbors=K)
+            t3 = time.perf_counter()
+        return (t1 - t0) + (t3 - t2), len(src)
+
+
 def cpu_baseline(workload, B, K, n_batches):
+    """Reported beside the CUDA number as a baseline only. kind 'reference': the unmodified reference (oracle/_ref);
+    kind 'port': the numpy oracle, when oracle/_ref is absent."""
+    try:
+        arm = ReferenceArm(workload, B, K)
+    except Exception as e:  # oracle/_ref absent
+        log("reference unavailable (", repr(e)[:120], "): timing the numpy oracle port instead")
+        arm = None
+    times = []
+    if arm is not None:
+        budget = time.time() + 25.0
+        for i in range(n_batches + 3):
+            dt, _ = arm.batch(i)
+            if i >= 3:
+                times.append(dt)
+            if time.time() > budget and len(times) >= 5:
+                break
+        med = float(np.median(times))
+        return {"value": B / med, "unit": "edges/s", "cores": os.cpu_count(), "kind": "reference", "ms_per_batch": med * 1e3,
+                "sample": f"{len(times)} batches of {B} edges after 3 warm-up, median; the unmodified reference (oracle/_ref: models/LSTEP.py, "
+                          f"utils/utils.py) on torch CPU, {os.cpu_count()} threads, full {workload}-shaped graph (E={arm.g.num_edges}), same weights, "
+                          f"T={T_HIST}; module-boundary functions only (fourier_transform_pe, {C_CALLS} x compute_neighborhood_pe, update_pe); "
+                          f"reference sampler build {arm.t_sampler:.1f} s (untimed)"}
     orc, g, adj, p, hist, n_edges = oracle_setup(workload, B, K, n_batches)
     rng = np.random.default_rng(3)
-    times = []
     start = n_edges - (n_batches + 3) * B
     for i in range(n_batches + 3):
         lo = start + i * B
@@ -627,33 +721,61 @@ def cpu_baseline(workload, B, K, n_batches):
 
 
 def run_reference(args, rank, world):
-    """The reference's own CPU implementation of the path cannot travel (Python sources under
-    /root/reference are not on the GPU box and may not be copied), so this arm times the oracle port."""
+    """`--impl reference`: the reference's own CPU implementation of the path (ReferenceArm) on this box's host cores, on the
+    CUDA arm's config / metric / unit; each step is one batch. Rank 0 alone runs it (N > 1: the other ranks exit)."""
     if rank != 0:
         return
     global T_HIST
-    if args.workload == "scaleout":
+    workload = args.workload
+    if workload == "scaleout":
         # the sharded arm's config: batch shape of the Flights config (B=2000, K=20), T = --scaleout-T
-        args.workload, T_HIST = "flights", args.scaleout_T
-    B, K = WORKLOADS[args.workload]
+        workload, T_HIST = "flights", args.scaleout_T
+    B, K = WORKLOADS[workload]
     steps, warm = args.steps, max(args.warmup, 1)
-    steps = min(steps, 60)  # each step is one batch of CPU work (~0.1 s); bounded
-    orc, g, adj, p, hist, n_edges = oracle_setup(args.workload, B, K, steps + warm)
-    rng = np.random.default_rng(3)
-    start = n_edges - (steps + warm) * B
-    tot = 0.0
-    for i in range(steps + warm):
-        neg = rng.choice(g.dst_node_ids, B)
-        dt = oracle_batch(orc, g, adj, p, hist, start + i * B, B, K, neg)
-        if i >= warm:
-            tot += dt
-    value = steps * B / tot
-    sample = f"{steps} batches of {B} edges on the first {n_edges} edges of the synthetic stream (oracle port, numpy + BLAS threads)"
+    steps = min(steps, 100)  # each step is one batch of CPU work (~0.1 s at B=200); bounded
+    warm = min(warm, 5)
+    kind = "reference"
+    try:
+        arm = ReferenceArm(workload, B, K)
+    except Exception as e:
+        log("reference unavailable (", repr(e)[:120], "): timing the numpy oracle port instead")
+        arm, kind = None, "port"
+    tot, edges = 0.0, 0
+    if arm is not None:
+        budget = time.time() + 150.0
+        done = 0
+        for i in range(steps + warm):
+            dt, ne = arm.batch(i)
+            if i >= warm:
+                tot += dt
+                edges += ne
+                done += 1
+            if time.time() > budget and done >= 3:
+                break
+        steps = done
+        g = arm.g
+        sample = (f"{steps} batches of {B} edges: the unmodified reference (oracle/_ref) on torch CPU, {os.cpu_count()} threads, full "
+                  f"{workload}-shaped graph, same weights as the CUDA arm, T={T_HIST}; module-boundary functions only")
+    else:
+        orc, g, adj, p, hist, n_edges = oracle_setup(workload, B, K, steps + warm)
+        rng = np.random.default_rng(3)
+        start = n_edges - (steps + warm) * B
+        for i in range(steps + warm):
+            neg = rng.choice(g.dst_node_ids, B)
+            dt = oracle_batch(orc, g, adj, p, hist, start + i * B, B, K, neg)
+            if i >= warm:
+                tot += dt
+                edges += B
+        g = synth.make_graph(workload, seed=0, num_edges=1000)
+        g_full = synth.SHAPES[workload]
+        sample = f"{steps} batches of {B} edges on the first {n_edges} edges of the synthetic stream (oracle port, numpy + BLAS threads)"
+    value = edges / tot
+    cfg = workload_config(workload, arm.g if arm is not None else synth.make_graph(workload, seed=0), B, K, 1)
     out = {"impl": "reference", "metric": "temporal edges/sec through PE update+aggregation; % HBM roofline", "value": value,
            "unit": "edges/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": tot / steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.workload}-shaped synthetic temporal graph, B={B}, K={K}, T={T_HIST}, d={D}, t={T_DIM}, C={C_CALLS}"},
-           "cpu_baseline": {"value": value, "unit": "edges/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "config": cfg,
+           "cpu_baseline": {"value": value, "unit": "edges/s", "cores": os.cpu_count(), "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(out)
 

@@ -268,6 +268,15 @@ int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, in
                   const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
                   uint32_t* err_flag, void* stream);
 
+/* n_steps consecutive batches of the resident stream in one call (steady state, ring full): host arrays lo / n_edges /
+ * ids_off[n_steps+1] / tmax / q_off describe the batches, `ids` (device) holds all their sorted unique node ids. Outputs of
+ * step i at nbr_out + i * out_step_stride. *head_io advances by one slot per step. */
+int lstep_pe_steps(const lstep_pe_stream* s, const lstep_csr* csr, int64_t n_steps, const int64_t* lo_host,
+                   const int64_t* n_edges_host, const int64_t* ids, const int64_t* ids_off_host, const double* tmax_host,
+                   int* head_io, int* len_io, const float* G, const int64_t* const* query_ids_host, const int64_t* q_off_host,
+                   int n_queries, float* nbr_out, int64_t out_step_stride, int K, const lstep_pe_mlp* mlp_nbr,
+                   const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-fed streaming step (csrc/host_step.cu): what a loop that holds the batch as HOST arrays calls
  * per batch (the hand-over train_LSTEP_link_prediction.py:204-313 / evaluate_model_utils.py:38-142 do
@@ -302,6 +311,20 @@ int lstep_pe_steps_host(lstep_host_stepper* h, const lstep_pe_stream* s, const l
                         const int64_t* const* query_ids_host_arrays, int n_queries, int* head_io, int* len_io,
                         const float* G, int K, const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace,
                         size_t workspace_bytes, uint32_t* err_flag, void* stream, float* results_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement / A-B plumbing (no reference counterpart).
+ * lstep_set_option: structural switches of the launch paths ("pdl", "gather_fuse", "mlp_pair", "phaseb_push",
+ * "early_append", "dft_prefetch", "dft_early_trigger", "dft_ctas_per_sm", "dft_generic", "gather_narrow", "mlp_ring",
+ * "host_memcpy", "mlp_umma", "mlp_umma_min_rows"); defaults are the measured winners, the LSTEP_* environment
+ * variables of DESIGN.md set them once at first use. None changes results beyond fp32 summation order.
+ * lstep_step_profile(1): every streaming step records CUDA events around its kernels; lstep_step_profile_read returns
+ * the six durations (ms) of the last step: DFT filter, fused gather, paired MLP, phase-B push, phase-B MLP, ring append.
+ * ------------------------------------------------------------------------------------------ */
+int lstep_set_option(const char* name, int value);
+int lstep_get_option(const char* name, int* value);
+int lstep_step_profile(int enable);
+int lstep_step_profile_read(float* ms6);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,12 @@ _SIGS = {
     "lstep_ring_load": (i32, [vp, vp, i64, i32, i32, i32, vp]),
     "lstep_pe_step": (i32, [C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, i32, i32, i32, vp,
                             C.POINTER(C.c_void_p), i32, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
+    "lstep_pe_steps": (i32, [C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32), vp,
+                             C.POINTER(C.c_void_p), vp, i32, vp, i64, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
+    "lstep_set_option": (i32, [C.c_char_p, i32]),
+    "lstep_get_option": (i32, [C.c_char_p, C.POINTER(i32)]),
+    "lstep_step_profile": (i32, [i32]),
+    "lstep_step_profile_read": (i32, [C.POINTER(C.c_float)]),
     "lstep_host_stepper_create": (i32, [i32, i64, i32, i32, C.POINTER(C.c_void_p)]),
     "lstep_host_stepper_destroy": (None, [vp]),
     "lstep_pe_step_host": (i32, [vp, C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, vp, vp, vp, vp, i64, i32, i32, i32, vp,

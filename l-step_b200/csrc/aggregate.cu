@@ -59,7 +59,7 @@ static int launch_nbr_aggregate_t(const float* pe, const double* q_time, const i
   if (threads > 512) return LSTEP_ERR_UNSUPPORTED;
   const size_t smem = (size_t)K * 8;
   if (smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
-  const int64_t grid = n_rows < (int64_t)kNumSMs * 16 ? n_rows : (int64_t)kNumSMs * 16;
+  const int64_t grid = n_rows < (int64_t)num_sms() * 16 ? n_rows : (int64_t)num_sms() * 16;
   if (v4)
     launch_k(nbr_aggregate_kernel<4, kLookup>, dim3((unsigned)grid), dim3(threads), smem, st, pe, q_time, nbr, nbr_t, n_rows, K, tw, d, t,
              t_pad, S, ldS, period, lk);
@@ -101,7 +101,7 @@ extern "C" int lstep_nbr_aggregate_bwd(const float* dS, const int32_t* nbr, int6
   if (n_rows < 0 || K <= 0 || d <= 0 || pe_rows <= 0) return LSTEP_ERR_INVALID_ARG;
   if (n_rows == 0) return LSTEP_OK;
   if (!dS || !nbr || !dpe) return LSTEP_ERR_INVALID_ARG;
-  const int64_t grid = n_rows < (int64_t)kNumSMs * 8 ? n_rows : (int64_t)kNumSMs * 8;
+  const int64_t grid = n_rows < (int64_t)num_sms() * 8 ? n_rows : (int64_t)num_sms() * 8;
   nbr_aggregate_bwd_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(dS, nbr, n_rows, K, d, t, dpe);
   return check_launch("nbr_aggregate_bwd");
 }
@@ -134,7 +134,7 @@ extern "C" int lstep_nbr_lookup_aggregate(const lstep_csr* csr, const int64_t* q
 extern "C" int lstep_time_features(const float* dt, int64_t n, const float* w, int t, float* out, void* stream) {
   if (n < 0 || t <= 0 || (n > 0 && (!dt || !w || !out))) return LSTEP_ERR_INVALID_ARG;
   if (n == 0) return LSTEP_OK;
-  const int64_t blocks = std::min<int64_t>(ceil_div(n * t, 256), (int64_t)kNumSMs * 8);
+  const int64_t blocks = std::min<int64_t>(ceil_div(n * t, 256), (int64_t)num_sms() * 8);
   time_features_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(dt, n, w, t, out);
   return check_launch("time_features");
 }

@@ -11,7 +11,36 @@ namespace lstep {
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+// SM count of the current device (B200: 148 = 2 dies x 74), queried once per process; grids are sized in multiples of it
+int num_sms();
+
+// Structural A/B switches. Initialised ONCE (first use) from the LSTEP_* environment variables DESIGN.md lists and changed
+// with lstep_set_option(); the launch paths read plain ints. Every default is the measured winner.
+struct Tuning {
+  int pdl = 1;                // programmatic dependent launch along the step's kernel chain      (LSTEP_NO_PDL=1 -> 0)
+  int gather_fuse = 1;        // a6 lookup+aggregate and a7 edge aggregate in one launch           (LSTEP_NO_GATHER_FUSE)
+  int mlp_pair = 1;           // neighbourhood MLP and phase-A MLP in one launch                   (LSTEP_NO_MLP_PAIR)
+  int phaseb_push = 1;        // push form of phase B (0: count / scan / fill / gather pull form)  (LSTEP_PHASEB_PULL)
+  int early_append = 1;       // ring append copies unchanged rows before its dependency wait      (LSTEP_NO_EARLY_APPEND)
+  int dft_prefetch = 1;       // DFT filter requests the older history rows before its wait        (LSTEP_NO_DFT_PREFETCH)
+  int dft_early_trigger = 0;  //                                                                   (LSTEP_DFT_EARLY_TRIGGER)
+  int dft_ctas_per_sm = 3;    //                                                                   (LSTEP_DFT_CTAS_PER_SM)
+  int dft_generic = 0;        // strided generic filter kernel instead of the bulk-copy one        (LSTEP_DFT_GENERIC)
+  int gather_narrow = 0;      // 128-thread gather CTAs                                            (LSTEP_GATHER_NARROW)
+  int mlp_ring = 0;           // all-columns ring MLP kernel instead of the cluster kernel         (LSTEP_MLP_RING)
+  int host_memcpy = 0;        // cudaMemcpyAsync instead of the copy-in kernel in the host-fed step (LSTEP_HOST_MEMCPY)
+  int mlp_umma = 1;           // tcgen05 tensor-core MLP for launches with >= mlp_umma_min_rows rows (LSTEP_NO_MLP_UMMA)
+  int mlp_umma_min_rows = 0;  //                                                                   (LSTEP_MLP_UMMA_MIN_ROWS)
+  int profile = 0;            // lstep_step_profile(): CUDA events around every kernel of the streaming step
+};
+Tuning& tuning();
+
+// lstep_step_profile(1): the streaming step records a CUDA event on its launch stream before its first kernel and after
+// each of its kernels (slots below). Events between kernels also serialise the chain (no programmatic overlap across an
+// event), so the durations are those of the step's own kernels run back to back on live data — the per-kernel roofline
+// figures of bench.py — while the step time itself is always measured with profiling off.
+enum ProfSlot { kProfStart = 0, kProfDft, kProfGather, kProfMlpPair, kProfPush, kProfMlpB, kProfAppend, kProfSlots };
+void prof_mark(cudaStream_t st, int slot);
 
 // last CUDA error text, for lstep_last_cuda_error()
 void set_cuda_error(cudaError_t e, const char* where);
@@ -73,7 +102,7 @@ __device__ __forceinline__ float4 ld_dep(const float4* p) { return __ldcg(p); }
 __device__ __forceinline__ int32_t ld_dep(const int32_t* p) { return __ldcg(p); }
 __device__ __forceinline__ int64_t ld_dep(const int64_t* p) { return (int64_t)__ldcg(reinterpret_cast<const long long*>(p)); }
 
-bool pdl_enabled();  // LSTEP_NO_PDL=1 turns the launch attribute off (A/B measurements)
+inline bool pdl_enabled() { return tuning().pdl != 0; }  // (LSTEP_NO_PDL=1 / lstep_set_option("pdl", 0): A/B measurements)
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {

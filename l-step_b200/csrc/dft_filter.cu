@@ -342,7 +342,7 @@ extern "C" int lstep_dft_collapse(const float* W_c64, const float* a, int T, int
   if (b > T) b = T;
   const size_t smem = sizeof(double) * 4 * (size_t)T;
   if (smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
-  dft_collapse_kernel<<<T < kNumSMs ? T : kNumSMs, 256, smem, as_stream(stream)>>>(
+  dft_collapse_kernel<<<T < num_sms() ? T : num_sms(), 256, smem, as_stream(stream)>>>(
       reinterpret_cast<const float2*>(W_c64), a, T, d, b, G);
   return check_launch("dft_collapse");
 }
@@ -359,11 +359,11 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
   if (dvec > kDftThreads) return LSTEP_ERR_UNSUPPORTED;
   const int groups = kDftThreads / dvec;
   const size_t smem = (size_t)groups * dvec * (v4 ? 16 : 4);
-  const int64_t grid = n_ids < (int64_t)kNumSMs * 6 ? n_ids : (int64_t)kNumSMs * 6;
+  const int64_t grid = n_ids < (int64_t)num_sms() * 6 ? n_ids : (int64_t)num_sms() * 6;
   cudaStream_t st = as_stream(stream);
   {
     // node-major history: bulk-async kernel (one CTA stages a node's whole block in shared memory)
-    static const bool no_bulk = getenv("LSTEP_DFT_GENERIC") != nullptr;
+    const bool no_bulk = tuning().dft_generic != 0;
     const size_t bulk_smem = ((size_t)Th * dvec + (size_t)groups * dvec) * 16;
     if (v4 && !no_bulk && time_stride == d && Th > 0 && bulk_smem <= 74 * 1024) {  // <= 74 KB: 3 CTAs per SM
       static bool attr_set = false;
@@ -375,8 +375,8 @@ int launch_dft_filter(const float* hist, int64_t node_stride, int64_t time_strid
         }
         attr_set = true;
       }
-      static const int per_sm = getenv("LSTEP_DFT_CTAS_PER_SM") ? atoi(getenv("LSTEP_DFT_CTAS_PER_SM")) : 3;
-      const int64_t bgrid = n_ids < (int64_t)kNumSMs * per_sm ? n_ids : (int64_t)kNumSMs * per_sm;
+      const int per_sm = tuning().dft_ctas_per_sm > 0 ? tuning().dft_ctas_per_sm : 3;
+      const int64_t bgrid = n_ids < (int64_t)num_sms() * per_sm ? n_ids : (int64_t)num_sms() * per_sm;
       launch_k(dft_filter_bulk_kernel, dim3((unsigned)bgrid), dim3(kDftThreads), bulk_smem, st, hist, node_stride, s0, ring, Th, d, ids,
                n_ids, G, out, out_stride, out_ids, prefetch_old_rows ? 1 : 0, early_trigger ? 1 : 0);
       return check_launch("dft_filter_bulk");
@@ -417,7 +417,7 @@ extern "C" int lstep_dft_filter_bwd(const float* hist, int64_t node_stride, int6
   const int dvec = v4 ? d / 4 : d;
   if (dvec > kDftThreads) return LSTEP_ERR_UNSUPPORTED;
   const int groups = kDftThreads / dvec;
-  int64_t slices = ceil_div((int64_t)kNumSMs * 4, ceil_div(Th, groups));
+  int64_t slices = ceil_div((int64_t)num_sms() * 4, ceil_div(Th, groups));
   if (slices > n_ids) slices = n_ids;
   if (slices < 1) slices = 1;
   dim3 grid((unsigned)ceil_div(Th, groups), (unsigned)slices);

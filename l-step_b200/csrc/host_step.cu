@@ -233,7 +233,7 @@ extern "C" int lstep_pe_step_host(lstep_host_stepper* h, const lstep_pe_stream* 
     if (!ok) return LSTEP_ERR_ID_RANGE;
   }
   const size_t bytes = 8 * n * (size_t)(5 + n_queries);
-  static const bool use_memcpy = getenv("LSTEP_HOST_MEMCPY") != nullptr;
+  const bool use_memcpy = tuning().host_memcpy != 0;
   // copy-in on its own stream: it only has to wait for the slot's previous use (synchronised above), so it runs
   // while the previous step is still computing; the compute stream picks it up through an event
   if (use_memcpy) {

@@ -296,7 +296,7 @@ static int launch_mlp_r(const float* A, int64_t lda, const float* pe, RowIds bas
     attr_set = true;
   }
   int64_t blocks = ceil_div(n_rows, R);
-  if (blocks > kNumSMs) blocks = kNumSMs;  // persistent: one CTA per SM walks the row tiles
+  if (blocks > num_sms()) blocks = num_sms();  // persistent: one CTA per SM walks the row tiles
   kern<<<(unsigned)blocks, G * ldo + 32, smem, st>>>(A, lda, pe, base_ids, n_rows, n_rows_dev, *m, ldo, out, out_stride, pe_inplace);
   return check_launch("pe_mlp");
 }
@@ -318,27 +318,17 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
   {
     // default: the cluster split-K kernel (csrc/mlp_cluster.cu); LSTEP_MLP_RING=1 selects the all-columns
     // weight-ring kernel below, which also serves shapes the cluster kernel does not cover
-    static const bool use_ring = getenv("LSTEP_MLP_RING") != nullptr || getenv("LSTEP_MLP_TC") != nullptr;
+    const bool use_ring = tuning().mlp_ring != 0;
     if (!use_ring) {
       const int rc = launch_pe_mlp_cluster(A, lda, pe, base_ids, n_rows, expected_rows, n_rows_dev, m, out, out_stride, pe_inplace, nullptr, nullptr, st, late_trigger);
-      if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
-    }
-  }
-  {
-    // The 3xTF32 tensor-core variant (csrc/mlp_tc.cu) is opt-in: measured on B200 it is not faster than the
-    // fp32 kernel at these sizes (both are bound by streaming the weights into each SM, and it streams twice
-    // the bytes) and its rounding is slightly outside the update_pe parity bar.
-    static const bool use_tc = getenv("LSTEP_MLP_TC") != nullptr;
-    if (use_tc) {
-      const int rc = launch_pe_mlp_tc(A, lda, pe, base_ids, n_rows, expected_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
       if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
     }
   }
   const int ldo = lstep_packed_ld(m->d);
   // rows per CTA: the largest tile that still gives about one CTA per SM; k-split while the CTA stays <= 1024 threads
   if (ldo <= 192) {  // 4 k-split groups of <= 192 threads + the producer warp = 800 threads
-    if (expected_rows >= (int64_t)kNumSMs * 24) return launch_mlp_r<8, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
-    if (expected_rows >= (int64_t)kNumSMs * 5) return launch_mlp_r<4, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
+    if (expected_rows >= (int64_t)num_sms() * 24) return launch_mlp_r<8, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
+    if (expected_rows >= (int64_t)num_sms() * 5) return launch_mlp_r<4, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
     return launch_mlp_r<2, 4>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
   }
   return launch_mlp_r<4, 1>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);

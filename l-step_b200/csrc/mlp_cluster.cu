@@ -94,6 +94,9 @@ struct FixedRows {
   // has nothing left to do after its dependency wait.
   float* ring_slot;
   int64_t ring_stride;
+  // pe_rows > 0: base ids outside [0, pe_rows) read row 0 instead of memory beyond the table (the lookup kernels have
+  // already raised LSTEP_FLAG_NODE_OUT_OF_RANGE for them: the caller sees IndexError, this kernel just must not fault)
+  int64_t pe_rows;
   // ids_stable: the base-id arrays of the launch are not written by any kernel of the stream (the streaming step's
   // query / batch node lists): the first link of the kernel's dependent load chain, id -> base row, is then taken
   // before the dependency wait.
@@ -228,6 +231,8 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   const ClShape sh = cl_shape(d, m.t, has_self, RB);
   const int ldo = sh.ldo, k1 = sh.k1, k2 = sh.k2, kc = sh.kc, ncg = sh.ncg;
   const uint32_t j = cluster_rank();
+  const int64_t pe_rows = fx.pe_rows;
+  auto clamp_row = [pe_rows](int64_t node) { return (pe_rows > 0 && (node < 0 || node >= pe_rows)) ? (int64_t)0 : node; };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthr = blockDim.x;
 
@@ -276,7 +281,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   if (ids_early && tid < RB) {
     const int64_t cl = second ? cluster_raw - split : cluster_raw;
     const int64_t row = cl * RB + tid;
-    s_node[tid] = row < n_rows ? base_ids.at(row) : 0;
+    s_node[tid] = row < n_rows ? clamp_row(base_ids.at(row)) : 0;
   }
   pdl_wait();  // from here on the kernel reads what the preceding kernels wrote
   TL_WAITED(fx.acc ? 4 : 2);
@@ -293,7 +298,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
   const bool idle = cluster_id >= n_tiles;  // a cluster without a row tile still completes the rendezvous and drains its copies
   if (!ids_early && tid < RB) {  // first dependent load chain of the kernel (id -> base row)
     const int64_t row = cluster_id * RB + tid;
-    s_node[tid] = (!idle && row < n_rows) ? base_ids.at_dep(row) : 0;
+    s_node[tid] = (!idle && row < n_rows) ? clamp_row(base_ids.at_dep(row)) : 0;
   }
   __syncthreads();
   if (idle) {
@@ -373,7 +378,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
     if (it > 0) {
       if (tid < RB) {
         const int64_t row = row0 + tid;
-        s_node[tid] = row < n_rows ? base_ids.at_dep(row) : 0;
+        s_node[tid] = row < n_rows ? clamp_row(base_ids.at_dep(row)) : 0;
       }
       __syncthreads();
     }
@@ -538,7 +543,7 @@ int launch_cl(const MlpJob& j0, const MlpJob* j1, const float* pe, FixedRows fx,
       return LSTEP_ERR_CUDA;
     }
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kNumSMs / kCl * kCl);
+    cfg.gridDim = dim3(num_sms() / kCl * kCl);
     cfg.blockDim = dim3(sh.nthreads);
     cfg.dynamicSmemBytes = 226 * 1024;
     cudaLaunchAttribute attr;
@@ -574,7 +579,7 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                           const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger,
                           float* ring_slot, int64_t ring_stride) {
-  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0, ring_slot, ring_stride, 0};
+  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0, ring_slot, ring_stride, 0, 0};
   const MlpJob j{A, lda, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace};
   // rows per cluster tile: the smallest tile that covers the launch in one round of ~32 co-resident clusters
   if (expected_rows <= 32 * 16) return launch_cl<4>(j, nullptr, pe, fx, st);
@@ -591,9 +596,10 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
 // Two float-input jobs in one launch (see MlpJob); LSTEP_ERR_UNSUPPORTED when they do not fit one round of clusters.
 int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, RowIds ids0, int64_t rows0, const lstep_pe_mlp* m0,
                                float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
-                               const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger) {
+                               const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger,
+                               int64_t pe_rows) {
   if (rows0 <= 0 || rows1 <= 0 || !out0 || !out1) return LSTEP_ERR_UNSUPPORTED;
-  const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0, nullptr, 0, 1};  // (the step's id lists are stable)
+  const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0, nullptr, 0, pe_rows, 1};  // (the step's id lists are stable)
   const MlpJob j0{A0, lda0, ids0, rows0, nullptr, *m0, out0, out_stride0, nullptr};
   const MlpJob j1{A1, lda1, ids1, rows1, nullptr, *m1, out1, out_stride1, nullptr};
   int rc = launch_cl<4>(j0, &j1, pe, fx, st);
@@ -605,7 +611,7 @@ int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, R
 
 // true when the cluster kernel covers this MLP shape (the push form of update_pe phase B depends on it)
 bool pe_mlp_cluster_supports(const lstep_pe_mlp* m) {
-  static const bool off = getenv("LSTEP_MLP_RING") != nullptr || getenv("LSTEP_MLP_TC") != nullptr;
+  const bool off = tuning().mlp_ring != 0;
   if (off || !m) return false;
   const ClShape sh = cl_shape(m->d, m->t, m->ws != nullptr, 32);
   return sh.smem_floats * sizeof(float) <= 226 * 1024 && sh.nthreads <= 512 && sh.ncg % kCl == 0;

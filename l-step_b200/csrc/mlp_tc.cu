@@ -314,7 +314,7 @@ static int launch_tc(const float* A, int64_t lda, const float* pe, RowIds base_i
     attr_set = true;
   }
   int64_t blocks = ceil_div(n_rows, R);
-  if (blocks > kNumSMs) blocks = kNumSMs;  // persistent: one CTA per SM walks the row tiles
+  if (blocks > num_sms()) blocks = num_sms();  // persistent: one CTA per SM walks the row tiles
   kern<<<(unsigned)blocks, (kTcWarps + 1) * 32, smem, st>>>(A, lda, pe, base_ids, n_rows, n_rows_dev, *m, ldo, out, out_stride, pe_inplace);
   return check_launch("pe_mlp_tc");
 }
@@ -326,7 +326,7 @@ int launch_pe_mlp_tc(const float* A, int64_t lda, const float* pe, RowIds base_i
   if (!m->w1_tc || !m->w2_tc || (m->ws && !m->ws_tc)) return LSTEP_ERR_UNSUPPORTED;
   const int NT = lstep_packed_ld(m->d) >> 3;
   if (NT > 3 * kTcWarps) return LSTEP_ERR_UNSUPPORTED;
-  const bool two = expected_rows >= (int64_t)kNumSMs * 24;  // 32-row tiles once 16-row tiles would wrap the SMs anyway
+  const bool two = expected_rows >= (int64_t)num_sms() * 24;  // 32-row tiles once 16-row tiles would wrap the SMs anyway
   if (NT <= kTcWarps) return two ? launch_tc<2, 1>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st)
                                  : launch_tc<1, 1>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st);
   if (NT <= 2 * kTcWarps) return two ? launch_tc<2, 2>(A, lda, pe, base_ids, n_rows, n_rows_dev, m, out, out_stride, pe_inplace, st)

@@ -29,7 +29,8 @@ void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, i
 bool update_push_available(const lstep_pe_mlp* mlp);
 int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, RowIds ids0, int64_t rows0, const lstep_pe_mlp* m0,
                                float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
-                               const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger);
+                               const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger,
+                               int64_t pe_rows);
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
                    void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows,
@@ -175,7 +176,7 @@ extern "C" size_t lstep_pe_step_workspace_bytes(int64_t max_ids, int64_t max_edg
 
 extern "C" int lstep_ring_load(const float* ring, float* cur, int64_t V1, int T, int d, int slot, void* stream) {
   if (!ring || !cur || V1 <= 0 || T <= 0 || d <= 0 || d % 4 != 0 || slot < 0 || slot >= T) return LSTEP_ERR_INVALID_ARG;
-  ring_load_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(ring, cur, V1, T, d, slot, 1, 0);
+  ring_load_kernel<<<num_sms() * 8, 256, 0, as_stream(stream)>>>(ring, cur, V1, T, d, slot, 1, 0);
   return check_launch("ring_load");
 }
 
@@ -186,10 +187,10 @@ extern "C" int lstep_ring_copy_rows(float* ring, float* cur, int64_t ring_rows, 
     return LSTEP_ERR_INVALID_ARG;
   if (ring_rows == 0) return LSTEP_OK;
   if (to_ring)
-    launch_k(ring_append_kernel, dim3(kNumSMs * 8), dim3(256), 0, as_stream(stream), cur, ring, ring_rows, T, d, slot, row_mul, row_add,
+    launch_k(ring_append_kernel, dim3(num_sms() * 8), dim3(256), 0, as_stream(stream), cur, ring, ring_rows, T, d, slot, row_mul, row_add,
              nullptr, 0);
   else
-    ring_load_kernel<<<kNumSMs * 8, 256, 0, as_stream(stream)>>>(ring, cur, ring_rows, T, d, slot, row_mul, row_add);
+    ring_load_kernel<<<num_sms() * 8, 256, 0, as_stream(stream)>>>(ring, cur, ring_rows, T, d, slot, row_mul, row_add);
   return check_launch("ring_copy_rows");
 }
 
@@ -212,17 +213,19 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   StepWs w = carve_step(workspace, n_ids, n_edges, n_queries, K, d, t, s->V1);
   cudaStream_t st = as_stream(stream);
   int rc;
+  prof_mark(st, kProfStart);
   // a3: filtered history of the batch nodes straight into the current table
   if (n_ids > 0) {
-    static const bool no_prefetch = getenv("LSTEP_NO_DFT_PREFETCH") != nullptr;
+    const bool no_prefetch = tuning().dft_prefetch == 0;
     // every step of this stream ends with "phase-B MLP (late trigger) -> ring append" when the push form and the early
     // append are in use: only then may the filter let the gather in at once (see dft_filter_bulk_kernel)
     // (LSTEP_DFT_EARLY_TRIGGER=1; measured within noise of the late trigger — 65.9 vs 64.9 us resident, 70.4 vs 72.3 us end
     // to end — so it stays opt-in)
-    static const bool want_early = getenv("LSTEP_DFT_EARLY_TRIGGER") != nullptr && getenv("LSTEP_NO_EARLY_APPEND") == nullptr;
+    const bool want_early = tuning().dft_early_trigger != 0 && tuning().early_append != 0;
     const bool early_trigger = want_early && n_queries > 0 && n_edges > 0 && update_push_available(mlp_upd);
     rc = launch_dft_filter(s->ring, (int64_t)T * d, d, head, T, len, d, ids, n_ids, G, s->cur, d, ids, stream, !no_prefetch, early_trigger);
     if (rc != LSTEP_OK) return rc;
+    prof_mark(st, kProfDft);
   }
   // a6 gather + a7 edge aggregate: one heterogeneous launch when both exist and the 128-bit paths apply
   const int64_t rows = (int64_t)n_queries * n_edges;
@@ -237,14 +240,14 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   float* new_rows = nullptr;
   int64_t ldA = 0;
   int32_t* counters = nullptr;
-  static const bool no_fuse = getenv("LSTEP_NO_GATHER_FUSE") != nullptr;
+  const bool no_fuse = tuning().gather_fuse == 0;
   // CTA shape of the fused gather: the stand-alone kernels' 192 threads (t time-frequency threads + d/4 table threads).
   // LSTEP_GATHER_NARROW=1: 128 threads — in a neighbourhood row 64 threads share the t time frequencies (two each) and
   // d/4 threads gather table rows; in an edge row the same threads are first time-frequency and then table threads
   // (t_pad_e = 0). It makes every CTA resident beside the DFT filter at once, but the instrumented timeline shows
   // the gather is not bound by residency: all its CTAs start within 4 us, lookups end 5 us later and the 1.6 M
   // cosines take ~9 us of issue-bound work either way.
-  static const bool wide = getenv("LSTEP_GATHER_NARROW") == nullptr;  // measured: no gain from the narrow shape (the cosine phase is issue bound)
+  const bool wide = tuning().gather_narrow == 0;  // measured: no gain from the narrow shape (the cosine phase is issue bound)
   const int t_al = (int)align_up((size_t)t, 32);
   const int t_half = (int)align_up((size_t)(t + 1) / 2, 32);
   const bool narrow = !wide && t_half + d / 4 <= 128 && t <= 128 && d / 4 <= 128;
@@ -254,7 +257,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   const bool vec_ok = d % 4 == 0 && w.lda % 4 == 0 && reinterpret_cast<uintptr_t>(s->cur) % 16 == 0 && threads <= 512;
   if (!no_fuse && rows > 0 && n_ids > 0 && n_edges > 0 && vec_ok && t == mlp_upd->t && d == mlp_upd->d) {
     update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters, &new_rows);
-    const int64_t cap = (int64_t)kNumSMs * 16;
+    const int64_t cap = (int64_t)num_sms() * 16;
     const int grid_q = (int)(rows < cap ? rows : cap), grid_e = (int)(n_ids < cap ? n_ids : cap);
     const size_t smem = std::max((size_t)K * 8, (size_t)threads * kSegPerThread * 8 + 32 * 4);
     if (smem <= 48 * 1024) {
@@ -262,6 +265,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
       launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads), smem, st, s->cur, tq, rows, K, mlp_nbr->tw, d, t, t_pad,
                t_pad_e, w.S, w.lda, n_edges, lk, grid_q, ids, n_ids, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
       if ((rc = check_launch("gather_ab")) != LSTEP_OK) return rc;
+      prof_mark(st, kProfGather);
       edges_done = true;
     }
   }
@@ -272,16 +276,17 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
     }
     // the neighbourhood MLP and phase A's MLP in ONE launch when they fit one round of clusters: neither writes the
     // table then (phase A's rows go to new_rows and are applied by the push kernel), so they need no order
-    static const bool no_pair = getenv("LSTEP_NO_MLP_PAIR") != nullptr;
+    const bool no_pair = tuning().mlp_pair == 0;
     if (edges_done && !no_pair && mlp_nbr->ws && mlp_upd->ws && update_push_available(mlp_upd)) {
       RowIds ida{};
       ida.p[0] = ids;
       ida.period = 0;
       rc = launch_pe_mlp_cluster_pair(s->cur, w.S, w.lda, q, rows, mlp_nbr, nbr_out, d, A, ldA, ida, n_ids, mlp_upd, new_rows, d, st,
-                                      /*late_trigger=*/true);
-      if (rc == LSTEP_OK)
+                                      /*late_trigger=*/true, s->V1);
+      if (rc == LSTEP_OK) {
         phase_a_done = true;
-      else if (rc != LSTEP_ERR_UNSUPPORTED)
+        prof_mark(st, kProfMlpPair);
+      } else if (rc != LSTEP_ERR_UNSUPPORTED)
         return rc;
     }
     if (!phase_a_done) {
@@ -297,14 +302,15 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
     stamp = 1;
   }
   int32_t* dirty = nullptr;
-  static const bool no_early_append = getenv("LSTEP_NO_EARLY_APPEND") != nullptr;
+  const bool no_early_append = tuning().early_append == 0;
   rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,
                       err_flag, stream, edges_done, no_early_append ? nullptr : &dirty, stamp, phase_a_done,
                       s->ring + (int64_t)append_slot * d, (int64_t)T * d);
   if (rc != LSTEP_OK) return rc;
   // 2 CTAs per SM: the append is resident (copying, then waiting for the phase-B MLP) while the NEXT step's DFT filter
   // wants to become resident and prefetch — it must leave thread slots and shared memory for it
-  launch_k(ring_append_kernel, dim3(kNumSMs * 2), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0, dirty, stamp);
+  launch_k(ring_append_kernel, dim3(num_sms() * 2), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0, dirty, stamp);
+  prof_mark(st, kProfAppend);
   return check_launch("ring_append");
 }
 }  // namespace lstep
@@ -317,6 +323,42 @@ extern "C" int lstep_pe_step(const lstep_pe_stream* s, const lstep_csr* csr, int
   if (!s || !s->src || !s->dst || !s->t || lo < 0) return LSTEP_ERR_INVALID_ARG;
   return pe_step_core(s, csr, s->src + lo, s->dst + lo, s->t + lo, n_edges, ids, n_ids, current_time, head, len, append_slot, G,
                       query_ids_host, n_queries, nbr_out, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag, stream);
+}
+
+/* A run of consecutive batches of the RESIDENT stream in one call (steady state: full history, one filter G): step i covers
+ * edges [lo[i], lo[i] + n_edges[i]), batch nodes ids + ids_off[i] .. ids_off[i+1], update time tmax[i]; query set c of step i
+ * is query_ids_host[c] + q_off[i] (n_edges[i] ids each); its outputs go to nbr_out + i * out_step_stride floats (0: every step
+ * overwrites the same buffer). The ring position advances by one slot per step; *head_io is updated. The host only pays the
+ * launches (6 per step), so the device is never waiting for the interpreter. */
+extern "C" int lstep_pe_steps(const lstep_pe_stream* s, const lstep_csr* csr, int64_t n_steps, const int64_t* lo_host,
+                              const int64_t* n_edges_host, const int64_t* ids, const int64_t* ids_off_host, const double* tmax_host,
+                              int* head_io, int* len_io, const float* G, const int64_t* const* query_ids_host,
+                              const int64_t* q_off_host, int n_queries, float* nbr_out, int64_t out_step_stride, int K,
+                              const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                              uint32_t* err_flag, void* stream) {
+  if (!s || !s->src || !s->dst || !s->t || n_steps < 0 || !lo_host || !n_edges_host || !ids || !ids_off_host || !tmax_host || !head_io ||
+      !len_io || n_queries < 0 || n_queries > 8 || (n_queries > 0 && (!query_ids_host || !q_off_host)))
+    return LSTEP_ERR_INVALID_ARG;
+  const int T = s->T;
+  if (*len_io != T) return LSTEP_ERR_INVALID_ARG;  // steady state only: while the ring fills the filter changes every step
+  int head = *head_io;
+  for (int64_t i = 0; i < n_steps; ++i) {
+    const int64_t* q[8] = {};
+    for (int c = 0; c < n_queries; ++c) q[c] = query_ids_host[c] + q_off_host[i];
+    const int64_t lo = lo_host[i];
+    if (lo < 0) return LSTEP_ERR_INVALID_ARG;
+    const int rc = pe_step_core(s, csr, s->src + lo, s->dst + lo, s->t + lo, n_edges_host[i], ids + ids_off_host[i],
+                                ids_off_host[i + 1] - ids_off_host[i], tmax_host[i], head, T, head, G, q, n_queries,
+                                nbr_out ? nbr_out + i * out_step_stride : nullptr, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag,
+                                stream);
+    if (rc != LSTEP_OK) {
+      *head_io = head;
+      return rc;
+    }
+    head = (head + 1) % T;
+  }
+  *head_io = head;
+  return LSTEP_OK;
 }
 
 LSTEP_TIMELINE_DEFINE(step)

@@ -488,7 +488,7 @@ static int phase_a(float* pe, const UpdateWs& w, const int64_t* ids, int64_t n_i
   const int t_pad = (int)align_up((size_t)t, 32);
   const int threads = (int)align_up((size_t)t_pad + dvec, 32);
   const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
-  const int64_t grid = n_ids < (int64_t)kNumSMs * 16 ? n_ids : (int64_t)kNumSMs * 16;
+  const int64_t grid = n_ids < (int64_t)num_sms() * 16 ? n_ids : (int64_t)num_sms() * 16;
   if (!edges_done) {  // (the streaming step forms the aggregate rows in its fused gather launch, csrc/step.cu)
     launch_k(edge_aggregate_kernel, dim3((unsigned)grid), dim3(threads), smem, st, pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d,
              t, t_pad, w.A, w.lda, w.counters);
@@ -529,7 +529,7 @@ static int phase_b_partial(float* pe, int64_t pe_rows, const UpdateWs& w, const 
   const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;  // distinct non-zero destinations
   const int warp_blocks = (int)ceil_div(max_dest > 0 ? max_dest : 1, 8);
   int hub_blocks = (int)(((total >> kChunkLog2) + total / (kHubLen + 1)) / 8) + 1;  // enough warps for every possible chunk task
-  if (hub_blocks > 4 * kNumSMs) hub_blocks = 4 * kNumSMs;
+  if (hub_blocks > 4 * num_sms()) hub_blocks = 4 * num_sms();
   const unsigned blocks = (unsigned)(warp_blocks + hub_blocks + 1);
   if (dvec <= 64 && t <= 128)
     launch_k(phaseB_gather_kernel<2, 4>, dim3(blocks), dim3(256), 0, st, pe, row_ids, K, w.ntB, w.off, w.list, w.hubs, w.hub_remaining, w.task_hub,
@@ -569,7 +569,7 @@ void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, i
 
 // the push form of phase B (and with it the side-buffer form of phase A) is available for this shape
 bool update_push_available(const lstep_pe_mlp* mlp) {
-  static const bool pull = getenv("LSTEP_PHASEB_PULL") != nullptr;
+  const bool pull = tuning().phaseb_push == 0;
   return !pull && mlp && (mlp->d + mlp->t) % 2 == 0 && mlp->d <= 256 && mlp->t <= 256 && pe_mlp_cluster_supports(mlp);
 }
 
@@ -627,6 +627,7 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
       rc = launch_phaseB_push(csr, ids, times, n_ids, n_valid, K, pe, d, t, mlp->tw, tc, w.claim_of, w.U, w.counters, w.push_acc,
                               w.slot_of, stamp, phase_a_in_new_rows ? w.new_rows : nullptr, err_flag, st);
       if (rc != LSTEP_OK) return rc;
+      prof_mark(st, kProfPush);
       const int64_t total = n_ids * (int64_t)K;
       const int64_t max_dest = total < pe_rows - 1 ? total : pe_rows - 1;
       lstep_pe_mlp noself = *mlp;
@@ -638,6 +639,7 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
       // with more rows than the chosen tile covers in one round of clusters just walks a second round
       rc = launch_pe_mlp_cluster(nullptr, 0, pe, single_ids(w.U), max_dest + 1, n_ids * 4, w.counters + 2, &noself, nullptr, 0, pe,
                                  w.push_acc, w.claim_of, st, dirty_out != nullptr, dirty_out ? ring_slot : nullptr, ring_stride);
+      prof_mark(st, kProfMlpB);
       return rc;
     }
   }
@@ -709,7 +711,7 @@ extern "C" int lstep_segment_sum_rows(const float* rows, int64_t ld, const int64
   if (n_seg < 0 || width <= 0) return LSTEP_ERR_INVALID_ARG;
   if (n_seg == 0) return LSTEP_OK;
   if (!rows || !seg_off || !out) return LSTEP_ERR_INVALID_ARG;
-  const int64_t grid = n_seg < (int64_t)kNumSMs * 8 ? n_seg : (int64_t)kNumSMs * 8;
+  const int64_t grid = n_seg < (int64_t)num_sms() * 8 ? n_seg : (int64_t)num_sms() * 8;
   segment_sum_rows_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(rows, ld, seg_off, n_seg, width, out, ldo);
   return check_launch("segment_sum_rows");
 }

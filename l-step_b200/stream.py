@@ -87,6 +87,17 @@ class PEStream:
         if Th > self.T:
             history = history[:, -self.T:, :]
             Th = self.T
+        # ids of the resident stream against the table and the sampler's CSR, once (the device-resident step reads and WRITES
+        # table / ring rows by these ids; the reference raises IndexError for an unknown node at its first lookup, Q8)
+        if len(self.ids_np):
+            lo_id, hi_id = int(self.ids_np.min()), int(self.ids_np.max())
+            if lo_id < 0 or hi_id >= V1:
+                raise IndexError(f"edge stream holds node id {hi_id if hi_id >= V1 else lo_id} but the PE table has {V1} rows")
+            samp = self.model.neighbor_sampler
+            if samp is not None and hi_id >= samp.num_rows:
+                raise IndexError(f"list index out of range: node id {hi_id} is unknown to the neighbor sampler ({samp.num_rows} rows)")
+            if samp is not None and samp.num_rows > V1:
+                raise IndexError(f"pe has {V1} rows but the sampler knows node ids up to {samp.num_rows - 1}")
         self.V1 = V1
         self.ring = torch.zeros((V1, self.T, d), dtype=torch.float32, device=self.dev)  # node-major: 68.8 KB / node
         self.ring[:, :Th, :] = history
@@ -103,8 +114,17 @@ class PEStream:
         self._ws_cap = (0, 0, 0)
         self.steps_done = 0
 
+    def check_errors(self):
+        """Synchronising read of the device error flag the step's lookups raise for query ids outside the sampler's
+        rows (such a query yields an empty neighbourhood and reads table row 0; nothing is written by query ids).
+        Raises IndexError like the reference's lookup (utils/utils.py:140, Q8). Called by export_history(), result()
+        and run(check=True); the host-fed calls validate ids on the host before anything is enqueued. Call it yourself
+        after a loop of step()."""
+        self.model.neighbor_sampler.check_errors()
+
     def export_history(self) -> torch.Tensor:
         """The history in the reference's layout [V1, Th, d], oldest first (for save_pe / torch.cat)."""
+        self.check_errors()
         idx = (self.head + torch.arange(self.len, device=self.dev)) % self.T
         return self.ring.index_select(1, idx).contiguous()
 
@@ -172,6 +192,63 @@ class PEStream:
             out = out.view(-1)[:max(C, 1) * n * self.d].view(max(C, 1), n, self.d)
         self._run(lo, n, self.ids[io:ie], self.batch_tmax[b], queries, out, batch_idx)
         return out
+
+    def run(self, b0: int, n_steps: int, queries, out: torch.Tensor = None, check: bool = False) -> torch.Tensor:
+        """Batches b0 .. b0+n_steps-1 of the resident stream in ONE native call (lstep_pe_steps): the per-batch loop
+        runs in C, so the host pays six kernel launches per step and nothing else. `queries`: list of device int64
+        tensors holding, for every query set, the node ids of ALL edges of those batches back to back (entry e belongs
+        to edge lo(b0) + e). Returns the neighbourhood PEs of the LAST step [C, n_last, d] (or fills `out`
+        [n_steps, C, B, d] with every step's). While the history ring is still filling, falls back to step().
+        check=True: read the device error flag afterwards (synchronises; IndexError for a query id unknown to the sampler)."""
+        if n_steps <= 0:
+            return None
+        lo0 = self.batch_lo[b0]
+        C = len(queries)
+        if self.len < self.T:
+            last = None
+            for i in range(n_steps):
+                lo, hi, _, _ = self.batch_arrays(b0 + i)
+                last = self.step(b0 + i, [q[lo - lo0:hi - lo0] for q in queries], None if out is None else out[i])
+            return last
+        lib, m = self._libc, self.model
+        B, d = self.B, self.d
+        los = np.asarray(self.batch_lo[b0:b0 + n_steps], dtype=np.int64)
+        his = np.minimum(los + B, self.stop)
+        ne = (his - los).astype(np.int64)
+        ids_off = np.asarray(self.ids_off[b0:b0 + n_steps + 1], dtype=np.int64)
+        tmax = np.asarray(self.batch_tmax[b0:b0 + n_steps], dtype=np.float64)
+        q_off = (los - lo0).astype(np.int64)
+        n_ids_max = int(np.diff(ids_off).max())
+        with torch.cuda.device(self.dev), torch.no_grad():
+            G = m._collapsed_filter(self.T, False)
+            ws = self._workspace(n_ids_max, int(ne.max()), C)
+            if out is None:
+                buf = torch.empty((max(C, 1), B, d), dtype=torch.float32, device=self.dev)
+                stride = 0
+            else:
+                buf = out
+                stride = max(C, 1) * B * d
+                if ne.min() != B:
+                    raise ValueError("run(out=...) needs full batches (a ragged last batch changes the [C, n, d] layout)")
+            qptrs = (C_void_p * max(C, 1))(*[q.data_ptr() for q in queries])
+            head, ln = ctypes.c_int(self.head), ctypes.c_int(self.len)
+            rc = lib.lstep_pe_steps(self._desc_ref, m.neighbor_sampler.csr_ref, n_steps, los.ctypes.data, ne.ctypes.data,
+                                    self.ids.data_ptr(), ids_off.ctypes.data, tmax.ctypes.data, C_byref(head), C_byref(ln), G.data_ptr(),
+                                    qptrs, q_off.ctypes.data, C, buf.data_ptr(), stride, self.K, m._mlp_ref("nbr"), m._mlp_ref("update"),
+                                    ws.data_ptr(), ws.numel(), m.neighbor_sampler._err.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream)
+            done = (head.value - self.head) % self.T if rc != 0 else n_steps
+            self.head = head.value
+            self.batch_idx += done
+            self.steps_done += done
+            if rc != 0:
+                _lib.check(rc, "lstep_pe_steps")
+        if check:
+            self.check_errors()
+        if out is not None:
+            return out
+        n_last = int(ne[-1])
+        return buf.view(-1)[:max(C, 1) * n_last * d].view(max(C, 1), n_last, d)
 
     # ---- host-fed steps (native stager: csrc/host_step.cu) -----------------------------------------
     def _stepper(self, n_edges: int, C: int):

@@ -683,3 +683,91 @@ def test_sharded_ranks_over_nccl(torch_cuda, world):
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert res.stdout.count("sharded == single GPU") == world, res.stdout[-2000:]
+
+
+def test_device_resident_stream_rejects_out_of_range_ids(torch_cuda):
+    """the device-resident path must not read or write beyond the table. The stream's own ids are
+    checked against the table / sampler when the history is adopted (IndexError, like the reference's first lookup, Q8);
+    a query id the sampler does not know raises the device error flag (IndexError at check_errors()), yields an empty
+    neighbourhood, reads table row 0 as its own row and leaves the update untouched."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream
+    g = synth.make_graph("tiny_bip", seed=5)
+    V, d, T, K, B = g.num_nodes, 172, 100, 20, 32
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin("full", g, s, 172, d, 100, T, K)[0].eval()
+    init = torch.from_numpy(seeded_normal(11, (V + 1, d), 0.3)).cuda()
+    e0 = g.num_edges - 6 * B
+    with pytest.raises(IndexError):  # table smaller than the ids of the stream
+        PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=init[:V - 3], start=e0)
+    bad_src = g.src_node_ids.copy()
+    bad_src[-1] = V + 9
+    with pytest.raises(IndexError):
+        PEStream(lstep, bad_src, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=init, start=e0)
+    a = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=init.clone(), start=e0)
+    b = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=init.clone(), start=e0)
+    lo, hi, _, _ = a.batch_arrays(0)
+    good = a.dst[lo:hi].clone()
+    bad = good.clone()
+    bad[3] = V + 1000  # far outside the table
+    bad[7] = -5
+    oa = a.step(0, [a.src[lo:hi], good]).clone()
+    ob = b.step(0, [b.src[lo:hi], bad]).clone()
+    a.check_errors()
+    with pytest.raises(IndexError):
+        b.check_errors()
+    b.check_errors()  # the flag is cleared by the read
+    assert torch.equal(a.cur, b.cur) and torch.equal(a.export_history(), b.export_history())
+    keep = torch.ones(hi - lo, dtype=torch.bool, device="cuda")
+    keep[3] = keep[7] = False
+    assert torch.equal(oa[0], ob[0]) and torch.equal(oa[1][keep], ob[1][keep])
+    assert torch.isfinite(ob).all()
+
+
+def test_native_multi_step_run_and_profile_are_bit_identical_to_single_steps(torch_cuda):
+    """PEStream.run (lstep_pe_steps: the per-batch loop in C) against PEStream.step, and the same steps with the per-kernel
+    event profile switched on (events between the kernels serialise the chain): tables, histories and outputs are
+    bit-identical; the profile returns one positive duration per kernel of the step."""
+    torch = torch_cuda
+    import ctypes
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream, _lib
+    lib = _lib.load()
+    g = synth.make_graph("tiny_bip", seed=8)
+    V, d, T, K, B = g.num_nodes, 172, 100, 20, 16
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin("full", g, s, 172, d, 100, T, K)[0].eval()
+    hist = torch.from_numpy(seeded_normal(21, (V + 1, T, d), 0.3)).cuda()  # full ring: steady state from the first step
+    e0 = g.num_edges - 24 * B
+    mk = lambda: PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=hist.clone(), start=e0)
+    a, b, c = mk(), mk(), mk()
+    neg = torch.from_numpy(np.random.default_rng(1).integers(1, V + 1, g.num_edges - e0).astype(np.int64)).cuda()
+    n = a.num_batches
+    outs_a = torch.empty((n, 3, B, d), device="cuda")
+    for i in range(n):
+        lo, hi, _, _ = a.batch_arrays(i)
+        outs_a[i] = a.step(i, [a.src[lo:hi], a.dst[lo:hi], neg[lo - e0:hi - e0]])
+    outs_b = torch.empty((n, 3, B, d), device="cuda")
+    half = n // 2
+    b.run(0, half, [b.src[e0:], b.dst[e0:], neg], out=outs_b[:half])
+    lo_h = b.batch_lo[half]
+    b.run(half, n - half, [b.src[lo_h:], b.dst[lo_h:], neg[lo_h - e0:]], out=outs_b[half:], check=True)
+    assert torch.equal(outs_a, outs_b)
+    assert torch.equal(a.cur, b.cur) and torch.equal(a.export_history(), b.export_history())
+    assert (a.head, a.len, a.batch_idx) == (b.head, b.len, b.batch_idx)
+    _lib.check(lib.lstep_step_profile(1), "profile on")
+    try:
+        ms = (ctypes.c_float * 6)()
+        for i in range(n):
+            lo, hi, _, _ = c.batch_arrays(i)
+            o = c.step(i, [c.src[lo:hi], c.dst[lo:hi], neg[lo - e0:hi - e0]])
+            _lib.check(lib.lstep_step_profile_read(ms), "profile read")
+            assert all(0.0 < ms[k] < 5.0 for k in range(6)), list(ms)
+            assert torch.equal(o, outs_a[i])
+    finally:
+        lib.lstep_step_profile(0)
+    assert torch.equal(a.cur, c.cur) and torch.equal(a.export_history(), c.export_history())
+    v = ctypes.c_int(-1)
+    assert lib.lstep_get_option(b"pdl", ctypes.byref(v)) == 0 and v.value == 1
+    assert lib.lstep_set_option(b"no_such_option", 1) != 0
