@@ -28,35 +28,11 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "mlp_job.cuh"
 
 namespace lstep {
 namespace {
 
-__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (!done) {
-    if (++spins > (1u << 24)) __trap();  // a lost bulk copy must fault, not hang the device
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(s_u32(bar)), "r"(parity)
-        : "memory");
-  }
-}
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
-               "l"(src), "r"(bytes), "r"(s_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_rank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -78,30 +54,6 @@ __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
 
 constexpr int kCl = 4;  // CTAs per cluster = k slices
-
-// Optional fixed-point input (update_pe phase B, csrc/update_push.cu): row r of the aggregate is
-// acc[r][0 .. d+t) in 32.32 fixed point instead of A[r][:]; reset_map[node of row r] is cleared once the
-// row has been consumed (the claim map of the push kernel returns to all-zero).
-struct FixedRows {
-  const unsigned long long* acc;
-  int32_t* reset_map;
-  // late_trigger: let the NEXT kernel of the chain become resident only once this kernel's CTAs are past their
-  // dependency wait, i.e. once everything BEFORE this kernel is complete. update_pe's phase-B push kernel relies on
-  // it: its lookup / claim phase runs before its own wait, concurrently with the phase-A MLP and with nothing else.
-  int late_trigger;
-  // ring_slot != NULL (streaming step): every result row is also written into the history ring's new slot,
-  // ring_slot + node * ring_stride — the step's ring append then only copies the rows this kernel does not write and
-  // has nothing left to do after its dependency wait.
-  float* ring_slot;
-  int64_t ring_stride;
-  // pe_rows > 0: base ids outside [0, pe_rows) read row 0 instead of memory beyond the table (the lookup kernels have
-  // already raised LSTEP_FLAG_NODE_OUT_OF_RANGE for them: the caller sees IndexError, this kernel just must not fault)
-  int64_t pe_rows;
-  // ids_stable: the base-id arrays of the launch are not written by any kernel of the stream (the streaming step's
-  // query / batch node lists): the first link of the kernel's dependent load chain, id -> base row, is then taken
-  // before the dependency wait.
-  int ids_stable;
-};
 
 #ifdef LSTEP_MLP_TIMING
 __device__ long long g_mlp_clk[16];
@@ -187,22 +139,6 @@ __device__ __forceinline__ void k_run(const float* __restrict__ w, int ldo, cons
       acc[2 * p + 1][c] = acc2[p][c].y;
     }
 }
-
-// One launch can carry TWO independent MLP jobs (different rows, weights and outputs) on disjoint sets of clusters:
-// clusters [0, split) run job 0, the rest job 1. The streaming step uses it for the neighbourhood MLP of the C query
-// sets and the phase-A MLP of update_pe, which both only read the table (phase A then writes its rows to a side
-// buffer that the push kernel applies): one launch, one set of fixed costs, instead of two links of the chain.
-struct MlpJob {
-  const float* A;
-  int64_t lda;
-  RowIds base_ids;
-  int64_t n_rows;
-  const int32_t* n_rows_dev;
-  lstep_pe_mlp m;
-  float* out;
-  int64_t out_stride;
-  float* pe_inplace;
-};
 
 template <int TR>
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
@@ -581,6 +517,10 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
                           float* ring_slot, int64_t ring_stride) {
   const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0, ring_slot, ring_stride, 0, 0};
   const MlpJob j{A, lda, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace};
+  if (pe_mlp_umma_wanted(m, expected_rows)) {  // large launches: tcgen05 3xTF32 kernel (csrc/mlp_umma.cu)
+    const int rc = launch_pe_mlp_umma(j, nullptr, pe, fx, st);
+    if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
+  }
   // rows per cluster tile: the smallest tile that covers the launch in one round of ~32 co-resident clusters
   if (expected_rows <= 32 * 16) return launch_cl<4>(j, nullptr, pe, fx, st);
   if (expected_rows <= 32 * 32) return launch_cl<8>(j, nullptr, pe, fx, st);
@@ -602,6 +542,10 @@ int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, R
   const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0, nullptr, 0, pe_rows, 1};  // (the step's id lists are stable)
   const MlpJob j0{A0, lda0, ids0, rows0, nullptr, *m0, out0, out_stride0, nullptr};
   const MlpJob j1{A1, lda1, ids1, rows1, nullptr, *m1, out1, out_stride1, nullptr};
+  if (pe_mlp_umma_wanted(m0, rows0 + rows1)) {
+    const int rc = launch_pe_mlp_umma(j0, &j1, pe, fx, st);
+    if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
+  }
   int rc = launch_cl<4>(j0, &j1, pe, fx, st);
   if (rc == LSTEP_ERR_UNSUPPORTED) rc = launch_cl<8>(j0, &j1, pe, fx, st);
   if (rc == LSTEP_ERR_UNSUPPORTED) rc = launch_cl<10>(j0, &j1, pe, fx, st);
