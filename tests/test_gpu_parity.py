@@ -713,8 +713,8 @@ def test_device_resident_stream_rejects_out_of_range_ids(torch_cuda):
     bad[3] = V + 1000  # far outside the table
     bad[7] = -5
     oa = a.step(0, [a.src[lo:hi], good]).clone()
+    a.check_errors()  # (the error flag lives in the sampler both streams share)
     ob = b.step(0, [b.src[lo:hi], bad]).clone()
-    a.check_errors()
     with pytest.raises(IndexError):
         b.check_errors()
     b.check_errors()  # the flag is cleared by the read
@@ -771,3 +771,47 @@ def test_native_multi_step_run_and_profile_are_bit_identical_to_single_steps(tor
     v = ctypes.c_int(-1)
     assert lib.lstep_get_option(b"pdl", ctypes.byref(v)) == 0 and v.value == 1
     assert lib.lstep_set_option(b"no_such_option", 1) != 0
+
+
+@pytest.mark.parametrize("tag", ["small", "full"])
+def test_tensor_core_mlp_matches_simt_mlp_and_float64(torch_cuda, tag, parity_log):
+    """The tcgen05 BF16x3 PE-MLP kernel (csrc/mlp_umma.cu; taken by launches of >= 1536 rows) against the fp32 SIMT cluster
+    kernel and a float64 evaluation of the same function, through lstep_pe_mlp_apply with the kernel forced either way:
+    row counts around the 64-row tile, one wave and several waves of tiles, with and without the self term's weights.
+    Bar: both kernels within 4e-6 * max(|y|, rms) of float64 — the tensor-core path must be as accurate as the SIMT one."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, _lib
+    lib = _lib.load()
+    g = synth.make_graph("tiny_bip" if tag == "full" else "tiny", seed=0)
+    F, d, t, T, K = dict(full=(172, 172, 100, 100, 20), small=(12, 12, 10, 8, 4))[tag]
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent")
+    lstep = build_dropin(tag, g, s, F, d, t, T, K)[0].eval()
+    V1 = 3000
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    pe = torch.randn((V1, d), device="cuda", generator=gen) * 0.3
+    worst = {"simt": 0.0, "umma": 0.0}
+    try:
+        for which, pre, selfn in (("nbr", "pe_neighbor_mlp", "self_update_neighbor_pe"), ("update", "pe_mlp", "self_update_pe")):
+            p = {k: v.double() for k, v in lstep.state_dict().items() if not k.startswith("fft")}
+            for n in (1, 63, 64, 65, 800, 9600, 20000):
+                A = torch.randn((n, d + t), device="cuda", generator=gen) * 2.0
+                ids = torch.randint(0, V1, (n,), device="cuda", generator=gen)
+                a64, b64 = A.double(), pe[ids].double()
+                h = torch.relu(a64 @ p[pre + "_1.weight"].T + p[pre + "_1.bias"])
+                z = h @ p[pre + "_2.weight"].T + p[pre + "_2.bias"] + b64 @ p[selfn + ".weight"].T + p[selfn + ".bias"]
+                want = b64 + torch.tanh(z)
+                scale = torch.maximum(want.abs(), want.pow(2).mean().sqrt())
+                for name, on in (("simt", 0), ("umma", 1)):
+                    _lib.check(lib.lstep_set_option(b"mlp_umma", on), "opt")
+                    _lib.check(lib.lstep_set_option(b"mlp_umma_min_rows", 0), "opt")
+                    out = torch.full((n, d), float("nan"), device="cuda")
+                    _lib.check(lib.lstep_pe_mlp_apply(_lib.ptr(A), _lib.ptr(pe), _lib.ptr(ids), n, lstep._mlp_ref(which), _lib.ptr(out), d, None,
+                                                      _lib.stream_ptr()), "mlp")
+                    e = float(((out.double() - want).abs() / scale).max())
+                    worst[name] = max(worst[name], e)
+                    assert e <= 4e-6, (tag, which, n, name, e)
+    finally:
+        lib.lstep_set_option(b"mlp_umma", 1)
+        lib.lstep_set_option(b"mlp_umma_min_rows", 1536)
+    parity_log[f"mlp_kernels/{tag}"] = worst
