@@ -815,3 +815,43 @@ def test_tensor_core_mlp_matches_simt_mlp_and_float64(torch_cuda, tag, parity_lo
         lib.lstep_set_option(b"mlp_umma", 1)
         lib.lstep_set_option(b"mlp_umma_min_rows", 1536)
     parity_log[f"mlp_kernels/{tag}"] = worst
+
+
+def test_stress_2000_steps_pdl_vs_plain_launches_bit_identical(torch_cuda):
+    """the step depends on work done BEFORE the dependency wait under programmatic dependent launch, on L2-coherent
+    loads of predecessor data and on inter-CTA claims in the push kernel. 2000 consecutive steps at the Reddit shape
+    (full graph, B = 200, T = 100) with the PDL chain and the same 2000 steps with plain stream launches (kernel
+    boundaries between all kernels) must leave bit-identical tables, histories and outputs."""
+    torch = torch_cuda
+    from lstep_b200 import NeighborSampler, PEStream, _lib
+    import bench
+    lib = _lib.load()
+    g = synth.make_graph("reddit", seed=0)
+    V1, B, K = g.num_nodes + 1, 200, 20
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V1)
+    model = bench.make_params_model(g, s, torch.device("cuda"))
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    hist = torch.randn((V1, 100, 172), device="cuda", generator=gen) * 0.1
+    hist[0] = 0
+    n_steps = 2000
+    e0 = g.num_edges - n_steps * B
+    neg = torch.from_numpy(np.random.default_rng(2).choice(np.unique(g.dst_node_ids), size=n_steps * B).astype(np.int64)).cuda()
+    res = []
+    try:
+        for pdl in (1, 0):
+            _lib.check(lib.lstep_set_option(b"pdl", pdl), "opt")
+            st = PEStream(model, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=hist, start=e0)
+            assert st.num_batches == n_steps and st.len == 100
+            outs = torch.empty((n_steps // 10, 4, B, 172), device="cuda")
+            for c in range(10):  # 10 native calls of 200 steps; the outputs of every 10th call's steps are kept
+                b0 = c * (n_steps // 10)
+                lo0 = st.batch_lo[b0]
+                st.run(b0, n_steps // 10, [st.src[lo0:], st.dst[lo0:], st.src[lo0:], neg[lo0 - e0:]], out=outs)
+            st.check_errors()
+            res.append((st.cur.clone(), st.export_history(), outs.clone()))
+            del st
+    finally:
+        lib.lstep_set_option(b"pdl", 1)
+    for a, b in zip(res[0], res[1]):
+        assert torch.equal(a, b)
+    assert torch.isfinite(res[0][0]).all()
