@@ -19,6 +19,11 @@ _LAZY = {
     "LocalGroup": "shard",
     "DistGroup": "shard",
     "ShardedPEStream": "shard",
+    "LaplacianPE": "pe_init",
+    "RandomWalkPE": "pe_init",
+    "save_pe": "pe_init",
+    "load_pe": "pe_init",
+    "NegativeEdgeSampler": "negative",
 }
 
 

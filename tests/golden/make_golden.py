@@ -285,8 +285,80 @@ def gen_replay(tag, pe_dim, time_dim, T, K, feat_dim, time_gap, V, E, B, n_eval_
     print("replay", tag, "AP", float(np.mean(out["ap"])), "AUC", float(np.mean(out["auc"])), "batches", len(losses))
 
 
+def gen_run_bracket():
+    """(f4) the reference's PE initialisation on a first-batch graph (train_LSTEP_link_prediction.py:168-189) through the
+    torch_geometric import shim, and a PE-history file written by the reference's own EarlyStopping.save_pe."""
+    import logging
+    import shutil
+    import tempfile
+    from utils.EarlyStopping import EarlyStopping
+    from utils.PositionalEncoding import LaplacianPE, RandomWalkPE
+    g = synth.make_graph("tiny", seed=3, num_nodes=300, num_edges=14000)
+    B = 50
+    src, dst = g.src_node_ids[:B], g.dst_node_ids[:B]
+    edge_index = torch.from_numpy(np.array([src.tolist() + dst.tolist(), dst.tolist() + src.tolist()]))
+    num_nodes = g.num_nodes + 1
+    out = dict(edge_index=edge_index.numpy(), num_nodes=np.int64(num_nodes))
+    out["rwpe_12"] = RandomWalkPE(edge_index, num_nodes, 12).numpy()
+    out["rwpe_40"] = RandomWalkPE(edge_index, num_nodes, 40).numpy()
+    torch.manual_seed(0)
+    pe, ew = LaplacianPE(edge_index, num_nodes, 12)
+    out["lappe_12"], out["lappe_edge_weight"] = pe.numpy(), ew.numpy()
+    torch.manual_seed(0)
+    out["lappe_sign"] = (-1 + 2 * torch.randint(0, 2, (12,))).numpy()
+    np.savez_compressed(golden_path("run_bracket.npz"), **out)
+    tmp = tempfile.mkdtemp()
+    try:
+        es = EarlyStopping(patience=1, save_model_folder=tmp, save_model_name="m", logger=logging.getLogger("golden"),
+                           save_trained_pe="pe", save_spatial_ne="ne", model_name="LSTEP")
+        hist = torch.from_numpy(seeded_normal(21, (61, 8, 12), 0.3))
+        es.save_pe(hist)
+        shutil.copyfile(es.save_trained_positional_encoding_path, golden_path("ref_saved_pe.pkl"))
+        assert torch.equal(es.load_pe(), hist)
+    finally:
+        shutil.rmtree(tmp)
+    print("run bracket done")
+
+
+def negative_batches(E, B):
+    """Batch starts used by the negative-sampler fixture: the first edges of the stream (few historical edges: the fall-back
+    to random_sample_with_collision_check runs) and the evaluation tail."""
+    return list(range(0, 6 * B, B)) + list(range(E - 120 * B, E, B))
+
+
+def gen_negatives():
+    """(f3) per-batch negatives of the reference's NegativeEdgeSampler for all three strategies, two passes each (the second
+    after reset_random_state, as every evaluation run starts: evaluate_model_utils.py:25-26)."""
+    g = synth.make_graph("tiny_bip", seed=3, num_nodes=300, num_edges=14000)
+    E, B = g.num_edges, 50
+    out = dict(B=np.int64(B), graph_ck=checksum(g.node_interact_times), starts=np.array(negative_batches(E, B), dtype=np.int64))
+    for strat in ("random", "historical", "inductive"):
+        s = NegativeEdgeSampler(g.src_node_ids, g.dst_node_ids, interact_times=g.node_interact_times,
+                                last_observed_time=g.node_interact_times[int(E * 0.7)], negative_sample_strategy=strat, seed=2)
+        for rep in range(2):
+            s.reset_random_state()
+            ns, nd = [], []
+            for lo in negative_batches(E, B):
+                hi = lo + B
+                if strat == "random":
+                    a, b = s.sample(size=B)
+                else:
+                    a, b = s.sample(size=B, batch_src_node_ids=g.src_node_ids[lo:hi], batch_dst_node_ids=g.dst_node_ids[lo:hi],
+                                    current_batch_start_time=g.node_interact_times[lo], current_batch_end_time=g.node_interact_times[hi - 1])
+                assert a.dtype == np.int64 and b.dtype == np.int64 and len(a) == B
+                ns.append(a)
+                nd.append(b)
+            out[f"{strat}_{rep}_src"], out[f"{strat}_{rep}_dst"] = np.stack(ns).astype(np.int32), np.stack(nd).astype(np.int32)
+    np.savez_compressed(golden_path("negatives.npz"), **out)
+    print("negatives done")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "module", "replay"]
+    which = sys.argv[1:] or ["sampler", "module", "replay", "bracket", "negatives"]
+    if "negatives" in which:
+        gen_negatives()
+    if "bracket" in which:
+        gen_run_bracket()
     if "sampler" in which:
         gen_sampler()
     if "module" in which:

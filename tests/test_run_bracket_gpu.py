@@ -1,0 +1,121 @@
+"""SURVEY §8(f) f4 — the step before and after the PE path: initial positional encoding (utils/PositionalEncoding.py:42-91)
+and PE-history checkpoint interop (utils/EarlyStopping.py:79-104), against fixtures written by the unmodified reference
+(tests/golden/make_golden.py::gen_run_bracket)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from common import golden_path, seeded_normal
+from lstep_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def test_random_walk_pe_matches_reference(torch_cuda):
+    torch = torch_cuda
+    from lstep_b200 import RandomWalkPE
+    z = np.load(golden_path("run_bracket.npz"))
+    ei = torch.from_numpy(z["edge_index"])
+    n = int(z["num_nodes"])
+    for L in (12, 40):
+        got = RandomWalkPE(ei, n, L).cpu().numpy()
+        want = z[f"rwpe_{L}"]
+        assert got.shape == want.shape and got.dtype == want.dtype
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-7)
+    assert (got[np.setdiff1d(np.arange(n), np.unique(z["edge_index"]))] == 0).all()  # isolated nodes
+    with pytest.raises(IndexError):
+        RandomWalkPE(torch.tensor([[0, n + 3], [n + 3, 0]]), n, 4)
+
+
+def test_laplacian_pe_spans_the_reference_eigenspaces(torch_cuda):
+    """Eigenvectors are defined up to the basis of each eigenspace (isolated nodes make eigenvalue 1 massively degenerate, and the
+    reference multiplies every column by a random sign), so parity is: same Laplacian entries, same random signs, the same
+    eigenvalues column by column (Rayleigh quotients), every column a unit eigenvector, and for the eigenvalues below 1
+    the reference's eigenvectors lie in the span of ours."""
+    torch = torch_cuda
+    from lstep_b200 import LaplacianPE
+    z = np.load(golden_path("run_bracket.npz"))
+    ei = torch.from_numpy(z["edge_index"])
+    n, k = int(z["num_nodes"]), 12
+    torch.manual_seed(0)
+    pe, ew = LaplacianPE(ei, n, k)
+    assert tuple(pe.shape) == (n, k) and pe.dtype == torch.float32
+    np.testing.assert_allclose(ew.cpu().numpy(), z["lappe_edge_weight"], rtol=1e-6, atol=1e-7)
+    # dense Laplacian of the whole (tiny) graph, float64
+    A = np.zeros((n, n))
+    src, dst = z["edge_index"]
+    keep = src != dst
+    np.add.at(A, (src[keep], dst[keep]), 1.0)
+    deg = A.sum(1)
+    dis = np.where(deg > 0, 1.0 / np.sqrt(np.maximum(deg, 1e-300)), 0.0)
+    L = np.eye(n) - dis[:, None] * A * dis[None, :]
+    ours, ref = pe.cpu().numpy().astype(np.float64), z["lappe_12"].astype(np.float64)
+    lam_all = np.linalg.eigvalsh(L)
+    for V in (ours, ref):
+        lam = np.einsum("ij,ij->j", V, L @ V)
+        np.testing.assert_allclose(np.linalg.norm(V, axis=0), 1.0, atol=1e-5)
+        np.testing.assert_allclose(np.linalg.norm(L @ V - V * lam, axis=0), 0.0, atol=2e-5)  # eigenvectors
+        np.testing.assert_allclose(np.sort(lam), lam_all[1:k + 1], atol=1e-5)  # of the k smallest eigenvalues after the first
+    lam_ref = np.einsum("ij,ij->j", ref, L @ ref)
+    lam_our = np.einsum("ij,ij->j", ours, L @ ours)
+    for j in np.nonzero(lam_ref < 1 - 1e-4)[0]:  # non-degenerate-with-isolated part: same invariant subspace
+        same = np.abs(lam_our - lam_ref[j]) < 1e-5
+        P = ours[:, same]
+        assert np.linalg.norm(P @ (P.T @ ref[:, j]) - ref[:, j]) < 1e-3, j
+    # the random column signs are the reference's draw
+    torch.manual_seed(0)
+    assert np.array_equal((-1 + 2 * torch.randint(0, 2, (k,))).numpy(), z["lappe_sign"])
+
+
+def test_pe_history_checkpoint_interop(torch_cuda):
+    """A history file written by the reference's EarlyStopping.save_pe loads into the streaming ring and comes back
+    bit-identical; a file written by lstep_b200.save_pe from a running stream is a plain tensor file the reference's
+    load_pe (= torch.load) reads."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream, load_pe, save_pe
+    hist = load_pe(golden_path("ref_saved_pe.pkl"))
+    assert isinstance(hist, torch.Tensor) and tuple(hist.shape) == (61, 8, 12)
+    assert torch.equal(hist, torch.from_numpy(seeded_normal(21, (61, 8, 12), 0.3)))
+    g = synth.make_graph("tiny", seed=0)
+    d, T, K, B = 12, 8, 4, 10
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=g.num_nodes + 1)
+    lstep = build_dropin("small", g, s, 12, d, 10, T, K)[0].eval()
+    st = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=hist.cuda(), start=g.num_edges - 5 * B)
+    assert torch.equal(st.export_history().cpu(), hist) and st.len == 8
+    for b in range(3):
+        lo, hi, _, _ = st.batch_arrays(b)
+        st.step(b, [st.src[lo:hi], st.dst[lo:hi]])
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "pe.pkl")
+        save_pe(st.export_history().cpu(), path)
+        back = torch.load(path)  # what utils/EarlyStopping.py:100-104 does
+        assert torch.equal(back, st.export_history().cpu()) and tuple(back.shape) == (61, 8, 12)
+        st2 = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=load_pe(path).cuda(),
+                       start=g.num_edges - 5 * B)
+        st2.batch_idx = st.batch_idx
+        lo, hi, _, _ = st.batch_arrays(3)
+        a = st.step(3, [st.src[lo:hi], st.dst[lo:hi]])
+        b2 = st2.step(3, [st2.src[lo:hi], st2.dst[lo:hi]])
+        assert torch.equal(a, b2) and torch.equal(st.cur, st2.cur)
+    try:  # and through the reference's own class when it travelled
+        from oracle import refload
+        ref = refload.load()
+    except Exception:
+        ref = None
+    if ref is not None:
+        import logging
+        with tempfile.TemporaryDirectory() as tmp:
+            es = ref.EarlyStopping(patience=1, save_model_folder=tmp, save_model_name="m", logger=logging.getLogger("t"),
+                                   save_trained_pe="pe", save_spatial_ne="ne", model_name="LSTEP")
+            save_pe(st.export_history().cpu(), es.save_trained_positional_encoding_path)
+            assert torch.equal(es.load_pe(), st.export_history().cpu())
