@@ -160,6 +160,16 @@ typedef struct lstep_pe_mlp {
 int lstep_time_features(const float* dt, int64_t n, const float* w, int t, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * f2 — edge / time mixer of LSTEP.aggregated_node_embeddings (models/LSTEP.py:146-167), collapsed: edge_mlp_1 (Linear)
+ * followed by edge_agg (Linear over the K axis) equals W1 (sum_k a_k C[i,k,:]) + (sum_k a_k) b1 + b_agg, so one pass
+ * forms X[i] = sum_k a_k [ (nbr_k != 0) cos(fp32(t_i - t_k) tw) || edge_feats[eid_k] ]  (row pitch t + Fe; the lookup
+ * of the K most recent neighbours and their edge ids happens inside). Rows >= n_valid are all-padding (zip truncation).
+ * ------------------------------------------------------------------------------------------ */
+int lstep_feature_aggregate(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int64_t n_valid,
+                            int K, const float* edge_feats, int64_t n_edge_rows, int Fe, const float* tw, int t,
+                            const float* agg_w /* [K] = edge_agg.weight */, float* X, uint32_t* err_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * a6 — neighbourhood PE aggregate (kernel K2, gather side) + MLP.
  * Replaces LSTEP.compute_neighborhood_pe (models/LSTEP.py:222-249) after the sampler call:
  *   S[i] = sum_k [ pe[nbr[i,k]] || mask_k * cos(fp32(q_time[i] - nbr_t[i,k]) * tw) ]

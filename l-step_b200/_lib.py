@@ -57,6 +57,7 @@ _SIGS = {
     "lstep_packed_tc_floats": (sz, [i32, i32]),
     "lstep_pack_linear_tc": (i32, [vp, i32, i32, vp, vp]),
     "lstep_time_features": (i32, [vp, i64, vp, i32, vp, vp]),
+    "lstep_feature_aggregate": (i32, [C.POINTER(CSR), vp, vp, i64, i64, i32, vp, i64, i32, vp, i32, vp, vp, vp, vp]),
     "lstep_nbr_aggregate": (i32, [vp, i64, vp, vp, vp, i64, i32, vp, i32, i32, vp, vp]),
     "lstep_nbr_lookup_aggregate": (i32, [C.POINTER(CSR), vp, vp, i64, i32, vp, i64, vp, i32, i32, vp, vp, vp]),
     "lstep_nbr_aggregate_bwd": (i32, [vp, vp, i64, i32, i32, i32, vp, i64, vp]),

@@ -35,6 +35,100 @@ __global__ void __launch_bounds__(256) nbr_aggregate_bwd_kernel(const float* __r
   }
 }
 
+// f2 — the edge / time mixer of LSTEP.aggregated_node_embeddings (models/LSTEP.py:146-167). The reference builds
+// [tf_k || edge_feat_k] for the K most recent neighbours, runs edge_mlp_1 (Linear) on each and then edge_agg (a Linear
+// over the K axis): both are linear and nothing non-linear sits between them, so
+//     edge_agg(edge_mlp_1(C))[i] = W1 (sum_k a_k C[i,k,:]) + (sum_k a_k) b1 + b_agg
+// and the [n, K, 272] intermediate (K x the flops and bytes) never needs to exist. This kernel forms
+//     X[i] = sum_k a_k [ (nbr_k != 0) cos(fp32(t_i - t_k) w) || edge_feat[eid_k] ]              ([n, t + Fe])
+// in one pass: warp 0 does the most-recent-K lookup (with edge ids), `t` threads own a time frequency, Fe/4 threads a
+// 128-bit column group of the gathered edge-feature rows. The two small Linear layers that follow run on X.
+__global__ void __launch_bounds__(512) feature_aggregate_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ c_nbr,
+                                                                const int32_t* __restrict__ c_eid, const double* __restrict__ c_t,
+                                                                int64_t num_rows, const int64_t* __restrict__ q_node,
+                                                                const double* __restrict__ q_time, int64_t n_rows, int64_t n_valid, int K,
+                                                                const float* __restrict__ edge_feats, int64_t n_edge_rows, int Fe,
+                                                                const float* __restrict__ tw, int t, int t_pad,
+                                                                const float* __restrict__ agg_w, float* __restrict__ X,
+                                                                uint32_t* __restrict__ err_flag) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* s_nbr = reinterpret_cast<int32_t*>(smem_raw);
+  int32_t* s_eid = s_nbr + K;
+  float* s_dt = reinterpret_cast<float*>(s_eid + K);
+  float* s_a = s_dt + K;
+  const int tid = threadIdx.x;
+  const bool v4 = (Fe % 4 == 0) && ((reinterpret_cast<uintptr_t>(edge_feats) & 15) == 0);
+  const int fvec = v4 ? Fe / 4 : Fe;
+  const int ldx = t + Fe;
+  for (int k = tid; k < K; k += blockDim.x) s_a[k] = agg_w[k];
+  for (int64_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+    if (tid < 32) {
+      int64_t first = 0;
+      int take = 0;
+      double tq = 0.0;
+      if (row < n_valid) {  // rows beyond min(len(ids), len(times)) stay all-padding (zip truncation, utils.py:169)
+        const int64_t node = q_node[row];
+        tq = q_time[row];
+        if (node < 0 || node >= num_rows) {
+          if (tid == 0 && err_flag) atomicOr(err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
+        } else {
+          warp_recent_range(indptr, c_t, node, tq, K, tid, first, take);
+        }
+      }
+      const int pad = K - take;
+      for (int k = tid; k < K; k += 32) {
+        int32_t n = 0, e = 0;
+        float tt = 0.f;
+        if (k >= pad) {
+          const int64_t at = first + (k - pad);
+          n = c_nbr[at];
+          e = c_eid[at];
+          tt = (float)c_t[at];
+        }
+        if (e < 0 || e >= n_edge_rows) {
+          if (err_flag) atomicOr(err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
+          e = 0;
+        }
+        s_nbr[k] = n;
+        s_eid[k] = e;
+        s_dt[k] = (float)(tq - (double)tt);  // numpy f64 - f32 -> f64, then .float() (LSTEP.py:153)
+      }
+    }
+    __syncthreads();
+    if (tid < t) {
+      const float w = tw[tid];
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k)
+        if (s_nbr[k] != 0) acc = fmaf(s_a[k], time_feature(s_dt[k], w), acc);
+      X[row * ldx + tid] = acc;
+    }
+    if (tid >= t_pad && tid - t_pad < fvec) {
+      const int cv = tid - t_pad;
+      if (v4) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < K; ++k) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(edge_feats + (int64_t)s_eid[k] * Fe) + cv);
+          const float a = s_a[k];
+          acc.x = fmaf(a, v.x, acc.x);
+          acc.y = fmaf(a, v.y, acc.y);
+          acc.z = fmaf(a, v.z, acc.z);
+          acc.w = fmaf(a, v.w, acc.w);
+        }
+        float* dst = X + row * ldx + t + 4 * cv;  // (row pitch t + Fe need not be 16-byte aligned)
+        dst[0] = acc.x;
+        dst[1] = acc.y;
+        dst[2] = acc.z;
+        dst[3] = acc.w;
+      } else {
+        float acc = 0.f;
+        for (int k = 0; k < K; ++k) acc = fmaf(s_a[k], __ldg(edge_feats + (int64_t)s_eid[k] * Fe + cv), acc);
+        X[row * ldx + t + cv] = acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // a5 stand-alone: out[i][j] = time_feature(dt[i], w[j]) (the function every fused kernel calls)
 __global__ void __launch_bounds__(256) time_features_kernel(const float* __restrict__ dt, int64_t n, const float* __restrict__ w, int t,
                                                             float* __restrict__ out) {
@@ -137,4 +231,22 @@ extern "C" int lstep_time_features(const float* dt, int64_t n, const float* w, i
   const int64_t blocks = std::min<int64_t>(ceil_div(n * t, 256), (int64_t)num_sms() * 8);
   time_features_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(dt, n, w, t, out);
   return check_launch("time_features");
+}
+
+extern "C" int lstep_feature_aggregate(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int64_t n_valid,
+                                       int K, const float* edge_feats, int64_t n_edge_rows, int Fe, const float* tw, int t,
+                                       const float* agg_w, float* X, uint32_t* err_flag, void* stream) {
+  if (n_rows < 0 || n_valid < 0 || n_valid > n_rows || K <= 0 || Fe <= 0 || t < 0 || n_edge_rows <= 0) return LSTEP_ERR_INVALID_ARG;
+  if (n_rows == 0) return LSTEP_OK;
+  if (!csr || !csr->eid || !q_node || !q_time || !edge_feats || !agg_w || !X || (t > 0 && !tw)) return LSTEP_ERR_INVALID_ARG;
+  const bool v4 = Fe % 4 == 0 && aligned16(edge_feats);
+  const int t_pad = (int)align_up((size_t)t, 32);
+  const int threads = (int)align_up((size_t)t_pad + (v4 ? Fe / 4 : Fe), 32);
+  const size_t smem = (size_t)K * 16;
+  if (threads > 512 || smem > 48 * 1024) return LSTEP_ERR_UNSUPPORTED;
+  const int64_t grid = std::min<int64_t>(n_rows, (int64_t)num_sms() * 16);
+  feature_aggregate_kernel<<<(unsigned)grid, threads, smem, as_stream(stream)>>>(csr->indptr, csr->nbr, csr->eid, csr->t, csr->num_rows, q_node,
+                                                                                 q_time, n_rows, n_valid, K, edge_feats, n_edge_rows, Fe, tw, t,
+                                                                                 t_pad, agg_w, X, err_flag);
+  return check_launch("feature_aggregate");
 }

@@ -8,8 +8,10 @@ positional-encoding methods on the hot path run as sm_100a CUDA kernels through 
     compute_neighborhood_pe   -> lstep_sample_recent_compact + lstep_neighborhood_pe (K1 + K2 + MLP)
     update_pe                 -> lstep_update_pe         (K1 + K2 scatter side + K4 ordered write-back)
 
-The feature branch (aggregated_node_embeddings) is not part of the PE path and stays PyTorch,
-but its two neighbour lookups go through the device sampler.
+The feature branch (aggregated_node_embeddings): the K-neighbour edge-feature / time mixer runs as one fused
+CUDA kernel (lstep_feature_aggregate: lookup + weighted gather + time features, with edge_mlp_1 / edge_agg collapsed by
+linearity) followed by the two small Linear layers; the masked mean over `time_gap` neighbours is identically zero for
+all-zero node features (every dataset of the reference) and runs as torch ops on the device lookup otherwise.
 
 There is no CPU path: PE tensors must live on the CUDA device the module was moved to.
 When autograd is recording (training), compute_neighborhood_pe and fourier_transform_pe use
@@ -364,12 +366,30 @@ class LSTEP(nn.Module):
         n_valid = min(n, len(node_interact_times))
         ids_dev, t_dev = self._upload([(node_ids, I64), (node_interact_times, F64)])
         with torch.cuda.device(ids_dev.device):
-            nbr, eid, nt = self._sample_full(ids_dev, t_dev, n, n_valid, int(num_neighbors))
-            edge_feats = self.edge_raw_features[eid]
-            dt = (t_dev[:, None] - nt.to(torch.float64)).float()  # f64 - f32 -> f64 -> float (LSTEP.py:153)
-            tf = self.time_encoder(dt).masked_fill((nbr == 0).unsqueeze(-1), 0.0)
-            x = self.edge_mlp_1(torch.cat([tf, edge_feats], dim=-1))
-            x = self.edge_agg(x.permute(0, 2, 1)).squeeze()
+            # edge / time mixer (LSTEP.py:152-167): edge_mlp_1 then edge_agg are both linear, so the fused kernel forms
+            # X = sum_k a_k [tf_k || edge_feat_k] and the 272x272 Linear runs once per row instead of once per neighbour
+            t_dim, Fe = self.time_feat_dim, self.edge_raw_features.shape[1]
+            K = int(num_neighbors)
+            if K != self.edge_agg.weight.shape[1]:
+                raise RuntimeError(f"mat1 and mat2 shapes cannot be multiplied (edge_agg expects {self.edge_agg.weight.shape[1]} neighbours, got {K})")
+            if torch.is_grad_enabled() and (self.edge_agg.weight.requires_grad or self.edge_mlp_1.weight.requires_grad):
+                # training: gradients must reach edge_agg / edge_mlp_1 through the per-neighbour form -> torch ops on the device lookup
+                nbr, eid, nt = self._sample_full(ids_dev, t_dev, n, n_valid, K)
+                dt = (t_dev[:, None] - nt.to(torch.float64)).float()  # f64 - f32 -> f64 -> float (LSTEP.py:153)
+                tf = self.time_encoder(dt).masked_fill((nbr == 0).unsqueeze(-1), 0.0)
+                x = self.edge_mlp_1(torch.cat([tf, self.edge_raw_features[eid]], dim=-1))
+                x = self.edge_agg(x.permute(0, 2, 1)).squeeze()
+            else:
+                a_w = self.edge_agg.weight.detach().reshape(-1).contiguous()
+                X = torch.empty((n, t_dim + Fe), dtype=torch.float32, device=ids_dev.device)
+                tw = self.time_encoder.w.weight.detach().reshape(-1).contiguous()
+                ef = self.edge_raw_features if self.edge_raw_features.is_contiguous() else self.edge_raw_features.contiguous()
+                _lib.check(_lib.load().lstep_feature_aggregate(s.csr_ref, _lib.ptr(ids_dev), _lib.ptr(t_dev), n, n_valid, K, _lib.ptr(ef), ef.shape[0],
+                                                               Fe, _lib.ptr(tw), t_dim, _lib.ptr(a_w), _lib.ptr(X), _lib.ptr(s._err), _lib.stream_ptr()),
+                           "lstep_feature_aggregate")
+                x = F.linear(X, self.edge_mlp_1.weight, self.edge_mlp_1.bias * a_w.sum()) + self.edge_agg.bias
+                if n == 1:
+                    x = x.squeeze()
             x = self.edge_mlp_2(F.relu(x))
             if self.use_dropout:
                 x = F.dropout(x, p=self.dropout)

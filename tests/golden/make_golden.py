@@ -320,6 +320,30 @@ def gen_run_bracket():
     print("run bracket done")
 
 
+def gen_feature_branch():
+    """(f2) LSTEP.aggregated_node_embeddings / combining_pe_raw_feat of the reference with non-zero edge features, once with the
+    datasets' all-zero node features and once with non-zero ones (the time_gap masked mean then matters)."""
+    g = synth.make_graph("tiny_bip", seed=0)
+    V1 = g.num_nodes + 1
+    lo = g.num_edges // 2
+    q_ids = np.concatenate([g.src_node_ids[lo:lo + 30], g.dst_node_ids[lo:lo + 30], g.src_node_ids[5:9], np.zeros(2, np.int64)])
+    q_t = np.concatenate([g.node_interact_times[lo:lo + 30]] * 2 + [g.node_interact_times[5:9], g.node_interact_times[lo:lo + 2]])
+    out = dict(q_ids=q_ids, q_t=q_t)
+    for name, nf_seed in (("zero_nf", None), ("rand_nf", 9)):
+        model, sampler, node_feats, edge_feats = build_model(g, 172, 100, 100, 20, 172)
+        lstep = model[0].eval()
+        if nf_seed is not None:
+            nf = seeded_normal(nf_seed, (V1, 172), 1.0)
+            nf[0] = 0
+            lstep.node_raw_features = torch.from_numpy(nf)
+        pe = torch.from_numpy(seeded_normal(5, (V1, 172), 0.3))
+        with torch.no_grad():
+            out[f"{name}_emb"] = lstep.aggregated_node_embeddings(q_ids, q_t, num_neighbors=20, time_gap=50).numpy()
+            out[f"{name}_comb"] = lstep.combining_pe_raw_feat(pe, q_ids, q_t, num_neighbors=20, time_gap=50).numpy()
+    np.savez_compressed(golden_path("feature_branch.npz"), **out)
+    print("feature branch done")
+
+
 def negative_batches(E, B):
     """Batch starts used by the negative-sampler fixture: the first edges of the stream (few historical edges: the fall-back
     to random_sample_with_collision_check runs) and the evaluation tail."""
@@ -354,7 +378,9 @@ def gen_negatives():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sampler", "module", "replay", "bracket", "negatives"]
+    which = sys.argv[1:] or ["sampler", "module", "replay", "bracket", "negatives", "feature"]
+    if "feature" in which:
+        gen_feature_branch()
     if "negatives" in which:
         gen_negatives()
     if "bracket" in which:

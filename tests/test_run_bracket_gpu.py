@@ -119,3 +119,38 @@ def test_pe_history_checkpoint_interop(torch_cuda):
                                    save_trained_pe="pe", save_spatial_ne="ne", model_name="LSTEP")
             save_pe(st.export_history().cpu(), es.save_trained_positional_encoding_path)
             assert torch.equal(es.load_pe(), st.export_history().cpu())
+
+
+@pytest.mark.parametrize("name,nf_seed", [("zero_nf", None), ("rand_nf", 9)])
+def test_feature_branch_matches_reference(torch_cuda, name, nf_seed):
+    """SURVEY f2 — LSTEP.aggregated_node_embeddings (models/LSTEP.py:139-220) and combining_pe_raw_feat (:251-266) with the fused
+    lookup + weighted gather + time-feature kernel (edge_mlp_1 / edge_agg collapsed by linearity) against the reference:
+    non-zero edge features, padded slots (edge row 0), node 0 queries, zero and non-zero node features. Bar 1e-5."""
+    torch = torch_cuda
+    from common import pe_close, seeded_edge_feats
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler
+    z = np.load(golden_path("feature_branch.npz"))
+    g = synth.make_graph("tiny_bip", seed=0)
+    V1 = g.num_nodes + 1
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent")
+    model = build_dropin("full", g, s, 172, 172, 100, 100, 20, edge_feats=seeded_edge_feats(g.num_edges, 172))
+    lstep = model[0].eval()
+    if nf_seed is not None:
+        nf = seeded_normal(nf_seed, (V1, 172), 1.0)
+        nf[0] = 0
+        lstep.node_raw_features = torch.from_numpy(nf).cuda()
+        lstep._node_feats_all_zero = False
+    pe = torch.from_numpy(seeded_normal(5, (V1, 172), 0.3)).cuda()
+    with torch.no_grad():
+        emb = lstep.aggregated_node_embeddings(z["q_ids"], z["q_t"], num_neighbors=20, time_gap=50)
+        comb = lstep.combining_pe_raw_feat(pe, z["q_ids"], z["q_t"], num_neighbors=20, time_gap=50)
+    for got, want, what in ((emb, z[f"{name}_emb"], "embeddings"), (comb, z[f"{name}_comb"], "combined")):
+        ok, worst = pe_close(got.cpu().numpy(), want)
+        assert ok, (name, what, worst)
+    # under autograd the per-neighbour torch form runs (gradients reach edge_agg / edge_mlp_1): same values
+    emb_g = lstep.aggregated_node_embeddings(z["q_ids"], z["q_t"], num_neighbors=20, time_gap=50)
+    assert emb_g.requires_grad
+    ok, worst = pe_close(emb_g.detach().cpu().numpy(), z[f"{name}_emb"])
+    assert ok, (name, "autograd form", worst)
+    s.check_errors()
