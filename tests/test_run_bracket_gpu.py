@@ -36,11 +36,14 @@ def test_random_walk_pe_matches_reference(torch_cuda):
         RandomWalkPE(torch.tensor([[0, n + 3], [n + 3, 0]]), n, 4)
 
 
-def test_laplacian_pe_spans_the_reference_eigenspaces(torch_cuda):
-    """Eigenvectors are defined up to the basis of each eigenspace (isolated nodes make eigenvalue 1 massively degenerate, and the
-    reference multiplies every column by a random sign), so parity is: same Laplacian entries, same random signs, the same
-    eigenvalues column by column (Rayleigh quotients), every column a unit eigenvector, and for the eigenvalues below 1
-    the reference's eigenvectors lie in the span of ours."""
+def test_laplacian_pe_is_the_eigenbasis_the_reference_approximates(torch_cuda):
+    """LaplacianPE's contract is "eigenvectors 1..k of the sym-normalised Laplacian by ascending eigenvalue, random column signs".
+    Column-wise equality with the reference is not defined: the first-batch graph has many components (26 zero eigenvalues in
+    this fixture) and V1 - 75 isolated nodes (eigenvalue 1), and ARPACK's Lanczos iteration returns an arbitrary selection
+    inside degenerate eigenvalues — in the fixture it finds 5 of the 26 zeros and then jumps to 0.042 ... 1.0. Checked instead:
+    both sides use the SAME Laplacian (the reference's columns are unit eigenvectors of ours to 1e-6, its edge weights equal
+    ours), the reference's eigenvalues all belong to the spectrum, ours are exactly the k smallest after the first with an
+    orthonormal basis, and the random signs are the reference's draw from the CPU generator."""
     torch = torch_cuda
     from lstep_b200 import LaplacianPE
     z = np.load(golden_path("run_bracket.npz"))
@@ -50,7 +53,6 @@ def test_laplacian_pe_spans_the_reference_eigenspaces(torch_cuda):
     pe, ew = LaplacianPE(ei, n, k)
     assert tuple(pe.shape) == (n, k) and pe.dtype == torch.float32
     np.testing.assert_allclose(ew.cpu().numpy(), z["lappe_edge_weight"], rtol=1e-6, atol=1e-7)
-    # dense Laplacian of the whole (tiny) graph, float64
     A = np.zeros((n, n))
     src, dst = z["edge_index"]
     keep = src != dst
@@ -60,18 +62,21 @@ def test_laplacian_pe_spans_the_reference_eigenspaces(torch_cuda):
     L = np.eye(n) - dis[:, None] * A * dis[None, :]
     ours, ref = pe.cpu().numpy().astype(np.float64), z["lappe_12"].astype(np.float64)
     lam_all = np.linalg.eigvalsh(L)
-    for V in (ours, ref):
+    for V in (ours, ref):  # unit eigenvectors of the same matrix
         lam = np.einsum("ij,ij->j", V, L @ V)
         np.testing.assert_allclose(np.linalg.norm(V, axis=0), 1.0, atol=1e-5)
-        np.testing.assert_allclose(np.linalg.norm(L @ V - V * lam, axis=0), 0.0, atol=2e-5)  # eigenvectors
-        np.testing.assert_allclose(np.sort(lam), lam_all[1:k + 1], atol=1e-5)  # of the k smallest eigenvalues after the first
-    lam_ref = np.einsum("ij,ij->j", ref, L @ ref)
+        np.testing.assert_allclose(np.linalg.norm(L @ V - V * lam, axis=0), 0.0, atol=2e-5)
+        assert all(np.abs(lam_all - x).min() < 1e-5 for x in lam)  # every Rayleigh quotient is an eigenvalue
     lam_our = np.einsum("ij,ij->j", ours, L @ ours)
-    for j in np.nonzero(lam_ref < 1 - 1e-4)[0]:  # non-degenerate-with-isolated part: same invariant subspace
-        same = np.abs(lam_our - lam_ref[j]) < 1e-5
-        P = ours[:, same]
-        assert np.linalg.norm(P @ (P.T @ ref[:, j]) - ref[:, j]) < 1e-3, j
-    # the random column signs are the reference's draw
+    np.testing.assert_allclose(np.sort(lam_our), lam_all[1:k + 1], atol=1e-5)      # exactly the k smallest after the first
+    np.testing.assert_allclose(ours.T @ ours, np.eye(k), atol=1e-5)                # orthonormal, also inside eigenspaces
+    # non-degenerate eigenvalues both sides found: same vector up to sign
+    lam_ref = np.einsum("ij,ij->j", ref, L @ ref)
+    mult = lambda x: int((np.abs(lam_all - x) < 1e-6).sum())
+    for j in range(k):
+        hit = np.nonzero(np.abs(lam_our - lam_ref[j]) < 1e-6)[0]
+        if mult(lam_ref[j]) == 1 and len(hit) == 1:
+            assert abs(abs(ours[:, hit[0]] @ ref[:, j]) - 1.0) < 1e-4, j
     torch.manual_seed(0)
     assert np.array_equal((-1 + 2 * torch.randint(0, 2, (k,))).numpy(), z["lappe_sign"])
 
