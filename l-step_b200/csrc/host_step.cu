@@ -250,7 +250,13 @@ extern "C" int lstep_pe_step_host(lstep_host_stepper* h, const lstep_pe_stream* 
   h->h2d_bytes += bytes;
   const int64_t* dp = reinterpret_cast<const int64_t*>(h->d_in[slot]);
   const int64_t* qdev[8];
-  for (int c = 0; c < n_queries; ++c) qdev[c] = dp + 5 * n + (size_t)c * n;
+  for (int c = 0; c < n_queries; ++c) {
+    // the same host array passed twice (negative sources == sources under random negative sampling) becomes the same
+    // device pointer, which is what pe_step_core recognises as an identical query set
+    int u = 0;
+    while (u < c && query_ids_host_arrays[u] != query_ids_host_arrays[c]) ++u;
+    qdev[c] = dp + 5 * n + (size_t)u * n;
+  }
   float* outp = nbr_out ? nbr_out : h->d_nbr[slot];
   int rc = pe_step_core(s, csr, dp, dp + n, reinterpret_cast<const double*>(dp + 2 * n), n_edges, dp + 3 * n, n_ids, tmax, head,
                         len, append_slot, G, qdev, n_queries, outp, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag,

@@ -19,6 +19,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "mlp_job.cuh"
 
 namespace lstep {
 
@@ -302,10 +303,6 @@ static int launch_mlp_r(const float* A, int64_t lda, const float* pe, RowIds bas
 }
 
 
-int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
-                          const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger = false,
-                          float* ring_slot = nullptr, int64_t ring_stride = 0);
 
 // n_rows is the host-side upper bound of rows; *n_rows_dev (optional) the device-side count.
 int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,

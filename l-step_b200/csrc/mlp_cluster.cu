@@ -440,17 +440,25 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(512, 1)
         o.y = bp[RBp] + tanhf(z.y);
         o.z = bp[2 * RBp] + tanhf(z.z);
         o.w = bp[3 * RBp] + tanhf(z.w);
-        float* dst = (out ? out + row * out_stride : pe_inplace + s_node[r] * (int64_t)d) + col;
         if (fx.ring_slot) {  // (d % 4 == 0 and 16-byte rows are preconditions of the streaming step)
           *reinterpret_cast<float4*>(fx.ring_slot + s_node[r] * fx.ring_stride + col) = o;
         }
-        if (o_vec && col + 3 < d) {
-          *reinterpret_cast<float4*>(dst) = o;
+        auto store = [&](float* dst) {
+          if (o_vec && col + 3 < d) {
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            dst[0] = o.x;
+            if (col + 1 < d) dst[1] = o.y;
+            if (col + 2 < d) dst[2] = o.z;
+            if (col + 3 < d) dst[3] = o.w;
+          }
+        };
+        if (out && jb.fan.n_out > 0) {  // identical query sets were computed once: fan the row out
+          const int64_t u = row / jb.fan.period, i = row % jb.fan.period;
+          for (int c = 0; c < jb.fan.n_out; ++c)
+            if (jb.fan.src_of[c] == u) store(out + (c * jb.fan.period + i) * out_stride + col);
         } else {
-          dst[0] = o.x;
-          if (col + 1 < d) dst[1] = o.y;
-          if (col + 2 < d) dst[2] = o.z;
-          if (col + 3 < d) dst[3] = o.w;
+          store((out ? out + row * out_stride : pe_inplace + s_node[r] * (int64_t)d) + col);
         }
       }
     }
@@ -514,9 +522,9 @@ int launch_cl(const MlpJob& j0, const MlpJob* j1, const float* pe, FixedRows fx,
 int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
                           const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
                           const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger,
-                          float* ring_slot, int64_t ring_stride) {
-  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0, ring_slot, ring_stride, 0, 0};
-  const MlpJob j{A, lda, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace};
+                          float* ring_slot, int64_t ring_stride, const OutFan* fan, int64_t pe_rows) {
+  const FixedRows fx{acc_fixed, reset_map, late_trigger ? 1 : 0, ring_slot, ring_stride, pe_rows, 0};
+  const MlpJob j{A, lda, base_ids, n_rows, n_rows_dev, *m, out, out_stride, pe_inplace, fan ? *fan : OutFan{}};
   if (pe_mlp_umma_wanted(m, expected_rows)) {  // large launches: tcgen05 3xTF32 kernel (csrc/mlp_umma.cu)
     const int rc = launch_pe_mlp_umma(j, nullptr, pe, fx, st);
     if (rc != LSTEP_ERR_UNSUPPORTED) return rc;
@@ -537,11 +545,11 @@ int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds b
 int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, RowIds ids0, int64_t rows0, const lstep_pe_mlp* m0,
                                float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
                                const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger,
-                               int64_t pe_rows) {
+                               int64_t pe_rows, const OutFan* fan0) {
   if (rows0 <= 0 || rows1 <= 0 || !out0 || !out1) return LSTEP_ERR_UNSUPPORTED;
   const FixedRows fx{nullptr, nullptr, late_trigger ? 1 : 0, nullptr, 0, pe_rows, 1};  // (the step's id lists are stable)
-  const MlpJob j0{A0, lda0, ids0, rows0, nullptr, *m0, out0, out_stride0, nullptr};
-  const MlpJob j1{A1, lda1, ids1, rows1, nullptr, *m1, out1, out_stride1, nullptr};
+  const MlpJob j0{A0, lda0, ids0, rows0, nullptr, *m0, out0, out_stride0, nullptr, fan0 ? *fan0 : OutFan{}};
+  const MlpJob j1{A1, lda1, ids1, rows1, nullptr, *m1, out1, out_stride1, nullptr, OutFan{}};
   if (pe_mlp_umma_wanted(m0, rows0 + rows1)) {
     const int rc = launch_pe_mlp_umma(j0, &j1, pe, fx, st);
     if (rc != LSTEP_ERR_UNSUPPORTED) return rc;

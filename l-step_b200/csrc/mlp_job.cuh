@@ -60,6 +60,16 @@ struct FixedRows {
 // clusters [0, split) run job 0, the rest job 1. The streaming step uses it for the neighbourhood MLP of the C query
 // sets and the phase-A MLP of update_pe, which both only read the table (phase A then writes its rows to a side
 // buffer that the push kernel applies): one launch, one set of fixed costs, instead of two links of the chain.
+// Output fan-out of a job whose rows are the rows of n_uniq DISTINCT query sets of `period` rows each while the caller
+// asked for n_out sets, some of them identical (the eval loop passes the batch's sources twice: positive and negative
+// source, evaluate_model_utils.py:51-52): computed row u * period + i is stored to every output set c with
+// src_of[c] == u, at out + (c * period + i) * out_stride. n_out == 0: plain out + row * out_stride.
+struct OutFan {
+  int64_t period;
+  int n_out;
+  signed char src_of[8];
+};
+
 struct MlpJob {
   const float* A;
   int64_t lda;
@@ -70,8 +80,22 @@ struct MlpJob {
   float* out;
   int64_t out_stride;
   float* pe_inplace;
+  OutFan fan;
 };
 
+
+// csrc/mlp_cluster.cu. expected_rows: the typical row count (n_rows is only an upper bound when n_rows_dev carries the real one);
+// acc_fixed / reset_map / ring_slot: see FixedRows; fan: see OutFan; pe_rows > 0 clamps base ids to the table.
+int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
+                          const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
+                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger = false,
+                          float* ring_slot = nullptr, int64_t ring_stride = 0, const OutFan* fan = nullptr, int64_t pe_rows = 0);
+// two float-input jobs in one launch; LSTEP_ERR_UNSUPPORTED when they do not fit one round of clusters
+int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, RowIds ids0, int64_t rows0, const lstep_pe_mlp* m0,
+                               float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
+                               const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger,
+                               int64_t pe_rows, const OutFan* fan0);
+bool pe_mlp_cluster_supports(const lstep_pe_mlp* m);
 
 // csrc/mlp_umma.cu: tensor-core form of the same launch (LSTEP_ERR_UNSUPPORTED when the shape / packing does not fit)
 int launch_pe_mlp_umma(const MlpJob& j0, const MlpJob* j1, const float* pe, FixedRows fx, cudaStream_t st);

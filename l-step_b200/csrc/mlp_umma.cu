@@ -470,21 +470,24 @@ __global__ void __launch_bounds__(kThreads, 1)
           o.y = b.y + tanhf(z8[kg * 4 + 1] + bias2[c + 1]);
           o.z = b.z + tanhf(z8[kg * 4 + 2] + bias2[c + 2]);
           o.w = b.w + tanhf(z8[kg * 4 + 3] + bias2[c + 3]);
-          if (o_vec && c + 3 < d) {
-            *reinterpret_cast<float4*>(orow + c) = o;
-            if (rrow) *reinterpret_cast<float4*>(rrow + c) = o;
-          } else {
-            orow[c] = o.x;
-            if (c + 1 < d) orow[c + 1] = o.y;
-            if (c + 2 < d) orow[c + 2] = o.z;
-            if (c + 3 < d) orow[c + 3] = o.w;
-            if (rrow) {
-              rrow[c] = o.x;
-              if (c + 1 < d) rrow[c + 1] = o.y;
-              if (c + 2 < d) rrow[c + 2] = o.z;
-              if (c + 3 < d) rrow[c + 3] = o.w;
+          auto store = [&](float* dst) {
+            if (o_vec && c + 3 < d) {
+              *reinterpret_cast<float4*>(dst) = o;
+            } else {
+              dst[0] = o.x;
+              if (c + 1 < d) dst[1] = o.y;
+              if (c + 2 < d) dst[2] = o.z;
+              if (c + 3 < d) dst[3] = o.w;
             }
+          };
+          if (jb.out && jb.fan.n_out > 0) {  // identical query sets were computed once: fan the row out
+            const int64_t u = row / jb.fan.period, i = row % jb.fan.period;
+            for (int cc = 0; cc < jb.fan.n_out; ++cc)
+              if (jb.fan.src_of[cc] == u) store(jb.out + (cc * jb.fan.period + i) * jb.out_stride + c);
+          } else {
+            store(orow + c);
           }
+          if (rrow) store(rrow + c);
         }
       }
       if (fx.reset_map && live && grp == 0 && my_half == 0) fx.reset_map[node] = 0;

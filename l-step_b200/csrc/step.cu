@@ -16,6 +16,7 @@
 
 #include "common.cuh"
 #include "gather_bodies.cuh"
+#include "mlp_job.cuh"
 
 namespace lstep {
 
@@ -27,10 +28,7 @@ int launch_nbr_lookup_aggregate(const lstep_csr* csr, RowIds q_node, const float
 void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows, float** A, int64_t* lda,
                        int32_t** counters, float** new_rows);
 bool update_push_available(const lstep_pe_mlp* mlp);
-int launch_pe_mlp_cluster_pair(const float* pe, const float* A0, int64_t lda0, RowIds ids0, int64_t rows0, const lstep_pe_mlp* m0,
-                               float* out0, int64_t out_stride0, const float* A1, int64_t lda1, RowIds ids1, int64_t rows1,
-                               const lstep_pe_mlp* m1, float* out1, int64_t out_stride1, cudaStream_t st, bool late_trigger,
-                               int64_t pe_rows);
+
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
                    void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows,
@@ -228,12 +226,30 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
     prof_mark(st, kProfDft);
   }
   // a6 gather + a7 edge aggregate: one heterogeneous launch when both exist and the 128-bit paths apply
-  const int64_t rows = (int64_t)n_queries * n_edges;
+  // identical query sets (the same device pointer: the eval loop's negative sources ARE the batch's sources under
+  // random negative sampling, evaluate_model_utils.py:51-52) are looked up, gathered and pushed through the MLP ONCE;
+  // the MLP's epilogue stores the row to every output set that asked for it (OutFan). Only on the paired-MLP path.
   RowIds q{};
+  OutFan fan{};
+  int n_uniq = 0;
   for (int c = 0; c < n_queries; ++c) {
     if (!query_ids_host[c]) return LSTEP_ERR_INVALID_ARG;
-    q.p[c] = query_ids_host[c];
+    int u = 0;
+    while (u < n_uniq && q.p[u] != query_ids_host[c]) ++u;
+    if (u == n_uniq) q.p[n_uniq++] = query_ids_host[c];
+    fan.src_of[c] = (signed char)u;
   }
+  const bool can_pair = tuning().mlp_pair != 0 && tuning().gather_fuse != 0 && mlp_nbr->ws && mlp_upd->ws && update_push_available(mlp_upd) &&
+                        pe_mlp_cluster_supports(mlp_nbr) && n_ids > 0 && n_edges > 0;
+  const bool dedup = tuning().query_dedup != 0 && can_pair && n_uniq < n_queries;
+  if (!dedup) {
+    for (int c = 0; c < n_queries; ++c) q.p[c] = query_ids_host[c];
+    n_uniq = n_queries;
+  } else {
+    fan.period = n_edges;
+    fan.n_out = n_queries;
+  }
+  const int64_t rows = (int64_t)n_uniq * n_edges;
   q.period = n_edges;
   bool edges_done = false, phase_a_done = false;
   float* A = nullptr;      // phase A's aggregate rows / result rows inside the update workspace
@@ -282,7 +298,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
       ida.p[0] = ids;
       ida.period = 0;
       rc = launch_pe_mlp_cluster_pair(s->cur, w.S, w.lda, q, rows, mlp_nbr, nbr_out, d, A, ldA, ida, n_ids, mlp_upd, new_rows, d, st,
-                                      /*late_trigger=*/true, s->V1);
+                                      /*late_trigger=*/true, s->V1, dedup ? &fan : nullptr);
       if (rc == LSTEP_OK) {
         phase_a_done = true;
         prof_mark(st, kProfMlpPair);
@@ -290,7 +306,11 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
         return rc;
     }
     if (!phase_a_done) {
-      rc = launch_pe_mlp(w.S, w.lda, s->cur, q, rows, rows, nullptr, mlp_nbr, nbr_out, d, nullptr, st);
+      if (dedup)  // the pair did not fit one round of clusters: the cluster kernel alone walks the tiles, same fan-out
+        rc = launch_pe_mlp_cluster(w.S, w.lda, s->cur, q, rows, rows, nullptr, mlp_nbr, nbr_out, d, nullptr, nullptr, nullptr, st, false, nullptr, 0,
+                                   &fan, s->V1);
+      else
+        rc = launch_pe_mlp(w.S, w.lda, s->cur, q, rows, rows, nullptr, mlp_nbr, nbr_out, d, nullptr, st);
       if (rc != LSTEP_OK) return rc;
     }
   }

@@ -27,6 +27,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "mlp_job.cuh"
 #include "gather_bodies.cuh"
 
 namespace lstep {
@@ -36,11 +37,6 @@ int launch_pe_mlp(const float* A, int64_t lda, const float* pe, RowIds base_ids,
                   cudaStream_t st, bool late_trigger = false);
 int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const double* q_time, int64_t n_rows, int64_t n_valid,
                         int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag, PhaseBHook hook, void* stream);
-int launch_pe_mlp_cluster(const float* A, int64_t lda, const float* pe, RowIds base_ids, int64_t n_rows, int64_t expected_rows,
-                          const int32_t* n_rows_dev, const lstep_pe_mlp* m, float* out, int64_t out_stride, float* pe_inplace,
-                          const unsigned long long* acc_fixed, int32_t* reset_map, cudaStream_t st, bool late_trigger = false,
-                          float* ring_slot = nullptr, int64_t ring_stride = 0);
-bool pe_mlp_cluster_supports(const lstep_pe_mlp* m);
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
                        unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st);

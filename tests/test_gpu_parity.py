@@ -855,3 +855,47 @@ def test_stress_2000_steps_pdl_vs_plain_launches_bit_identical(torch_cuda):
     for a, b in zip(res[0], res[1]):
         assert torch.equal(a, b)
     assert torch.isfinite(res[0][0]).all()
+
+
+def test_identical_query_sets_are_computed_once_with_identical_results(torch_cuda):
+    """The eval loop passes the batch's sources twice (positive source, negative source under random negative sampling:
+    evaluate_model_utils.py:51-52). The step recognises identical sets (same device pointer / same host array), computes
+    them once and fans the rows out in the MLP epilogue: outputs, tables and histories must be bit-identical to the step
+    with the optimisation off, for the device-resident and the host-fed step, B = 200 (SIMT MLP) and B = 2000 (tcgen05 MLP)."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream, _lib
+    lib = _lib.load()
+    for B in (200, 2000):
+        g = synth.make_graph("reddit", seed=1, num_edges=40_000)
+        V, d, T, K = g.num_nodes, 172, 100, 20
+        s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+        lstep = build_dropin("full", g, s, 172, d, 100, T, K)[0].eval()
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        hist = torch.randn((V + 1, T, d), device="cuda", generator=gen) * 0.2
+        e0 = g.num_edges - 4 * B
+        neg_np = np.random.default_rng(0).integers(1, V + 1, g.num_edges - e0).astype(np.int64)
+        neg = torch.from_numpy(neg_np).cuda()
+        res = []
+        try:
+            for dedup in (1, 0):
+                _lib.check(lib.lstep_set_option(b"query_dedup", dedup), "opt")
+                st = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=hist, start=e0)
+                outs = []
+                for b in range(2):
+                    lo, hi, _, _ = st.batch_arrays(b)
+                    src_view = st.src[lo:hi]
+                    outs.append(st.step(b, [src_view, st.dst[lo:hi], src_view, neg[lo - e0:hi - e0]]).clone())
+                for b in range(2, 4):  # host-fed: the same numpy array object twice
+                    lo, hi, _, _ = st.batch_arrays(b)
+                    src_np = g.src_node_ids[lo:hi]
+                    outs.append(torch.from_numpy(st.step_host(src_np, g.dst_node_ids[lo:hi], g.node_interact_times[lo:hi],
+                                                              [src_np, g.dst_node_ids[lo:hi], src_np, neg_np[lo - e0:hi - e0]])))
+                st.check_errors()
+                res.append((outs, st.cur.clone(), st.export_history()))
+        finally:
+            lib.lstep_set_option(b"query_dedup", 1)
+        for a, b_ in zip(res[0][0], res[1][0]):
+            assert torch.equal(a, b_)
+        assert torch.equal(res[0][0][0][0], res[0][0][0][2])  # the two source sets' outputs are the same rows
+        assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
