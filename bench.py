@@ -298,68 +298,75 @@ def run_ours(args, rank, world, own_pg=True):
 
 
 def run_sharded(args, rank, world, own_pg=True):
-    """BASELINE config 5: scale-out graph (10 M nodes), node-id sharded PE history / CSR, NCCL all-to-all row
-    exchanges (l-step_b200/shard.py). The batch is replicated, so the total work is fixed as N grows
-    (strong scaling). T = 20 history steps so that the ring (137.6 GB in total) fits from N = 1 upwards."""
+    """BASELINE config 5: the scale-out graph (10 M nodes), PE history ring sharded by node id over the ranks, current table and
+    temporal CSR replicated, one NCCL all-gather of the DFT-filtered rows per step (l-step_b200/shard.py::ReplicatedTableRank).
+    The batch is replicated: every rank filters the batch nodes whose history it owns (1/N of the filter's HBM traffic),
+    computes its 1/N share of the neighbourhood queries and runs update_pe in full, so the work per rank shrinks with N only
+    in those two parts ("scaling": "strong"; the point of sharding here is CAPACITY: 688 GB of history at T = 100). T is
+    stated with every point: --scaleout-T (default 12: the N = 1 point must fit one GPU next to the replicated state)."""
     import torch
     import torch.distributed as dist
-    from lstep_b200 import LSTEP, DistGroup, ShardedPEStream, ShardRank, _lib
+    from lstep_b200 import LSTEP, ReplicatedTableRank, ReplicatedTableStream, _lib
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if not own_pg:
-        pass
-    elif world > 1:
+    if own_pg and world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    else:  # degenerate group of one: same code path, no peers
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("MASTER_PORT", "29533")
-        dist.init_process_group("nccl", rank=0, world_size=1, device_id=dev)
     lib = _lib.load()
     assert lib.lstep_device_ok() == 1
     B, K, T = 2000, 20, args.scaleout_T
     V, E = args.scaleout_nodes, args.scaleout_edges
     t0 = time.time()
-    g = synth.make_graph("scaleout", seed=0, num_nodes=V, num_edges=E)
+    src, dst, tt = synth.make_scaleout_device(V, E, dev, seed=0)
+    torch.cuda.synchronize()
     t_gen = time.time() - t0
+    if world > 1:  # every rank must hold the same stream
+        ck = torch.stack([src.sum().double(), dst.sum().double(), tt.sum()])
+        lo_, hi_ = ck.clone(), ck.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        assert torch.equal(lo_, hi_), "ranks generated different edge streams"
     torch.manual_seed(0)
-    node_feats = np.zeros((2, 172), dtype=np.float32)
-    m = LSTEP(node_feats, np.zeros((1, 172), dtype=np.float32), None, None, pe_dim=D, num_neighbors=20, time_feat_dim=T_DIM,
-              num_fft_batches=T, device=dev).to(dev).eval()
+    m = LSTEP(np.zeros((2, 172), dtype=np.float32), np.zeros((1, 172), dtype=np.float32), None, None, pe_dim=D, num_neighbors=20,
+              time_feat_dim=T_DIM, num_fft_batches=T, device=dev).to(dev).eval()
     gen = torch.Generator(device=dev).manual_seed(1)
     init = torch.randn((V + 1, D), device=dev, generator=gen) * 0.1
     init[0] = 0
+    W, Ksteps = max(args.warmup, 3), args.steps
+    if not own_pg:  # riding along with the headline run: a bounded sample
+        W, Ksteps = min(W, 10), min(Ksteps, 100)
+    W = max(W, T + 5)  # full history before the clock starts
+    n_e2e = min(Ksteps, 50)
     e0 = int(E * 0.7) // B * B
+    stop = min(E, e0 + (W + Ksteps + n_e2e + 2) * B)
     t0 = time.time()
-    rk = ShardRank(m, rank, world, g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids, V, B, K, init, start=e0)
+    rk = ReplicatedTableRank(m, rank, world, src, dst, tt, V, B, K, init, start=e0, stop=stop)
     del init
     torch.cuda.synchronize()
     t_setup = time.time() - t0
-    sh = ShardedPEStream(rk, DistGroup())
-    nb = (E - e0 + B - 1) // B
-    rng = np.random.default_rng(2)
-    dst_pool = np.unique(g.dst_node_ids[:2_000_000])
+    sh = ReplicatedTableStream(rk)
+    nb = rk.num_batches
+    neg_all = torch.randint(1, V + 1, (stop - e0,), device=dev, generator=torch.Generator(device=dev).manual_seed(2))
 
     def queries(b):
         lo, hi = rk.batch(b)
-        return [g.src_node_ids[lo:hi], g.dst_node_ids[lo:hi], g.src_node_ids[lo:hi], rng.choice(dst_pool, hi - lo)]
+        return [rk.src[lo:hi], rk.dst[lo:hi], rk.src[lo:hi], neg_all[lo - e0:hi - e0]]
 
-    W, Ksteps = max(args.warmup, 3), args.steps
-    if not own_pg:  # riding along with the replica run: a bounded sample
-        W, Ksteps = min(W, 30), min(Ksteps, 100)
-    W = max(W, T + 5)  # full history before the clock starts
     step_no = 0
     for _ in range(W):
         sh.step(step_no % nb, queries(step_no % nb))
         step_no += 1
     torch.cuda.synchronize()
-    dist.barrier()
+    rk.sampler.check_errors()
+    if world > 1:
+        dist.barrier()
     clocks = ClockSampler(local)
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rk.bytes_x1 = rk.bytes_x2 = 0
+    rk.bytes_allgather = 0
     edges = 0
+    torch.cuda._sleep(int(2.0e6))  # the host queues the first steps behind a spin: the region is device-bound
     ev0.record()
     for _ in range(Ksteps):
         b = step_no % nb
@@ -372,57 +379,67 @@ def run_sharded(args, rank, world, own_pg=True):
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
     tm = torch.tensor([ms], device=dev)
-    dist.barrier()
-    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     ms_max = float(tm.item())
     value = edges / (ms_max * 1e-3)  # the batch is replicated: edges of the job, not per rank
-    # end to end: same step with the per-query row sums read back to the host every step
-    n_e2e = min(Ksteps, 100)
-    d2h = 0
+    # end to end: the negatives of every step come from host memory and this rank's per-query row sums go back to it
+    neg_host = neg_all.cpu().numpy()
+    d2h = h2d = 0
     e_edges = 0
-    h0 = m.h2d_bytes
-    dist.barrier()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter()
     ev0.record()
     for _ in range(n_e2e):
         b = step_no % nb
-        out = sh.step(b, queries(b))
+        lo, hi = rk.batch(b)
+        q_off, q_rows = rk.share(b)
+        negs = torch.from_numpy(neg_host[lo - e0:hi - e0]).to(dev, non_blocking=True)
+        h2d += negs.numel() * 8
+        out = sh.step(b, [rk.src[lo:hi], rk.dst[lo:hi], rk.src[lo:hi], negs])
         r = out.sum(dim=2).cpu()
         d2h += r.numel() * 4
-        lo, hi = rk.batch(b)
         e_edges += hi - lo
         step_no += 1
     ev1.record()
     torch.cuda.synchronize()
-    tm = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
-    dist.barrier()
-    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    e2e = {"value": e_edges / (float(tm.item()) * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": (m.h2d_bytes - h0) / n_e2e,
-           "d2h_bytes_per_step": d2h / n_e2e, "steps": n_e2e, "api": "ShardedPEStream.step (numpy queries in, per-query row sums out), per rank"}
-    x = torch.tensor([rk.bytes_x1, rk.bytes_x2], dtype=torch.float64, device=dev)
-    dist.all_reduce(x)
+    tm = torch.tensor([max(ev0.elapsed_time(ev1), (time.perf_counter() - t_wall) * 1e3)], device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    e2e = {"value": e_edges / (float(tm.item()) * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d / n_e2e, "d2h_bytes_per_step": d2h / n_e2e,
+           "steps": n_e2e, "api": "ReplicatedTableStream.step per rank: the step's negative ids from host memory, this rank's per-query row "
+                                  "sums back to the host (a synchronising read every step)"}
+    x = torch.tensor([float(rk.bytes_allgather)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(x)
+    free_b, total_b = torch.cuda.mem_get_info(dev)
     if rank == 0:
-        hbm_peak, peak_src = peaks()
         out = {
             "metric": "temporal edges/sec through PE update+aggregation; % HBM roofline", "value": value, "unit": "edges/s",
             "n_gpus": world, "steps": Ksteps, "warmup": W, "ms_per_step": ms_max / Ksteps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"scale-out synthetic temporal graph, V={V}, first E={E} edges of the stream, B={B}, K={K}, T={T}, d={D}, "
-                                   f"t={T_DIM}, C={C_CALLS}",
-                       "parallelism": f"PE history ring + CSR sharded by node id over {world} GPU(s) (owner = id mod N), current table cached "
-                                      "per rank, 2 NCCL all-to-all row exchanges per step",
-                       "l2_policy": f"inputs larger than L2: history ring {(V + 1) * T * D * 4 / 1e9 / world:.1f} GB per rank",
-                       "graph_gen_s": t_gen, "shard_setup_s": t_setup,
-                       "nvlink_bytes_per_step_all_ranks": {"rows_fetch": float(x[0].item()) / Ksteps, "partials": float(x[1].item()) / Ksteps}},
+            "config": {"workload": f"scale-out synthetic temporal graph, V={V}, E={E} (Zipf 0.8 endpoints, generated on the device), B={B}, K={K}, "
+                                   f"T={T}, d={D}, t={T_DIM}, C={C_CALLS}",
+                       "parallelism": f"PE history ring sharded by node id over {world} GPU(s) (owner = id mod N), current table + temporal CSR "
+                                      "replicated, one NCCL all-gather of the DFT-filtered batch rows per step, a6 queries split 1/N, update_pe replicated",
+                       "l2_policy": f"inputs larger than L2: history ring {(V + 1) * T * D * 4 / 1e9 / world:.1f} GB per rank, CSR {2 * E * 16 / 1e9:.1f} GB"},
+            "run_info": {"graph_gen_s": t_gen, "setup_s": t_setup, "hbm_used_GB": (total_b - free_b) / 1e9,
+                         "nvlink_bytes_per_step_all_ranks": float(x[0].item()) / Ksteps},
             "clocks": clk, "e2e": e2e,
-            "gpu_launches": int(Ksteps * 12 * world),
+            "gpu_launches": int(Ksteps * 7 * world),
             "roofline": None, "cpu_baseline": None,
         }
         if own_pg:
             emit(out)
     else:
         out = None
-    if own_pg:
+    if own_pg and world > 1:
         dist.destroy_process_group()
+    del sh, rk, src, dst, tt, neg_all
+    torch.cuda.empty_cache()
     return out
 
 
@@ -809,8 +826,9 @@ def main():
     ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS) + ["scaleout"])
     ap.add_argument("--replicas", action="store_true", help="N > 1: only the replicas of the single-GPU workload (skip the sharded scale-out sample)")
     ap.add_argument("--scaleout-nodes", type=int, default=10_000_000)
-    ap.add_argument("--scaleout-edges", type=int, default=40_000_000)
-    ap.add_argument("--scaleout-T", type=int, default=20)
+    ap.add_argument("--scaleout-edges", type=int, default=100_000_000)
+    ap.add_argument("--scaleout-T", type=int, default=12, help="history steps per node of the scale-out arm (12 fits the N = 1 point; 100 needs 8 GPUs)")
+    ap.add_argument("--no-scaleout", action="store_true", help="N = 1: skip the scale-out sample that rides along with the headline run")
     ap.add_argument("--scaleout-timeout", type=float, default=420.0, help="seconds the scale-out sample may take at N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-batches", type=int, default=40)
@@ -826,23 +844,24 @@ def main():
         run_reference(args, rank, world)
     elif args.workload == "scaleout":
         run_sharded(args, rank, world)
-    elif world > 1:
-        # N > 1: the headline workload does not shard at this size (7 MB table, strictly sequential 200-edge batches), so
-        # the main line is N independent replicas of it (weak scaling, comparable with the N = 1 line). The sharded
-        # scale-out graph of BASELINE config 5 (node-id sharded PE table, NCCL all-to-all) is measured in the same
-        # run and reported under "scaleout" (strong scaling: the batch is replicated, the state is split).
+    else:
+        # The headline workload does not shard at this size (7 MB table, strictly sequential 200-edge batches): at N > 1 the main
+        # line is N independent replicas of it (weak scaling, comparable with the N = 1 line). The scale-out graph of BASELINE
+        # config 5 (history ring sharded by node id, NCCL all-gather per step) is measured in the same run — at EVERY N,
+        # N = 1 included, so that the record holds its whole 1 -> 8 curve — and reported under "scaleout" (strong scaling).
         import torch
-        import torch.distributed as dist
-        local = int(os.environ.get("LOCAL_RANK", 0))
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if world > 1:
+            import torch.distributed as dist
+            local = int(os.environ.get("LOCAL_RANK", 0))
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         out = run_ours(args, rank, world, own_pg=False)
         extra = None
-        if not args.replicas:
+        if not (args.replicas or args.no_scaleout):
             # the main line must survive the extra arm: an exception is caught, and a hang (a collective that never
             # completes) is cut by a watchdog that prints the main line and leaves
             def bail():
-                log(f"scale-out arm exceeded {args.scaleout_timeout:.0f} s: reporting the replica line only")
+                log(f"scale-out arm exceeded {args.scaleout_timeout:.0f} s: reporting the main line only")
                 if rank == 0:
                     out["scaleout"] = {"error": f"timed out after {args.scaleout_timeout:.0f} s"}
                     emit(out)
@@ -858,15 +877,14 @@ def main():
             dog.cancel()
         if rank == 0:
             if extra is not None:
-                out["scaleout"] = {k: extra[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "e2e", "error")
-                                   if k in extra}
+                out["scaleout"] = {k: extra[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "config", "run_info", "e2e",
+                                                         "error") if k in extra}
             emit(out)
-        try:
-            dist.destroy_process_group()
-        except Exception:
-            pass
-    else:
-        run_ours(args, rank, world)
+        if world > 1:
+            try:
+                dist.destroy_process_group()
+            except Exception:
+                pass
 
 
 if __name__ == "__main__":

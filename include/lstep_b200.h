@@ -287,6 +287,14 @@ int lstep_pe_steps(const lstep_pe_stream* s, const lstep_csr* csr, int64_t n_ste
                    int n_queries, float* nbr_out, int64_t out_step_stride, int K, const lstep_pe_mlp* mlp_nbr,
                    const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream);
 
+/* One rank's share of a step on a node-id sharded group with a replicated table and CSR and a sharded history ring: lstep_pe_step
+ * without the DFT filter and the ring append (both owner-local, done by the caller around an all-gather of the filtered rows);
+ * the a6 query sets cover edges [q_off, q_off + q_rows) of the batch, query_ids_host[c] pointing at the first of those ids. */
+int lstep_pe_step_sharded(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, int64_t n_edges, const int64_t* ids,
+                          int64_t n_ids, double current_time, const int64_t* const* query_ids_host, int n_queries, int64_t q_off,
+                          int64_t q_rows, float* nbr_out, int K, const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd,
+                          void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Host-fed streaming step (csrc/host_step.cu): what a loop that holds the batch as HOST arrays calls
  * per batch (the hand-over train_LSTEP_link_prediction.py:204-313 / evaluate_model_utils.py:38-142 do

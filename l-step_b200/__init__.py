@@ -19,6 +19,9 @@ _LAZY = {
     "LocalGroup": "shard",
     "DistGroup": "shard",
     "ShardedPEStream": "shard",
+    "ReplicatedTableRank": "shard",
+    "ReplicatedLocalGroup": "shard",
+    "ReplicatedTableStream": "shard",
     "LaplacianPE": "pe_init",
     "RandomWalkPE": "pe_init",
     "save_pe": "pe_init",

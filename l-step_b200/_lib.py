@@ -80,6 +80,8 @@ _SIGS = {
                             C.POINTER(C.c_void_p), i32, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
     "lstep_pe_steps": (i32, [C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, vp, vp, vp, vp, vp, C.POINTER(i32), C.POINTER(i32), vp,
                              C.POINTER(C.c_void_p), vp, i32, vp, i64, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
+    "lstep_pe_step_sharded": (i32, [C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, C.POINTER(C.c_void_p), i32, i64, i64,
+                                    vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
     "lstep_set_option": (i32, [C.c_char_p, i32]),
     "lstep_get_option": (i32, [C.c_char_p, C.POINTER(i32)]),
     "lstep_step_profile": (i32, [i32]),

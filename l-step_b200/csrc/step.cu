@@ -193,14 +193,40 @@ extern "C" int lstep_ring_copy_rows(float* ring, float* cur, int64_t ring_rows, 
 }
 
 namespace lstep {
+// Variations of the step for one rank of a node-id sharded group (lstep_pe_step_sharded): the DFT filter and the ring
+// append are done by the caller (owner-local, around an all-gather), and the a6 queries cover only this rank's share
+// [q_off, q_off + q_rows) of the batch's edges.
+struct StepOpts {
+  bool skip_dft = false, skip_append = false;
+  int64_t q_off = 0, q_rows = -1;  // -1: all n_edges
+};
+
+int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* src, const int64_t* dst, const double* tq,
+                    int64_t n_edges, const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
+                    const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
+                    const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                    uint32_t* err_flag, void* stream, const StepOpts& opt);
+
 // The step on explicit batch pointers (src/dst/tq = the batch's n_edges endpoints and times on the device).
 int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* src, const int64_t* dst, const double* tq,
                  int64_t n_edges, const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
                  const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
                  const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
                  uint32_t* err_flag, void* stream) {
-  if (!s || !csr || !mlp_nbr || !mlp_upd || !G || n_edges < 0 || n_ids < 0 || K <= 0 || n_queries < 0 || n_queries > 8)
+  return pe_step_core_ex(s, csr, src, dst, tq, n_edges, ids, n_ids, current_time, head, len, append_slot, G, query_ids_host, n_queries, nbr_out,
+                         K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag, stream, StepOpts{});
+}
+
+int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* src, const int64_t* dst, const double* tq,
+                    int64_t n_edges, const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
+                    const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
+                    const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                    uint32_t* err_flag, void* stream, const StepOpts& opt) {
+  if (!s || !csr || !mlp_nbr || !mlp_upd || (!G && !opt.skip_dft) || n_edges < 0 || n_ids < 0 || K <= 0 || n_queries < 0 || n_queries > 8)
     return LSTEP_ERR_INVALID_ARG;
+  const int64_t q_rows = opt.q_rows < 0 ? n_edges : opt.q_rows;
+  if (opt.q_off < 0 || opt.q_off + q_rows > n_edges) return LSTEP_ERR_INVALID_ARG;
+  const double* tq_q = tq + opt.q_off;  // edge times of the a6 queries
   if (!s->ring || !s->cur || !src || !dst || !tq || s->V1 <= 0 || s->T <= 0 || s->d != mlp_nbr->d || s->d % 4 != 0)
     return LSTEP_ERR_INVALID_ARG;
   if (head < 0 || head >= s->T || len < 0 || len > s->T || append_slot < 0 || append_slot >= s->T) return LSTEP_ERR_INVALID_ARG;
@@ -213,7 +239,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   int rc;
   prof_mark(st, kProfStart);
   // a3: filtered history of the batch nodes straight into the current table
-  if (n_ids > 0) {
+  if (n_ids > 0 && !opt.skip_dft) {
     const bool no_prefetch = tuning().dft_prefetch == 0;
     // every step of this stream ends with "phase-B MLP (late trigger) -> ring append" when the push form and the early
     // append are in use: only then may the filter let the gather in at once (see dft_filter_bulk_kernel)
@@ -241,16 +267,16 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   }
   const bool can_pair = tuning().mlp_pair != 0 && tuning().gather_fuse != 0 && mlp_nbr->ws && mlp_upd->ws && update_push_available(mlp_upd) &&
                         pe_mlp_cluster_supports(mlp_nbr) && n_ids > 0 && n_edges > 0;
-  const bool dedup = tuning().query_dedup != 0 && can_pair && n_uniq < n_queries;
+  const bool dedup = tuning().query_dedup != 0 && can_pair && n_uniq < n_queries && q_rows > 0;
   if (!dedup) {
     for (int c = 0; c < n_queries; ++c) q.p[c] = query_ids_host[c];
     n_uniq = n_queries;
   } else {
-    fan.period = n_edges;
+    fan.period = q_rows;
     fan.n_out = n_queries;
   }
-  const int64_t rows = (int64_t)n_uniq * n_edges;
-  q.period = n_edges;
+  const int64_t rows = (int64_t)n_uniq * q_rows;
+  q.period = q_rows;
   bool edges_done = false, phase_a_done = false;
   float* A = nullptr;      // phase A's aggregate rows / result rows inside the update workspace
   float* new_rows = nullptr;
@@ -278,8 +304,8 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
     const size_t smem = std::max((size_t)K * 8, (size_t)threads * kSegPerThread * 8 + 32 * 4);
     if (smem <= 48 * 1024) {
       LookupArgs lk{csr->indptr, csr->nbr, csr->t, csr->num_rows, q, err_flag};
-      launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads), smem, st, s->cur, tq, rows, K, mlp_nbr->tw, d, t, t_pad,
-               t_pad_e, w.S, w.lda, n_edges, lk, grid_q, ids, n_ids, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
+      launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads), smem, st, s->cur, tq_q, rows, K, mlp_nbr->tw, d, t, t_pad,
+               t_pad_e, w.S, w.lda, q_rows, lk, grid_q, ids, n_ids, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
       if ((rc = check_launch("gather_ab")) != LSTEP_OK) return rc;
       prof_mark(st, kProfGather);
       edges_done = true;
@@ -287,7 +313,7 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   }
   if (rows > 0) {
     if (!edges_done) {
-      rc = launch_nbr_lookup_aggregate(csr, q, s->cur, tq, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, err_flag, st);
+      rc = launch_nbr_lookup_aggregate(csr, q, s->cur, tq_q, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, err_flag, st);
       if (rc != LSTEP_OK) return rc;
     }
     // the neighbourhood MLP and phase A's MLP in ONE launch when they fit one round of clusters: neither writes the
@@ -324,11 +350,12 @@ int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* 
   int32_t* dirty = nullptr;
   const bool no_early_append = tuning().early_append == 0;
   rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,
-                      err_flag, stream, edges_done, no_early_append ? nullptr : &dirty, stamp, phase_a_done,
+                      err_flag, stream, edges_done, (no_early_append || opt.skip_append) ? nullptr : &dirty, stamp, phase_a_done,
                       s->ring + (int64_t)append_slot * d, (int64_t)T * d);
   if (rc != LSTEP_OK) return rc;
   // 2 CTAs per SM: the append is resident (copying, then waiting for the phase-B MLP) while the NEXT step's DFT filter
   // wants to become resident and prefetch — it must leave thread slots and shared memory for it
+  if (opt.skip_append) return LSTEP_OK;
   launch_k(ring_append_kernel, dim3(num_sms() * 2), dim3(256), 0, st, s->cur, s->ring, s->V1, T, d, append_slot, 1, 0, dirty, stamp);
   prof_mark(st, kProfAppend);
   return check_launch("ring_append");
@@ -379,6 +406,26 @@ extern "C" int lstep_pe_steps(const lstep_pe_stream* s, const lstep_csr* csr, in
   }
   *head_io = head;
   return LSTEP_OK;
+}
+
+/* One rank's share of a step on a node-id sharded group with a replicated table and CSR (l-step_b200/shard.py::ReplicatedTableRank):
+ * everything of lstep_pe_step EXCEPT the DFT filter (the caller filters the batch nodes whose history it owns, all-gathers the
+ * filtered rows and scatters them into s->cur before this call) and the ring append (the caller appends the rows it owns with
+ * lstep_ring_copy_rows). The a6 query sets cover the edges [q_off, q_off + q_rows) of the batch only — this rank's share —
+ * query_ids_host[c] pointing at the first of those ids; outputs [n_queries, q_rows, d]. update_pe runs in full on every rank
+ * (identical inputs, deterministic kernels: the replicas of the table stay bit-identical without any exchange). */
+extern "C" int lstep_pe_step_sharded(const lstep_pe_stream* s, const lstep_csr* csr, int64_t lo, int64_t n_edges, const int64_t* ids,
+                                     int64_t n_ids, double current_time, const int64_t* const* query_ids_host, int n_queries,
+                                     int64_t q_off, int64_t q_rows, float* nbr_out, int K, const lstep_pe_mlp* mlp_nbr,
+                                     const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes, uint32_t* err_flag,
+                                     void* stream) {
+  if (!s || !s->src || !s->dst || !s->t || lo < 0 || q_rows < 0) return LSTEP_ERR_INVALID_ARG;
+  StepOpts opt;
+  opt.skip_dft = opt.skip_append = true;
+  opt.q_off = q_off;
+  opt.q_rows = q_rows;
+  return pe_step_core_ex(s, csr, s->src + lo, s->dst + lo, s->t + lo, n_edges, ids, n_ids, current_time, 0, 0, 0, nullptr, query_ids_host,
+                         q_rows > 0 ? n_queries : 0, nbr_out, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag, stream, opt);
 }
 
 LSTEP_TIMELINE_DEFINE(step)

@@ -357,3 +357,186 @@ class ShardedPEStream:
         rk.bytes_x2 += int(st["send_rows"].numel() * 4 + rr.numel() * 4)
         rk.p3(st, ru, rr)
         return out.view(len(queries), st["nB"], rk.d)
+
+
+# =============================================================================================
+# Replicated table, sharded history (the default scale-out layout of bench.py --workload scaleout)
+# =============================================================================================
+class ReplicatedTableRank:
+    """Rank r of G for graphs whose PE HISTORY does not fit one GPU (BASELINE config 5: 10 M nodes; the history ring is
+    V1 x T x d x 4 B = 688 GB at T = 100, the current table 6.9 GB, the temporal CSR of 5e8 edges 16 GB):
+
+        sharded      history ring   float32[V1/G][T][d]      rows of the nodes v with v % G == r (spreads hubs)
+        replicated   current table  float32[V1][d], temporal CSR, resident edge stream
+
+    Per step the only data one rank needs from another is the DFT-filtered row of the batch nodes whose history it does
+    not hold, so a step is
+        p1   DFT filter (a3) of the OWNED batch nodes off the local ring                      1/G of the filter's HBM traffic
+        X    one NCCL all-gather of the filtered rows (N x d x 4 B = 1.7 MB at B = 2000), scattered into every replica
+        p2   lstep_pe_step_sharded: a6 for this rank's 1/G share of the query rows; update_pe (a7 / a8) in full on every
+             rank — identical inputs and deterministic kernels keep the table replicas bit-identical with no exchange;
+             ring append of the owned rows
+    with NO host synchronisation and no data-dependent message sizes: which rank owns which batch node follows from the
+    (replicated) batch, so every split size is known on the host of every rank, and the per-batch plan (sorted unique
+    ids, owned ids, scatter order) is computed once for the whole resident stream like PEStream's. Compared with the
+    owner-computes / all-to-all layout above (table sharded too; kept as ShardRank for reference and tested against this
+    one) it trades 1/G of the update's arithmetic for the removal of two data-dependent all-to-all exchanges whose
+    host-side planning cost 10x the step's kernels."""
+
+    def __init__(self, model: LSTEP, rank: int, world: int, src, dst, t, num_nodes: int, batch_size: int, num_neighbors: int,
+                 initial_pe: torch.Tensor, start: int = 0, stop: int = None, device=None, sampler: NeighborSampler = None):
+        self.m, self.rank, self.G = model, int(rank), int(world)
+        self.dev = dev = torch.device(device) if device is not None else model._dev()
+        self.B, self.K, self.T = int(batch_size), int(num_neighbors), model.num_fft_batches
+        self.d, self.t_dim = model.pe_dim, model.time_feat_dim
+        self.V1 = int(num_nodes) + 1
+        lib = self.lib = _lib.load()
+        as_dev = lambda a, dt: (a.to(dev, dt) if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt))
+        with torch.cuda.device(dev):
+            self.src, self.dst, self.tt = as_dev(src, torch.int64), as_dev(dst, torch.int64), as_dev(t, torch.float64)
+            E = int(self.src.shape[0])
+            stop = E if stop is None else int(stop)
+            self.start, self.stop = int(start), stop
+            if sampler is None:
+                eid = torch.arange(1, E + 1, dtype=torch.int64, device=dev)
+                sampler = NeighborSampler.from_edges(self.src, self.dst, eid, self.tt, "recent", device=dev, num_rows=self.V1)
+                del eid
+            self.sampler = model.neighbor_sampler = sampler
+            # table with one spare row: padded slots of the all-gather are scattered there
+            self._cur_full = torch.empty((self.V1 + 1, self.d), dtype=torch.float32, device=dev)
+            self._cur_full[:self.V1] = initial_pe.to(dev, torch.float32)
+            self._cur_full[self.V1].zero_()
+            self.cur = self._cur_full[:self.V1]
+            self.rows_local = (self.V1 - self.rank + self.G - 1) // self.G  # owned node ids: rank, rank + G, ...
+            self.ring = torch.zeros((max(self.rows_local, 1), self.T, self.d), dtype=torch.float32, device=dev)
+            self.head, self.len = 0, 1
+            _lib.check(lib.lstep_ring_copy_rows(_lib.ptr(self.ring), _lib.ptr(self.cur), self.rows_local, self.T, self.d, 0, self.G, self.rank, 1,
+                                                _lib.stream_ptr()), "ring init")
+            self.desc = _lib.PEStreamDesc(self.src.data_ptr(), self.dst.data_ptr(), self.tt.data_ptr(), self.ring.data_ptr(), self.cur.data_ptr(),
+                                          self.V1, self.T, self.d)
+            # ---- per-batch plan of the resident stream [start, stop): one pass on the host, uploaded once
+            B, G = self.B, self.G
+            src_h = self.src[self.start:stop].cpu().numpy()
+            dst_h = self.dst[self.start:stop].cpu().numpy()
+            t_h = self.tt[self.start:stop].cpu().numpy()
+            self.num_batches = nb = (stop - self.start + B - 1) // B
+            ids_l, mine_l, scat_l = [], [], []
+            self.ids_off, self.mine_off, self.scat_off, self.max_n, self.tmax = [0], [0], [0], [], []
+            for b in range(nb):
+                lo, hi = b * B, min((b + 1) * B, stop - self.start)
+                ids = np.unique(np.concatenate([src_h[lo:hi], dst_h[lo:hi]]))
+                own = ids % G
+                counts = np.bincount(own, minlength=G)
+                mx = int(counts.max()) if len(ids) else 0
+                scat = np.full((G, max(mx, 1)), self.V1, dtype=np.int64)  # padded slots -> the spare row
+                for g in range(G):
+                    scat[g, :counts[g]] = ids[own == g]
+                ids_l.append(ids)
+                mine_l.append(ids[own == self.rank] // G)  # rows of the local ring
+                scat_l.append(scat.reshape(-1))
+                self.ids_off.append(self.ids_off[-1] + len(ids))
+                self.mine_off.append(self.mine_off[-1] + len(mine_l[-1]))
+                self.scat_off.append(self.scat_off[-1] + scat.size)
+                self.max_n.append(max(mx, 1))
+                self.tmax.append(float(t_h[lo:hi].max()))
+            cat = lambda xs: torch.from_numpy(np.concatenate(xs) if xs else np.zeros(0, np.int64)).to(dev)
+            self.ids, self.mine_local, self.scat = cat(ids_l), cat(mine_l), cat(scat_l)
+            if len(ids_l) and int(max(x.max() for x in ids_l if len(x))) >= self.V1:
+                raise IndexError("edge stream holds a node id outside the PE table")
+            need = lib.lstep_pe_step_workspace_bytes(2 * B, B, 8, self.K, self.d, self.t_dim, self.V1)
+            self.ws = torch.empty(need + 4096, dtype=torch.uint8, device=dev)
+            _lib.check(lib.lstep_update_pe_workspace_init(_lib.ptr(self.ws), self.ws.numel(), self.V1, _lib.stream_ptr()), "ws init")
+            self._gbuf = torch.empty((G * 2 * B, self.d), dtype=torch.float32, device=dev)  # all-gather buffer (>= G * max_n rows)
+            self._mine = torch.empty((2 * B, self.d), dtype=torch.float32, device=dev)
+        self.batch_idx = 0
+        self.bytes_allgather = 0
+
+    def batch(self, b: int):
+        lo = self.start + b * self.B
+        return lo, min(lo + self.B, self.stop)
+
+    def share(self, b: int):
+        """(q_off, q_rows): this rank's share of the batch's edges for the a6 queries."""
+        lo, hi = self.batch(b)
+        n = hi - lo
+        return self.rank * n // self.G, (self.rank + 1) * n // self.G - self.rank * n // self.G
+
+    # ---- p1: filter the owned batch nodes off the local ring into a padded send block -----------------------------------
+    def p1(self, b: int) -> torch.Tensor:
+        lib, T, d = self.lib, self.T, self.d
+        n_mine = self.mine_off[b + 1] - self.mine_off[b]
+        mx = self.max_n[b]
+        send = self._mine[:mx]
+        bmask = min(max(self.batch_idx, 0), T) if self.len < T else T
+        with torch.cuda.device(self.dev), torch.no_grad():
+            if n_mine:
+                Gt = self.m._collapsed_filter(bmask, False)
+                loc = self.mine_local[self.mine_off[b]:self.mine_off[b + 1]]
+                _lib.check(lib.lstep_dft_filter(_lib.ptr(self.ring), T * d, d, self.head, T, self.len, d, _lib.ptr(loc), n_mine, _lib.ptr(Gt),
+                                                _lib.ptr(send), d, _lib.stream_ptr()), "dft_filter")
+        return send
+
+    # ---- p2: scatter the gathered rows, run this rank's share of the step, append the owned rows ---------------------------
+    def p2(self, b: int, gathered: torch.Tensor, queries, out: torch.Tensor = None) -> torch.Tensor:
+        """gathered: [G * max_n, d] = every rank's padded block in rank order. queries: device int64 tensors with the ids of
+        ALL edges of the batch (this rank reads its share). Returns [C, q_rows, d]."""
+        lib, T, d, G = self.lib, self.T, self.d, self.G
+        lo, hi = self.batch(b)
+        n = hi - lo
+        q_off, q_rows = self.share(b)
+        C = len(queries)
+        with torch.cuda.device(self.dev), torch.no_grad():
+            self._cur_full.index_copy_(0, self.scat[self.scat_off[b]:self.scat_off[b + 1]], gathered)
+            if out is None:
+                out = torch.empty((max(C, 1), q_rows, d), dtype=torch.float32, device=self.dev)
+            ids = self.ids[self.ids_off[b]:self.ids_off[b + 1]]
+            qptrs = (ctypes.c_void_p * max(C, 1))(*[q.data_ptr() + 8 * q_off for q in queries])
+            _lib.check(lib.lstep_pe_step_sharded(ctypes.byref(self.desc), self.sampler.csr_ref, lo, n, _lib.ptr(ids), ids.shape[0], self.tmax[b],
+                                                 qptrs, C, q_off, q_rows, _lib.ptr(out), self.K, self.m._mlp_ref("nbr"), self.m._mlp_ref("update"),
+                                                 _lib.ptr(self.ws), self.ws.numel(), _lib.ptr(self.sampler._err), _lib.stream_ptr()),
+                       "lstep_pe_step_sharded")
+            if self.len < T:
+                slot, self.len = (self.head + self.len) % T, self.len + 1
+            else:
+                slot, self.head = self.head, (self.head + 1) % T
+            _lib.check(lib.lstep_ring_copy_rows(_lib.ptr(self.ring), _lib.ptr(self.cur), self.rows_local, T, d, slot, G, self.rank, 1,
+                                                _lib.stream_ptr()), "ring append")
+        self.batch_idx += 1
+        return out
+
+    def export_history_rows(self) -> torch.Tensor:
+        """[rows_local, len, d], oldest first: row l = node l * G + rank."""
+        idx = (self.head + torch.arange(self.len, device=self.dev)) % self.T
+        return self.ring.index_select(1, idx)[:self.rows_local]
+
+
+class ReplicatedLocalGroup:
+    """All G ranks in one process on one device, in lock step (tests): the all-gather is a concatenation."""
+
+    def __init__(self, ranks):
+        self.ranks, self.G = ranks, len(ranks)
+
+    def step(self, b: int, queries):
+        blocks = [rk.p1(b).clone() for rk in self.ranks]
+        gathered = torch.cat(blocks)
+        return [rk.p2(b, gathered, queries) for rk in self.ranks]
+
+
+class ReplicatedTableStream:
+    """One process per GPU (torchrun): this rank's state + the NCCL all-gather."""
+
+    def __init__(self, rank_state: ReplicatedTableRank, group=None):
+        import torch.distributed as dist
+        self.rk, self.dist, self.group = rank_state, dist, group
+
+    def step(self, b: int, queries, out: torch.Tensor = None) -> torch.Tensor:
+        rk = self.rk
+        send = rk.p1(b)
+        mx = rk.max_n[b]
+        gathered = rk._gbuf[:rk.G * mx]
+        if rk.G > 1:
+            self.dist.all_gather_into_tensor(gathered, send, group=self.group)
+            rk.bytes_allgather += gathered.numel() * 4
+        else:
+            gathered = send
+        return rk.p2(b, gathered, queries, out)

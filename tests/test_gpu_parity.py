@@ -899,3 +899,42 @@ def test_identical_query_sets_are_computed_once_with_identical_results(torch_cud
             assert torch.equal(a, b_)
         assert torch.equal(res[0][0][0][0], res[0][0][0][2])  # the two source sets' outputs are the same rows
         assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_replicated_table_sharded_history_is_bit_identical_to_single_gpu(torch_cuda, world):
+    """The scale-out layout (history ring sharded by node id, table and CSR replicated, one all-gather of the filtered rows
+    per step; l-step_b200/shard.py::ReplicatedTableRank) with all ranks emulated in one process: every replica's table,
+    the owners' history rows and each rank's share of the a6 outputs must be BIT-identical to the single-GPU stream — the
+    same kernels see the same inputs — through the masked (ring filling) and the steady regime."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream, ReplicatedLocalGroup, ReplicatedTableRank
+    g = synth.make_graph("tiny_bip", seed=4, num_nodes=300, num_edges=9000)
+    V, d, K, B = g.num_nodes, 172, 20, 48
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    model = build_dropin("full", g, s, 172, d, 100, 100, K)
+    lstep = model[0].eval()
+    init = torch.from_numpy(seeded_normal(17, (V + 1, d), 0.3)).cuda()
+    init[0] = 0
+    e0 = g.num_edges - 115 * B - 7  # 116 batches (ragged tail): the ring (T = 100) fills after 99 of them
+    st = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=init.clone(), start=e0)
+    ranks = [ReplicatedTableRank(lstep, r, world, g.src_node_ids, g.dst_node_ids, g.node_interact_times, V, B, K, init.clone(), start=e0, sampler=s)
+             for r in range(world)]
+    grp = ReplicatedLocalGroup(ranks)
+    assert ranks[0].num_batches == st.num_batches
+    neg = torch.from_numpy(np.random.default_rng(3).integers(1, V + 1, g.num_edges - e0).astype(np.int64)).cuda()
+    for b in range(st.num_batches):
+        lo, hi, _, _ = st.batch_arrays(b)
+        qs = [st.src[lo:hi], st.dst[lo:hi], st.src[lo:hi], neg[lo - e0:hi - e0].contiguous()]
+        want = st.step(b, qs)
+        outs = grp.step(b, qs)
+        got = torch.cat(outs, dim=1)
+        assert got.shape == want.shape and torch.equal(got, want), b
+        if b % 20 == 0 or b == st.num_batches - 1:
+            for rk in ranks:
+                assert torch.equal(rk.cur, st.cur), (b, rk.rank)
+    h = st.export_history()
+    for rk in ranks:
+        assert torch.equal(rk.export_history_rows(), h[rk.rank::world]), rk.rank
+    s.check_errors()
