@@ -828,6 +828,8 @@ def main():
     ap.add_argument("--scaleout-nodes", type=int, default=10_000_000)
     ap.add_argument("--scaleout-edges", type=int, default=100_000_000)
     ap.add_argument("--scaleout-T", type=int, default=12, help="history steps per node of the scale-out arm (12 fits the N = 1 point; 100 needs 8 GPUs)")
+    ap.add_argument("--scaleout-history", default="changelog", choices=["changelog", "ring"],
+                    help="scale-out arm's history: change-log (base + changed rows; N = 1 holds T = 100) or the dense ring sharded by node id")
     ap.add_argument("--no-scaleout", action="store_true", help="N = 1: skip the scale-out sample that rides along with the headline run")
     ap.add_argument("--scaleout-timeout", type=float, default=420.0, help="seconds the scale-out sample may take at N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")

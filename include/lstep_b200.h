@@ -41,6 +41,7 @@ typedef enum lstep_status {
 /* bits set in the device `err_flag` word by kernels */
 #define LSTEP_FLAG_NODE_OUT_OF_RANGE 1u /* utils/utils.py:140 would raise IndexError */
 #define LSTEP_FLAG_UNSORTED_STREAM 2u
+#define LSTEP_FLAG_CHANGELOG_FULL 4u /* a step changed more rows than the change-log history has event capacity for */
 
 const char* lstep_strerror(int status);
 const char* lstep_last_cuda_error(void);
@@ -294,6 +295,47 @@ int lstep_pe_step_sharded(const lstep_pe_stream* s, const lstep_csr* csr, int64_
                           int64_t n_ids, double current_time, const int64_t* const* query_ids_host, int n_queries, int64_t q_off,
                           int64_t q_rows, float* nbr_out, int K, const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd,
                           void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Change-log PE history (csrc/changelog.cu): the history [V1, T, d] of the loops (a4 / f1) stored as base rows + the rows
+ * every step changed, instead of T full snapshots — V1 + T * (rows changed per step) rows: 7.8 GB instead of 688 GB for
+ * the 10 M-node graph at T = 100, and 9 MB instead of 13.8 GB written per step. x[v, f] = the row of the latest event of v
+ * at a window index <= f, else base[v]: the same function of time, so the collapsed DFT filter becomes
+ * out[n] = sum_versions (sum of G over the span a version covers) * version row.
+ *   base     [rows][d]        value at the window's oldest step            ev_cnt  [T]     events per window slot
+ *   ev_node  [T][cap]         node of an event                             ev_hash [T][H]  open addressing: node << 32 | index
+ *   ev_row   [T][cap][d]      its row                                      ev_mask [rows][4] bit s: the node has an event in slot s
+ * All zero-initialised except ev_hash (all ones). H = power of two >= 2 * cap; T <= 128. Node-id sharded groups: a rank
+ * holds the nodes v with v % row_mul == row_add at local row (v - row_add) / row_mul (1, 0: everything).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct lstep_changelog {
+  float* base;
+  int32_t* ev_node;
+  float* ev_row;
+  int32_t* ev_cnt;
+  unsigned long long* ev_hash;
+  uint32_t* ev_mask;
+  int64_t rows;
+  int T, cap, H, d;
+  int64_t row_mul, row_add;
+} lstep_changelog;
+
+/* out[out_ids ? out_ids[i] : i] = filtered history of node ids[i] over the window (head = slot of its oldest step, len steps) */
+int lstep_changelog_filter(const lstep_changelog* cl, int head, int len, const int64_t* ids, int64_t n_ids, const float* G,
+                           float* out, int64_t out_stride, const int64_t* out_ids, void* stream);
+/* retire (optional) the events of `slot` into the base rows, then record table[v] for v in U[0 .. min(n_u, *n_u_dev)) and for
+ * the ids whose stamp_map entry differs from `stamp` (U == NULL: every id) as the slot's new events */
+int lstep_changelog_append(const lstep_changelog* cl, int slot, int retire, const float* table, const int64_t* U,
+                           const int32_t* n_u_dev, int64_t n_u, const int64_t* ids, int64_t n_ids, const int32_t* stamp_map, int stamp,
+                           int with_row0 /* also the padding row 0, which every update_pe call zeroes */, uint32_t* err_flag, void* stream);
+/* lstep_pe_step on a change-log history (s->ring unused). phase 0: filter + step + append; 1: filter only; 2: step + append
+ * (sharded groups filter with lstep_changelog_filter, all-gather, scatter, then call phase 2). q_off / q_rows as in
+ * lstep_pe_step_sharded (q_rows < 0: all edges). */
+int lstep_pe_step_changelog(const lstep_pe_stream* s, const lstep_changelog* cl, const lstep_csr* csr, int64_t lo, int64_t n_edges,
+                            const int64_t* ids, int64_t n_ids, double current_time, int head, int len, const float* G,
+                            const int64_t* const* query_ids_host, int n_queries, int64_t q_off, int64_t q_rows, float* nbr_out, int K,
+                            const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                            uint32_t* err_flag, void* stream, int phase);
 
 /* ------------------------------------------------------------------------------------------
  * Host-fed streaming step (csrc/host_step.cu): what a loop that holds the batch as HOST arrays calls

@@ -15,6 +15,7 @@ _LAZY = {
     "TimeEncoder": "modules",
     "MergeLayer": "modules",
     "PEStream": "stream",
+    "ChangeLogStream": "stream",
     "ShardRank": "shard",
     "LocalGroup": "shard",
     "DistGroup": "shard",

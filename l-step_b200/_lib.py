@@ -32,6 +32,12 @@ class PEStreamDesc(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("t", vp), ("ring", vp), ("cur", vp), ("V1", i64), ("T", i32), ("d", i32)]
 
 
+class ChangeLog(C.Structure):
+    """struct lstep_changelog"""
+    _fields_ = [("base", vp), ("ev_node", vp), ("ev_row", vp), ("ev_cnt", vp), ("ev_hash", vp), ("ev_mask", vp), ("rows", i64),
+                ("T", i32), ("cap", i32), ("H", i32), ("d", i32), ("row_mul", i64), ("row_add", i64)]
+
+
 class PEMLP(C.Structure):
     """struct lstep_pe_mlp"""
     _fields_ = [("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("ws", vp), ("bs", vp), ("tw", vp), ("d", i32), ("t", i32),
@@ -82,6 +88,10 @@ _SIGS = {
                              C.POINTER(C.c_void_p), vp, i32, vp, i64, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
     "lstep_pe_step_sharded": (i32, [C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, C.POINTER(C.c_void_p), i32, i64, i64,
                                     vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp]),
+    "lstep_changelog_filter": (i32, [C.POINTER(ChangeLog), i32, i32, vp, i64, vp, vp, i64, vp, vp]),
+    "lstep_changelog_append": (i32, [C.POINTER(ChangeLog), i32, i32, vp, vp, vp, i64, vp, i64, vp, i32, i32, vp, vp]),
+    "lstep_pe_step_changelog": (i32, [C.POINTER(PEStreamDesc), C.POINTER(ChangeLog), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, i32, i32, vp,
+                                      C.POINTER(C.c_void_p), i32, i64, i64, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp, i32]),
     "lstep_set_option": (i32, [C.c_char_p, i32]),
     "lstep_get_option": (i32, [C.c_char_p, C.POINTER(i32)]),
     "lstep_step_profile": (i32, [i32]),
@@ -160,3 +170,4 @@ def stream_ptr():
 
 
 FLAG_NODE_OUT_OF_RANGE = 1
+FLAG_CHANGELOG_FULL = 4

@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "gather_bodies.cuh"
 #include "mlp_job.cuh"
+#include "step_core.cuh"
 
 namespace lstep {
 
@@ -27,7 +28,6 @@ int launch_nbr_lookup_aggregate(const lstep_csr* csr, RowIds q_node, const float
                                 const float* tw, int d, int t, float* S, int64_t ldS, uint32_t* err_flag, cudaStream_t st);
 void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows, float** A, int64_t* lda,
                        int32_t** counters, float** new_rows);
-bool update_push_available(const lstep_pe_mlp* mlp);
 
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
@@ -193,20 +193,6 @@ extern "C" int lstep_ring_copy_rows(float* ring, float* cur, int64_t ring_rows, 
 }
 
 namespace lstep {
-// Variations of the step for one rank of a node-id sharded group (lstep_pe_step_sharded): the DFT filter and the ring
-// append are done by the caller (owner-local, around an all-gather), and the a6 queries cover only this rank's share
-// [q_off, q_off + q_rows) of the batch's edges.
-struct StepOpts {
-  bool skip_dft = false, skip_append = false;
-  int64_t q_off = 0, q_rows = -1;  // -1: all n_edges
-};
-
-int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* src, const int64_t* dst, const double* tq,
-                    int64_t n_edges, const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
-                    const float* G, const int64_t* const* query_ids_host, int n_queries, float* nbr_out, int K,
-                    const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
-                    uint32_t* err_flag, void* stream, const StepOpts& opt);
-
 // The step on explicit batch pointers (src/dst/tq = the batch's n_edges endpoints and times on the device).
 int pe_step_core(const lstep_pe_stream* s, const lstep_csr* csr, const int64_t* src, const int64_t* dst, const double* tq,
                  int64_t n_edges, const int64_t* ids, int64_t n_ids, double current_time, int head, int len, int append_slot,
@@ -347,6 +333,7 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
     g_stamp = 1;
     stamp = 1;
   }
+  if (opt.stamp_out) *opt.stamp_out = stamp;
   int32_t* dirty = nullptr;
   const bool no_early_append = tuning().early_append == 0;
   rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,

@@ -563,6 +563,14 @@ void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, i
   *new_rows = w.new_rows;
 }
 
+void update_ws_phase_b_lists(void* workspace, int64_t n_ids, int64_t n_edges, int K, int d, int t, int64_t pe_rows, const int64_t** U,
+                             const int32_t** n_dest_dev, const int32_t** stamp_map) {
+  UpdateWs w = carve(workspace, n_ids, n_edges, K, d, t, pe_rows);
+  *U = w.U;
+  *n_dest_dev = w.counters + 2;
+  *stamp_map = w.slot_of;
+}
+
 // the push form of phase B (and with it the side-buffer form of phase A) is available for this shape
 bool update_push_available(const lstep_pe_mlp* mlp) {
   const bool pull = tuning().phaseb_push == 0;

@@ -938,3 +938,58 @@ def test_replicated_table_sharded_history_is_bit_identical_to_single_gpu(torch_c
     for rk in ranks:
         assert torch.equal(rk.export_history_rows(), h[rk.rank::world]), rk.rank
     s.check_errors()
+
+
+@pytest.mark.parametrize("tag,Th0", [("small", 1), ("full", 1), ("full", 100)])
+def test_changelog_history_matches_dense_ring(torch_cuda, tag, Th0, parity_log):
+    """ChangeLogStream (history = base rows + the rows every step changed; csrc/changelog.cu) against the dense-ring PEStream
+    on the same stream: through the filling (masked) regime and the steady regime with retiring events, from an initial
+    table (Th0 = 1) and from an imported dense history in which every row differs between snapshots (Th0 = T). The filter
+    sums the same products in another grouping (span sums of G), so values agree to fp32 rounding, not bit for bit:
+    outputs and tables within 1e-5 (every element), and the history the log replays equals the ring's, snapshot by
+    snapshot, to the same bar. The log must also stay well below the dense ring's size."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import ChangeLogStream, NeighborSampler, PEStream
+    z = np.load(golden_path(f"replay_{tag}.npz"))
+    d, T, K, t_dim, F, B = (int(z[k]) for k in ("pe_dim", "T", "K", "time_dim", "feat_dim", "B"))
+    V, E, e0 = int(z["V"]), int(z["E"]), int(z["e0"])
+    g = synth.make_graph("tiny", seed=int(z["graph_seed"]), num_nodes=V, num_edges=E)
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin(tag, g, s, F, d, t_dim, T, K)[0].eval()
+    Th = min(Th0, T)
+    hist0 = seeded_normal(int(z["hist0_seed"]), (V + 1, Th, d), 0.3)
+    hist0[0] = 0
+    mk = lambda cls, **kw: cls(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=torch.from_numpy(hist0).cuda(),
+                               start=e0, **kw)
+    a, b = mk(PEStream), mk(ChangeLogStream, event_capacity=V + 1)
+    assert torch.equal(b.export_history(), a.export_history()) and torch.equal(a.cur, b.cur)
+    neg = torch.from_numpy(z["neg_dst"].astype(np.int64)).cuda()
+    n_steps = min(a.num_batches, T + 30)
+    worst_out = worst_tab = 0.0
+    for i in range(n_steps):
+        lo, hi, _, _ = a.batch_arrays(i)
+        qs = [a.src[lo:hi], a.dst[lo:hi], neg[i][:hi - lo].contiguous()]
+        oa, ob = a.step(i, qs), b.step(i, qs)
+        ok, w = pe_close(ob.cpu().numpy(), oa.cpu().numpy())
+        worst_out = max(worst_out, w)
+        assert ok, (i, "outputs", w)
+        ok, w = pe_close(b.cur.cpu().numpy(), a.cur.cpu().numpy())
+        worst_tab = max(worst_tab, w)
+        assert ok, (i, "table", w)
+        assert (a.head, a.len) == (b.head, b.len)
+    b.check_errors()
+    ha, hb = a.export_history(), b.export_history()
+    assert ha.shape == hb.shape
+    ok, w = pe_close(hb.cpu().numpy(), ha.cpu().numpy())
+    assert ok, ("history", w)
+    assert torch.equal(hb[:, -1, :], b.cur)
+    parity_log[f"changelog/{tag}/Th0={Th0}"] = {"steps": n_steps, "worst_output": worst_out, "worst_table": worst_tab, "history": w,
+                                               "log_bytes": b.history_bytes(), "dense_bytes": int(a.ring.numel() * 4)}
+    # capacity overflow is reported, not silently dropped
+    c = mk(ChangeLogStream, event_capacity=8) if Th0 == 1 else None
+    if c is not None:
+        lo, hi, _, _ = c.batch_arrays(0)
+        c.step(0, [c.src[lo:hi]])
+        with pytest.raises(Exception):
+            c.check_errors()
