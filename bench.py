@@ -302,8 +302,9 @@ def run_sharded(args, rank, world, own_pg=True):
     temporal CSR replicated, one NCCL all-gather of the DFT-filtered rows per step (l-step_b200/shard.py::ReplicatedTableRank).
     The batch is replicated: every rank filters the batch nodes whose history it owns (1/N of the filter's HBM traffic),
     computes its 1/N share of the neighbourhood queries and runs update_pe in full, so the work per rank shrinks with N only
-    in those two parts ("scaling": "strong"; the point of sharding here is CAPACITY: 688 GB of history at T = 100). T is
-    stated with every point: --scaleout-T (default 12: the N = 1 point must fit one GPU next to the replicated state)."""
+    in those two parts ("scaling": "strong"). --scaleout-history changelog (default): the owners keep the history as a change
+    log (base rows + the rows every step changed: 13 GB instead of 688 GB at T = 100), so every N — N = 1 included — runs the
+    full T = 100; --scaleout-history ring: the dense ring sharded by node id (T = 12 so that N = 1 fits). T is stated with every point."""
     import torch
     import torch.distributed as dist
     from lstep_b200 import LSTEP, ReplicatedTableRank, ReplicatedTableStream, _lib
@@ -315,7 +316,9 @@ def run_sharded(args, rank, world, own_pg=True):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     assert lib.lstep_device_ok() == 1
-    B, K, T = 2000, 20, args.scaleout_T
+    hist_kind = args.scaleout_history
+    B, K = 2000, 20
+    T = args.scaleout_T if args.scaleout_T else (T_HIST if hist_kind == "changelog" else 12)
     V, E = args.scaleout_nodes, args.scaleout_edges
     t0 = time.time()
     src, dst, tt = synth.make_scaleout_device(V, E, dev, seed=0)
@@ -341,7 +344,7 @@ def run_sharded(args, rank, world, own_pg=True):
     e0 = int(E * 0.7) // B * B
     stop = min(E, e0 + (W + Ksteps + n_e2e + 2) * B)
     t0 = time.time()
-    rk = ReplicatedTableRank(m, rank, world, src, dst, tt, V, B, K, init, start=e0, stop=stop)
+    rk = ReplicatedTableRank(m, rank, world, src, dst, tt, V, B, K, init, start=e0, stop=stop, history=hist_kind)
     del init
     torch.cuda.synchronize()
     t_setup = time.time() - t0
@@ -358,7 +361,7 @@ def run_sharded(args, rank, world, own_pg=True):
         sh.step(step_no % nb, queries(step_no % nb))
         step_no += 1
     torch.cuda.synchronize()
-    rk.sampler.check_errors()
+    rk.check_errors()
     if world > 1:
         dist.barrier()
     clocks = ClockSampler(local)
@@ -423,10 +426,12 @@ def run_sharded(args, rank, world, own_pg=True):
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"scale-out synthetic temporal graph, V={V}, E={E} (Zipf 0.8 endpoints, generated on the device), B={B}, K={K}, "
                                    f"T={T}, d={D}, t={T_DIM}, C={C_CALLS}",
-                       "parallelism": f"PE history ring sharded by node id over {world} GPU(s) (owner = id mod N), current table + temporal CSR "
+                       "parallelism": f"PE history ({'change log: base rows + the rows every step changed' if hist_kind == 'changelog' else 'dense ring'}) "
+                                      f"sharded by node id over {world} GPU(s) (owner = id mod N), current table + temporal CSR "
                                       "replicated, one NCCL all-gather of the DFT-filtered batch rows per step, a6 queries split 1/N, update_pe replicated",
-                       "l2_policy": f"inputs larger than L2: history ring {(V + 1) * T * D * 4 / 1e9 / world:.1f} GB per rank, CSR {2 * E * 16 / 1e9:.1f} GB"},
-            "run_info": {"graph_gen_s": t_gen, "setup_s": t_setup, "hbm_used_GB": (total_b - free_b) / 1e9,
+                       "l2_policy": f"inputs larger than L2: history {rk.history_bytes() / 1e9:.1f} GB per rank (dense [V1, T, d] would be "
+                                    f"{(V + 1) * T * D * 4 / 1e9:.0f} GB in total), table {(V + 1) * D * 4 / 1e9:.1f} GB, CSR {2 * E * 16 / 1e9:.1f} GB"},
+            "run_info": {"graph_gen_s": t_gen, "setup_s": t_setup, "hbm_used_GB": (total_b - free_b) / 1e9, "history": hist_kind, "T": T,
                          "nvlink_bytes_per_step_all_ranks": float(x[0].item()) / Ksteps},
             "clocks": clk, "e2e": e2e,
             "gpu_launches": int(Ksteps * 7 * world),
@@ -746,7 +751,7 @@ def run_reference(args, rank, world):
     workload = args.workload
     if workload == "scaleout":
         # the sharded arm's config: batch shape of the Flights config (B=2000, K=20), T = --scaleout-T
-        workload, T_HIST = "flights", args.scaleout_T
+        workload, T_HIST = "flights", (args.scaleout_T or T_HIST)
     B, K = WORKLOADS[workload]
     steps, warm = args.steps, max(args.warmup, 1)
     steps = min(steps, 100)  # each step is one batch of CPU work (~0.1 s at B=200); bounded
@@ -827,7 +832,8 @@ def main():
     ap.add_argument("--replicas", action="store_true", help="N > 1: only the replicas of the single-GPU workload (skip the sharded scale-out sample)")
     ap.add_argument("--scaleout-nodes", type=int, default=10_000_000)
     ap.add_argument("--scaleout-edges", type=int, default=100_000_000)
-    ap.add_argument("--scaleout-T", type=int, default=12, help="history steps per node of the scale-out arm (12 fits the N = 1 point; 100 needs 8 GPUs)")
+    ap.add_argument("--scaleout-T", type=int, default=0, help="history steps per node of the scale-out arm (default: 100 with the change-log "
+                    "history; 12 with the dense ring, whose N = 1 point must fit one GPU — T = 100 needs 8 GPUs there)")
     ap.add_argument("--scaleout-history", default="changelog", choices=["changelog", "ring"],
                     help="scale-out arm's history: change-log (base + changed rows; N = 1 holds T = 100) or the dense ring sharded by node id")
     ap.add_argument("--no-scaleout", action="store_true", help="N = 1: skip the scale-out sample that rides along with the headline run")

@@ -384,7 +384,13 @@ class ReplicatedTableRank:
     host-side planning cost 10x the step's kernels."""
 
     def __init__(self, model: LSTEP, rank: int, world: int, src, dst, t, num_nodes: int, batch_size: int, num_neighbors: int,
-                 initial_pe: torch.Tensor, start: int = 0, stop: int = None, device=None, sampler: NeighborSampler = None):
+                 initial_pe: torch.Tensor, start: int = 0, stop: int = None, device=None, sampler: NeighborSampler = None,
+                 history: str = "ring", event_capacity: int = None):
+        """history: "ring" = dense ring of the owned nodes' snapshots (V1/G x T rows); "changelog" = change-log history of the
+        owned nodes (csrc/changelog.cu: V1/G base rows + the owned rows every step changed), which holds T = 100 for the
+        10 M-node graph on ONE GPU and writes ~9 MB per step instead of one row per owned node."""
+        assert history in ("ring", "changelog")
+        self.history = history
         self.m, self.rank, self.G = model, int(rank), int(world)
         self.dev = dev = torch.device(device) if device is not None else model._dev()
         self.B, self.K, self.T = int(batch_size), int(num_neighbors), model.num_fft_batches
@@ -408,11 +414,32 @@ class ReplicatedTableRank:
             self._cur_full[self.V1].zero_()
             self.cur = self._cur_full[:self.V1]
             self.rows_local = (self.V1 - self.rank + self.G - 1) // self.G  # owned node ids: rank, rank + G, ...
-            self.ring = torch.zeros((max(self.rows_local, 1), self.T, self.d), dtype=torch.float32, device=dev)
             self.head, self.len = 0, 1
-            _lib.check(lib.lstep_ring_copy_rows(_lib.ptr(self.ring), _lib.ptr(self.cur), self.rows_local, self.T, self.d, 0, self.G, self.rank, 1,
-                                                _lib.stream_ptr()), "ring init")
-            self.desc = _lib.PEStreamDesc(self.src.data_ptr(), self.dst.data_ptr(), self.tt.data_ptr(), self.ring.data_ptr(), self.cur.data_ptr(),
+            if history == "ring":
+                self.ring = torch.zeros((max(self.rows_local, 1), self.T, self.d), dtype=torch.float32, device=dev)
+                _lib.check(lib.lstep_ring_copy_rows(_lib.ptr(self.ring), _lib.ptr(self.cur), self.rows_local, self.T, self.d, 0, self.G, self.rank, 1,
+                                                    _lib.stream_ptr()), "ring init")
+                ring_ptr = self.ring.data_ptr()
+            else:
+                if self.T > 128:
+                    raise _lib.LstepError("the change-log history supports T <= 128 window steps")
+                T, d = self.T, self.d
+                cap = event_capacity if event_capacity is not None else min(self.rows_local, 2 * (2 * int(batch_size) * (self.K + 1) + 2) // self.G + 1024)
+                self.cap = cap = int(max(cap, 1))
+                H = 1
+                while H < 2 * cap:
+                    H *= 2
+                self.base = self.cur[self.rank::self.G].contiguous().clone()
+                self.ev_node = torch.zeros((T, cap), dtype=torch.int32, device=dev)
+                self.ev_row = torch.empty((T, cap, d), dtype=torch.float32, device=dev)
+                self.ev_cnt = torch.zeros(T, dtype=torch.int32, device=dev)
+                self.ev_hash = torch.full((T, H), -1, dtype=torch.int64, device=dev)
+                self.ev_mask = torch.zeros((max(self.rows_local, 1), 4), dtype=torch.int32, device=dev)
+                self.cl = _lib.ChangeLog(self.base.data_ptr(), self.ev_node.data_ptr(), self.ev_row.data_ptr(), self.ev_cnt.data_ptr(),
+                                         self.ev_hash.data_ptr(), self.ev_mask.data_ptr(), max(self.rows_local, 1), T, cap, H, d, self.G, self.rank)
+                self.ring = None
+                ring_ptr = None
+            self.desc = _lib.PEStreamDesc(self.src.data_ptr(), self.dst.data_ptr(), self.tt.data_ptr(), ring_ptr, self.cur.data_ptr(),
                                           self.V1, self.T, self.d)
             # ---- per-batch plan of the resident stream [start, stop): one pass on the host, uploaded once
             B, G = self.B, self.G
@@ -432,7 +459,7 @@ class ReplicatedTableRank:
                 for g in range(G):
                     scat[g, :counts[g]] = ids[own == g]
                 ids_l.append(ids)
-                mine_l.append(ids[own == self.rank] // G)  # rows of the local ring
+                mine_l.append(ids[own == self.rank] // G if history == "ring" else ids[own == self.rank])  # ring rows / global ids
                 scat_l.append(scat.reshape(-1))
                 self.ids_off.append(self.ids_off[-1] + len(ids))
                 self.mine_off.append(self.mine_off[-1] + len(mine_l[-1]))
@@ -472,8 +499,12 @@ class ReplicatedTableRank:
             if n_mine:
                 Gt = self.m._collapsed_filter(bmask, False)
                 loc = self.mine_local[self.mine_off[b]:self.mine_off[b + 1]]
-                _lib.check(lib.lstep_dft_filter(_lib.ptr(self.ring), T * d, d, self.head, T, self.len, d, _lib.ptr(loc), n_mine, _lib.ptr(Gt),
-                                                _lib.ptr(send), d, _lib.stream_ptr()), "dft_filter")
+                if self.history == "ring":
+                    _lib.check(lib.lstep_dft_filter(_lib.ptr(self.ring), T * d, d, self.head, T, self.len, d, _lib.ptr(loc), n_mine, _lib.ptr(Gt),
+                                                    _lib.ptr(send), d, _lib.stream_ptr()), "dft_filter")
+                else:
+                    _lib.check(lib.lstep_changelog_filter(ctypes.byref(self.cl), self.head, self.len, _lib.ptr(loc), n_mine, _lib.ptr(Gt), _lib.ptr(send),
+                                                          d, None, _lib.stream_ptr()), "changelog_filter")
         return send
 
     # ---- p2: scatter the gathered rows, run this rank's share of the step, append the owned rows ---------------------------
@@ -491,6 +522,17 @@ class ReplicatedTableRank:
                 out = torch.empty((max(C, 1), q_rows, d), dtype=torch.float32, device=self.dev)
             ids = self.ids[self.ids_off[b]:self.ids_off[b + 1]]
             qptrs = (ctypes.c_void_p * max(C, 1))(*[q.data_ptr() + 8 * q_off for q in queries])
+            if self.history == "changelog":  # step + retire / append of the owned rows' events (phase 2: the filter is done)
+                _lib.check(lib.lstep_pe_step_changelog(ctypes.byref(self.desc), ctypes.byref(self.cl), self.sampler.csr_ref, lo, n, _lib.ptr(ids),
+                                                       ids.shape[0], self.tmax[b], self.head, self.len, None, qptrs, C, q_off, q_rows, _lib.ptr(out),
+                                                       self.K, self.m._mlp_ref("nbr"), self.m._mlp_ref("update"), _lib.ptr(self.ws), self.ws.numel(),
+                                                       _lib.ptr(self.sampler._err), _lib.stream_ptr(), 2), "lstep_pe_step_changelog")
+                if self.len < T:
+                    self.len += 1
+                else:
+                    self.head = (self.head + 1) % T
+                self.batch_idx += 1
+                return out
             _lib.check(lib.lstep_pe_step_sharded(ctypes.byref(self.desc), self.sampler.csr_ref, lo, n, _lib.ptr(ids), ids.shape[0], self.tmax[b],
                                                  qptrs, C, q_off, q_rows, _lib.ptr(out), self.K, self.m._mlp_ref("nbr"), self.m._mlp_ref("update"),
                                                  _lib.ptr(self.ws), self.ws.numel(), _lib.ptr(self.sampler._err), _lib.stream_ptr()),
@@ -504,8 +546,29 @@ class ReplicatedTableRank:
         self.batch_idx += 1
         return out
 
+    def check_errors(self):
+        flag = int(self.sampler._err.item())
+        if flag & _lib.FLAG_CHANGELOG_FULL:
+            self.sampler._err.zero_()
+            raise _lib.LstepError(f"a step changed more owned rows than the change-log history's event capacity ({self.cap})")
+        self.sampler.check_errors()
+
+    def history_bytes(self) -> int:
+        ts = (self.ring,) if self.history == "ring" else (self.base, self.ev_node, self.ev_row, self.ev_cnt, self.ev_hash, self.ev_mask)
+        return sum(t.numel() * t.element_size() for t in ts)
+
     def export_history_rows(self) -> torch.Tensor:
         """[rows_local, len, d], oldest first: row l = node l * G + rank."""
+        if self.history == "changelog":
+            snap = self.base.clone()
+            out = torch.empty((self.rows_local, self.len, self.d), dtype=torch.float32, device=self.dev)
+            cnt = self.ev_cnt.cpu().tolist()
+            for f in range(self.len):
+                slot = (self.head + f) % self.T
+                if cnt[slot]:
+                    snap[(self.ev_node[slot, :cnt[slot]].long() - self.rank) // self.G] = self.ev_row[slot, :cnt[slot]]
+                out[:, f, :] = snap[:self.rows_local]
+            return out
         idx = (self.head + torch.arange(self.len, device=self.dev)) % self.T
         return self.ring.index_select(1, idx)[:self.rows_local]
 

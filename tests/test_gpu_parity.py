@@ -901,6 +901,41 @@ def test_identical_query_sets_are_computed_once_with_identical_results(torch_cud
         assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
 
 
+@pytest.mark.parametrize("world", [1, 3])
+def test_replicated_table_sharded_changelog_matches_single_gpu_changelog(torch_cuda, world):
+    """Same layout with the owners' history kept as a change log: every replica's table, each rank's share of the outputs and
+    the owners' replayed history rows are BIT-identical to the single-GPU ChangeLogStream (same kernels, same inputs; the
+    owner-local filter maps global ids to local rows)."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import ChangeLogStream, NeighborSampler, ReplicatedLocalGroup, ReplicatedTableRank
+    g = synth.make_graph("tiny_bip", seed=4, num_nodes=300, num_edges=9000)
+    V, d, K, B = g.num_nodes, 172, 20, 48
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin("fullu", g, s, 172, d, 100, 100, K)[0].eval()
+    init = torch.from_numpy(seeded_normal(17, (V + 1, d), 0.3)).cuda()
+    init[0] = 0
+    e0 = g.num_edges - 115 * B - 7
+    st = ChangeLogStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=init.clone(), start=e0)
+    ranks = [ReplicatedTableRank(lstep, r, world, g.src_node_ids, g.dst_node_ids, g.node_interact_times, V, B, K, init.clone(), start=e0, sampler=s,
+                                 history="changelog") for r in range(world)]
+    grp = ReplicatedLocalGroup(ranks)
+    neg = torch.from_numpy(np.random.default_rng(3).integers(1, V + 1, g.num_edges - e0).astype(np.int64)).cuda()
+    for b in range(st.num_batches):
+        lo, hi, _, _ = st.batch_arrays(b)
+        qs = [st.src[lo:hi], st.dst[lo:hi], st.src[lo:hi], neg[lo - e0:hi - e0].contiguous()]
+        want = st.step(b, qs)
+        got = torch.cat(grp.step(b, qs), dim=1)
+        assert torch.equal(got, want), b
+    for rk in ranks:
+        assert torch.equal(rk.cur, st.cur), rk.rank
+        rk.check_errors()
+    h = st.export_history()
+    for rk in ranks:
+        assert torch.equal(rk.export_history_rows(), h[rk.rank::world]), rk.rank
+    assert sum(rk.history_bytes() for rk in ranks) < 1.3 * st.history_bytes() + 4e6
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 8])
 def test_replicated_table_sharded_history_is_bit_identical_to_single_gpu(torch_cuda, world):
     """The scale-out layout (history ring sharded by node id, table and CSR replicated, one all-gather of the filtered rows
@@ -940,14 +975,16 @@ def test_replicated_table_sharded_history_is_bit_identical_to_single_gpu(torch_c
     s.check_errors()
 
 
-@pytest.mark.parametrize("tag,Th0", [("small", 1), ("full", 1), ("full", 100)])
-def test_changelog_history_matches_dense_ring(torch_cuda, tag, Th0, parity_log):
+@pytest.mark.parametrize("tag,Th0,bar", [("small", 1, 1e-5), ("fullu", 1, 1e-5), ("fullu", 100, 1e-5), ("full", 1, 3e-4)])
+def test_changelog_history_matches_dense_ring(torch_cuda, tag, Th0, bar, parity_log):
     """ChangeLogStream (history = base rows + the rows every step changed; csrc/changelog.cu) against the dense-ring PEStream
     on the same stream: through the filling (masked) regime and the steady regime with retiring events, from an initial
     table (Th0 = 1) and from an imported dense history in which every row differs between snapshots (Th0 = T). The filter
     sums the same products in another grouping (span sums of G), so values agree to fp32 rounding, not bit for bit:
-    outputs and tables within 1e-5 (every element), and the history the log replays equals the ring's, snapshot by
-    snapshot, to the same bar. The log must also stay well below the dense ring's size."""
+    two FREE-RUNNING recurrences are compared, so the bar is 1e-5 (every element of outputs, tables and replayed
+    history) for the small model and the realistic weights, and 3e-4 for the stress weights (x2), where update_pe is
+    ill-conditioned on row 0 / hub rows (profiles/r02_parity_errors.json: the fp32 reference itself is up to 4.7e-5
+    from float64 after ONE step there) and any 1e-7 difference in the filter is amplified step after step."""
     torch = torch_cuda
     from harness import build_dropin
     from lstep_b200 import ChangeLogStream, NeighborSampler, PEStream
@@ -971,17 +1008,17 @@ def test_changelog_history_matches_dense_ring(torch_cuda, tag, Th0, parity_log):
         lo, hi, _, _ = a.batch_arrays(i)
         qs = [a.src[lo:hi], a.dst[lo:hi], neg[i][:hi - lo].contiguous()]
         oa, ob = a.step(i, qs), b.step(i, qs)
-        ok, w = pe_close(ob.cpu().numpy(), oa.cpu().numpy())
+        ok, w = pe_close(ob.cpu().numpy(), oa.cpu().numpy(), bar)
         worst_out = max(worst_out, w)
         assert ok, (i, "outputs", w)
-        ok, w = pe_close(b.cur.cpu().numpy(), a.cur.cpu().numpy())
+        ok, w = pe_close(b.cur.cpu().numpy(), a.cur.cpu().numpy(), bar)
         worst_tab = max(worst_tab, w)
         assert ok, (i, "table", w)
         assert (a.head, a.len) == (b.head, b.len)
     b.check_errors()
     ha, hb = a.export_history(), b.export_history()
     assert ha.shape == hb.shape
-    ok, w = pe_close(hb.cpu().numpy(), ha.cpu().numpy())
+    ok, w = pe_close(hb.cpu().numpy(), ha.cpu().numpy(), bar)
     assert ok, ("history", w)
     assert torch.equal(hb[:, -1, :], b.cur)
     parity_log[f"changelog/{tag}/Th0={Th0}"] = {"steps": n_steps, "worst_output": worst_out, "worst_table": worst_tab, "history": w,
