@@ -325,7 +325,8 @@ def run_sharded(args, rank, world, own_pg=True):
     torch.cuda.synchronize()
     t_gen = time.time() - t0
     if world > 1:  # every rank must hold the same stream
-        ck = torch.stack([src.sum().double(), dst.sum().double(), tt.sum()])
+        # exact integer checksums (a floating-point sum of 1e8 doubles may be reduced in another order on another device)
+        ck = torch.stack([src.sum(), dst.sum(), tt.view(torch.int64).sum(), src[::1009].sum() ^ dst[::1013].sum()])
         lo_, hi_ = ck.clone(), ck.clone()
         dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
