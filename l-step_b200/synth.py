@@ -125,9 +125,11 @@ def unique_batch_nodes(src: np.ndarray, dst: np.ndarray) -> np.ndarray:
 def make_scaleout_device(num_nodes: int, num_edges: int, device, seed: int = 0, zipf_s: float = 0.8, t_span: float = 2.68e6,
                          chunk: int = 50_000_000):
     """The scale-out edge stream (BASELINE config 5) generated ON the device — 5e8 edges are 12 GB and take minutes with
-    numpy on the host, and every rank of a group needs the same stream: a seeded CUDA generator gives every rank (same
-    GPU type, same call sequence) the same tensors. Same construction as make_graph: endpoints = truncated Zipf(s) over a
-    random permutation of the ids 1..V, timestamps = sorted uniform float64. Returns (src, dst, t) device tensors."""
+    numpy on the host, and every rank of a group needs the same stream: a seeded CUDA Philox generator gives every rank
+    the same uniform draws (torch.randperm on the device is NOT reproducible across GPUs — measured: ranks disagreed — so
+    the popularity ranks are scattered over the ids by an affine bijection instead of a random permutation). Otherwise the
+    construction of make_graph: endpoints = truncated Zipf(s) over scrambled ids 1..V, timestamps = sorted uniform
+    float64. Returns (src, dst, t) device tensors."""
     import torch
     dev = torch.device(device)
     gen = torch.Generator(device=dev).manual_seed(seed)
@@ -136,17 +138,20 @@ def make_scaleout_device(num_nodes: int, num_edges: int, device, seed: int = 0, 
     cdf /= cdf[-1].clone()
     del ranks
     out = []
-    for _ in range(2):
-        perm = torch.randperm(num_nodes, generator=gen, device=dev)
+    import math
+    for side in range(2):
+        mul = 7_368_787 + 2 * side  # affine bijection rank -> id: (mul * r + add) mod V with gcd(mul, V) = 1
+        while math.gcd(mul, num_nodes) != 1:
+            mul += 2
+        add = (1_234_567 * (seed + 1) + 7_654_321 * side) % num_nodes
         ids = torch.empty(num_edges, dtype=torch.int64, device=dev)
         for lo in range(0, num_edges, chunk):
             hi = min(lo + chunk, num_edges)
             u = torch.rand(hi - lo, generator=gen, device=dev, dtype=torch.float64)
             r = torch.searchsorted(cdf, u).clamp_(max=num_nodes - 1)
-            ids[lo:hi] = perm[r] + 1
+            ids[lo:hi] = (r * mul + add) % num_nodes + 1
             del u, r
         out.append(ids)
-        del perm
     del cdf
     t = torch.rand(num_edges, generator=gen, device=dev, dtype=torch.float64).mul_(t_span)
     t = torch.sort(t).values
