@@ -133,10 +133,13 @@ def make_scaleout_device(num_nodes: int, num_edges: int, device, seed: int = 0, 
     import torch
     dev = torch.device(device)
     gen = torch.Generator(device=dev).manual_seed(seed)
-    ranks = torch.arange(1, num_nodes + 1, dtype=torch.float64, device=dev)
-    cdf = torch.cumsum(ranks.pow_(-zipf_s), 0)
-    cdf /= cdf[-1].clone()
-    del ranks
+    # the CDF on the host (a parallel prefix sum on the device rounds differently from run to run / device to device —
+    # measured: the low bits differed between two GPUs — and a draw next to a CDF step would then pick another node)
+    p = np.arange(1, num_nodes + 1, dtype=np.float64) ** (-zipf_s)
+    cdf_h = np.cumsum(p)
+    cdf_h /= cdf_h[-1]
+    cdf = torch.from_numpy(cdf_h).to(dev)
+    del p, cdf_h
     out = []
     import math
     for side in range(2):
