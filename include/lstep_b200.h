@@ -365,12 +365,14 @@ void lstep_host_stepper_bytes(const lstep_host_stepper* h, uint64_t* h2d_bytes, 
 /* A run of consecutive batches in one call (an evaluation split, evaluate_model_utils.py:38-142): the loop over
  * lstep_pe_step_host / lstep_host_step_result is done natively, results read one step behind. Full history ring only
  * (*len_io == T, one collapsed filter G); batch b = edges [b*batch_size, min((b+1)*batch_size, n_total)) of the host
- * arrays; results_host [n_batches][n_queries][batch_size]; *head_io is advanced. Synchronous on return. */
+ * arrays; results_host [n_batches][n_queries][batch_size]; *head_io is advanced. Synchronous on return.
+ * On an error in batch k (e.g. LSTEP_ERR_ID_RANGE) batches [0, k) HAVE been applied: *head_io and *n_done_out (may be
+ * NULL) report the ring position reached and the number of batches applied, so the caller's state stays consistent. */
 int lstep_pe_steps_host(lstep_host_stepper* h, const lstep_pe_stream* s, const lstep_csr* csr, int64_t n_total,
                         int64_t batch_size, const int64_t* src_host, const int64_t* dst_host, const double* t_host,
                         const int64_t* const* query_ids_host_arrays, int n_queries, int* head_io, int* len_io,
                         const float* G, int K, const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace,
-                        size_t workspace_bytes, uint32_t* err_flag, void* stream, float* results_host);
+                        size_t workspace_bytes, uint32_t* err_flag, void* stream, float* results_host, int64_t* n_done_out);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement / A-B plumbing (no reference counterpart).

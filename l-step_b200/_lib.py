@@ -102,7 +102,8 @@ _SIGS = {
                                  C.POINTER(C.c_void_p), i32, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp,
                                  C.POINTER(i64)]),
     "lstep_pe_steps_host": (i32, [vp, C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, i64, vp, vp, vp, C.POINTER(C.c_void_p), i32,
-                                  C.POINTER(i32), C.POINTER(i32), vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp, vp]),
+                                  C.POINTER(i32), C.POINTER(i32), vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp, vp,
+                                  C.POINTER(i64)]),
     "lstep_host_step_result": (i32, [vp, i64, C.POINTER(C.POINTER(C.c_float)), C.POINTER(i64)]),
     "lstep_host_stepper_bytes": (None, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }

@@ -314,7 +314,8 @@ extern "C" int lstep_pe_steps_host(lstep_host_stepper* h, const lstep_pe_stream*
                                    const int64_t* const* query_ids_host_arrays, int n_queries, int* head_io, int* len_io,
                                    const float* G, int K, const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd,
                                    void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream,
-                                   float* results_host) {
+                                   float* results_host, int64_t* n_done_out) {
+  if (n_done_out) *n_done_out = 0;
   if (!h || !s || !head_io || !len_io || !results_host || n_total < 0 || batch_size <= 0 || batch_size > h->max_edges)
     return LSTEP_ERR_INVALID_ARG;
   if (n_queries < 0 || n_queries > 8 || (n_queries > 0 && !query_ids_host_arrays)) return LSTEP_ERR_INVALID_ARG;
@@ -339,17 +340,29 @@ extern "C" int lstep_pe_steps_host(lstep_host_stepper* h, const lstep_pe_stream*
     // full ring: the oldest slot (head) is overwritten, then becomes the newest
     int rc = lstep_pe_step_host(h, s, csr, n, src_host + lo, dst_host + lo, t_host + lo, nullptr, 0, head, s->T, head, G, q, n_queries,
                                 nullptr, K, mlp_nbr, mlp_upd, workspace, workspace_bytes, err_flag, stream, &ticket);
-    if (rc != LSTEP_OK) return rc;
+    if (rc != LSTEP_OK) {
+      // batches [0, b) HAVE been applied to the ring: report the position reached (head, and the count in *len_io's place is
+      // not possible — len stays T — so the caller derives it from the returned head and n_done below) and drain the pending result
+      if (pending >= 0) (void)collect(pending, pending_b, pending_n);
+      *head_io = head;
+      if (n_done_out) *n_done_out = b;
+      return rc;
+    }
     head = (head + 1) % s->T;
-    if (pending >= 0 && (rc = collect(pending, pending_b, pending_n)) != LSTEP_OK) return rc;
+    if (pending >= 0 && (rc = collect(pending, pending_b, pending_n)) != LSTEP_OK) {
+      *head_io = head;
+      if (n_done_out) *n_done_out = b + 1;
+      return rc;
+    }
     pending = ticket;
     pending_b = b;
     pending_n = n;
   }
+  *head_io = head;
+  if (n_done_out) *n_done_out = b;
   if (pending >= 0) {
     const int rc = collect(pending, pending_b, pending_n);
     if (rc != LSTEP_OK) return rc;
   }
-  *head_io = head;
   return LSTEP_OK;
 }

@@ -190,9 +190,8 @@ class LSTEP(nn.Module):
             raise IndexError(f"{what}: index out of range (table has {limit} rows)")
 
     def _packed_mlp(self, which: str) -> "_lib.PEMLP":
-        names = {"update": ("pe_mlp_1", "pe_mlp_2", "self_update_pe"),
-                 "nbr": ("pe_neighbor_mlp_1", "pe_neighbor_mlp_2", "self_update_neighbor_pe")}[which]
-        params = [p for n in names for p in (getattr(self, n).weight, getattr(self, n).bias)] + [self.time_encoder.w.weight]
+        names = self._MLP_NAMES[which]
+        params = self._mlp_params(which)
         key = tuple((p.data_ptr(), p._version) for p in params)
         hit = self._pack_cache.get(which)
         if hit is not None and hit[0] == key:
@@ -224,22 +223,43 @@ class LSTEP(nn.Module):
         self._pack_cache[which] = entry
         return st
 
+    _MLP_NAMES = {"update": ("pe_mlp_1", "pe_mlp_2", "self_update_pe"),
+                  "nbr": ("pe_neighbor_mlp_1", "pe_neighbor_mlp_2", "self_update_neighbor_pe")}
+
+    def invalidate_packed_weights(self):
+        """Drop the packed copies of the PE-MLP weights and the collapsed DFT filters. Needed only after an in-place edit
+        THROUGH `.data` (p.data.mul_(...), p.data.copy_(...)), which changes neither the tensor's version counter nor
+        its address; every other change (optimizer steps, load_state_dict, .to(), replacing a submodule or a Parameter)
+        is detected on the next call."""
+        self._pack_cache.clear()
+        self._pack_fast.clear()
+        self._filter_cache.clear()
+
+    def _mlp_params(self, which: str):
+        # the LIVE Parameter objects, fetched without nn.Module.__getattr__'s fallback chain
+        mods = self._modules
+        out = []
+        for n in self._MLP_NAMES[which]:
+            p = mods[n]._parameters
+            out += [p["weight"], p["bias"]]
+        out.append(mods["time_encoder"]._modules["w"]._parameters["weight"])
+        return out
+
     def _mlp_ref(self, which: str):
-        # fast path (two calls per step on the streaming API): the parameter tensors are remembered, and a packed copy is
-        # reused while none of them has been modified in place (the tuple of _version counters is unchanged). Every
-        # 64th call also compares the storage addresses (a parameter moved by .to() / .data assignment keeps its version).
+        # fast path (two calls per step on the streaming API): a packed copy is reused while every live parameter is the
+        # same object at the same address with the same version counter — seven identity / integer compares per call, so
+        # .to(), .data = assignment, load_state_dict, in-place optimizer steps and replaced submodules are all seen at once
+        # (ADVICE r1). In-place edits through .data change none of those: call invalidate_packed_weights().
         fast = self._pack_fast.get(which)
         if fast is not None:
-            params, key, ref, vers = fast
-            self._pack_calls += 1
-            if tuple(p._version for p in params) == vers and (self._pack_calls & 63 or all(p.data_ptr() == q for p, (q, _) in zip(params, key))):
+            params, sig, ref = fast
+            live = self._mlp_params(which)
+            if all(a is b for a, b in zip(live, params)) and tuple((p.data_ptr(), p._version) for p in live) == sig:
                 return ref
         self._packed_mlp(which)
-        names = {"update": ("pe_mlp_1", "pe_mlp_2", "self_update_pe"),
-                 "nbr": ("pe_neighbor_mlp_1", "pe_neighbor_mlp_2", "self_update_neighbor_pe")}[which]
-        params = [p for n in names for p in (getattr(self, n).weight, getattr(self, n).bias)] + [self.time_encoder.w.weight]
         entry = self._pack_cache[which]
-        self._pack_fast[which] = (params, entry[0], entry[3], tuple(v for _, v in entry[0]))
+        params = self._mlp_params(which)
+        self._pack_fast[which] = (params, tuple((p.data_ptr(), p._version) for p in params), entry[3])
         return entry[3]
 
     # ---- a3: DFT filter ---------------------------------------------------------------------
@@ -475,6 +495,10 @@ class LSTEP(nn.Module):
         src, dst = np.asarray(batch_src_node_ids), np.asarray(batch_dst_node_ids)
         times = np.asarray(node_interact_times)
         n_ids, n_edges = len(node_ids), len(src)
+        if n_ids > 1 and not bool(np.all(node_ids[1:] > node_ids[:-1])) and len(np.unique(node_ids)) != n_ids:
+            # phase A runs in place on pe[node_ids]: a duplicate id would let one row be read after another block rewrote it
+            # (the reference's callers always pass torch.unique()'d ids: evaluate_model_utils.py:54-55, train:221-222)
+            raise ValueError("update_pe: node_ids must be unique")
         if len(dst) != n_edges or len(times) != n_edges:
             raise RuntimeError("batch_src_node_ids, batch_dst_node_ids and node_interact_times must have the same length")
         for a, what in ((node_ids, "node_ids"), (src, "batch_src_node_ids"), (dst, "batch_dst_node_ids")):

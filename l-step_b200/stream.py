@@ -70,6 +70,8 @@ class PEStream:
         self.batch_tmax = [float(self.t_np[lo:min(lo + self.B, self.stop)].max()) for lo in self.batch_lo]
         self._host_stepper = None
         self._ticket_shape = {}
+        self._drained = {}  # public ticket -> result read out before its stepper was replaced
+        self._epoch = 0
         self._libc = _lib.load()
         self.V1 = None
         self.batch_idx = 0
@@ -256,7 +258,14 @@ class PEStream:
         st = self._host_stepper
         if st is None or st[1] < n_edges or st[2] < C:
             if st is not None:
+                # a larger batch / more query sets than the stepper was sized for: results of tickets still outstanding
+                # are read out first (the native ticket numbering restarts with the new stepper; public tickets carry the
+                # stepper's epoch so an old one can never alias a new one)
+                for tk in sorted(self._ticket_shape)[-self.HOST_SLOTS:]:  # older ones: result slot already reused
+                    self._drained[tk] = self._result_now(tk)
+                self._ticket_shape.clear()
                 lib.lstep_host_stepper_destroy(st[0])
+                self._epoch += 1
             h = C_void_p()
             cap_e, cap_c = max(self.B, n_edges), max(C, 4)
             with torch.cuda.device(self.dev):
@@ -331,9 +340,10 @@ class PEStream:
         self.head, self.len = new_head, new_len
         self.batch_idx = bi + 1
         self.steps_done += 1
-        tk = ticket.value
+        tk = (self._epoch << 32) | ticket.value
         self._ticket_shape[tk] = (C, n)
-        self._ticket_shape.pop(tk - 2 * self.HOST_SLOTS, None)
+        self._ticket_shape.pop(tk - self.HOST_SLOTS, None)
+        self._drained.pop(tk - 2 * self.HOST_SLOTS, None)
         m.h2d_bytes += 8 * n * (5 + C)  # what lstep_pe_step_host copies: src, dst, t, <= 2n ids, C query sets
         return tk
 
@@ -372,27 +382,36 @@ class PEStream:
         G = m._collapsed_filter(self.T, False)
         ws = self._workspace(2 * B, B, C)
         qptrs = (C_void_p * max(C, 1))(*[q[lo:].ctypes.data for q in qs])
-        head, ln = ctypes.c_int(self.head), ctypes.c_int(self.len)
+        head, ln, done = ctypes.c_int(self.head), ctypes.c_int(self.len), ctypes.c_int64(0)
         sub = res[lo // B:]
         samp = m.neighbor_sampler
         rc = lib.lstep_pe_steps_host(h, self._desc_ref, samp.csr_ref, n_total - lo, B, src[lo:].ctypes.data, dst[lo:].ctypes.data,
                                      times[lo:].ctypes.data, qptrs, C, C_byref(head), C_byref(ln), G.data_ptr(), self.K,
                                      m._mlp_ref("nbr"), m._mlp_ref("update"), ws.data_ptr(), ws.numel(), samp._err.data_ptr(),
-                                     torch.cuda.current_stream().cuda_stream, sub.ctypes.data)
-        if rc != 0:
-            _lib.check(rc, "lstep_pe_steps_host")
-        steps = (n_total - lo + B - 1) // B
+                                     torch.cuda.current_stream().cuda_stream, sub.ctypes.data, C_byref(done))
+        # batches applied before an error stay applied: the host-side ring position follows the device ring either way
+        steps = done.value
         self.head = head.value
         self.batch_idx += steps
         self.steps_done += steps
-        m.h2d_bytes += 8 * (n_total - lo) * (5 + C)
+        m.h2d_bytes += 8 * min(steps * B, n_total - lo) * (5 + C)
+        if rc != 0:
+            _lib.check(rc, "lstep_pe_steps_host")
         return res
 
     def result(self, ticket: int) -> np.ndarray:
         """Per-query row sums [C, n] of step `ticket` (waits for that step's device-to-host copy)."""
+        r = self._drained.pop(ticket, None)
+        if r is not None:
+            return r
+        if ticket >> 32 != self._epoch or ticket not in self._ticket_shape:
+            raise KeyError(f"result: ticket {ticket} is not outstanding (already read, or overwritten: the last {self.HOST_SLOTS} are kept)")
+        return self._result_now(ticket)
+
+    def _result_now(self, ticket: int) -> np.ndarray:
         p = ctypes.POINTER(ctypes.c_float)()
         nf = ctypes.c_int64(0)
-        rc = self._libc.lstep_host_step_result(self._host_stepper[0], ticket, C_byref(p), C_byref(nf))
+        rc = self._libc.lstep_host_step_result(self._host_stepper[0], ticket & 0xFFFFFFFF, C_byref(p), C_byref(nf))
         if rc != 0:
             _lib.check(rc, "lstep_host_step_result")
         C, n = self._ticket_shape[ticket]
