@@ -556,23 +556,24 @@ def test_run_host_error_midway_keeps_host_state_in_step_with_the_ring(torch_cuda
     from harness import build_dropin
     from lstep_b200 import NeighborSampler, PEStream
     g = synth.make_graph("tiny_bip", seed=8)
-    V, d, T, K, B = g.num_nodes, 172, 6, 20, 16
+    V, d, T, K, B = g.num_nodes, 172, 100, 20, 16
     s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
     lstep = build_dropin("full", g, s, 172, d, 100, T, K)[0].eval()
     init = seeded_normal(17, (V + 1, d), 0.3)
     init[0] = 0
-    e0 = g.num_edges - 30 * B
+    e0 = g.num_edges - 122 * B
+    NF = 104  # good batches first: the ring (T = 100) is full after 99 of them
     mk = lambda: PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=torch.from_numpy(init).cuda(), start=e0)
     a, b = mk(), mk()
     src, dst, tt = g.src_node_ids[e0:].copy(), g.dst_node_ids[e0:].copy(), g.node_interact_times[e0:]
-    fill = 8 * B  # ring (T = 6) is full after 5 steps; 8 good batches first
+    fill = NF * B
     b.run_host(src[:fill], dst[:fill], tt[:fill], [src[:fill]])
     k_bad = 5
     bad = src.copy()
     bad[fill + k_bad * B + 3] = V + 11
     with pytest.raises(IndexError):
         b.run_host(bad[fill:fill + 10 * B], dst[fill:fill + 10 * B], tt[fill:fill + 10 * B], [src[fill:fill + 10 * B]])
-    for i in range(8 + k_bad):
+    for i in range(NF + k_bad):
         lo, hi, _, _ = a.batch_arrays(i)
         a.step(i, [a.src[lo:hi]])
     assert (b.head, b.len, b.batch_idx, b.steps_done) == (a.head, a.len, a.batch_idx, a.steps_done)
@@ -580,7 +581,7 @@ def test_run_host_error_midway_keeps_host_state_in_step_with_the_ring(torch_cuda
     # both continue from there
     lo = fill + k_bad * B
     got = b.run_host(src[lo:lo + 3 * B], dst[lo:lo + 3 * B], tt[lo:lo + 3 * B], [src[lo:lo + 3 * B]])
-    for i in range(8 + k_bad, 8 + k_bad + 3):
+    for i in range(NF + k_bad, NF + k_bad + 3):
         l2, h2, _, _ = a.batch_arrays(i)
         out = a.step(i, [a.src[l2:h2]])
     np.testing.assert_allclose(got[-1, 0], out[0].sum(dim=1).cpu().numpy(), rtol=1e-5, atol=1e-5)
