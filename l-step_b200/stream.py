@@ -261,8 +261,11 @@ class PEStream:
                 # a larger batch / more query sets than the stepper was sized for: results of tickets still outstanding
                 # are read out first (the native ticket numbering restarts with the new stepper; public tickets carry the
                 # stepper's epoch so an old one can never alias a new one)
-                for tk in sorted(self._ticket_shape)[-self.HOST_SLOTS:]:  # older ones: result slot already reused
-                    self._drained[tk] = self._result_now(tk)
+                for tk in sorted(self._ticket_shape):
+                    try:
+                        self._drained[tk] = self._result_now(tk)
+                    except ValueError:  # result slot already reused by later steps (e.g. a run_host call): nothing to keep
+                        pass
                 self._ticket_shape.clear()
                 lib.lstep_host_stepper_destroy(st[0])
                 self._epoch += 1
