@@ -298,16 +298,16 @@ def run_ours(args, rank, world, own_pg=True):
 
 
 def run_sharded(args, rank, world, own_pg=True):
-    """BASELINE config 5: the scale-out graph (10 M nodes), PE history ring sharded by node id over the ranks, current table and
-    temporal CSR replicated, one NCCL all-gather of the DFT-filtered rows per step (l-step_b200/shard.py::ReplicatedTableRank).
-    The batch is replicated: every rank filters the batch nodes whose history it owns (1/N of the filter's HBM traffic),
-    computes its 1/N share of the neighbourhood queries and runs update_pe in full, so the work per rank shrinks with N only
-    in those two parts ("scaling": "strong"). --scaleout-history changelog (default): the owners keep the history as a change
-    log (base rows + the rows every step changed: 13 GB instead of 688 GB at T = 100), so every N — N = 1 included — runs the
-    full T = 100; --scaleout-history ring: the dense ring sharded by node id (T = 12 so that N = 1 fits). T is stated with every point."""
+    """BASELINE config 5: the scale-out graph (10 M nodes) on a PEER GROUP (l-step_b200/peer.py, csrc/peer.cu): every rank keeps a
+    replica of the current table and of the temporal CSR and owns the nodes v % N == rank — their PE history (change log: base
+    rows + the rows every step changed, 13 GB instead of 688 GB at T = 100) and 1/N of every phase of the step (DFT filter, a6
+    query rows, update_pe phase A and phase B). Owners store the rows they change into the other replicas through NVLink peer
+    pointers (CUDA IPC); two flag barriers per step in peer memory; no NCCL call and no host synchronisation on the step's
+    path. The batch is replicated, so the work per rank shrinks with N ("scaling": "strong"). The timed region is ONE native
+    call for all K steps (lstep_pe_steps_peer) queued behind a spin kernel."""
     import torch
     import torch.distributed as dist
-    from lstep_b200 import LSTEP, ReplicatedTableRank, ReplicatedTableStream, _lib
+    from lstep_b200 import LSTEP, PeerRank, _lib
 
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -316,9 +316,8 @@ def run_sharded(args, rank, world, own_pg=True):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     assert lib.lstep_device_ok() == 1
-    hist_kind = args.scaleout_history
     B, K = 2000, 20
-    T = args.scaleout_T if args.scaleout_T else (T_HIST if hist_kind == "changelog" else 12)
+    T = args.scaleout_T if args.scaleout_T else T_HIST
     V, E = args.scaleout_nodes, args.scaleout_edges
     t0 = time.time()
     src, dst, tt = synth.make_scaleout_device(V, E, dev, seed=0)
@@ -345,22 +344,28 @@ def run_sharded(args, rank, world, own_pg=True):
     e0 = int(E * 0.7) // B * B
     stop = min(E, e0 + (W + Ksteps + n_e2e + 2) * B)
     t0 = time.time()
-    rk = ReplicatedTableRank(m, rank, world, src, dst, tt, V, B, K, init, start=e0, stop=stop, history=hist_kind)
+    rk = PeerRank(m, rank, world, src, dst, tt, V, B, K, init, start=e0, stop=stop)
     del init
+    rk.connect_ipc()
     torch.cuda.synchronize()
     t_setup = time.time() - t0
-    sh = ReplicatedTableStream(rk)
     nb = rk.num_batches
-    neg_all = torch.randint(1, V + 1, (stop - e0,), device=dev, generator=torch.Generator(device=dev).manual_seed(2))
+    # negative destinations, indexed by global edge position (only [e0, stop) is read)
+    neg_all = torch.zeros(stop, dtype=torch.int64, device=dev)
+    neg_all[e0:] = torch.randint(1, V + 1, (stop - e0,), device=dev, generator=torch.Generator(device=dev).manual_seed(2))
+    q_arrays = [rk.src, rk.dst, rk.src, neg_all]
 
     def queries(b):
         lo, hi = rk.batch(b)
-        return [rk.src[lo:hi], rk.dst[lo:hi], rk.src[lo:hi], neg_all[lo - e0:hi - e0]]
+        return [rk.src[lo:hi], rk.dst[lo:hi], rk.src[lo:hi], neg_all[lo:hi]]
 
     step_no = 0
-    for _ in range(W):
-        sh.step(step_no % nb, queries(step_no % nb))
+    out = torch.empty((C_CALLS, B // world + 1, D), dtype=torch.float32, device=dev)
+    for _ in range(T + 2):  # the history fills step by step (the filter changes with its length)
+        rk.step(step_no, queries(step_no))
         step_no += 1
+    rk.run(step_no, W - (T + 2), q_arrays, out=out)  # the rest of the warm-up through the native multi-step call
+    step_no += W - (T + 2)
     torch.cuda.synchronize()
     rk.check_errors()
     if world > 1:
@@ -368,20 +373,16 @@ def run_sharded(args, rank, world, own_pg=True):
     clocks = ClockSampler(local)
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    rk.bytes_allgather = 0
-    edges = 0
     torch.cuda._sleep(int(2.0e6))  # the host queues the first steps behind a spin: the region is device-bound
     ev0.record()
-    for _ in range(Ksteps):
-        b = step_no % nb
-        sh.step(b, queries(b))
-        lo, hi = rk.batch(b)
-        edges += hi - lo
-        step_no += 1
+    rk.run(step_no, Ksteps, q_arrays, out=out)
     ev1.record()
     torch.cuda.synchronize()
+    edges = int(rk.n_edges[step_no:step_no + Ksteps].sum())
+    step_no += Ksteps
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
+    rk.check_errors()
     tm = torch.tensor([ms], device=dev)
     if world > 1:
         dist.barrier()
@@ -389,7 +390,7 @@ def run_sharded(args, rank, world, own_pg=True):
     ms_max = float(tm.item())
     value = edges / (ms_max * 1e-3)  # the batch is replicated: edges of the job, not per rank
     # end to end: the negatives of every step come from host memory and this rank's per-query row sums go back to it
-    neg_host = neg_all.cpu().numpy()
+    neg_host = neg_all[e0:].cpu().numpy()
     d2h = h2d = 0
     e_edges = 0
     if world > 1:
@@ -397,56 +398,67 @@ def run_sharded(args, rank, world, own_pg=True):
     t_wall = time.perf_counter()
     ev0.record()
     for _ in range(n_e2e):
-        b = step_no % nb
+        b = step_no
         lo, hi = rk.batch(b)
-        q_off, q_rows = rk.share(b)
         negs = torch.from_numpy(neg_host[lo - e0:hi - e0]).to(dev, non_blocking=True)
         h2d += negs.numel() * 8
-        out = sh.step(b, [rk.src[lo:hi], rk.dst[lo:hi], rk.src[lo:hi], negs])
-        r = out.sum(dim=2).cpu()
+        o = rk.step(b, [rk.src[lo:hi], rk.dst[lo:hi], rk.src[lo:hi], negs])
+        r = o.sum(dim=2).cpu()
         d2h += r.numel() * 4
         e_edges += hi - lo
         step_no += 1
     ev1.record()
     torch.cuda.synchronize()
+    rk.check_errors()
     tm = torch.tensor([max(ev0.elapsed_time(ev1), (time.perf_counter() - t_wall) * 1e3)], device=dev)
     if world > 1:
         dist.barrier()
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     e2e = {"value": e_edges / (float(tm.item()) * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d / n_e2e, "d2h_bytes_per_step": d2h / n_e2e,
-           "steps": n_e2e, "api": "ReplicatedTableStream.step per rank: the step's negative ids from host memory, this rank's per-query row "
-                                  "sums back to the host (a synchronising read every step)"}
-    x = torch.tensor([float(rk.bytes_allgather)], dtype=torch.float64, device=dev)
+           "steps": n_e2e, "api": "PeerRank.step per rank (one call per batch): the step's negative ids from host memory, this rank's "
+                                  "per-query row sums back to the host (a synchronising read every step)"}
+    # replica check: every rank's table must equal rank 0's (checksums of a strided sample + of the rows the last step changed)
+    rk.barrier()
+    torch.cuda.synchronize()
+    ck = torch.stack([rk.cur[::997].double().sum(), rk.cur[::997].double().abs().sum(), rk.cur[rk.ids[-4000:]].double().sum()])
+    lo_, hi_ = ck.clone(), ck.clone()
     if world > 1:
-        dist.all_reduce(x)
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    replicas_equal = bool(torch.equal(lo_, hi_))
+    # rows a step changes (peer stores): owned filtered rows + owned final rows go to N-1 replicas, phase-A rows to N buffers
+    n_ids_mean = float(np.diff(rk.ids_off).mean())
     free_b, total_b = torch.cuda.mem_get_info(dev)
     if rank == 0:
-        out = {
+        out_d = {
             "metric": "temporal edges/sec through PE update+aggregation; % HBM roofline", "value": value, "unit": "edges/s",
             "n_gpus": world, "steps": Ksteps, "warmup": W, "ms_per_step": ms_max / Ksteps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"scale-out synthetic temporal graph, V={V}, E={E} (Zipf 0.8 endpoints, generated on the device), B={B}, K={K}, "
                                    f"T={T}, d={D}, t={T_DIM}, C={C_CALLS}",
-                       "parallelism": f"PE history ({'change log: base rows + the rows every step changed' if hist_kind == 'changelog' else 'dense ring'}) "
-                                      f"sharded by node id over {world} GPU(s) (owner = id mod N), current table + temporal CSR "
-                                      "replicated, one NCCL all-gather of the DFT-filtered batch rows per step, a6 queries split 1/N, update_pe replicated",
+                       "parallelism": f"peer group of {world} GPU(s): node v is owned by rank v mod N (its PE history as a change log, 1/N of the DFT "
+                                      "filter, of the a6 query rows, of update_pe phase A and phase B); current table + temporal CSR replicated, "
+                                      "owners store changed rows into the other replicas over NVLink peer pointers (CUDA IPC), two flag barriers "
+                                      "per step in peer memory; no NCCL call on the step's path",
                        "l2_policy": f"inputs larger than L2: history {rk.history_bytes() / 1e9:.1f} GB per rank (dense [V1, T, d] would be "
                                     f"{(V + 1) * T * D * 4 / 1e9:.0f} GB in total), table {(V + 1) * D * 4 / 1e9:.1f} GB, CSR {2 * E * 16 / 1e9:.1f} GB"},
-            "run_info": {"graph_gen_s": t_gen, "setup_s": t_setup, "hbm_used_GB": (total_b - free_b) / 1e9, "history": hist_kind, "T": T,
-                         "nvlink_bytes_per_step_all_ranks": float(x[0].item()) / Ksteps},
+            "run_info": {"graph_gen_s": t_gen, "setup_s": t_setup, "hbm_used_GB": (total_b - free_b) / 1e9, "history": "changelog", "T": T,
+                         "timed_region": "K steps in one native call (PeerRank.run -> lstep_pe_steps_peer) queued behind a spin kernel; CUDA events, max over ranks",
+                         "batch_nodes_mean": n_ids_mean, "replicas_equal_after_run": replicas_equal},
             "clocks": clk, "e2e": e2e,
-            "gpu_launches": int(Ksteps * 7 * world),
+            "gpu_launches": int(Ksteps * 12 * world),
             "roofline": None, "cpu_baseline": None,
         }
         if own_pg:
-            emit(out)
+            emit(out_d)
     else:
-        out = None
+        out_d = None
+    rk.close()
     if own_pg and world > 1:
         dist.destroy_process_group()
-    del sh, rk, src, dst, tt, neg_all
+    del rk, src, dst, tt, neg_all
     torch.cuda.empty_cache()
-    return out
+    return out_d
 
 
 KERNELS = ["dft_filter", "gather_ab (a6 lookup+aggregate || a7 edge aggregate)", "pe_mlp pair (neighbourhood MLP || phase-A MLP)",

@@ -42,6 +42,7 @@ typedef enum lstep_status {
 #define LSTEP_FLAG_NODE_OUT_OF_RANGE 1u /* utils/utils.py:140 would raise IndexError */
 #define LSTEP_FLAG_UNSORTED_STREAM 2u
 #define LSTEP_FLAG_CHANGELOG_FULL 4u /* a step changed more rows than the change-log history has event capacity for */
+#define LSTEP_FLAG_PEER_TIMEOUT 8u   /* a peer GPU did not reach a step barrier within the time limit (peer group step) */
 
 const char* lstep_strerror(int status);
 const char* lstep_last_cuda_error(void);
@@ -336,6 +337,71 @@ int lstep_pe_step_changelog(const lstep_pe_stream* s, const lstep_changelog* cl,
                             const int64_t* const* query_ids_host, int n_queries, int64_t q_off, int64_t q_rows, float* nbr_out, int K,
                             const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
                             uint32_t* err_flag, void* stream, int phase);
+
+/* ------------------------------------------------------------------------------------------
+ * Peer group: the scale-out step over NVLink peer memory (csrc/peer.cu; BASELINE config 5).
+ * One process per GPU. Every rank keeps a REPLICA of the current PE table and of the temporal CSR and OWNS the nodes
+ * v with v % world == rank: their PE history (change log), their share of every phase of the step, and the duty to
+ * publish every row it changes. A step on rank r:
+ *     filter      DFT filter of the owned batch nodes; the filtered row is stored into EVERY replica (peer stores)
+ *     barrier 1   (flag exchange through peer memory, no host, no NCCL)
+ *     gather      a6 for this rank's 1/world share of the query rows || a7 edge aggregate of the OWNED batch nodes
+ *     MLP pair    neighbourhood MLP of the share || phase-A MLP of the owned batch nodes; the phase-A rows are stored
+ *                 into every rank's new_rows buffer at the node's position in the batch's id list
+ *     barrier 2
+ *     push        most-recent-K lookup of ALL batch nodes (replicated, cheap), accumulation only for the OWNED
+ *                 destinations (u % world == rank); the owned batch nodes' phase-A rows are applied to the local table
+ *     MLP (B)     over the owned destinations
+ *     append      the owned changed rows (owned batch nodes + owned destinations + row 0 on rank 0) become events of
+ *                 the change log AND are stored into every other replica; the next step's barrier 1 publishes them.
+ * Nothing a rank reads between two barriers is written by another rank in that interval (csrc/peer.cu states the
+ * argument), so the replicas agree at every barrier 1 and the results are those of the single-GPU step, bit for bit
+ * (phase B's sums are exact fixed point, hence independent of which rank adds them).
+ * Memory that peers write (table replica, new_rows, flags) is allocated with lstep_ipc_alloc (cudaMalloc) and shared
+ * with the CUDA IPC handles of lstep_ipc_export / lstep_ipc_open; in a single process (tests) plain device pointers of
+ * several rank states can be used instead.
+ * ------------------------------------------------------------------------------------------ */
+#define LSTEP_MAX_PEERS 16
+typedef struct lstep_peer_group {
+  int rank, world;
+  float* table[LSTEP_MAX_PEERS];     /* table replica of every rank, [V1 (+ spare rows), d]; table[rank] == s->cur */
+  float* new_rows[LSTEP_MAX_PEERS];  /* phase-A row buffer of every rank, [max batch nodes, d] */
+  uint32_t* flags[LSTEP_MAX_PEERS];  /* flag block of every rank, uint32[LSTEP_MAX_PEERS]: flags[g][r] = last barrier epoch
+                                        rank r has announced to rank g (zero-initialised, epochs start at 1) */
+} lstep_peer_group;
+int lstep_ipc_alloc(size_t bytes, void** ptr);                         /* cudaMalloc + zero fill */
+int lstep_ipc_free(void* ptr);
+int lstep_ipc_export(void* ptr, unsigned char handle_out[64]);         /* cudaIpcGetMemHandle */
+int lstep_ipc_open(const unsigned char handle[64], void** ptr);        /* cudaIpcOpenMemHandle (enables peer access) */
+int lstep_ipc_close(void* ptr);
+/* announce `epoch` to every rank / wait until every rank has announced it (bounded: after ~timeout_ms the wait gives up
+ * and raises LSTEP_FLAG_PEER_TIMEOUT in *err_flag instead of hanging the device) */
+int lstep_peer_signal(const lstep_peer_group* g, uint32_t epoch, void* stream);
+int lstep_peer_wait(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, void* stream);
+/* One step of this rank (see above). ids = the batch's sorted unique node ids (all of them, replicated); ids_mine = the owned
+ * ones, pos_mine[i] = index of ids_mine[i] in ids. The a6 query sets cover edges [q_off, q_off + q_rows) of the batch,
+ * query_ids_host[c] pointing at the first of those ids; outputs [n_queries, q_rows, d]. epoch_base: barrier 1 uses
+ * epoch_base + 1, barrier 2 epoch_base + 2 (the caller advances it by 2 per step, identically on every rank).
+ * phases: bit 0 = filter + signal 1; bit 1 = wait 1 .. signal 2; bit 2 = wait 2 .. append (7 = the whole step; a
+ * single-process group of several rank states runs each bit for every rank before the next). */
+int lstep_pe_step_peer(const lstep_pe_stream* s, const lstep_changelog* cl, const lstep_csr* csr, const lstep_peer_group* grp,
+                       int64_t lo, int64_t n_edges, const int64_t* ids, int64_t n_ids, const int64_t* ids_mine,
+                       const int64_t* pos_mine, int64_t n_mine, double current_time, int head, int len, const float* G,
+                       const int64_t* const* query_ids_host, int n_queries, int64_t q_off, int64_t q_rows, float* nbr_out, int K,
+                       const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                       uint32_t* err_flag, uint32_t epoch_base, int timeout_ms, int phases, void* stream);
+/* A run of consecutive steady-state steps (len == T) in one call: the host only pays the launches. Arrays indexed by step i:
+ * lo / n_edges / tmax; ids + ids_off[i] .. ids_off[i+1]; ids_mine / pos_mine + mine_off[i] .. mine_off[i+1]; query set c of
+ * step i = query_ids_host[c] + q_base[i] (n_edges[i] ids; this rank's share of them is taken here:
+ * [rank * n / world, (rank+1) * n / world)); outputs of step i at nbr_out + i * out_step_stride floats. *head_io and
+ * *epoch_io are advanced. */
+int lstep_pe_steps_peer(const lstep_pe_stream* s, const lstep_changelog* cl, const lstep_csr* csr, const lstep_peer_group* grp,
+                        int64_t n_steps, const int64_t* lo_host, const int64_t* n_edges_host, const double* tmax_host,
+                        const int64_t* ids, const int64_t* ids_off_host, const int64_t* ids_mine, const int64_t* pos_mine,
+                        const int64_t* mine_off_host, int* head_io, const float* G, const int64_t* const* query_ids_host,
+                        const int64_t* q_base_host, int n_queries, float* nbr_out, int64_t out_step_stride, int K,
+                        const lstep_pe_mlp* mlp_nbr, const lstep_pe_mlp* mlp_upd, void* workspace, size_t workspace_bytes,
+                        uint32_t* err_flag, uint32_t* epoch_io, int timeout_ms, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Host-fed streaming step (csrc/host_step.cu): what a loop that holds the batch as HOST arrays calls

@@ -23,6 +23,8 @@ _LAZY = {
     "ReplicatedTableRank": "shard",
     "ReplicatedLocalGroup": "shard",
     "ReplicatedTableStream": "shard",
+    "PeerRank": "peer",
+    "PeerLocalGroup": "peer",
     "LaplacianPE": "pe_init",
     "RandomWalkPE": "pe_init",
     "save_pe": "pe_init",

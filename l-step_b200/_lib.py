@@ -38,6 +38,11 @@ class ChangeLog(C.Structure):
                 ("T", i32), ("cap", i32), ("H", i32), ("d", i32), ("row_mul", i64), ("row_add", i64)]
 
 
+class PeerGroup(C.Structure):
+    """struct lstep_peer_group"""
+    _fields_ = [("rank", i32), ("world", i32), ("table", vp * 16), ("new_rows", vp * 16), ("flags", vp * 16)]
+
+
 class PEMLP(C.Structure):
     """struct lstep_pe_mlp"""
     _fields_ = [("w1", vp), ("b1", vp), ("w2", vp), ("b2", vp), ("ws", vp), ("bs", vp), ("tw", vp), ("d", i32), ("t", i32),
@@ -92,6 +97,19 @@ _SIGS = {
     "lstep_changelog_append": (i32, [C.POINTER(ChangeLog), i32, i32, vp, vp, vp, i64, vp, i64, vp, i32, i32, vp, vp]),
     "lstep_pe_step_changelog": (i32, [C.POINTER(PEStreamDesc), C.POINTER(ChangeLog), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, i32, i32, vp,
                                       C.POINTER(C.c_void_p), i32, i64, i64, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp, i32]),
+    "lstep_ipc_alloc": (i32, [sz, C.POINTER(C.c_void_p)]),
+    "lstep_ipc_free": (i32, [vp]),
+    "lstep_ipc_export": (i32, [vp, C.POINTER(C.c_ubyte)]),
+    "lstep_ipc_open": (i32, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
+    "lstep_ipc_close": (i32, [vp]),
+    "lstep_peer_signal": (i32, [C.POINTER(PeerGroup), C.c_uint32, vp]),
+    "lstep_peer_wait": (i32, [C.POINTER(PeerGroup), C.c_uint32, i32, vp, vp]),
+    "lstep_pe_step_peer": (i32, [C.POINTER(PEStreamDesc), C.POINTER(ChangeLog), C.POINTER(CSR), C.POINTER(PeerGroup), i64, i64, vp, i64, vp, vp, i64,
+                                 C.c_double, i32, i32, vp, C.POINTER(C.c_void_p), i32, i64, i64, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz,
+                                 vp, C.c_uint32, i32, i32, vp]),
+    "lstep_pe_steps_peer": (i32, [C.POINTER(PEStreamDesc), C.POINTER(ChangeLog), C.POINTER(CSR), C.POINTER(PeerGroup), i64, vp, vp, vp, vp, vp, vp, vp,
+                                  vp, C.POINTER(i32), vp, C.POINTER(C.c_void_p), vp, i32, vp, i64, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz,
+                                  vp, C.POINTER(C.c_uint32), i32, vp]),
     "lstep_set_option": (i32, [C.c_char_p, i32]),
     "lstep_get_option": (i32, [C.c_char_p, C.POINTER(i32)]),
     "lstep_step_profile": (i32, [i32]),
@@ -172,3 +190,4 @@ def stream_ptr():
 
 FLAG_NODE_OUT_OF_RANGE = 1
 FLAG_CHANGELOG_FULL = 4
+FLAG_PEER_TIMEOUT = 8

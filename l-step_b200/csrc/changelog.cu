@@ -54,10 +54,17 @@ __device__ __forceinline__ int hash_find(const unsigned long long* __restrict__ 
   return -1;
 }
 
+// Table replicas of the other ranks of a peer group (csrc/peer.cu): a row written to the local table is stored to the same
+// row of every replica as well (NVLink peer stores; published by the group's next barrier).
+struct PeerTables {
+  float* p[LSTEP_MAX_PEERS];
+  int n;  // number of OTHER replicas
+};
+
 // One CTA (128 threads) per batch node.
 __global__ void __launch_bounds__(128) changelog_filter_kernel(lstep_changelog cl, int head, int len, const int64_t* __restrict__ ids,
                                                                int64_t n_ids, const float* __restrict__ G, float* __restrict__ out,
-                                                               int64_t out_stride, const int64_t* __restrict__ out_ids) {
+                                                               int64_t out_stride, const int64_t* __restrict__ out_ids, PeerTables peers) {
   __shared__ int s_idx[128];    // event index at window position f, or -1
   __shared__ int s_evf[129];    // window positions that carry an event (ascending), then `len`
   __shared__ int s_evi[128];
@@ -132,9 +139,11 @@ __global__ void __launch_bounds__(128) changelog_filter_kernel(lstep_changelog c
       }
       const int64_t orow = out_ids ? out_ids[n] : n;
       *reinterpret_cast<float4*>(out + orow * out_stride + 4 * tid) = acc;
+      for (int g = 0; g < peers.n; ++g) *reinterpret_cast<float4*>(peers.p[g] + orow * out_stride + 4 * tid) = acc;
     }
     __syncthreads();
   }
+  if (peers.n) __threadfence_system();
 }
 
 // The events of `slot` (the step leaving the window) become base rows; their mask bits are cleared.
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(256) changelog_append_kernel(lstep_changelog c
                                                                const int64_t* __restrict__ U, const int32_t* __restrict__ n_u_dev, int64_t n_u,
                                                                const int64_t* __restrict__ ids, int64_t n_ids,
                                                                const int32_t* __restrict__ stamp_map, int stamp, int with_row0,
-                                                               uint32_t* err_flag) {
+                                                               uint32_t* err_flag, PeerTables peers) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   if (n_u_dev) {
@@ -181,13 +190,19 @@ __global__ void __launch_bounds__(256) changelog_append_kernel(lstep_changelog c
     int idx = 0;
     if (lane == 0) idx = atomicAdd(cl.ev_cnt + slot, 1);
     idx = __shfl_sync(kFull, idx, 0);
+    const float4* srow = reinterpret_cast<const float4*>(table + v * (int64_t)cl.d);
     if (idx >= cl.cap) {
       if (lane == 0 && err_flag) atomicOr(err_flag, LSTEP_FLAG_CHANGELOG_FULL);
+      for (int g = 0; g < peers.n; ++g)  // the replicas must not diverge even when the event is lost
+        for (int c = lane; c < dvec; c += 32) reinterpret_cast<float4*>(peers.p[g] + v * (int64_t)cl.d)[c] = __ldcg(srow + c);
       continue;
     }
-    const float4* srow = reinterpret_cast<const float4*>(table + v * (int64_t)cl.d);
     float4* drow = reinterpret_cast<float4*>(cl.ev_row + ((size_t)slot * cl.cap + idx) * cl.d);
-    for (int c = lane; c < dvec; c += 32) drow[c] = __ldcg(srow + c);
+    for (int c = lane; c < dvec; c += 32) {
+      const float4 x = __ldcg(srow + c);
+      drow[c] = x;
+      for (int g = 0; g < peers.n; ++g) reinterpret_cast<float4*>(peers.p[g] + v * (int64_t)cl.d)[c] = x;  // publish the owned row
+    }
     if (lane == 0) {
       cl.ev_node[(size_t)slot * cl.cap + idx] = (int32_t)v;
       unsigned long long* tab = cl.ev_hash + (size_t)slot * cl.H;
@@ -197,6 +212,7 @@ __global__ void __launch_bounds__(256) changelog_append_kernel(lstep_changelog c
       atomicOr(cl.ev_mask + lrow * 4 + (slot >> 5), 1u << (slot & 31));
     }
   }
+  if (peers.n) __threadfence_system();
 }
 
 bool valid(const lstep_changelog* cl) {
@@ -211,13 +227,32 @@ bool valid(const lstep_changelog* cl) {
 
 using namespace lstep;
 
+namespace lstep {
+static PeerTables other_tables(const lstep_peer_group* grp) {
+  PeerTables pt{};
+  if (grp)
+    for (int g = 0; g < grp->world; ++g)
+      if (g != grp->rank) pt.p[pt.n++] = grp->table[g];
+  return pt;
+}
+int changelog_filter_peer(const lstep_changelog* cl, int head, int len, const int64_t* ids, int64_t n_ids, const float* G, float* out,
+                          int64_t out_stride, const int64_t* out_ids, const lstep_peer_group* grp, void* stream);
+int changelog_append_peer(const lstep_changelog* cl, int slot, int retire, const float* table, const int64_t* U, const int32_t* n_u_dev,
+                          int64_t n_u, const int64_t* ids, int64_t n_ids, const int32_t* stamp_map, int stamp, int with_row0,
+                          uint32_t* err_flag, const lstep_peer_group* grp, void* stream);
+}  // namespace lstep
+
 extern "C" int lstep_changelog_filter(const lstep_changelog* cl, int head, int len, const int64_t* ids, int64_t n_ids, const float* G,
                                       float* out, int64_t out_stride, const int64_t* out_ids, void* stream) {
+  return changelog_filter_peer(cl, head, len, ids, n_ids, G, out, out_stride, out_ids, nullptr, stream);
+}
+int lstep::changelog_filter_peer(const lstep_changelog* cl, int head, int len, const int64_t* ids, int64_t n_ids, const float* G, float* out,
+                                 int64_t out_stride, const int64_t* out_ids, const lstep_peer_group* grp, void* stream) {
   if (!valid(cl) || head < 0 || head >= cl->T || len < 0 || len > cl->T || n_ids < 0) return LSTEP_ERR_INVALID_ARG;
   if (n_ids == 0) return LSTEP_OK;
   if (!ids || !G || !out || out_stride % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return LSTEP_ERR_INVALID_ARG;
   const int64_t grid = std::min<int64_t>(n_ids, (int64_t)num_sms() * 16);
-  changelog_filter_kernel<<<(unsigned)grid, 128, 0, as_stream(stream)>>>(*cl, head, len, ids, n_ids, G, out, out_stride, out_ids);
+  changelog_filter_kernel<<<(unsigned)grid, 128, 0, as_stream(stream)>>>(*cl, head, len, ids, n_ids, G, out, out_stride, out_ids, other_tables(grp));
   return check_launch("changelog_filter");
 }
 
@@ -227,6 +262,11 @@ extern "C" int lstep_changelog_filter(const lstep_changelog* cl, int head, int l
 extern "C" int lstep_changelog_append(const lstep_changelog* cl, int slot, int retire, const float* table, const int64_t* U,
                                       const int32_t* n_u_dev, int64_t n_u, const int64_t* ids, int64_t n_ids, const int32_t* stamp_map,
                                       int stamp, int with_row0, uint32_t* err_flag, void* stream) {
+  return changelog_append_peer(cl, slot, retire, table, U, n_u_dev, n_u, ids, n_ids, stamp_map, stamp, with_row0, err_flag, nullptr, stream);
+}
+int lstep::changelog_append_peer(const lstep_changelog* cl, int slot, int retire, const float* table, const int64_t* U, const int32_t* n_u_dev,
+                                 int64_t n_u, const int64_t* ids, int64_t n_ids, const int32_t* stamp_map, int stamp, int with_row0,
+                                 uint32_t* err_flag, const lstep_peer_group* grp, void* stream) {
   if (!valid(cl) || slot < 0 || slot >= cl->T || n_u < 0 || n_ids < 0 || !table) return LSTEP_ERR_INVALID_ARG;
   if ((n_u > 0 && !U) || (n_ids > 0 && !ids)) return LSTEP_ERR_INVALID_ARG;
   cudaStream_t st = as_stream(stream);
@@ -244,7 +284,8 @@ extern "C" int lstep_changelog_append(const lstep_changelog* cl, int slot, int r
   if (n_u + n_ids == 0 && !with_row0) return LSTEP_OK;
   const int64_t warps = n_u + n_ids + 1;
   const int64_t grid = std::min<int64_t>(ceil_div(warps * 32, 256), (int64_t)num_sms() * 8);
-  changelog_append_kernel<<<(unsigned)grid, 256, 0, st>>>(*cl, slot, table, U, n_u_dev, n_u, ids, n_ids, stamp_map, stamp, with_row0, err_flag);
+  changelog_append_kernel<<<(unsigned)grid, 256, 0, st>>>(*cl, slot, table, U, n_u_dev, n_u, ids, n_ids, stamp_map, stamp, with_row0, err_flag,
+                                                          other_tables(grp));
   return check_launch("changelog_append");
 }
 

@@ -153,6 +153,13 @@ struct RowIds {
   }
   __device__ __forceinline__ int64_t time_index(int64_t row) const { return period ? row % period : row; }
 };
+// update_pe inside a peer group (csrc/peer.cu): this rank accumulates / rewrites only the phase-B destinations u with
+// u % mul == add and applies only the phase-A rows of the batch nodes it owns; new_rows holds phase A's rows of ALL batch
+// nodes (row i = ids[i], written by their owners through peer memory).
+struct PushOwner {
+  int mul = 1, add = 0;
+  const float* new_rows = nullptr;
+};
 inline RowIds single_ids(const int64_t* ids) {
   RowIds r{};
   r.p[0] = ids;

@@ -32,7 +32,10 @@ void update_ws_phase_a(void* workspace, int64_t n_ids, int64_t n_edges, int K, i
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
                    void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows,
-                   float* ring_slot, int64_t ring_stride);
+                   float* ring_slot, int64_t ring_stride, const PushOwner* owner = nullptr);
+int launch_phase_a_to_new_rows(const float* pe, void* workspace, int64_t ws_ids, int64_t ws_edges, int K, int64_t pe_rows, const int64_t* ids,
+                               int64_t n_ids, const int64_t* src, const int64_t* dst, const double* times, int64_t n_edges, float tc,
+                               const lstep_pe_mlp* mlp, bool aggregate_done, cudaStream_t st);
 
 // a6's neighbourhood aggregate (blocks [0, grid_q)) and a7's edge aggregate (the rest) in ONE launch: both only
 // read the current table and neither depends on the other, so the short edge kernel (and its hub chain) hides
@@ -252,7 +255,7 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
     fan.src_of[c] = (signed char)u;
   }
   const bool can_pair = tuning().mlp_pair != 0 && tuning().gather_fuse != 0 && mlp_nbr->ws && mlp_upd->ws && update_push_available(mlp_upd) &&
-                        pe_mlp_cluster_supports(mlp_nbr) && n_ids > 0 && n_edges > 0;
+                        pe_mlp_cluster_supports(mlp_nbr) && (opt.peer ? opt.peer->n_mine : n_ids) > 0 && n_edges > 0;
   const bool dedup = tuning().query_dedup != 0 && can_pair && n_uniq < n_queries && q_rows > 0;
   if (!dedup) {
     for (int c = 0; c < n_queries; ++c) q.p[c] = query_ids_host[c];
@@ -263,6 +266,14 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
   }
   const int64_t rows = (int64_t)n_uniq * q_rows;
   q.period = q_rows;
+  // peer group (csrc/peer.cu): phase A covers the batch nodes this rank owns; the step may be issued in two halves
+  const PeerPlan* peer = opt.peer;
+  if (peer && (!peer->grp || peer->n_mine < 0 || (peer->n_mine > 0 && (!peer->ids_mine || !peer->pos_mine)) || !update_push_available(mlp_upd) ||
+               !opt.skip_dft || !opt.skip_append))
+    return LSTEP_ERR_INVALID_ARG;
+  const int64_t* ids_a = peer ? peer->ids_mine : ids;
+  const int64_t n_a = peer ? peer->n_mine : n_ids;
+  const bool first_half = !peer || (peer->phases & 2) != 0, second_half = !peer || (peer->phases & 4) != 0;
   bool edges_done = false, phase_a_done = false;
   float* A = nullptr;      // phase A's aggregate rows / result rows inside the update workspace
   float* new_rows = nullptr;
@@ -283,21 +294,21 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
   const int t_pad_e = narrow ? 0 : t_al;
   const int threads = narrow ? 128 : (int)align_up((size_t)t_al + d / 4, 32);
   const bool vec_ok = d % 4 == 0 && w.lda % 4 == 0 && reinterpret_cast<uintptr_t>(s->cur) % 16 == 0 && threads <= 512;
-  if (!no_fuse && rows > 0 && n_ids > 0 && n_edges > 0 && vec_ok && t == mlp_upd->t && d == mlp_upd->d) {
+  if (first_half && !no_fuse && rows > 0 && n_a > 0 && n_edges > 0 && vec_ok && t == mlp_upd->t && d == mlp_upd->d) {
     update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters, &new_rows);
     const int64_t cap = (int64_t)num_sms() * 16;
-    const int grid_q = (int)(rows < cap ? rows : cap), grid_e = (int)(n_ids < cap ? n_ids : cap);
+    const int grid_q = (int)(rows < cap ? rows : cap), grid_e = (int)(n_a < cap ? n_a : cap);
     const size_t smem = std::max((size_t)K * 8, (size_t)threads * kSegPerThread * 8 + 32 * 4);
     if (smem <= 48 * 1024) {
       LookupArgs lk{csr->indptr, csr->nbr, csr->t, csr->num_rows, q, err_flag};
       launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads), smem, st, s->cur, tq_q, rows, K, mlp_nbr->tw, d, t, t_pad,
-               t_pad_e, w.S, w.lda, q_rows, lk, grid_q, ids, n_ids, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
+               t_pad_e, w.S, w.lda, q_rows, lk, grid_q, ids_a, n_a, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
       if ((rc = check_launch("gather_ab")) != LSTEP_OK) return rc;
       prof_mark(st, kProfGather);
       edges_done = true;
     }
   }
-  if (rows > 0) {
+  if (first_half && rows > 0) {
     if (!edges_done) {
       rc = launch_nbr_lookup_aggregate(csr, q, s->cur, tq_q, rows, K, mlp_nbr->tw, d, t, w.S, w.lda, err_flag, st);
       if (rc != LSTEP_OK) return rc;
@@ -307,9 +318,9 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
     const bool no_pair = tuning().mlp_pair == 0;
     if (edges_done && !no_pair && mlp_nbr->ws && mlp_upd->ws && update_push_available(mlp_upd)) {
       RowIds ida{};
-      ida.p[0] = ids;
+      ida.p[0] = ids_a;
       ida.period = 0;
-      rc = launch_pe_mlp_cluster_pair(s->cur, w.S, w.lda, q, rows, mlp_nbr, nbr_out, d, A, ldA, ida, n_ids, mlp_upd, new_rows, d, st,
+      rc = launch_pe_mlp_cluster_pair(s->cur, w.S, w.lda, q, rows, mlp_nbr, nbr_out, d, A, ldA, ida, n_a, mlp_upd, new_rows, d, st,
                                       /*late_trigger=*/true, s->V1, dedup ? &fan : nullptr);
       if (rc == LSTEP_OK) {
         phase_a_done = true;
@@ -326,6 +337,27 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
       if (rc != LSTEP_OK) return rc;
     }
   }
+  PushOwner own{};
+  if (peer) {
+    if (first_half) {
+      // phase A's rows of the owned batch nodes (stand-alone launches when the paired launch did not apply), then into every
+      // rank's new_rows buffer at the node's position in the batch's id list, then barrier 2 is announced
+      if (!phase_a_done) {
+        rc = launch_phase_a_to_new_rows(s->cur, w.update, n_ids, n_edges, K, s->V1, ids_a, n_a, src, dst, tq, n_edges, (float)current_time,
+                                        mlp_upd, edges_done, st);
+        if (rc != LSTEP_OK) return rc;
+      }
+      update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters, &new_rows);
+      if (n_a > 0 && (rc = peer_rows_bcast(new_rows, n_a, d, peer->pos_mine, peer->grp, 1, st)) != LSTEP_OK) return rc;
+      if ((rc = peer_signal(peer->grp, peer->epoch2, st)) != LSTEP_OK) return rc;
+    }
+    if (!second_half) return LSTEP_OK;
+    if ((rc = peer_wait(peer->grp, peer->epoch2, peer->timeout_ms, err_flag, st)) != LSTEP_OK) return rc;
+    edges_done = phase_a_done = true;
+    own.mul = peer->grp->world;
+    own.add = peer->grp->rank;
+    own.new_rows = peer->grp->new_rows[peer->grp->rank];
+  }
   // a7 + a8
   static std::atomic<int> g_stamp{0};
   int stamp = ++g_stamp;
@@ -338,7 +370,7 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
   const bool no_early_append = tuning().early_append == 0;
   rc = update_pe_impl(s->cur, s->V1, csr, ids, n_ids, src, dst, tq, n_edges, current_time, K, mlp_upd, w.update, w.update_bytes,
                       err_flag, stream, edges_done, (no_early_append || opt.skip_append) ? nullptr : &dirty, stamp, phase_a_done,
-                      s->ring + (int64_t)append_slot * d, (int64_t)T * d);
+                      s->ring + (int64_t)append_slot * d, (int64_t)T * d, peer ? &own : nullptr);
   if (rc != LSTEP_OK) return rc;
   // 2 CTAs per SM: the append is resident (copying, then waiting for the phase-B MLP) while the NEXT step's DFT filter
   // wants to become resident and prefetch — it must leave thread slots and shared memory for it

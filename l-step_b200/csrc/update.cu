@@ -39,7 +39,8 @@ int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const doubl
                         int K, int32_t* out_nbr, float* out_t, uint32_t* err_flag, PhaseBHook hook, void* stream);
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
-                       unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st);
+                       unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st,
+                       int own_mul = 1, int own_add = 0);
 
 constexpr int kRow0Parts = 64;
 constexpr int kHubLen = 4;     // a warp reduces a destination's slot list serially (~430 dependent instructions per
@@ -495,6 +496,40 @@ static int phase_a(float* pe, const UpdateWs& w, const int64_t* ids, int64_t n_i
   return launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, nullptr, 0, pe, st, true);
 }
 
+}  // namespace lstep
+namespace lstep {
+// phase A's aggregate rows of `ids` into the update workspace (resets the phase-B counters), then its MLP into the
+// workspace's new_rows buffer (row i = ids[i]) instead of the table: the stand-alone form of what the streaming step does
+// inside its fused gather / paired MLP launches. n_ids == 0 only resets the counters.
+int launch_phase_a_to_new_rows(const float* pe, void* workspace, int64_t ws_ids, int64_t ws_edges, int K, int64_t pe_rows, const int64_t* ids,
+                               int64_t n_ids, const int64_t* src, const int64_t* dst, const double* times, int64_t n_edges, float tc,
+                               const lstep_pe_mlp* mlp, bool aggregate_done, cudaStream_t st) {
+  const int d = mlp->d, t = mlp->t;
+  UpdateWs w = carve(workspace, ws_ids, ws_edges, K, d, t, pe_rows);
+  if (n_ids == 0) {
+    cudaError_t e = cudaMemsetAsync(w.counters, 0, sizeof(int32_t) * 8, st);
+    if (e != cudaSuccess) {
+      set_cuda_error(e, "phase_a counters");
+      return LSTEP_ERR_CUDA;
+    }
+    return LSTEP_OK;
+  }
+  if (!aggregate_done) {
+    const int dvec = d / 4;
+    const int t_pad = (int)align_up((size_t)t, 32);
+    const int threads = (int)align_up((size_t)t_pad + dvec, 32);
+    const size_t smem = (size_t)threads * kSegPerThread * 8 + 32 * 4;
+    const int64_t grid = n_ids < (int64_t)num_sms() * 16 ? n_ids : (int64_t)num_sms() * 16;
+    launch_k(edge_aggregate_kernel, dim3((unsigned)grid), dim3(threads), smem, st, pe, ids, n_ids, src, dst, times, n_edges, tc, mlp->tw, d, t,
+             t_pad, w.A, w.lda, w.counters);
+    const int rc = check_launch("edge_aggregate");
+    if (rc != LSTEP_OK) return rc;
+  }
+  return launch_pe_mlp(w.A, w.lda, pe, single_ids(ids), n_ids, n_ids, nullptr, mlp, w.new_rows, d, nullptr, st, true);
+}
+}  // namespace lstep
+namespace lstep {
+
 // phase B, aggregation half: lookup of (csr_ids[i], q_times[i]) for i < n_valid, inverse index, per
 // destination reduction of [pe[row_ids[i]] || tf]. Leaves U (distinct destinations, + 0 when any slot
 // was padding), the aggregate rows A and the device counters in the workspace.
@@ -580,7 +615,7 @@ bool update_push_available(const lstep_pe_mlp* mlp) {
 int update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids, const int64_t* src,
                    const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K, const lstep_pe_mlp* mlp,
                    void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream, bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows,
-                   float* ring_slot, int64_t ring_stride);
+                   float* ring_slot, int64_t ring_stride, const PushOwner* owner = nullptr);
 }  // namespace lstep
 
 extern "C" int lstep_update_pe(float* pe, int64_t pe_rows, const lstep_csr* csr, const int64_t* ids, int64_t n_ids,
@@ -596,7 +631,9 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
                           const int64_t* dst, const double* times, int64_t n_edges, double current_time, int K,
                           const lstep_pe_mlp* mlp, void* workspace, size_t workspace_bytes, uint32_t* err_flag, void* stream,
                           bool edges_done, int32_t** dirty_out, int stamp, bool phase_a_in_new_rows, float* ring_slot,
-                          int64_t ring_stride) {
+                          int64_t ring_stride, const PushOwner* owner) {
+  // owner (peer group, csrc/peer.cu): phase B of the destinations this rank owns only; phase A's rows of ALL batch nodes
+  // are read from owner->new_rows (row i = ids[i], gathered from the owners), the owned ones are applied to `pe`.
   // ring_slot / ring_stride (streaming step, with dirty_out): the phase-B MLP also writes its rows into the history
   // ring's new slot, so the caller's ring append only has to copy the rows NOT carrying `stamp`.
   // phase_a_in_new_rows (streaming step): phase A's MLP has already run (in the caller's paired launch) and left its
@@ -622,6 +659,7 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
     return LSTEP_OK;
   }
   if (phase_a_in_new_rows && !update_push_available(mlp)) return LSTEP_ERR_INVALID_ARG;
+  if (owner && (!phase_a_in_new_rows || !owner->new_rows || owner->mul < 1 || owner->add < 0 || owner->add >= owner->mul)) return LSTEP_ERR_INVALID_ARG;
   if (!phase_a_in_new_rows && (rc = phase_a(pe, w, ids, n_ids, src, dst, times, n_edges, tc, mlp, st, edges_done)) != LSTEP_OK) return rc;
   const int64_t n_valid = n_ids < n_edges ? n_ids : n_edges;  // zip(node_ids, times) truncation (Q1)
   {
@@ -629,7 +667,8 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
     // lands, then the MLP straight off the accumulator rows. LSTEP_PHASEB_PULL=1 selects the pull form below.
     if (update_push_available(mlp)) {
       rc = launch_phaseB_push(csr, ids, times, n_ids, n_valid, K, pe, d, t, mlp->tw, tc, w.claim_of, w.U, w.counters, w.push_acc,
-                              w.slot_of, stamp, phase_a_in_new_rows ? w.new_rows : nullptr, err_flag, st);
+                              w.slot_of, stamp, owner ? owner->new_rows : (phase_a_in_new_rows ? w.new_rows : nullptr), err_flag, st,
+                              owner ? owner->mul : 1, owner ? owner->add : 0);
       if (rc != LSTEP_OK) return rc;
       prof_mark(st, kProfPush);
       const int64_t total = n_ids * (int64_t)K;
@@ -641,7 +680,7 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
       if (dirty_out) *dirty_out = w.slot_of;
       // expected rows: ~4 distinct sampled neighbours per batch node on the benchmark graphs (measured 3.9); a launch
       // with more rows than the chosen tile covers in one round of clusters just walks a second round
-      rc = launch_pe_mlp_cluster(nullptr, 0, pe, single_ids(w.U), max_dest + 1, n_ids * 4, w.counters + 2, &noself, nullptr, 0, pe,
+      rc = launch_pe_mlp_cluster(nullptr, 0, pe, single_ids(w.U), max_dest + 1, n_ids * 4 / (owner ? owner->mul : 1) + 1, w.counters + 2, &noself, nullptr, 0, pe,
                                  w.push_acc, w.claim_of, st, dirty_out != nullptr, dirty_out ? ring_slot : nullptr, ring_stride);
       prof_mark(st, kProfMlpB);
       return rc;

@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
                                                           int64_t n_ids, int64_t n_valid, int K, float* pe, int d, int t,
                                                           const float* __restrict__ tw, float tc, int32_t* claim_of,
                                                           int64_t* __restrict__ U, int32_t* counters,
-                                                          unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag) {
+                                                          unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag,
+                                                          int own_mul, int own_add) {
+  // own_mul > 1 (peer group, csrc/peer.cu): this rank accumulates only the destinations u with u % own_mul == own_add and
+  // applies only the phase-A rows of the batch nodes it owns; the lookup of every batch node is replicated.
   // Dependency structure (programmatic dependent launch): the kernel in front is the phase-A MLP, launched with
   // a LATE trigger, so this kernel is resident only after everything before that MLP has completed. The lookup
   // and the claim phase touch nothing the phase-A MLP reads or writes (CSR, ids, claim map, counters, U, the
@@ -97,7 +100,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
         u = c_nbr[e];
         dt = tc - (float)c_t[e];  // neighbour times are returned as fp32 (utils.py:166,208), then fp32 - fp32
       }
-      const bool active = k < k_hi && u > 0;
+      const bool active = k < k_hi && u > 0 && (own_mul == 1 || u % own_mul == own_add);
       z += __popc(__ballot_sync(kFull, k < k_hi && u <= 0));
       const unsigned grp = __match_any_sync(kFull, active ? u : -(lane + 1));
       const int leader = __ffs(grp) - 1;
@@ -142,8 +145,9 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
         s_slot[k - k_lo] = active ? j : -1;
       }
     }
-    // ---- the padding destination: node 0 collects z * pe[ids[row]]
+    // ---- the padding destination: node 0 collects z * pe[ids[row]] (on the rank that owns node 0)
     int j0 = -1;
+    if (own_add != 0) z = 0;
     if (z > 0) {
       bool won = false;
       if (lane == 0) {
@@ -200,7 +204,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
 
   pdl_wait();  // phase A has written the table
   TL_WAITED(3);
-  if (blockIdx.x == 0)
+  if (blockIdx.x == 0 && own_add == 0)  // (peer group: the owner of row 0 only — its final row reaches the other replicas from there)
     for (int c = threadIdx.x; c < d; c += blockDim.x) pe[c] = 0.f;  // pe[0] = 0 (LSTEP.py:317); no batch row reads row 0 below
 
   // ---- this row's PE in fixed point (phase-A table), once per warp. new_rows != NULL (streaming step): phase A
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
     const int c = lane + 32 * q;
     fx[q] = (c < d && node > 0) ? __float2ll_rn(ld_dep(src_row + c) * kFixScale) : 0ll;
   }
-  if (new_rows && part == 0 && node > 0)  // row 0 is zeroed above (LSTEP.py:317 follows the phase-A write)
+  if (new_rows && part == 0 && node > 0 && (own_mul == 1 || node % own_mul == own_add))  // row 0 is zeroed above (LSTEP.py:317 follows the phase-A write)
     for (int c = threadIdx.x; c < d; c += blockDim.x) pe[node * (int64_t)d + c] = ld_dep(src_row + c);
   for (int k = warp; k < k_hi - k_lo; k += nwarps) {
     const int j = s_slot[k];
@@ -242,15 +246,17 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
 // destinations U[0 .. counters[2])
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
-                       unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st) {
+                       unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st,
+                       int own_mul, int own_add) {
+  if (own_mul < 1 || own_add < 0 || own_add >= own_mul) return LSTEP_ERR_INVALID_ARG;
   if (!csr || !ids || !q_time || !dirty || n_ids <= 0 || K <= 0 || (d + t) % 2 != 0) return LSTEP_ERR_INVALID_ARG;
   const size_t smem = (size_t)((K + kPushSplit - 1) / kPushSplit) * 12;
   if (d <= 6 * 32 && t <= 4 * 32)
     launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag);
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, own_mul, own_add);
   else if (d <= 8 * 32 && t <= 8 * 32)
     launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag);
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, own_mul, own_add);
   else
     return LSTEP_ERR_UNSUPPORTED;
   return check_launch("phaseB_push");

@@ -737,6 +737,65 @@ def test_sharded_ranks_over_nccl(torch_cuda, world):
     assert res.stdout.count("sharded == single GPU") == world, res.stdout[-2000:]
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_peer_group_emulated_is_bit_identical_to_single_gpu(torch_cuda, world):
+    """The peer-group step (owner-computes filter / phase A / phase B, replicas kept equal by the owners' stores, two flag
+    barriers per step; l-step_b200/peer.py, csrc/peer.cu) with all ranks emulated in one process — peer pointers are plain
+    device pointers, each phase issued for every rank before the next: every replica's table at every step, each rank's
+    share of the a6 outputs and the owners' replayed history must be BIT-identical to the single-GPU ChangeLogStream
+    through the filling and the steady regime (ragged last batch; ranks that own no batch node at world = 8)."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import ChangeLogStream, NeighborSampler, PeerLocalGroup, PeerRank
+    g = synth.make_graph("tiny_bip", seed=4, num_nodes=300, num_edges=9000)
+    V, d, K, B = g.num_nodes, 172, 20, 48
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin("fullu", g, s, 172, d, 100, 100, K)[0].eval()
+    init = torch.from_numpy(seeded_normal(17, (V + 1, d), 0.3)).cuda()
+    init[0] = 0
+    e0 = g.num_edges - 115 * B - 7
+    st = ChangeLogStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, initial_pe=init.clone(), start=e0)
+    ranks = [PeerRank(lstep, r, world, g.src_node_ids, g.dst_node_ids, g.node_interact_times, V, B, K, init.clone(), start=e0, sampler=s)
+             for r in range(world)]
+    grp = PeerLocalGroup(ranks)
+    neg = torch.from_numpy(np.random.default_rng(3).integers(1, V + 1, g.num_edges - e0).astype(np.int64)).cuda()
+    for b in range(st.num_batches):
+        lo, hi, _, _ = st.batch_arrays(b)
+        qs = [st.src[lo:hi], st.dst[lo:hi], st.src[lo:hi], neg[lo - e0:hi - e0].contiguous()]
+        want = st.step(b, qs)
+        got = torch.cat(grp.step(b, qs), dim=1)
+        assert got.shape == want.shape and torch.equal(got, want), b
+        if b % 10 == 0 or b == st.num_batches - 1:
+            # replicas agree with the single-GPU table once the owners' stores are published (= at the next barrier 1)
+            for rk in ranks:
+                assert torch.equal(rk.cur, st.cur), (b, rk.rank)
+    grp.barrier()
+    for rk in ranks:
+        rk.check_errors()
+    h = st.export_history()
+    for rk in ranks:
+        assert torch.equal(rk.export_history_rows(), h[rk.rank::world]), rk.rank
+
+
+@pytest.mark.parametrize("world", [2])
+def test_peer_group_over_ipc(torch_cuda, world):
+    """The same comparison with REAL ranks: one process per GPU under torchrun, CUDA IPC peer pointers, NVLink peer stores and
+    flag barriers (tests/run_peer_ipc_check.py), step by step and through the native multi-step call. Needs `world` GPUs."""
+    import os
+    import subprocess
+    import sys
+    torch = torch_cuda
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, this box has {torch.cuda.device_count()}")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29900 + os.getpid() % 90
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(root, "tests", "run_peer_ipc_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.stdout.count("peer group == single GPU") == world, res.stdout[-2000:]
+
+
 def test_device_resident_stream_rejects_out_of_range_ids(torch_cuda):
     """the device-resident path must not read or write beyond the table. The stream's own ids are
     checked against the table / sampler when the history is adopted (IndexError, like the reference's first lookup, Q8);
