@@ -342,7 +342,7 @@ def run_sharded(args, rank, world, own_pg=True):
     W = max(W, T + 5)  # full history before the clock starts
     n_e2e = min(Ksteps, 50)
     e0 = int(E * 0.7) // B * B
-    stop = min(E, e0 + (W + Ksteps + n_e2e + 2) * B)
+    stop = min(E, e0 + (W + Ksteps + n_e2e + 12) * B)
     t0 = time.time()
     rk = PeerRank(m, rank, world, src, dst, tt, V, B, K, init, start=e0, stop=stop)
     del init
@@ -417,6 +417,27 @@ def run_sharded(args, rank, world, own_pg=True):
     e2e = {"value": e_edges / (float(tm.item()) * 1e-3), "unit": "edges/s", "h2d_bytes_per_step": h2d / n_e2e, "d2h_bytes_per_step": d2h / n_e2e,
            "steps": n_e2e, "api": "PeerRank.step per rank (one call per batch): the step's negative ids from host memory, this rank's "
                                   "per-query row sums back to the host (a synchronising read every step)"}
+    # per-kernel times of this rank's share (events between kernels; medians over 8 steps), waits = time lost to the other ranks
+    import ctypes
+    names = ["filter+signal1", "wait1", "gather_ab", "mlp_pair", "bcast+signal2", "wait2", "push", "mlp_B", "append"]
+    _lib.check(lib.lstep_step_profile(1), "profile on")
+    rows_ms = []
+    try:
+        for _ in range(8):
+            b = step_no
+            rk.step(b, queries(b))
+            step_no += 1
+            ms9 = (ctypes.c_float * 9)()
+            _lib.check(lib.lstep_step_profile_read_all(ms9, 9), "profile read")
+            rows_ms.append(list(ms9))
+    finally:
+        lib.lstep_step_profile(0)
+    med = np.median(np.asarray(rows_ms), axis=0)
+    per_kernel = {n: float(v) for n, v in zip(names, med)}
+    all_pk = [per_kernel]
+    if world > 1:
+        all_pk = [None] * world
+        dist.all_gather_object(all_pk, per_kernel)
     # replica check: every rank's table must equal rank 0's (checksums of a strided sample + of the rows the last step changed)
     rk.barrier()
     torch.cuda.synchronize()
@@ -444,7 +465,8 @@ def run_sharded(args, rank, world, own_pg=True):
                                     f"{(V + 1) * T * D * 4 / 1e9:.0f} GB in total), table {(V + 1) * D * 4 / 1e9:.1f} GB, CSR {2 * E * 16 / 1e9:.1f} GB"},
             "run_info": {"graph_gen_s": t_gen, "setup_s": t_setup, "hbm_used_GB": (total_b - free_b) / 1e9, "history": "changelog", "T": T,
                          "timed_region": "K steps in one native call (PeerRank.run -> lstep_pe_steps_peer) queued behind a spin kernel; CUDA events, max over ranks",
-                         "batch_nodes_mean": n_ids_mean, "replicas_equal_after_run": replicas_equal},
+                         "batch_nodes_mean": n_ids_mean, "replicas_equal_after_run": replicas_equal,
+                         "per_kernel_ms_median_by_rank": all_pk},
             "clocks": clk, "e2e": e2e,
             "gpu_launches": int(Ksteps * 12 * world),
             "roofline": None, "cpu_baseline": None,

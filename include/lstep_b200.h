@@ -353,7 +353,8 @@ int lstep_pe_step_changelog(const lstep_pe_stream* s, const lstep_changelog* cl,
  *                 destinations (u % world == rank); the owned batch nodes' phase-A rows are applied to the local table
  *     MLP (B)     over the owned destinations
  *     append      the owned changed rows (owned batch nodes + owned destinations + row 0 on rank 0) become events of
- *                 the change log AND are stored into every other replica; the next step's barrier 1 publishes them.
+ *                 the change log AND are copied, as one contiguous block, into every other rank's inbox; the receivers
+ *                 scatter them into their replicas right after the next step's barrier 1.
  * Nothing a rank reads between two barriers is written by another rank in that interval (csrc/peer.cu states the
  * argument), so the replicas agree at every barrier 1 and the results are those of the single-GPU step, bit for bit
  * (phase B's sums are exact fixed point, hence independent of which rank adds them).
@@ -368,7 +369,14 @@ typedef struct lstep_peer_group {
   float* new_rows[LSTEP_MAX_PEERS];  /* phase-A row buffer of every rank, [max batch nodes, d] */
   uint32_t* flags[LSTEP_MAX_PEERS];  /* flag block of every rank, uint32[LSTEP_MAX_PEERS]: flags[g][r] = last barrier epoch
                                         rank r has announced to rank g (zero-initialised, epochs start at 1) */
+  void* inbox[LSTEP_MAX_PEERS];      /* inbox of every rank, lstep_peer_inbox_bytes(world, inbox_cap, d) bytes: one block per SOURCE
+                                        rank = { int32 count, pad; int32 node[inbox_cap]; float row[inbox_cap][d] } — the rows a
+                                        rank changed in a step, written CONTIGUOUSLY by their owner (scattered peer stores
+                                        into a multi-GB replica thrash the peer-mapping TLB: 43 GB/s measured against 500 GB/s
+                                        contiguous, profiles/r02_peer_bw.txt) and scattered into the table by the receiver */
+  int64_t inbox_cap;                 /* rows per source block (>= the change log's event capacity) */
 } lstep_peer_group;
+size_t lstep_peer_inbox_bytes(int world, int64_t inbox_cap, int d);
 int lstep_ipc_alloc(size_t bytes, void** ptr);                         /* cudaMalloc + zero fill */
 int lstep_ipc_free(void* ptr);
 int lstep_ipc_export(void* ptr, unsigned char handle_out[64]);         /* cudaIpcGetMemHandle */
@@ -378,6 +386,14 @@ int lstep_ipc_close(void* ptr);
  * and raises LSTEP_FLAG_PEER_TIMEOUT in *err_flag instead of hanging the device) */
 int lstep_peer_signal(const lstep_peer_group* g, uint32_t epoch, void* stream);
 int lstep_peer_wait(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, void* stream);
+/* announce `epoch`, wait for every rank, then apply the inboxes (the rows the last step changed): afterwards, in stream order,
+ * this rank's replica equals every other one (what a caller does before it reads the table after the last step) */
+int lstep_peer_sync_tables(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, int d, int64_t V1, void* stream);
+/* dst[g][dst_rows[i]][0..d) = src[i][0..d) for every rank g whose bit is set in rank_mask (dst_rows NULL: row i); which = 0: the
+ * table replicas, 1: the new_rows buffers. The building block of the step's row publication (also used to measure the
+ * peer-store bandwidth, profiles/peer_bw.py). */
+int lstep_peer_rows_bcast(const float* src, int64_t n_rows, int d, const int64_t* dst_rows, const lstep_peer_group* grp, int which,
+                          uint32_t rank_mask, void* stream);
 /* One step of this rank (see above). ids = the batch's sorted unique node ids (all of them, replicated); ids_mine = the owned
  * ones, pos_mine[i] = index of ids_mine[i] in ids. The a6 query sets cover edges [q_off, q_off + q_rows) of the batch,
  * query_ids_host[c] pointing at the first of those ids; outputs [n_queries, q_rows, d]. epoch_base: barrier 1 uses
@@ -453,6 +469,10 @@ int lstep_set_option(const char* name, int value);
 int lstep_get_option(const char* name, int* value);
 int lstep_step_profile(int enable);
 int lstep_step_profile_read(float* ms6);
+/* every mark of the last profiled step, peer-group marks included (n >= 9): DFT filter (+ barrier-1 announcement), wait on
+ * barrier 1, fused gather, paired MLP, phase-A row broadcast (+ barrier-2 announcement), wait on barrier 2, phase-B push,
+ * phase-B MLP, append; -1 where no mark was recorded */
+int lstep_step_profile_read_all(float* ms, int n);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,8 @@ class ChangeLog(C.Structure):
 
 class PeerGroup(C.Structure):
     """struct lstep_peer_group"""
-    _fields_ = [("rank", i32), ("world", i32), ("table", vp * 16), ("new_rows", vp * 16), ("flags", vp * 16)]
+    _fields_ = [("rank", i32), ("world", i32), ("table", vp * 16), ("new_rows", vp * 16), ("flags", vp * 16), ("inbox", vp * 16),
+                ("inbox_cap", i64)]
 
 
 class PEMLP(C.Structure):
@@ -97,12 +98,15 @@ _SIGS = {
     "lstep_changelog_append": (i32, [C.POINTER(ChangeLog), i32, i32, vp, vp, vp, i64, vp, i64, vp, i32, i32, vp, vp]),
     "lstep_pe_step_changelog": (i32, [C.POINTER(PEStreamDesc), C.POINTER(ChangeLog), C.POINTER(CSR), i64, i64, vp, i64, C.c_double, i32, i32, vp,
                                       C.POINTER(C.c_void_p), i32, i64, i64, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz, vp, vp, i32]),
+    "lstep_peer_inbox_bytes": (sz, [i32, i64, i32]),
     "lstep_ipc_alloc": (i32, [sz, C.POINTER(C.c_void_p)]),
     "lstep_ipc_free": (i32, [vp]),
     "lstep_ipc_export": (i32, [vp, C.POINTER(C.c_ubyte)]),
     "lstep_ipc_open": (i32, [C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]),
     "lstep_ipc_close": (i32, [vp]),
+    "lstep_peer_rows_bcast": (i32, [vp, i64, i32, vp, C.POINTER(PeerGroup), i32, C.c_uint32, vp]),
     "lstep_peer_signal": (i32, [C.POINTER(PeerGroup), C.c_uint32, vp]),
+    "lstep_peer_sync_tables": (i32, [C.POINTER(PeerGroup), C.c_uint32, i32, vp, i32, i64, vp]),
     "lstep_peer_wait": (i32, [C.POINTER(PeerGroup), C.c_uint32, i32, vp, vp]),
     "lstep_pe_step_peer": (i32, [C.POINTER(PEStreamDesc), C.POINTER(ChangeLog), C.POINTER(CSR), C.POINTER(PeerGroup), i64, i64, vp, i64, vp, vp, i64,
                                  C.c_double, i32, i32, vp, C.POINTER(C.c_void_p), i32, i64, i64, vp, i32, C.POINTER(PEMLP), C.POINTER(PEMLP), vp, sz,
@@ -114,6 +118,7 @@ _SIGS = {
     "lstep_get_option": (i32, [C.c_char_p, C.POINTER(i32)]),
     "lstep_step_profile": (i32, [i32]),
     "lstep_step_profile_read": (i32, [C.POINTER(C.c_float)]),
+    "lstep_step_profile_read_all": (i32, [C.POINTER(C.c_float), i32]),
     "lstep_host_stepper_create": (i32, [i32, i64, i32, i32, C.POINTER(C.c_void_p)]),
     "lstep_host_stepper_destroy": (None, [vp]),
     "lstep_pe_step_host": (i32, [vp, C.POINTER(PEStreamDesc), C.POINTER(CSR), i64, vp, vp, vp, vp, i64, i32, i32, i32, vp,

@@ -139,12 +139,13 @@ extern "C" int lstep_step_profile(int enable) {
   return LSTEP_OK;
 }
 
-/* ms[i] = duration of kernel i of the LAST profiled step: 0 DFT filter, 1 fused gather, 2 paired MLP, 3 phase-B push,
- * 4 phase-B MLP, 5 ring append; -1 where that kernel was not launched. Synchronises on the step's last event. */
-extern "C" int lstep_step_profile_read(float* ms6) {
+/* ms[i - 1] = time between the previous recorded mark and mark i of the LAST profiled step, for every slot of ProfSlot
+ * (csrc/common.cuh): 0 DFT filter, 1 wait on barrier 1 (peer group), 2 fused gather, 3 paired MLP, 4 phase-A row broadcast (peer
+ * group), 5 wait on barrier 2 (peer group), 6 phase-B push, 7 phase-B MLP, 8 append; -1 where no mark was recorded. */
+extern "C" int lstep_step_profile_read_all(float* ms, int n) {
   using namespace lstep;
-  if (!ms6) return LSTEP_ERR_INVALID_ARG;
-  for (int i = 0; i < 6; ++i) ms6[i] = -1.f;
+  if (!ms || n < kProfSlots - 1) return LSTEP_ERR_INVALID_ARG;
+  for (int i = 0; i < n; ++i) ms[i] = -1.f;
   if (!g_prof_have || !(g_prof_seen & 1u)) return LSTEP_ERR_INVALID_ARG;
   int last = 0;
   for (int i = 1; i < kProfSlots; ++i)
@@ -155,8 +156,20 @@ extern "C" int lstep_step_profile_read(float* ms6) {
     if (!(g_prof_seen & (1u << i))) continue;
     float v = 0.f;
     if (cudaEventElapsedTime(&v, g_prof_ev[prev], g_prof_ev[i]) != cudaSuccess) return LSTEP_ERR_CUDA;
-    ms6[i - 1] = v;
+    ms[i - 1] = v;
     prev = i;
   }
   return LSTEP_OK;
+}
+
+/* ms6[i] = duration of kernel i of the LAST profiled step: 0 DFT filter, 1 fused gather, 2 paired MLP, 3 phase-B push,
+ * 4 phase-B MLP, 5 ring append; -1 where that kernel was not launched. Synchronises on the step's last event. */
+extern "C" int lstep_step_profile_read(float* ms6) {
+  using namespace lstep;
+  if (!ms6) return LSTEP_ERR_INVALID_ARG;
+  float all[kProfSlots];
+  const int rc = lstep_step_profile_read_all(all, kProfSlots);
+  static const int pick[6] = {kProfDft, kProfGather, kProfMlpPair, kProfPush, kProfMlpB, kProfAppend};
+  for (int i = 0; i < 6; ++i) ms6[i] = rc == LSTEP_OK ? all[pick[i] - 1] : -1.f;
+  return rc;
 }

@@ -40,7 +40,9 @@ Tuning& tuning();
 // each of its kernels (slots below). Events between kernels also serialise the chain (no programmatic overlap across an
 // event), so the durations are those of the step's own kernels run back to back on live data — the per-kernel roofline
 // figures of bench.py — while the step time itself is always measured with profiling off.
-enum ProfSlot { kProfStart = 0, kProfDft, kProfGather, kProfMlpPair, kProfPush, kProfMlpB, kProfAppend, kProfSlots };
+// (peer group step, csrc/peer.cu: kProfDft = owned filter + announcement of barrier 1, kProfWait1 / kProfWait2 = time spent waiting
+// for the other ranks, kProfBcast = phase-A rows into every rank's buffer + announcement of barrier 2)
+enum ProfSlot { kProfStart = 0, kProfDft, kProfWait1, kProfGather, kProfMlpPair, kProfBcast, kProfWait2, kProfPush, kProfMlpB, kProfAppend, kProfSlots };
 void prof_mark(cudaStream_t st, int slot);
 
 // last CUDA error text, for lstep_last_cuda_error()
@@ -153,6 +155,13 @@ struct RowIds {
   }
   __device__ __forceinline__ int64_t time_index(int64_t row) const { return period ? row % period : row; }
 };
+// push form of update_pe's phase B (csrc/update_push.cu): the padding row 0 collects a contribution from EVERY batch node with
+// a padded slot (most nodes of a 10 M-node graph): thousands of 64-bit atomics per column on one accumulator row. They go to
+// kPushRow0Parts partial rows instead (selected by the batch row), which the last CTA of the kernel folds into row 0's
+// accumulator and returns to zero. Part of the update workspace's zero-initialised head.
+constexpr int kPushRow0Parts = 32;
+constexpr int kPushRow0Cols = 256;  // >= d
+constexpr size_t kPushRow0Bytes = sizeof(unsigned long long) * kPushRow0Parts * kPushRow0Cols;
 // update_pe inside a peer group (csrc/peer.cu): this rank accumulates / rewrites only the phase-B destinations u with
 // u % mul == add and applies only the phase-A rows of the batch nodes it owns; new_rows holds phase A's rows of ALL batch
 // nodes (row i = ids[i], written by their owners through peer memory).

@@ -51,9 +51,6 @@ namespace lstep {
 
 int changelog_filter_peer(const lstep_changelog* cl, int head, int len, const int64_t* ids, int64_t n_ids, const float* G, float* out,
                           int64_t out_stride, const int64_t* out_ids, const lstep_peer_group* grp, void* stream);
-int changelog_append_peer(const lstep_changelog* cl, int slot, int retire, const float* table, const int64_t* U, const int32_t* n_u_dev,
-                          int64_t n_u, const int64_t* ids, int64_t n_ids, const int32_t* stamp_map, int stamp, int with_row0,
-                          uint32_t* err_flag, const lstep_peer_group* grp, void* stream);
 
 namespace {
 
@@ -76,6 +73,8 @@ bool valid_group(const lstep_peer_group* g) {
 // dst[g][dst_rows[i]][:] = src[i][:] for every rank g (the local one included): one warp per row
 __global__ void __launch_bounds__(256) peer_rows_bcast_kernel(const float* __restrict__ src, int64_t n_rows, int d,
                                                               const int64_t* __restrict__ dst_rows, PeerPtrs dst) {
+  pdl_wait();  // every inserted kernel of the peer step: wait first, then let the successor become resident (late trigger)
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const int dvec = d >> 2;
@@ -90,15 +89,142 @@ __global__ void __launch_bounds__(256) peer_rows_bcast_kernel(const float* __res
   __threadfence_system();
 }
 
+// ---- inbox: the rows a rank changed in a step, as one contiguous block per (source, destination) pair --------------------
+__host__ __device__ inline size_t inbox_rows_off(int64_t cap) { return align_up(16 + 4 * (size_t)cap, 256); }
+__host__ __device__ inline size_t inbox_stride(int64_t cap, int d) { return align_up(inbox_rows_off(cap) + (size_t)cap * d * 4, 256); }
+
+struct InboxPtrs {
+  unsigned char* p[LSTEP_MAX_PEERS];  // the OTHER ranks' blocks for this source (publish) / this rank's blocks of the other sources (apply)
+  int n;
+};
+
+// events [0, cnt) of the change log's slot -> every other rank's inbox block for this rank: count, node ids, rows
+__global__ void __launch_bounds__(256) peer_publish_kernel(lstep_changelog cl, int slot, InboxPtrs dst, int64_t cap) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int cnt = min(min(__ldcg(cl.ev_cnt + slot), cl.cap), (int)cap);
+  const int dvec = cl.d >> 2;
+  const int64_t gtid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  const int32_t* node = cl.ev_node + (size_t)slot * cl.cap;
+  const float4* rows = reinterpret_cast<const float4*>(cl.ev_row + (size_t)slot * cl.cap * cl.d);
+  const size_t roff = inbox_rows_off(cap);
+  if (gtid == 0)
+    for (int g = 0; g < dst.n; ++g) *reinterpret_cast<int32_t*>(dst.p[g]) = cnt;
+  for (int64_t i = gtid; i < cnt; i += nthr) {
+    const int32_t v = __ldcg(node + i);
+    for (int g = 0; g < dst.n; ++g) reinterpret_cast<int32_t*>(dst.p[g] + 16)[i] = v;
+  }
+  const int64_t total = (int64_t)cnt * dvec;
+  constexpr int kPer = 4;
+  for (int64_t base = 0; base < total; base += nthr * kPer) {
+    float4 x[kPer];
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const int64_t i = base + gtid + e * nthr;
+      if (i < total) x[e] = __ldcg(rows + i);
+    }
+#pragma unroll
+    for (int e = 0; e < kPer; ++e) {
+      const int64_t i = base + gtid + e * nthr;
+      if (i < total)
+        for (int g = 0; g < dst.n; ++g) reinterpret_cast<float4*>(dst.p[g] + roff)[i] = x[e];
+    }
+  }
+  __threadfence_system();
+}
+
+// is v in the ascending list a[0 .. n)? 32-ary search by a full warp (all lanes pass the same arguments)
+__device__ __forceinline__ bool warp_contains_sorted(const int64_t* __restrict__ a, int64_t n, int64_t v, int lane) {
+  int64_t lo = 0, hi = n;
+  while (hi - lo > 32) {
+    const int64_t len = hi - lo;
+    const int64_t p = lo + (len * (lane + 1)) / 33;
+    const int j = __popc(__ballot_sync(kFull, a[p] < v));  // pivots 0 .. j-1 are < v, pivot j (if any) is >= v
+    const int64_t pa = lo + (len * j) / 33, pb = lo + (len * (j + 1)) / 33;
+    if (j < 32) hi = pb + 1;
+    if (j > 0) lo = pa + 1;
+  }
+  const bool hit = lo + lane < hi && a[lo + lane] == v;
+  return __any_sync(kFull, hit);
+}
+
+// barrier wait + application of the inbox: every CTA waits (thread 0 polls this rank's own flag block), then the CTAs share
+// the rows of all source blocks: table[node[i]] = row[i] — EXCEPT for the nodes of skip_ids (the current batch's nodes,
+// ascending): their owners' filter has already stored this step's filtered row, which is newer than the previous step's
+// final row waiting in the inbox.
+__global__ void __launch_bounds__(256) peer_wait_apply_kernel(const uint32_t* flags, int world, uint32_t epoch, unsigned long long timeout_ns,
+                                                              uint32_t* err_flag, InboxPtrs src, int64_t cap, float* table, int d, int64_t V1,
+                                                              const int64_t* __restrict__ skip_ids, int64_t n_skip, FlagPtrs announce) {
+  __shared__ int s_ok;
+  pdl_wait();
+  pdl_launch_dependents();
+  // announce.n > 0: this launch also ANNOUNCES the epoch (block 0; every earlier kernel of the stream has completed and fenced
+  // its peer stores) — the barrier is then one launch instead of two
+  if (blockIdx.x == 0 && announce.n > 0) {
+    __threadfence_system();
+    if ((int)threadIdx.x < announce.n)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(announce.p[threadIdx.x] + announce.rank), "r"(epoch) : "memory");
+  }
+  if (threadIdx.x == 0) {
+    bool ok = true;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (int g = 0; g < world && ok; ++g) {
+      for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + g) : "memory");
+        if ((int32_t)(v - epoch) >= 0) break;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > timeout_ns) {
+          ok = false;
+          break;
+        }
+        __nanosleep(100);
+      }
+    }
+    if (!ok && err_flag && blockIdx.x == 0) atomicOr(err_flag, LSTEP_FLAG_PEER_TIMEOUT);
+    s_ok = ok;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (!s_ok) return;
+  const int dvec = d >> 2;
+  const size_t roff = inbox_rows_off(cap);
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int g = 0; g < src.n; ++g) {
+    const unsigned char* blk = src.p[g];
+    const int cnt = min(__ldcg(reinterpret_cast<const int32_t*>(blk)), (int)cap);
+    const int32_t* node = reinterpret_cast<const int32_t*>(blk + 16);
+    const float4* rows = reinterpret_cast<const float4*>(blk + roff);
+    for (int64_t i = warp; i < cnt; i += n_warps) {
+      const int64_t v = __ldcg(node + i);
+      if (v < 0 || v >= V1) continue;
+      if (n_skip > 0 && warp_contains_sorted(skip_ids, n_skip, v, lane)) continue;
+      for (int c = lane; c < dvec; c += 32) reinterpret_cast<float4*>(table + v * (int64_t)d)[c] = __ldcg(rows + i * dvec + c);
+    }
+  }
+}
+
 __global__ void peer_signal_kernel(FlagPtrs f, uint32_t epoch) {
+  pdl_wait();
+  pdl_launch_dependents();
   // every earlier kernel of the stream has completed (plain launch) and fenced its peer stores; fence again, then announce
   __threadfence_system();
   const int g = threadIdx.x;
   if (g < f.n) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f.p[g] + f.rank), "r"(epoch) : "memory");
 }
 
-__global__ void peer_wait_kernel(const uint32_t* flags, int world, uint32_t epoch, unsigned long long timeout_ns, uint32_t* err_flag) {
+__global__ void peer_wait_kernel(const uint32_t* flags, int world, uint32_t epoch, unsigned long long timeout_ns, uint32_t* err_flag,
+                                 FlagPtrs announce) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int g = threadIdx.x;
+  if (announce.n > 0) {  // (see peer_wait_apply_kernel)
+    __threadfence_system();
+    if (g < announce.n) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(announce.p[g] + announce.rank), "r"(epoch) : "memory");
+  }
   bool ok = true;
   if (g < world) {
     unsigned long long t0;
@@ -128,7 +254,7 @@ int peer_rows_bcast(const float* src, int64_t n_rows, int d, const int64_t* dst_
   PeerPtrs dst{};
   for (int g = 0; g < grp->world; ++g) dst.p[dst.n++] = which == 0 ? grp->table[g] : grp->new_rows[g];
   const int64_t grid = std::min<int64_t>(ceil_div(n_rows * 32, 256), (int64_t)num_sms() * 8);
-  peer_rows_bcast_kernel<<<(unsigned)grid, 256, 0, st>>>(src, n_rows, d, dst_rows, dst);
+  launch_k(peer_rows_bcast_kernel, dim3((unsigned)grid), dim3(256), 0, st, src, n_rows, d, dst_rows, dst);
   return check_launch("peer_rows_bcast");
 }
 
@@ -138,20 +264,73 @@ int peer_signal(const lstep_peer_group* g, uint32_t epoch, cudaStream_t st) {
   for (int i = 0; i < g->world; ++i) f.p[i] = g->flags[i];
   f.n = g->world;
   f.rank = g->rank;
-  peer_signal_kernel<<<1, 32, 0, st>>>(f, epoch);
+  launch_k(peer_signal_kernel, dim3(1), dim3(32), 0, st, f, epoch);
   return check_launch("peer_signal");
 }
 
-int peer_wait(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, cudaStream_t st) {
+static FlagPtrs flag_ptrs(const lstep_peer_group* g, bool announce) {
+  FlagPtrs f{};
+  if (announce) {
+    for (int i = 0; i < g->world; ++i) f.p[i] = g->flags[i];
+    f.n = g->world;
+    f.rank = g->rank;
+  }
+  return f;
+}
+
+int peer_wait(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, cudaStream_t st, bool announce) {
   if (!valid_group(g)) return LSTEP_ERR_INVALID_ARG;
   const unsigned long long ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
-  peer_wait_kernel<<<1, 32, 0, st>>>(g->flags[g->rank], g->world, epoch, ns, err_flag);
+  launch_k(peer_wait_kernel, dim3(1), dim3(32), 0, st, (const uint32_t*)g->flags[g->rank], g->world, epoch, ns, err_flag, flag_ptrs(g, announce));
   return check_launch("peer_wait");
+}
+
+static bool valid_inbox(const lstep_peer_group* g) {
+  if (g->world == 1) return true;
+  if (g->inbox_cap <= 0) return false;
+  for (int i = 0; i < g->world; ++i)
+    if (!g->inbox[i]) return false;
+  return true;
+}
+
+// the events of the change log's `slot` into every other rank's inbox
+static int peer_publish(const lstep_changelog* cl, int slot, const lstep_peer_group* g, int64_t expect_rows, cudaStream_t st) {
+  if (g->world == 1) return LSTEP_OK;
+  if (!valid_inbox(g) || g->inbox_cap < cl->cap) return LSTEP_ERR_INVALID_ARG;
+  InboxPtrs dst{};
+  const size_t stride = inbox_stride(g->inbox_cap, cl->d);
+  for (int i = 0; i < g->world; ++i)
+    if (i != g->rank) dst.p[dst.n++] = static_cast<unsigned char*>(g->inbox[i]) + (size_t)g->rank * stride;
+  const int64_t work = std::max<int64_t>(expect_rows, 1) * (cl->d / 4);
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, 256 * 4), (int64_t)num_sms() * 4));
+  launch_k(peer_publish_kernel, dim3((unsigned)grid), dim3(256), 0, st, *cl, slot, dst, g->inbox_cap);
+  return check_launch("peer_publish");
+}
+
+// wait for barrier `epoch`, then scatter the other ranks' inbox blocks into this rank's table replica
+static int peer_wait_apply(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, int d, int64_t V1, int64_t expect_rows,
+                           const int64_t* skip_ids, int64_t n_skip, cudaStream_t st, bool announce) {
+  if (g->world == 1) return peer_wait(g, epoch, timeout_ms, err_flag, st, announce);
+  if (!valid_inbox(g)) return LSTEP_ERR_INVALID_ARG;
+  InboxPtrs src{};
+  const size_t stride = inbox_stride(g->inbox_cap, d);
+  for (int i = 0; i < g->world; ++i)
+    if (i != g->rank) src.p[src.n++] = static_cast<unsigned char*>(g->inbox[g->rank]) + (size_t)i * stride;
+  const unsigned long long ns = (unsigned long long)(timeout_ms > 0 ? timeout_ms : 2000) * 1000000ull;
+  const int64_t grid = std::max<int64_t>(1, std::min<int64_t>(ceil_div(std::max<int64_t>(expect_rows, 1) * 32, 256), (int64_t)num_sms() * 4));
+  launch_k(peer_wait_apply_kernel, dim3((unsigned)grid), dim3(256), 0, st, (const uint32_t*)g->flags[g->rank], g->world, epoch, ns, err_flag, src,
+           g->inbox_cap, g->table[g->rank], d, V1, skip_ids, n_skip, flag_ptrs(g, announce));
+  return check_launch("peer_wait_apply");
 }
 
 }  // namespace lstep
 
 using namespace lstep;
+
+extern "C" size_t lstep_peer_inbox_bytes(int world, int64_t inbox_cap, int d) {
+  if (world < 1 || world > LSTEP_MAX_PEERS || inbox_cap <= 0 || d <= 0 || d % 4 != 0) return 0;
+  return (size_t)world * inbox_stride(inbox_cap, d);
+}
 
 extern "C" int lstep_ipc_alloc(size_t bytes, void** ptr) {
   if (!ptr || bytes == 0) return LSTEP_ERR_INVALID_ARG;
@@ -205,9 +384,35 @@ extern "C" int lstep_ipc_close(void* ptr) {
   return LSTEP_OK;
 }
 
+/* dst[g][dst_rows[i]] = src[i] for every rank g whose bit is set in rank_mask (which: 0 = table replicas, 1 = new_rows buffers) */
+extern "C" int lstep_peer_rows_bcast(const float* src, int64_t n_rows, int d, const int64_t* dst_rows, const lstep_peer_group* grp, int which,
+                                     uint32_t rank_mask, void* stream) {
+  if (!grp) return LSTEP_ERR_INVALID_ARG;
+  lstep_peer_group g2 = *grp;
+  int n = 0;
+  for (int g = 0; g < grp->world && g < LSTEP_MAX_PEERS; ++g)
+    if (rank_mask & (1u << g)) {
+      g2.table[n] = grp->table[g];
+      g2.new_rows[n] = grp->new_rows[g];
+      g2.flags[n] = grp->flags[g];
+      ++n;
+    }
+  if (n == 0) return LSTEP_OK;
+  g2.world = n;
+  g2.rank = 0;
+  return peer_rows_bcast(src, n_rows, d, dst_rows, &g2, which, as_stream(stream));
+}
+
 extern "C" int lstep_peer_signal(const lstep_peer_group* g, uint32_t epoch, void* stream) { return peer_signal(g, epoch, as_stream(stream)); }
+/* announce `epoch`, wait for every rank, then apply the inboxes: afterwards (stream order) every replica holds every rank's rows */
+extern "C" int lstep_peer_sync_tables(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, int d, int64_t V1, void* stream) {
+  if (!valid_group(g) || d <= 0 || d % 4 != 0 || V1 <= 0) return LSTEP_ERR_INVALID_ARG;
+  int rc = peer_signal(g, epoch, as_stream(stream));
+  if (rc != LSTEP_OK) return rc;
+  return peer_wait_apply(g, epoch, timeout_ms, err_flag, d, V1, 1 << 16, nullptr, 0, as_stream(stream), false);
+}
 extern "C" int lstep_peer_wait(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, void* stream) {
-  return peer_wait(g, epoch, timeout_ms, err_flag, as_stream(stream));
+  return peer_wait(g, epoch, timeout_ms, err_flag, as_stream(stream), false);
 }
 
 extern "C" int lstep_pe_step_peer(const lstep_pe_stream* s, const lstep_changelog* cl, const lstep_csr* csr, const lstep_peer_group* grp,
@@ -226,11 +431,19 @@ extern "C" int lstep_pe_step_peer(const lstep_pe_stream* s, const lstep_changelo
   cudaStream_t st = as_stream(stream);
   int rc;
   if (phases & 1) {
+    prof_mark(st, kProfStart);
     if (n_mine > 0 && (rc = changelog_filter_peer(cl, head, len, ids_mine, n_mine, G, s->cur, s->d, ids_mine, grp, stream)) != LSTEP_OK) return rc;
-    if ((rc = peer_signal(grp, epoch_base + 1, st)) != LSTEP_OK) return rc;
+    // (a whole step in one call: the wait launch below announces the barrier itself)
+    if ((phases & 2) == 0 && (rc = peer_signal(grp, epoch_base + 1, st)) != LSTEP_OK) return rc;
+    prof_mark(st, kProfDft);
   }
   if (!(phases & 6)) return LSTEP_OK;
-  if ((phases & 2) && (rc = peer_wait(grp, epoch_base + 1, timeout_ms, err_flag, st)) != LSTEP_OK) return rc;
+  if (phases & 2) {
+    // (rows a step changes: ~ (K + 1) per batch node at most; the grid is sized for a typical 8 per batch node)
+    if ((rc = peer_wait_apply(grp, epoch_base + 1, timeout_ms, err_flag, s->d, s->V1, n_ids * 8, ids, n_ids, st, (phases & 1) != 0)) != LSTEP_OK)
+      return rc;
+    prof_mark(st, kProfWait1);
+  }
   PeerPlan plan;
   plan.grp = grp;
   plan.ids_mine = ids_mine;
@@ -261,8 +474,10 @@ extern "C" int lstep_pe_step_peer(const lstep_pe_stream* s, const lstep_changelo
   }
   const bool full = len == cl->T;
   const int slot = full ? head : (head + len) % cl->T;
-  return changelog_append_peer(cl, slot, full ? 1 : 0, s->cur, U, n_dest, n_u_max, ids, n_ids, stamp_map, stamp, n_ids > 0 ? 1 : 0, err_flag, grp,
-                               stream);
+  rc = lstep_changelog_append(cl, slot, full ? 1 : 0, s->cur, U, n_dest, n_u_max, ids, n_ids, stamp_map, stamp, n_ids > 0 ? 1 : 0, err_flag, stream);
+  if (rc == LSTEP_OK) rc = peer_publish(cl, slot, grp, n_ids * 8 / grp->world + 1, st);
+  prof_mark(st, kProfAppend);
+  return rc;
 }
 
 extern "C" int lstep_pe_steps_peer(const lstep_pe_stream* s, const lstep_changelog* cl, const lstep_csr* csr, const lstep_peer_group* grp,

@@ -226,7 +226,7 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
   StepWs w = carve_step(workspace, n_ids, n_edges, n_queries, K, d, t, s->V1);
   cudaStream_t st = as_stream(stream);
   int rc;
-  prof_mark(st, kProfStart);
+  if (!opt.peer) prof_mark(st, kProfStart);
   // a3: filtered history of the batch nodes straight into the current table
   if (n_ids > 0 && !opt.skip_dft) {
     const bool no_prefetch = tuning().dft_prefetch == 0;
@@ -349,10 +349,12 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
       }
       update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters, &new_rows);
       if (n_a > 0 && (rc = peer_rows_bcast(new_rows, n_a, d, peer->pos_mine, peer->grp, 1, st)) != LSTEP_OK) return rc;
-      if ((rc = peer_signal(peer->grp, peer->epoch2, st)) != LSTEP_OK) return rc;
+      if (!second_half && (rc = peer_signal(peer->grp, peer->epoch2, st)) != LSTEP_OK) return rc;  // (else the wait launch announces)
+      prof_mark(st, kProfBcast);
     }
     if (!second_half) return LSTEP_OK;
-    if ((rc = peer_wait(peer->grp, peer->epoch2, peer->timeout_ms, err_flag, st)) != LSTEP_OK) return rc;
+    if ((rc = peer_wait(peer->grp, peer->epoch2, peer->timeout_ms, err_flag, st, first_half)) != LSTEP_OK) return rc;
+    prof_mark(st, kProfWait2);
     edges_done = phase_a_done = true;
     own.mul = peer->grp->world;
     own.add = peer->grp->rank;

@@ -40,7 +40,7 @@ int launch_sample_count(const lstep_csr* csr, const int64_t* q_node, const doubl
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
                        unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st,
-                       int own_mul = 1, int own_add = 0);
+                       unsigned long long* row0_part, int own_mul = 1, int own_add = 0);
 
 constexpr int kRow0Parts = 64;
 constexpr int kHubLen = 4;     // a warp reduces a destination's slot list serially (~430 dependent instructions per
@@ -51,6 +51,7 @@ struct UpdateWs {
   int32_t* cnt_of;   // [pe_rows]  zero between calls
   int32_t* slot_of;  // [pe_rows]  pull form: slot index of a destination; push form: stamp of the last step whose phase B changed the row
   int32_t* claim_of; // [pe_rows]  zero between calls (push form of phase B: 0 free, -1 being set up, j+1 = accumulator row j)
+  unsigned long long* push_row0;  // [kPushRow0Parts][kPushRow0Cols] zero between calls: partial sums of the padding row (push form)
   unsigned long long* hub_acc;  // [#long lists][d+t] 32.32 fixed-point accumulators (zeroed per call by the scan kernel)
   int32_t* counters; // [8]: 0=M, 1=has_zero, 2=n_dest, 3=n_hubs, 4=n_hub_tasks
   int32_t* src32;    // [E]
@@ -86,6 +87,7 @@ static UpdateWs carve(void* base, int64_t n_ids, int64_t n_edges, int K, int d, 
   w.cnt_of = (int32_t*)take(sizeof(int32_t) * pe_rows);
   w.slot_of = (int32_t*)take(sizeof(int32_t) * pe_rows);
   w.claim_of = (int32_t*)take(sizeof(int32_t) * pe_rows);
+  w.push_row0 = (unsigned long long*)take(kPushRow0Bytes);
   w.counters = (int32_t*)take(sizeof(int32_t) * 8);
   w.src32 = (int32_t*)take(sizeof(int32_t) * (n_edges + 4));
   w.dst32 = (int32_t*)take(sizeof(int32_t) * (n_edges + 4));
@@ -449,7 +451,7 @@ extern "C" size_t lstep_update_pe_workspace_bytes(int64_t n_ids, int64_t n_edges
 extern "C" int lstep_update_pe_workspace_init(void* workspace, size_t workspace_bytes, int64_t pe_rows, void* stream) {
   // the per-node maps at the head of the workspace (counter, slot, claim) must be zero on entry; every call
   // leaves them zero
-  const size_t head = 3 * align_up(sizeof(int32_t) * (size_t)pe_rows, 256);
+  const size_t head = 3 * align_up(sizeof(int32_t) * (size_t)pe_rows, 256) + kPushRow0Bytes;
   if (!workspace || pe_rows <= 0 || workspace_bytes < head) return LSTEP_ERR_INVALID_ARG;
   cudaError_t e = cudaMemsetAsync(workspace, 0, head, as_stream(stream));
   if (e != cudaSuccess) {
@@ -668,7 +670,7 @@ int lstep::update_pe_impl(float* pe, int64_t pe_rows, const lstep_csr* csr, cons
     if (update_push_available(mlp)) {
       rc = launch_phaseB_push(csr, ids, times, n_ids, n_valid, K, pe, d, t, mlp->tw, tc, w.claim_of, w.U, w.counters, w.push_acc,
                               w.slot_of, stamp, owner ? owner->new_rows : (phase_a_in_new_rows ? w.new_rows : nullptr), err_flag, st,
-                              owner ? owner->mul : 1, owner ? owner->add : 0);
+                              w.push_row0, owner ? owner->mul : 1, owner ? owner->add : 0);
       if (rc != LSTEP_OK) return rc;
       prof_mark(st, kProfPush);
       const int64_t total = n_ids * (int64_t)K;

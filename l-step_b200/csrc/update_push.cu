@@ -7,7 +7,7 @@
 // The pull form in csrc/update.cu builds an inverse index (count -> scan -> fill) and then reduces every
 // destination's slot list in the reference's order: four launches and a single-CTA scan, 40 us of a 110 us
 // step for ~1 MB of useful traffic. Here every contribution is ADDED WHERE IT LANDS:
-//   * kPushSplit small CTAs per batch node i, each owning a quarter of the K slots (the SM-side issue rate of
+//   * up to four small CTAs per batch node i (push_split_for), each owning a share of the K slots (the SM-side issue rate of
 //     64-bit reductions, ~1.3 cycles per lane, is what bounds the kernel: many small CTAs spread it evenly over
 //     the 148 SMs); warp 0 of each does the most-recent-K lookup (same 32-ary search as csrc/sampler.cu);
 //   * each distinct destination u is given a compact accumulator row on first touch: atomicCAS on a per-node
@@ -26,8 +26,12 @@
 namespace lstep {
 
 constexpr float kFixScale = 4294967296.f;  // 2^32
-constexpr int kPushSplit = 4;              // CTAs per batch node
-constexpr int kPushThreads = 64;
+constexpr int kPushThreads = 128;          // upper bound (launch bounds); small batches use 64-thread CTAs
+// CTAs per batch node: each repeats the node's lookup, so the split only pays while the launch has too few CTAs to fill
+// the GPU. Reddit shape (B = 200, ~310 batch nodes): 4 CTAs of 64 threads per node = 1 240 CTAs. B = 2000 (~3 800 batch
+// nodes): at 4 per node the launch is 15 208 CTAs = 3.2 waves of a 32-CTA-per-SM GPU, each wave a full lookup + claim latency
+// chain (73.6 us, profiles/r02_ncu_scaleout_kernels.txt); one 128-thread CTA per node is a single wave.
+inline int push_split_for(int64_t n_ids) { return n_ids <= 1184 ? 4 : (n_ids <= 2368 ? 2 : 1); }
 
 template <int DQ, int TQ>
 __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ c_nbr,
@@ -37,7 +41,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
                                                           const float* __restrict__ tw, float tc, int32_t* claim_of,
                                                           int64_t* __restrict__ U, int32_t* counters,
                                                           unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag,
-                                                          int own_mul, int own_add) {
+                                                          unsigned long long* row0_part, int own_mul, int own_add, int kPushSplit) {
   // own_mul > 1 (peer group, csrc/peer.cu): this rank accumulates only the destinations u with u % own_mul == own_add and
   // applies only the phase-A rows of the batch nodes it owns; the lookup of every batch node is replicated.
   // Dependency structure (programmatic dependent launch): the kernel in front is the phase-A MLP, launched with
@@ -59,7 +63,31 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
   const int part = blockIdx.x % kPushSplit;
   const int Kp = (K + kPushSplit - 1) / kPushSplit;
   const int k_lo = min(K, part * Kp), k_hi = min(K, k_lo + Kp);  // this CTA's slots
-  if (k_lo >= k_hi) return;
+  // the CTA that finishes last folds the partial sums of the padding row into its accumulator row (counters[5] counts
+  // finished CTAs; zeroed with the other counters by the step's edge-aggregate launch)
+  auto finish = [&]() {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(counters + 5, 1) == (int)gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int c0 = atomicAdd(claim_of + 0, 0);
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      long long sum = 0;
+      for (int p = 0; p < kPushRow0Parts; ++p) {
+        const long long v = (long long)__ldcg(row0_part + p * kPushRow0Cols + c);
+        sum += v;
+        if (v != 0) row0_part[p * kPushRow0Cols + c] = 0ull;
+      }
+      if (sum != 0 && c0 > 0) atomicAdd(acc + (size_t)(c0 - 1) * in1 + c, (unsigned long long)sum);
+    }
+  };
+  if (k_lo >= k_hi) {
+    finish();
+    return;
+  }
 
   if (warp == 0) {
     // ---- lookup: strictly-earlier count by warp-cooperative 32-ary search, last min(K, c) entries right-aligned
@@ -231,7 +259,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
     }
   }
   if (s_z > 0 && warp == nwarps - 1) {
-    unsigned long long* rowp = acc + (size_t)s_j0 * in1;
+    unsigned long long* rowp = row0_part + (size_t)(row % kPushRow0Parts) * kPushRow0Cols;
     const long long zz = s_z;
 #pragma unroll
     for (int q = 0; q < DQ; ++q) {
@@ -239,6 +267,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
       if (c < d) atomicAdd(rowp + c, (unsigned long long)(zz * fx[q]));
     }
   }
+  finish();
   TL_EXIT(3);
 }
 
@@ -247,16 +276,18 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
 int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q_time, int64_t n_ids, int64_t n_valid, int K,
                        float* pe, int d, int t, const float* tw, float tc, int32_t* claim_of, int64_t* U, int32_t* counters,
                        unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag, cudaStream_t st,
-                       int own_mul, int own_add) {
-  if (own_mul < 1 || own_add < 0 || own_add >= own_mul) return LSTEP_ERR_INVALID_ARG;
+                       unsigned long long* row0_part, int own_mul, int own_add) {
+  if (own_mul < 1 || own_add < 0 || own_add >= own_mul || !row0_part || d > kPushRow0Cols) return LSTEP_ERR_INVALID_ARG;
   if (!csr || !ids || !q_time || !dirty || n_ids <= 0 || K <= 0 || (d + t) % 2 != 0) return LSTEP_ERR_INVALID_ARG;
-  const size_t smem = (size_t)((K + kPushSplit - 1) / kPushSplit) * 12;
+  const int split = push_split_for(n_ids);
+  const int threads = split == 4 ? 64 : kPushThreads;
+  const size_t smem = (size_t)((K + split - 1) / split) * 12;
   if (d <= 6 * 32 && t <= 4 * 32)
-    launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, own_mul, own_add);
+    launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)(n_ids * split)), dim3(threads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, row0_part, own_mul, own_add, split);
   else if (d <= 8 * 32 && t <= 8 * 32)
-    launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)(n_ids * kPushSplit)), dim3(kPushThreads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, own_mul, own_add);
+    launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)(n_ids * split)), dim3(threads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, row0_part, own_mul, own_add, split);
   else
     return LSTEP_ERR_UNSUPPORTED;
   return check_launch("phaseB_push");

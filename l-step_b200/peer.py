@@ -86,7 +86,7 @@ class PeerRank:
                 sampler = NeighborSampler.from_edges(self.src, self.dst, eid, self.tt, "recent", device=dev, num_rows=self.V1)
                 del eid
             self.sampler = model.neighbor_sampler = sampler
-            # ---- memory the peers store into: table replica, phase-A row buffer, barrier flags
+            # ---- memory the peers store into: table replica, phase-A row buffer, barrier flags (and the inbox below)
             self._mem_table = _DevMem(lib, self.V1 * d * 4)
             self._mem_rows = _DevMem(lib, 2 * B * d * 4)
             self._mem_flags = _DevMem(lib, 16 * 4)
@@ -95,11 +95,14 @@ class PeerRank:
             self.new_rows = self._mem_rows.tensor((2 * B, d), torch.float32, dev)
             # ---- change log of the owned nodes
             self.rows_local = (self.V1 - self.rank + G - 1) // G
-            cap = event_capacity if event_capacity is not None else min(self.rows_local, 2 * (2 * B * (self.K + 1) + 2) // G + 1024)
+            # (the same on every rank: the inbox blocks, one per source rank, are laid out by it)
+            cap = event_capacity if event_capacity is not None else min((self.V1 + G - 1) // G, 2 * (2 * B * (self.K + 1) + 2) // G + 1024)
             self.cap = cap = int(max(cap, 1))
             H = 1
             while H < 2 * cap:
                 H *= 2
+            # inbox: one block per source rank for the rows that rank changed in a step
+            self._mem_inbox = _DevMem(lib, max(int(lib.lstep_peer_inbox_bytes(G, cap, d)), 256))
             self.base = self.cur[self.rank::G].contiguous().clone()
             self.ev_node = torch.zeros((T, cap), dtype=torch.int32, device=dev)
             self.ev_row = torch.empty((T, cap, d), dtype=torch.float32, device=dev)
@@ -143,29 +146,29 @@ class PeerRank:
         self._opened = []
 
     # ---- group wiring ---------------------------------------------------------------------------------------------------
-    def set_group(self, tables, rows, flags):
-        """Device pointers (ints) of every rank's table replica / new_rows buffer / flag block, indexed by rank."""
+    def set_group(self, tables, rows, flags, inboxes):
+        """Device pointers (ints) of every rank's table replica / new_rows buffer / flag block / inbox, indexed by rank."""
         g = _lib.PeerGroup()
-        g.rank, g.world = self.rank, self.G
+        g.rank, g.world, g.inbox_cap = self.rank, self.G, self.cap
         for i in range(self.G):
-            g.table[i], g.new_rows[i], g.flags[i] = tables[i], rows[i], flags[i]
+            g.table[i], g.new_rows[i], g.flags[i], g.inbox[i] = tables[i], rows[i], flags[i], inboxes[i]
         assert g.table[self.rank] == self.cur.data_ptr()
         self.grp = g
 
     def local_ptrs(self):
-        return self._mem_table.ptr, self._mem_rows.ptr, self._mem_flags.ptr
+        return self._mem_table.ptr, self._mem_rows.ptr, self._mem_flags.ptr, self._mem_inbox.ptr
 
     def connect_ipc(self, group=None):
         """One process per GPU: exchange the CUDA IPC handles of the three peer-written blocks through torch.distributed and open
         the other ranks' (cudaIpcOpenMemHandle enables peer access over NVLink)."""
         import torch.distributed as dist
-        mine = (self.rank, self._mem_table.handle(), self._mem_rows.handle(), self._mem_flags.handle())
+        mine = (self.rank, self._mem_table.handle(), self._mem_rows.handle(), self._mem_flags.handle(), self._mem_inbox.handle())
         allh = [None] * self.G
         if self.G > 1:
             dist.all_gather_object(allh, mine, group=group)
         else:
             allh = [mine]
-        ptrs = [[0] * self.G for _ in range(3)]
+        ptrs = [[0] * self.G for _ in range(4)]
         for r, *hs in allh:
             for k, h in enumerate(hs):
                 if r == self.rank:
@@ -262,11 +265,11 @@ class PeerRank:
         return out
 
     def barrier(self):
-        """Every rank's stores up to here are visible in every replica once the kernels this enqueues have run."""
+        """Barrier + application of the inboxes: once the kernels this enqueues have run, this replica holds every rank's rows."""
         e = (self.epoch.value + 1) & 0xffffffff
         with torch.cuda.device(self.dev):
-            _lib.check(self.lib.lstep_peer_signal(ctypes.byref(self.grp), e, _lib.stream_ptr()), "peer_signal")
-            _lib.check(self.lib.lstep_peer_wait(ctypes.byref(self.grp), e, self.timeout_ms, _lib.ptr(self.sampler._err), _lib.stream_ptr()), "peer_wait")
+            _lib.check(self.lib.lstep_peer_sync_tables(ctypes.byref(self.grp), e, self.timeout_ms, _lib.ptr(self.sampler._err), self.d, self.V1,
+                                                       _lib.stream_ptr()), "peer_sync_tables")
         self.epoch = ctypes.c_uint32((self.epoch.value + 2) & 0xffffffff)
 
     def check_errors(self):
@@ -301,7 +304,8 @@ class PeerLocalGroup:
 
     def __init__(self, ranks):
         self.ranks, self.G = ranks, len(ranks)
-        ptrs = [[rk.local_ptrs()[k] for rk in ranks] for k in range(3)]
+        assert len({rk.cap for rk in ranks}) == 1
+        ptrs = [[rk.local_ptrs()[k] for rk in ranks] for k in range(4)]
         for rk in ranks:
             rk.set_group(*ptrs)
 
@@ -318,6 +322,4 @@ class PeerLocalGroup:
             e = (rk.epoch.value + 1) & 0xffffffff
             _lib.check(rk.lib.lstep_peer_signal(ctypes.byref(rk.grp), e, _lib.stream_ptr()), "peer_signal")
         for rk in self.ranks:
-            e = (rk.epoch.value + 1) & 0xffffffff
-            _lib.check(rk.lib.lstep_peer_wait(ctypes.byref(rk.grp), e, rk.timeout_ms, _lib.ptr(rk.sampler._err), _lib.stream_ptr()), "peer_wait")
-            rk.epoch = ctypes.c_uint32((rk.epoch.value + 2) & 0xffffffff)
+            rk.barrier()
