@@ -468,7 +468,7 @@ def run_sharded(args, rank, world, own_pg=True):
                          "batch_nodes_mean": n_ids_mean, "replicas_equal_after_run": replicas_equal,
                          "per_kernel_ms_median_by_rank": all_pk},
             "clocks": clk, "e2e": e2e,
-            "gpu_launches": int(Ksteps * 12 * world),
+            "gpu_launches": int(Ksteps * 10 * world),
             "roofline": None, "cpu_baseline": None,
         }
         if own_pg:

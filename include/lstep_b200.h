@@ -342,9 +342,11 @@ int lstep_pe_step_changelog(const lstep_pe_stream* s, const lstep_changelog* cl,
  * Peer group: the scale-out step over NVLink peer memory (csrc/peer.cu; BASELINE config 5).
  * One process per GPU. Every rank keeps a REPLICA of the current PE table and of the temporal CSR and OWNS the nodes
  * v with v % world == rank: their PE history (change log), their share of every phase of the step, and the duty to
- * publish every row it changes. A step on rank r:
- *     filter      DFT filter of the owned batch nodes; the filtered row is stored into EVERY replica (peer stores)
- *     barrier 1   (flag exchange through peer memory, no host, no NCCL)
+ * make every row it changes available. A step on rank r:
+ *     filter      DFT filter of the owned batch nodes into the local table and, at the node's position in the batch's id list,
+ *                 into every other rank's filt buffer
+ *     barrier 1   (flag exchange through peer memory, no host, no NCCL) + refresh of the replica in the same launch: the rows
+ *                 the previous step changed on the other ranks (this rank's inbox) and the other owners' filtered rows
  *     gather      a6 for this rank's 1/world share of the query rows || a7 edge aggregate of the OWNED batch nodes
  *     MLP pair    neighbourhood MLP of the share || phase-A MLP of the owned batch nodes; the phase-A rows are stored
  *                 into every rank's new_rows buffer at the node's position in the batch's id list
@@ -353,30 +355,32 @@ int lstep_pe_step_changelog(const lstep_pe_stream* s, const lstep_changelog* cl,
  *                 destinations (u % world == rank); the owned batch nodes' phase-A rows are applied to the local table
  *     MLP (B)     over the owned destinations
  *     append      the owned changed rows (owned batch nodes + owned destinations + row 0 on rank 0) become events of
- *                 the change log AND are copied, as one contiguous block, into every other rank's inbox; the receivers
- *                 scatter them into their replicas right after the next step's barrier 1.
+ *                 the change log
+ *     publish     ... and are copied, as one contiguous block, into every other rank's inbox.
  * Nothing a rank reads between two barriers is written by another rank in that interval (csrc/peer.cu states the
- * argument), so the replicas agree at every barrier 1 and the results are those of the single-GPU step, bit for bit
+ * argument), so the replicas agree after every refresh and the results are those of the single-GPU step, bit for bit
  * (phase B's sums are exact fixed point, hence independent of which rank adds them).
- * Memory that peers write (table replica, new_rows, flags) is allocated with lstep_ipc_alloc (cudaMalloc) and shared
+ * Memory that peers write (inbox, filt, new_rows, flags) is allocated with lstep_ipc_alloc (cudaMalloc) and shared
  * with the CUDA IPC handles of lstep_ipc_export / lstep_ipc_open; in a single process (tests) plain device pointers of
  * several rank states can be used instead.
  * ------------------------------------------------------------------------------------------ */
 #define LSTEP_MAX_PEERS 16
 typedef struct lstep_peer_group {
   int rank, world;
-  float* table[LSTEP_MAX_PEERS];     /* table replica of every rank, [V1 (+ spare rows), d]; table[rank] == s->cur */
-  float* new_rows[LSTEP_MAX_PEERS];  /* phase-A row buffer of every rank, [max batch nodes, d] */
+  float* table[LSTEP_MAX_PEERS];     /* table[rank] = this rank's table replica (== s->cur); the other entries are unused */
+  /* WRITTEN by the other ranks — small, fixed regions only (scattered accesses to a multi-GB peer mapping, and reads of peer
+   * memory, are slow: profiles/r02_peer_bw.txt, profiles/r02_scaleout_history.md): */
+  float* new_rows[LSTEP_MAX_PEERS];  /* phase-A row buffer of every rank, [max batch nodes, d], row p = the node at position p of
+                                        the batch's id list, written by its owner */
+  float* filt[LSTEP_MAX_PEERS];      /* filtered-row buffer of every rank, same indexing, written by the owners' filter kernels */
+  void* inbox[LSTEP_MAX_PEERS];      /* inbox of every rank, lstep_peer_inbox_bytes(world, cap, d) bytes: one block per SOURCE rank =
+                                        { int32 count, pad[3]; int32 node[cap]; float row[cap][d] } — the rows that rank changed
+                                        in the previous step, copied there by its publish kernel */
   uint32_t* flags[LSTEP_MAX_PEERS];  /* flag block of every rank, uint32[LSTEP_MAX_PEERS]: flags[g][r] = last barrier epoch
                                         rank r has announced to rank g (zero-initialised, epochs start at 1) */
-  void* inbox[LSTEP_MAX_PEERS];      /* inbox of every rank, lstep_peer_inbox_bytes(world, inbox_cap, d) bytes: one block per SOURCE
-                                        rank = { int32 count, pad; int32 node[inbox_cap]; float row[inbox_cap][d] } — the rows a
-                                        rank changed in a step, written CONTIGUOUSLY by their owner (scattered peer stores
-                                        into a multi-GB replica thrash the peer-mapping TLB: 43 GB/s measured against 500 GB/s
-                                        contiguous, profiles/r02_peer_bw.txt) and scattered into the table by the receiver */
-  int64_t inbox_cap;                 /* rows per source block (>= the change log's event capacity) */
+  int64_t cap;                       /* rows per inbox block (>= the change logs' event capacity; the same on every rank) */
 } lstep_peer_group;
-size_t lstep_peer_inbox_bytes(int world, int64_t inbox_cap, int d);
+size_t lstep_peer_inbox_bytes(int world, int64_t cap, int d);
 int lstep_ipc_alloc(size_t bytes, void** ptr);                         /* cudaMalloc + zero fill */
 int lstep_ipc_free(void* ptr);
 int lstep_ipc_export(void* ptr, unsigned char handle_out[64]);         /* cudaIpcGetMemHandle */
@@ -386,8 +390,8 @@ int lstep_ipc_close(void* ptr);
  * and raises LSTEP_FLAG_PEER_TIMEOUT in *err_flag instead of hanging the device) */
 int lstep_peer_signal(const lstep_peer_group* g, uint32_t epoch, void* stream);
 int lstep_peer_wait(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, void* stream);
-/* announce `epoch`, wait for every rank, then apply the inboxes (the rows the last step changed): afterwards, in stream order,
- * this rank's replica equals every other one (what a caller does before it reads the table after the last step) */
+/* announce `epoch`, wait for every rank, then apply the inbox (the rows the last step changed on the other ranks): afterwards, in
+ * stream order, this rank's replica equals every other one (what a caller does before it reads the table after the last step) */
 int lstep_peer_sync_tables(const lstep_peer_group* g, uint32_t epoch, int timeout_ms, uint32_t* err_flag, int d, int64_t V1, void* stream);
 /* dst[g][dst_rows[i]][0..d) = src[i][0..d) for every rank g whose bit is set in rank_mask (dst_rows NULL: row i); which = 0: the
  * table replicas, 1: the new_rows buffers. The building block of the step's row publication (also used to measure the

@@ -40,8 +40,8 @@ class ChangeLog(C.Structure):
 
 class PeerGroup(C.Structure):
     """struct lstep_peer_group"""
-    _fields_ = [("rank", i32), ("world", i32), ("table", vp * 16), ("new_rows", vp * 16), ("flags", vp * 16), ("inbox", vp * 16),
-                ("inbox_cap", i64)]
+    _fields_ = [("rank", i32), ("world", i32), ("table", vp * 16), ("new_rows", vp * 16), ("filt", vp * 16), ("inbox", vp * 16),
+                ("flags", vp * 16), ("cap", i64)]
 
 
 class PEMLP(C.Structure):

@@ -54,11 +54,12 @@ __device__ __forceinline__ int hash_find(const unsigned long long* __restrict__ 
   return -1;
 }
 
-// Table replicas of the other ranks of a peer group (csrc/peer.cu): a row written to the local table is stored to the same
-// row of every replica as well (NVLink peer stores; published by the group's next barrier).
-struct PeerTables {
+// Optional extra destinations of a filtered row (peer group, csrc/peer.cu): row n also goes to p[g] + ids[n] * out_stride — the
+// other ranks' filt buffers, indexed by the node's position in the batch's id list (small, fixed regions of peer memory).
+struct Out2 {
   float* p[LSTEP_MAX_PEERS];
-  int n;  // number of OTHER replicas
+  int n;
+  const int64_t* ids;
 };
 
 // A node's value is piecewise constant over the window: version 0 = the base row, version j = the row of its j-th event;
@@ -133,19 +134,22 @@ __device__ __forceinline__ void filter_versions(const lstep_changelog& cl, int h
   }
 }
 __device__ __forceinline__ void filter_store(float* __restrict__ out, int64_t orow, int64_t out_stride, int lane, bool has2, const FilterAcc& acc,
-                                             const PeerTables& peers) {
+                                             const Out2& o2, int64_t n) {
   *reinterpret_cast<float4*>(out + orow * out_stride + 4 * lane) = acc.a0;
   if (has2) *reinterpret_cast<float4*>(out + orow * out_stride + 4 * (lane + 32)) = acc.a1;
-  for (int g = 0; g < peers.n; ++g) {
-    *reinterpret_cast<float4*>(peers.p[g] + orow * out_stride + 4 * lane) = acc.a0;
-    if (has2) *reinterpret_cast<float4*>(peers.p[g] + orow * out_stride + 4 * (lane + 32)) = acc.a1;
+  if (o2.n) {
+    const int64_t off = o2.ids[n] * out_stride;
+    for (int g = 0; g < o2.n; ++g) {
+      *reinterpret_cast<float4*>(o2.p[g] + off + 4 * lane) = acc.a0;
+      if (has2) *reinterpret_cast<float4*>(o2.p[g] + off + 4 * (lane + 32)) = acc.a1;
+    }
   }
 }
 
 __global__ void __launch_bounds__(kFilterWarps * 32, 2) changelog_filter_kernel(lstep_changelog cl, int head, int len, const int64_t* __restrict__ ids,
                                                                                 int64_t n_ids, const float* __restrict__ G, float* __restrict__ out,
                                                                                 int64_t out_stride, const int64_t* __restrict__ out_ids,
-                                                                                PeerTables peers) {
+                                                                                Out2 o2) {
   __shared__ int s_evf_all[kFilterWarps][130];  // window positions that carry an event (ascending), then `len`
   __shared__ int s_evi_all[kFilterWarps][129];  // their event indices
   __shared__ int s_ne[kFilterWarps];            // events of the warp's node, -1: no node / done by the warp itself
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 2) changelog_filter_kernel(
         if (lane < dvec) {
           FilterAcc acc{make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
           filter_versions(cl, head, lrow, s_evf, s_evi, ne, 0, 1, Gv, lane, has2, acc);
-          filter_store(out, out_ids ? out_ids[n] : n, out_stride, lane, has2, acc, peers);
+          filter_store(out, out_ids ? out_ids[n] : n, out_stride, lane, has2, acc, o2, n);
         }
         ne = -1;
       }
@@ -232,12 +236,12 @@ __global__ void __launch_bounds__(kFilterWarps * 32, 2) changelog_filter_kernel(
             acc.a1.w += p1.w;
           }
         }
-        filter_store(out, out_ids ? out_ids[n_w] : n_w, out_stride, lane, has2, acc, peers);
+        filter_store(out, out_ids ? out_ids[n_w] : n_w, out_stride, lane, has2, acc, o2, n_w);
       }
       __syncthreads();
     }
   }
-  if (peers.n) __threadfence_system();
+  if (o2.n) __threadfence_system();
 }
 
 // The events of `slot` (the step leaving the window) become base rows; their mask bits are cleared; the slot is made ready
@@ -373,30 +377,28 @@ bool valid(const lstep_changelog* cl) {
 using namespace lstep;
 
 namespace lstep {
-static PeerTables other_tables(const lstep_peer_group* grp) {
-  PeerTables pt{};
-  if (grp)
-    for (int g = 0; g < grp->world; ++g)
-      if (g != grp->rank) pt.p[pt.n++] = grp->table[g];
-  return pt;
-}
 int changelog_filter_peer(const lstep_changelog* cl, int head, int len, const int64_t* ids, int64_t n_ids, const float* G, float* out,
-                          int64_t out_stride, const int64_t* out_ids, const lstep_peer_group* grp, void* stream);
+                          int64_t out_stride, const int64_t* out_ids, float* const* out2, int n_out2, const int64_t* out2_ids, void* stream);
 }  // namespace lstep
 
 extern "C" int lstep_changelog_filter(const lstep_changelog* cl, int head, int len, const int64_t* ids, int64_t n_ids, const float* G,
                                       float* out, int64_t out_stride, const int64_t* out_ids, void* stream) {
-  return changelog_filter_peer(cl, head, len, ids, n_ids, G, out, out_stride, out_ids, nullptr, stream);
+  return changelog_filter_peer(cl, head, len, ids, n_ids, G, out, out_stride, out_ids, nullptr, 0, nullptr, stream);
 }
 int lstep::changelog_filter_peer(const lstep_changelog* cl, int head, int len, const int64_t* ids, int64_t n_ids, const float* G, float* out,
-                                 int64_t out_stride, const int64_t* out_ids, const lstep_peer_group* grp, void* stream) {
+                                 int64_t out_stride, const int64_t* out_ids, float* const* out2, int n_out2, const int64_t* out2_ids, void* stream) {
+  if (n_out2 < 0 || n_out2 > LSTEP_MAX_PEERS || (n_out2 > 0 && (!out2 || !out2_ids))) return LSTEP_ERR_INVALID_ARG;
+  Out2 o2{};
+  for (int g = 0; g < n_out2; ++g) o2.p[g] = out2[g];
+  o2.n = n_out2;
+  o2.ids = out2_ids;
   if (!valid(cl) || head < 0 || head >= cl->T || len < 0 || len > cl->T || n_ids < 0) return LSTEP_ERR_INVALID_ARG;
   if (n_ids == 0) return LSTEP_OK;
   if (!ids || !G || !out || out_stride % 4 != 0 || (reinterpret_cast<uintptr_t>(out) & 15)) return LSTEP_ERR_INVALID_ARG;
   if (cl->d > 256) return LSTEP_ERR_UNSUPPORTED;  // (a lane owns two 16-byte column groups)
   const int64_t grid = std::min<int64_t>(ceil_div(n_ids, kFilterWarps), (int64_t)num_sms() * 8);
   launch_k(changelog_filter_kernel, dim3((unsigned)grid), dim3(kFilterWarps * 32), 0, as_stream(stream), *cl, head, len, ids, n_ids, G, out, out_stride,
-           out_ids, other_tables(grp));
+           out_ids, o2);
   return check_launch("changelog_filter");
 }
 

@@ -2,10 +2,10 @@
 
 One process per GPU. Every rank keeps a replica of the current PE table and of the temporal CSR and OWNS the nodes v with
 v % world == rank: their PE history (change log) and every piece of the step whose result is a row of an owned node —
-1 / world of the DFT filter, of the a6 query rows, of update_pe's phase A and phase B. Owners store the rows they change
-straight into the other replicas through peer pointers (CUDA IPC over NVLink / NVSwitch); two flag barriers per step, also
-in peer memory, order those stores against the readers. No NCCL call, no host synchronisation and no data-dependent message
-size is on the step's path. The protocol and the argument why two barriers suffice are in csrc/peer.cu; the C entry points
+1 / world of the DFT filter, of the a6 query rows, of update_pe's phase A and phase B. Owners copy the rows they change, as
+contiguous blocks, into small fixed inbox regions of the other ranks through peer pointers (CUDA IPC over NVLink / NVSwitch);
+every rank scatters its inbox into its replica right after the first of the two flag barriers of a step (also in peer memory).
+No NCCL call, no host synchronisation and no data-dependent message size is on the step's path. The protocol and the argument why two barriers suffice are in csrc/peer.cu; the C entry points
 are lstep_pe_step_peer / lstep_pe_steps_peer (include/lstep_b200.h).
 
     PeerRank         this rank's state: table replica, change log of the owned nodes, per-batch plan, peer-shared buffers
@@ -86,23 +86,23 @@ class PeerRank:
                 sampler = NeighborSampler.from_edges(self.src, self.dst, eid, self.tt, "recent", device=dev, num_rows=self.V1)
                 del eid
             self.sampler = model.neighbor_sampler = sampler
-            # ---- memory the peers store into: table replica, phase-A row buffer, barrier flags (and the inbox below)
-            self._mem_table = _DevMem(lib, self.V1 * d * 4)
-            self._mem_rows = _DevMem(lib, 2 * B * d * 4)
-            self._mem_flags = _DevMem(lib, 16 * 4)
-            self.cur = self._mem_table.tensor((self.V1, d), torch.float32, dev)
-            self.cur.copy_(initial_pe.to(dev, torch.float32))
-            self.new_rows = self._mem_rows.tensor((2 * B, d), torch.float32, dev)
-            # ---- change log of the owned nodes
+            # ---- memory the other ranks WRITE (cudaMalloc + CUDA IPC; small fixed regions): phase-A row buffer, filtered-row buffer,
+            # inbox (one block per source rank for the rows it changed in a step), barrier flags
             self.rows_local = (self.V1 - self.rank + G - 1) // G
-            # (the same on every rank: the inbox blocks, one per source rank, are laid out by it)
+            # (the same on every rank: the inbox blocks are laid out by it)
             cap = event_capacity if event_capacity is not None else min((self.V1 + G - 1) // G, 2 * (2 * B * (self.K + 1) + 2) // G + 1024)
             self.cap = cap = int(max(cap, 1))
             H = 1
             while H < 2 * cap:
                 H *= 2
-            # inbox: one block per source rank for the rows that rank changed in a step
+            self._mem_rows = _DevMem(lib, 2 * B * d * 4)
+            self._mem_filt = _DevMem(lib, 2 * B * d * 4)
             self._mem_inbox = _DevMem(lib, max(int(lib.lstep_peer_inbox_bytes(G, cap, d)), 256))
+            self._mem_flags = _DevMem(lib, 16 * 4)
+            self.cur = torch.empty((self.V1, d), dtype=torch.float32, device=dev)
+            self.cur.copy_(initial_pe.to(dev, torch.float32))
+            self.new_rows = self._mem_rows.tensor((2 * B, d), torch.float32, dev)
+            # ---- change log of the owned nodes
             self.base = self.cur[self.rank::G].contiguous().clone()
             self.ev_node = torch.zeros((T, cap), dtype=torch.int32, device=dev)
             self.ev_row = torch.empty((T, cap, d), dtype=torch.float32, device=dev)
@@ -146,29 +146,31 @@ class PeerRank:
         self._opened = []
 
     # ---- group wiring ---------------------------------------------------------------------------------------------------
-    def set_group(self, tables, rows, flags, inboxes):
-        """Device pointers (ints) of every rank's table replica / new_rows buffer / flag block / inbox, indexed by rank."""
+    _SHARED = ("_mem_rows", "_mem_filt", "_mem_inbox", "_mem_flags")
+
+    def set_group(self, rows, filts, inboxes, flags):
+        """Device pointers (ints) of every rank's new_rows buffer / filt buffer / inbox / flag block, indexed by rank."""
         g = _lib.PeerGroup()
-        g.rank, g.world, g.inbox_cap = self.rank, self.G, self.cap
+        g.rank, g.world, g.cap = self.rank, self.G, self.cap
         for i in range(self.G):
-            g.table[i], g.new_rows[i], g.flags[i], g.inbox[i] = tables[i], rows[i], flags[i], inboxes[i]
-        assert g.table[self.rank] == self.cur.data_ptr()
+            g.new_rows[i], g.filt[i], g.inbox[i], g.flags[i] = rows[i], filts[i], inboxes[i], flags[i]
+        g.table[self.rank] = self.cur.data_ptr()
         self.grp = g
 
     def local_ptrs(self):
-        return self._mem_table.ptr, self._mem_rows.ptr, self._mem_flags.ptr, self._mem_inbox.ptr
+        return tuple(getattr(self, m).ptr for m in self._SHARED)
 
     def connect_ipc(self, group=None):
         """One process per GPU: exchange the CUDA IPC handles of the three peer-written blocks through torch.distributed and open
         the other ranks' (cudaIpcOpenMemHandle enables peer access over NVLink)."""
         import torch.distributed as dist
-        mine = (self.rank, self._mem_table.handle(), self._mem_rows.handle(), self._mem_flags.handle(), self._mem_inbox.handle())
+        mine = (self.rank,) + tuple(getattr(self, m).handle() for m in self._SHARED)
         allh = [None] * self.G
         if self.G > 1:
             dist.all_gather_object(allh, mine, group=group)
         else:
             allh = [mine]
-        ptrs = [[0] * self.G for _ in range(4)]
+        ptrs = [[0] * self.G for _ in range(len(self._SHARED))]
         for r, *hs in allh:
             for k, h in enumerate(hs):
                 if r == self.rank:
@@ -265,7 +267,8 @@ class PeerRank:
         return out
 
     def barrier(self):
-        """Barrier + application of the inboxes: once the kernels this enqueues have run, this replica holds every rank's rows."""
+        """Barrier + application of the inbox: once the kernels this enqueues have run, this replica holds the rows every rank changed
+        in the last step."""
         e = (self.epoch.value + 1) & 0xffffffff
         with torch.cuda.device(self.dev):
             _lib.check(self.lib.lstep_peer_sync_tables(ctypes.byref(self.grp), e, self.timeout_ms, _lib.ptr(self.sampler._err), self.d, self.V1,
@@ -305,7 +308,7 @@ class PeerLocalGroup:
     def __init__(self, ranks):
         self.ranks, self.G = ranks, len(ranks)
         assert len({rk.cap for rk in ranks}) == 1
-        ptrs = [[rk.local_ptrs()[k] for rk in ranks] for k in range(4)]
+        ptrs = [[rk.local_ptrs()[k] for rk in ranks] for k in range(len(PeerRank._SHARED))]
         for rk in ranks:
             rk.set_group(*ptrs)
 

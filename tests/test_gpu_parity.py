@@ -766,7 +766,7 @@ def test_peer_group_emulated_is_bit_identical_to_single_gpu(torch_cuda, world):
         got = torch.cat(grp.step(b, qs), dim=1)
         assert got.shape == want.shape and torch.equal(got, want), b
         if b % 10 == 0 or b == st.num_batches - 1:
-            # a replica holds the other owners' rows of a step once their inbox blocks are applied (normally at the next step's
+            # a replica holds the other owners' rows of a step once it has pulled them (normally at the next step's
             # barrier 1; here by an extra synchronisation, which later steps must tolerate)
             grp.barrier()
             for rk in ranks:
