@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
                                                           const float* __restrict__ tw, float tc, int32_t* claim_of,
                                                           int64_t* __restrict__ U, int32_t* counters,
                                                           unsigned long long* acc, int32_t* dirty, int stamp, const float* new_rows, uint32_t* err_flag,
-                                                          unsigned long long* row0_part, int own_mul, int own_add, int kPushSplit) {
+                                                          unsigned long long* row0_part, int own_mul, int own_add, int kPushSplit,
+                                                          int use_parts) {
   // own_mul > 1 (peer group, csrc/peer.cu): this rank accumulates only the destinations u with u % own_mul == own_add and
   // applies only the phase-A rows of the batch nodes it owns; the lookup of every batch node is replicated.
   // Dependency structure (programmatic dependent launch): the kernel in front is the phase-A MLP, launched with
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
   // finished CTAs; zeroed with the other counters by the step's edge-aggregate launch)
   auto finish = [&]() {
     __shared__ int s_last;
+    if (!use_parts) return;  // (small batches add to the padding row's accumulator directly: the contention is small there)
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(counters + 5, 1) == (int)gridDim.x - 1;
@@ -76,11 +78,16 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
     const int c0 = atomicAdd(claim_of + 0, 0);
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
       long long sum = 0;
-      for (int p = 0; p < kPushRow0Parts; ++p) {
-        const long long v = (long long)__ldcg(row0_part + p * kPushRow0Cols + c);
-        sum += v;
-        if (v != 0) row0_part[p * kPushRow0Cols + c] = 0ull;
+#pragma unroll
+      for (int p0 = 0; p0 < kPushRow0Parts; p0 += 8) {  // eight loads in flight
+        long long v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (long long)__ldcg(row0_part + (p0 + u) * kPushRow0Cols + c);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum += v[u];
       }
+#pragma unroll
+      for (int p = 0; p < kPushRow0Parts; ++p) row0_part[p * kPushRow0Cols + c] = 0ull;
       if (sum != 0 && c0 > 0) atomicAdd(acc + (size_t)(c0 - 1) * in1 + c, (unsigned long long)sum);
     }
   };
@@ -259,7 +266,7 @@ __global__ void __launch_bounds__(kPushThreads) phaseB_push_kernel(const int64_t
     }
   }
   if (s_z > 0 && warp == nwarps - 1) {
-    unsigned long long* rowp = row0_part + (size_t)(row % kPushRow0Parts) * kPushRow0Cols;
+    unsigned long long* rowp = use_parts ? row0_part + (size_t)(row % kPushRow0Parts) * kPushRow0Cols : acc + (size_t)s_j0 * in1;
     const long long zz = s_z;
 #pragma unroll
     for (int q = 0; q < DQ; ++q) {
@@ -284,12 +291,13 @@ int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q
   // of one warp per SM all ~3 800 replicated lookups of a B = 2000 batch are in flight in a single wave)
   const int threads = own_mul >= 4 ? 32 : (split == 4 ? 64 : kPushThreads);
   const size_t smem = (size_t)((K + split - 1) / split) * 12;
+  const int use_parts = split < 4 ? 1 : 0;  // padding-row partial sums + fold: only where thousands of CTAs would hit one row
   if (d <= 6 * 32 && t <= 4 * 32)
     launch_k(phaseB_push_kernel<6, 4>, dim3((unsigned)(n_ids * split)), dim3(threads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, row0_part, own_mul, own_add, split);
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, row0_part, own_mul, own_add, split, use_parts);
   else if (d <= 8 * 32 && t <= 8 * 32)
     launch_k(phaseB_push_kernel<8, 8>, dim3((unsigned)(n_ids * split)), dim3(threads), smem, st, csr->indptr, csr->nbr, csr->t, csr->num_rows, ids,
-             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, row0_part, own_mul, own_add, split);
+             q_time, n_ids, n_valid, K, pe, d, t, tw, tc, claim_of, U, counters, acc, dirty, stamp, new_rows, err_flag, row0_part, own_mul, own_add, split, use_parts);
   else
     return LSTEP_ERR_UNSUPPORTED;
   return check_launch("phaseB_push");
