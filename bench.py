@@ -316,7 +316,7 @@ def run_sharded(args, rank, world, own_pg=True):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     assert lib.lstep_device_ok() == 1
-    B, K = 2000, 20
+    B, K = args.scaleout_batch, 20
     T = args.scaleout_T if args.scaleout_T else T_HIST
     V, E = args.scaleout_nodes, args.scaleout_edges
     t0 = time.time()
@@ -866,6 +866,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="reddit", choices=sorted(WORKLOADS) + ["scaleout"])
     ap.add_argument("--replicas", action="store_true", help="N > 1: only the replicas of the single-GPU workload (skip the sharded scale-out sample)")
+    ap.add_argument("--scaleout-batch", type=int, default=2000, help="edges per step of the scale-out arm (BASELINE config 5 is quoted at 2000)")
     ap.add_argument("--scaleout-nodes", type=int, default=10_000_000)
     ap.add_argument("--scaleout-edges", type=int, default=100_000_000)
     ap.add_argument("--scaleout-T", type=int, default=0, help="history steps per node of the scale-out arm (default: 100 with the change-log "
