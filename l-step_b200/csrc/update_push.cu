@@ -287,9 +287,9 @@ int launch_phaseB_push(const lstep_csr* csr, const int64_t* ids, const double* q
   if (own_mul < 1 || own_add < 0 || own_add >= own_mul || !row0_part || d > kPushRow0Cols) return LSTEP_ERR_INVALID_ARG;
   if (!csr || !ids || !q_time || !dirty || n_ids <= 0 || K <= 0 || (d + t) % 2 != 0) return LSTEP_ERR_INVALID_ARG;
   const int split = push_split_for(n_ids);
-  // (peer group of >= 4 ranks: a CTA accumulates only the ~K / world slots this rank owns — one warp is enough, and with 32 CTAs
-  // of one warp per SM all ~3 800 replicated lookups of a B = 2000 batch are in flight in a single wave)
-  const int threads = own_mul >= 4 ? 32 : (split == 4 ? 64 : kPushThreads);
+  // (peer group of >= 4 ranks: a CTA accumulates only the ~K / world slots this rank owns — two warps are enough, and twice as many
+  // CTAs are resident for the replicated lookups; ONE warp per CTA was measured slower: push 42 -> 51 us at N=4, 37 -> 43 us at N=8)
+  const int threads = (split == 4 || own_mul >= 4) ? 64 : kPushThreads;
   const size_t smem = (size_t)((K + split - 1) / split) * 12;
   const int use_parts = split < 4 ? 1 : 0;  // padding-row partial sums + fold: only where thousands of CTAs would hit one row
   if (d <= 6 * 32 && t <= 4 * 32)
