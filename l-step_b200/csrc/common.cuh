@@ -30,6 +30,7 @@ struct Tuning {
   int mlp_ring = 0;           // all-columns ring MLP kernel instead of the cluster kernel         (LSTEP_MLP_RING)
   int host_memcpy = 0;        // cudaMemcpyAsync instead of the copy-in kernel in the host-fed step (LSTEP_HOST_MEMCPY)
   int query_dedup = 1;        // identical query sets of a step are computed once                  (LSTEP_NO_QUERY_DEDUP)
+  int gather_pipe = 1;        // multi-row gather CTAs with a look-ahead lookup warp (B = 2000)     (LSTEP_NO_GATHER_PIPE)
   int mlp_umma = 1;           // tcgen05 tensor-core MLP for launches with >= mlp_umma_min_rows rows (LSTEP_NO_MLP_UMMA)
   int mlp_umma_min_rows = 1536;  //                                                                (LSTEP_MLP_UMMA_MIN_ROWS)
   int profile = 0;            // lstep_step_profile(): CUDA events around every kernel of the streaming step

@@ -142,6 +142,108 @@ __device__ __forceinline__ void nbr_aggregate_rows(int64_t first_row, int64_t ro
   }
 }
 
+// The same rows for launches in which a CTA walks SEVERAL query rows (B = 2000: 6 000 rows over one wave of CTAs): an extra warp
+// (threads [lk_base, lk_base + 32)) does nothing but the most-recent-K lookups and runs ONE ROW AHEAD of the cosine / table
+// threads through a double-buffered neighbour list — the lookup is a chain of ~5 dependent L2 / HBM round trips (~3 us)
+// during which, in the form above, the other 160 threads of the CTA wait. Same arithmetic, same order: results are
+// bit-identical to nbr_aggregate_rows. (float4 table path only; late_wait as above.)
+__device__ __forceinline__ void nbr_aggregate_rows_piped(int64_t first_row, int64_t row_stride, bool late_wait, const float* __restrict__ pe,
+                                                         const double* __restrict__ q_time, int64_t n_rows, int K,
+                                                         const float* __restrict__ tw, int d, int t, int t_pad, float* __restrict__ S,
+                                                         int64_t ldS, int64_t period, LookupArgs lk, int tf_threads, int lk_base) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int32_t* s_nbr_all = reinterpret_cast<int32_t*>(smem_raw);       // [2][K]
+  float* s_dt_all = reinterpret_cast<float*>(s_nbr_all + 2 * K);   // [2][K]
+  const int tid = threadIdx.x;
+  const int dvec = d / 4;
+  const bool is_lk = tid >= lk_base && tid < lk_base + 32;
+  const int lane = tid - lk_base;
+  auto lookup = [&](int64_t row, int buf) {  // (lookup warp only)
+    int32_t* s_nbr = s_nbr_all + buf * K;
+    float* s_dt = s_dt_all + buf * K;
+    const double tq = q_time[period ? row % period : row];
+    const int64_t node = lk.q_node.at(row);
+    int64_t first = 0;
+    int take = 0;
+    if (node < 0 || node >= lk.num_rows) {
+      if (lane == 0 && lk.err_flag) atomicOr(lk.err_flag, LSTEP_FLAG_NODE_OUT_OF_RANGE);
+    } else {
+      warp_recent_range(lk.indptr, lk.c_t, node, tq, K, lane, first, take);
+    }
+    const int pad = K - take;
+    for (int k = lane; k < K; k += 32) {
+      int32_t n = 0;
+      float tt = 0.f;
+      if (k >= pad) {
+        const int64_t e = first + (k - pad);
+        n = lk.c_nbr[e];
+        tt = (float)lk.c_t[e];  // the sampler returns fp32 times (utils.py:166,208)
+      }
+      s_nbr[k] = n;
+      s_dt[k] = (float)(tq - (double)tt);  // f64 - f32 promotes to f64, then .float() (LSTEP.py:228-230)
+    }
+  };
+  if (is_lk && first_row < n_rows) lookup(first_row, 0);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t row = first_row; row < n_rows; row += row_stride, buf ^= 1) {
+    const int32_t* s_nbr = s_nbr_all + buf * K;
+    const float* s_dt = s_dt_all + buf * K;
+    if (is_lk) {
+      if (row + row_stride < n_rows) lookup(row + row_stride, buf ^ 1);
+    } else {
+      if (tid < tf_threads) {
+        for (int f = tid; f < t; f += tf_threads) {
+          const float w = tw[f];
+          float acc = 0.f;
+          for (int k = 0; k < K; ++k)
+            if (s_nbr[k] != 0) acc += time_feature(s_dt[k], w);
+          S[row * ldS + d + f] = acc;
+        }
+      }
+      if (tid >= t_pad && tid - t_pad < dvec) {
+        if (late_wait) pdl_wait();
+        const int cv = tid - t_pad;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int k = 0;
+        for (; k + 10 <= K; k += 10) {
+          float4 v[10];
+#pragma unroll
+          for (int u = 0; u < 10; ++u) v[u] = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k + u] * d) + cv);
+#pragma unroll
+          for (int u = 0; u < 10; ++u) {
+            acc.x += v[u].x;
+            acc.y += v[u].y;
+            acc.z += v[u].z;
+            acc.w += v[u].w;
+          }
+        }
+        for (; k + 4 <= K; k += 4) {
+          float4 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k + u] * d) + cv);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            acc.x += v[u].x;
+            acc.y += v[u].y;
+            acc.z += v[u].z;
+            acc.w += v[u].w;
+          }
+        }
+        for (; k < K; ++k) {
+          const float4 v = ld_dep(reinterpret_cast<const float4*>(pe + (int64_t)s_nbr[k] * d) + cv);
+          acc.x += v.x;
+          acc.y += v.y;
+          acc.z += v.z;
+          acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(S + row * ldS)[cv] = acc;
+      }
+    }
+    __syncthreads();  // buf is consumed and buf ^ 1 is filled: swap
+  }
+}
+
 // dpe[nbr[i,k], :] += dS[i, :d]   (training only; fp32 atomics)
 
 // phase A: one CTA per batch node. Threads [0,t): time frequencies; [t_pad, t_pad+d/4): PE columns.

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict_
                                                         const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                                         const double* __restrict__ times, int64_t n_edges, float tc,
                                                         const float* __restrict__ tw_u, float* __restrict__ A, int64_t lda,
-                                                        int32_t* __restrict__ counters) {
+                                                        int32_t* __restrict__ counters, int lk_base) {
   // The kernel in front (the DFT filter, launched with a late trigger: this kernel is resident only after
   // everything before the filter has completed) writes the table and nothing else this kernel touches. Lookups,
   // edge scans and all cosines therefore run BEFORE the dependency wait, next to the HBM-bound filter; only the
@@ -57,10 +57,14 @@ __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict_
 #ifdef LSTEP_TIMELINE
   if (threadIdx.x == 0) atomicMax(&g_timeline[((int)blockIdx.x < grid_q ? 9 : 10) * 4 + 2], gtimer());  // last CTA START (nbr / edge)
 #endif
-  if ((int)blockIdx.x < grid_q)
-    nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, true, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk,
-                                t_pad < t ? t_pad : t);
-  else
+  // lk_base > 0: the CTAs walk several query rows each; the warp at threads [lk_base, lk_base + 32) looks one row ahead
+  if ((int)blockIdx.x < grid_q) {
+    if (lk_base > 0)
+      nbr_aggregate_rows_piped(blockIdx.x, grid_q, true, pe, q_time, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk, t_pad < t ? t_pad : t, lk_base);
+    else
+      nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, true, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk,
+                                  t_pad < t ? t_pad : t);
+  } else
     edge_aggregate_rows((int64_t)blockIdx.x - grid_q, (int64_t)gridDim.x - grid_q, (int)blockIdx.x == grid_q, true, pe, ids, n_ids, src, dst,
                         times, n_edges, tc, tw_u, d, t, t_pad_e, A, lda, counters);
 #ifdef LSTEP_TIMELINE
@@ -297,12 +301,17 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
   if (first_half && !no_fuse && rows > 0 && n_a > 0 && n_edges > 0 && vec_ok && t == mlp_upd->t && d == mlp_upd->d) {
     update_ws_phase_a(w.update, n_ids, n_edges, K, d, t, s->V1, &A, &ldA, &counters, &new_rows);
     const int64_t cap = (int64_t)num_sms() * 16;
-    const int grid_q = (int)(rows < cap ? rows : cap), grid_e = (int)(n_a < cap ? n_a : cap);
-    const size_t smem = std::max((size_t)K * 8, (size_t)threads * kSegPerThread * 8 + 32 * 4);
+    // more query rows than one launch has CTAs for (B = 2000): one wave of CTAs with a look-ahead lookup warp each (gather_pipe)
+    const bool piped = tuning().gather_pipe != 0 && !narrow && rows > cap && threads + 32 <= 512;
+    const int threads_l = piped ? threads + 32 : threads;
+    const int64_t cap_q = piped ? (int64_t)num_sms() * (2048 / threads_l) : cap;
+    const int grid_q = (int)(rows < cap_q ? rows : cap_q), grid_e = (int)(n_a < cap ? n_a : cap);
+    const size_t smem = std::max((size_t)K * 8 * (piped ? 2 : 1), (size_t)threads_l * kSegPerThread * 8 + 32 * 4);
     if (smem <= 48 * 1024) {
       LookupArgs lk{csr->indptr, csr->nbr, csr->t, csr->num_rows, q, err_flag};
-      launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads), smem, st, s->cur, tq_q, rows, K, mlp_nbr->tw, d, t, t_pad,
-               t_pad_e, w.S, w.lda, q_rows, lk, grid_q, ids_a, n_a, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters);
+      launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads_l), smem, st, s->cur, tq_q, rows, K, mlp_nbr->tw, d, t, t_pad,
+               t_pad_e, w.S, w.lda, q_rows, lk, grid_q, ids_a, n_a, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters,
+               piped ? threads : 0);
       if ((rc = check_launch("gather_ab")) != LSTEP_OK) return rc;
       prof_mark(st, kProfGather);
       edges_done = true;

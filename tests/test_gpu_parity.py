@@ -1014,6 +1014,47 @@ def test_identical_query_sets_are_computed_once_with_identical_results(torch_cud
         assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
 
 
+def test_piped_multi_row_gather_is_bit_identical(torch_cuda):
+    """B = 2000 steps have more query rows (3 distinct sets x 2000) than the fused gather launch has CTAs: its CTAs then walk several
+    rows each with an extra warp looking one row ahead (nbr_aggregate_rows_piped, csrc/gather_bodies.cuh). Outputs, tables and
+    histories must be bit-identical to the one-lookup-then-work form (option gather_pipe = 0), with and without query dedup."""
+    torch = torch_cuda
+    from harness import build_dropin
+    from lstep_b200 import NeighborSampler, PEStream, _lib
+    lib = _lib.load()
+    B = 2000
+    g = synth.make_graph("flights", seed=2, num_edges=60_000)
+    V, d, T, K = g.num_nodes, 172, 100, 20
+    s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
+    lstep = build_dropin("fullu", g, s, 172, d, 100, T, K)[0].eval()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    hist = torch.randn((V + 1, T, d), device="cuda", generator=gen) * 0.2
+    e0 = g.num_edges - 3 * B - 11  # ragged last batch
+    neg = torch.from_numpy(np.random.default_rng(1).integers(1, V + 1, g.num_edges - e0).astype(np.int64)).cuda()
+    res = {}
+    try:
+        for dedup in (1, 0):
+            for pipe in (1, 0):
+                _lib.check(lib.lstep_set_option(b"query_dedup", dedup), "opt")
+                _lib.check(lib.lstep_set_option(b"gather_pipe", pipe), "opt")
+                st = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=hist, start=e0)
+                outs = []
+                for b in range(st.num_batches):
+                    lo, hi, _, _ = st.batch_arrays(b)
+                    sv = st.src[lo:hi]
+                    outs.append(st.step(b, [sv, st.dst[lo:hi], sv, neg[lo - e0:hi - e0]]).clone())
+                st.check_errors()
+                res[(dedup, pipe)] = (outs, st.cur.clone(), st.export_history())
+    finally:
+        lib.lstep_set_option(b"query_dedup", 1)
+        lib.lstep_set_option(b"gather_pipe", 1)
+    ref = res[(1, 0)]
+    for key, got in res.items():
+        for a, b_ in zip(ref[0], got[0]):
+            assert torch.equal(a, b_), key
+        assert torch.equal(ref[1], got[1]) and torch.equal(ref[2], got[2]), key
+
+
 @pytest.mark.parametrize("world", [1, 3])
 def test_replicated_table_sharded_changelog_matches_single_gpu_changelog(torch_cuda, world):
     """Same layout with the owners' history kept as a change log: every replica's table, each rank's share of the outputs and
