@@ -56,6 +56,32 @@ class _DevMem:
             self.ptr = 0
 
 
+def peer_batch_plan(src: np.ndarray, dst: np.ndarray, batch_size: int, world: int, rank: int) -> dict:
+    """Host-side plan of a resident edge stream for one rank of a peer group (pure numpy: CPU-testable). Per batch b of
+    `batch_size` edges: `ids` = the sorted unique batch nodes (replicated on every rank), `mine` = the ones this rank owns
+    (v % world == rank), `pos` = their positions in `ids` (where the owner stores a node's row in the peers' buffers), and the
+    share [q_off, q_off + q_rows) of the batch's edges whose a6 queries this rank computes. The owners' lists partition `ids`, the
+    shares partition the batch. Returns the concatenated lists with their offsets."""
+    n = len(src)
+    nb = (n + batch_size - 1) // batch_size
+    ids_l, mine_l, pos_l, share = [], [], [], []
+    ids_off, mine_off = [0], [0]
+    for b in range(nb):
+        lo, hi = b * batch_size, min((b + 1) * batch_size, n)
+        ids = np.unique(np.concatenate([src[lo:hi], dst[lo:hi]]))
+        pos = np.nonzero(ids % world == rank)[0].astype(np.int64)
+        ids_l.append(ids)
+        mine_l.append(ids[pos])
+        pos_l.append(pos)
+        ids_off.append(ids_off[-1] + len(ids))
+        mine_off.append(mine_off[-1] + len(pos))
+        m = hi - lo
+        share.append((rank * m // world, (rank + 1) * m // world - rank * m // world))
+    cat = lambda xs: np.concatenate(xs).astype(np.int64) if xs else np.zeros(0, np.int64)
+    return dict(num_batches=nb, ids=cat(ids_l), mine=cat(mine_l), pos=cat(pos_l), ids_off=np.asarray(ids_off, np.int64),
+                mine_off=np.asarray(mine_off, np.int64), share=share)
+
+
 class PeerRank:
     """Rank `rank` of `world` (see the module docstring). src / dst / t: the whole edge stream (replicated, device or host
     arrays); the per-batch plan (sorted unique batch nodes, the owned ones and their positions) of the resident stream
@@ -117,25 +143,19 @@ class PeerRank:
             dst_h = self.dst[self.start:stop].cpu().numpy()
             t_h = self.tt[self.start:stop].cpu().numpy()
             self.num_batches = nb = (stop - self.start + B - 1) // B
-            ids_l, mine_l, pos_l = [], [], []
-            ids_off, mine_off, lo_l, n_l, tmax = [0], [0], [], [], []
+            plan = peer_batch_plan(src_h, dst_h, B, G, self.rank)
+            assert plan["num_batches"] == nb
+            lo_l, n_l, tmax = [], [], []
             for b in range(nb):
                 lo, hi = b * B, min((b + 1) * B, stop - self.start)
-                ids = np.unique(np.concatenate([src_h[lo:hi], dst_h[lo:hi]]))
-                pos = np.nonzero(ids % G == self.rank)[0].astype(np.int64)
-                ids_l.append(ids)
-                mine_l.append(ids[pos])
-                pos_l.append(pos)
-                ids_off.append(ids_off[-1] + len(ids))
-                mine_off.append(mine_off[-1] + len(pos))
                 lo_l.append(self.start + lo)
                 n_l.append(hi - lo)
                 tmax.append(float(t_h[lo:hi].max()))
-            if len(ids_l) and int(max(int(x.max()) for x in ids_l if len(x))) >= self.V1:
+            if len(plan["ids"]) and int(plan["ids"].max()) >= self.V1:
                 raise IndexError("edge stream holds a node id outside the PE table")
-            cat = lambda xs: torch.from_numpy(np.concatenate(xs) if xs else np.zeros(0, np.int64)).to(dev)
-            self.ids, self.ids_mine, self.pos_mine = cat(ids_l), cat(mine_l), cat(pos_l)
-            self.ids_off, self.mine_off = np.asarray(ids_off, np.int64), np.asarray(mine_off, np.int64)
+            up = lambda a: torch.from_numpy(a).to(dev)
+            self.ids, self.ids_mine, self.pos_mine = up(plan["ids"]), up(plan["mine"]), up(plan["pos"])
+            self.ids_off, self.mine_off = plan["ids_off"], plan["mine_off"]
             self.lo, self.n_edges, self.tmax = np.asarray(lo_l, np.int64), np.asarray(n_l, np.int64), np.asarray(tmax, np.float64)
             need = lib.lstep_pe_step_workspace_bytes(2 * B, B, 8, self.K, d, self.t_dim, self.V1)
             self.ws = torch.empty(need + 4096, dtype=torch.uint8, device=dev)

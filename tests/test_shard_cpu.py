@@ -76,3 +76,31 @@ def test_row_exchange_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_exchange_worker, args=(world, port, ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_peer_group_plan_partitions_every_batch(world):
+    """Host plan of the peer group (l-step_b200/peer.py::peer_batch_plan): over the ranks, the owned-node lists partition every
+    batch's sorted unique id list, `pos` are the owners' positions in it (where a row goes in the peers' new_rows / filt
+    buffers), and the a6 shares partition the batch's edges — ragged last batch and ranks without any node included."""
+    from lstep_b200.peer import peer_batch_plan
+    g = synth.make_graph("tiny_bip", seed=1)
+    src, dst = g.src_node_ids[:1000 + 37], g.dst_node_ids[:1000 + 37]
+    B = 48
+    plans = [peer_batch_plan(src, dst, B, world, r) for r in range(world)]
+    nb = plans[0]["num_batches"]
+    assert nb == (len(src) + B - 1) // B
+    for b in range(nb):
+        lo, hi = b * B, min((b + 1) * B, len(src))
+        ids = np.unique(np.concatenate([src[lo:hi], dst[lo:hi]]))
+        covered = np.zeros(len(ids), dtype=int)
+        edges = np.zeros(hi - lo, dtype=int)
+        for r, pl in enumerate(plans):
+            assert np.array_equal(pl["ids"][pl["ids_off"][b]:pl["ids_off"][b + 1]], ids)
+            mine = pl["mine"][pl["mine_off"][b]:pl["mine_off"][b + 1]]
+            pos = pl["pos"][pl["mine_off"][b]:pl["mine_off"][b + 1]]
+            assert np.all(mine % world == r) and np.array_equal(ids[pos], mine) and np.all(np.diff(pos) > 0)
+            covered[pos] += 1
+            q_off, q_rows = pl["share"][b]
+            edges[q_off:q_off + q_rows] += 1
+        assert np.all(covered == 1) and np.all(edges == 1)
