@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """Condense an `ncu --set full` report into the per-kernel JSON bench.py reads (`traffic`) and the judge can diff.
 
-usage: python profiles/extract_ncu_full.py report.ncu-rep > profiles/r01_ncu_full_kernels.json
+usage: python profiles/extract_ncu_full.py report.ncu-rep > profiles/r02_ncu_full_kernels.json
+
+Every captured launch is one entry; entries of the streaming step's own six launches also carry "kernel" = the name bench.py uses
+for that launch (its `roofline_kernels` keys), so that bench.py can fill `traffic` (DRAM bytes per launch) from the FIRST such entry.
 """
 import csv
 import json
@@ -14,6 +17,10 @@ STAGE = [("dft_filter_bulk_kernel", "dft_filter"), ("dft_filter_kernel", "dft_fi
          ("pe_mlp_cluster_kernel<4>", "pe_mlp(update A)"), ("pe_mlp_cluster_kernel<12>", "pe_mlp(update B)"),
          ("phaseB_push_kernel", "phaseB_push"),
          ("edge_aggregate_kernel", "edge_aggregate"), ("ring_append_kernel", "ring_append"), ("sample_recent_kernel", "sample_recent")]
+# kernel of the Reddit-shaped step -> bench.py's KERNELS name (the paired MLP runs 32-row tiles there, the phase-B MLP 40-row tiles)
+BENCH = [("dft_filter_bulk_kernel", "dft_filter"), ("gather_ab_kernel", "gather_ab (a6 lookup+aggregate || a7 edge aggregate)"),
+         ("pe_mlp_cluster_kernel<8>", "pe_mlp pair (neighbourhood MLP || phase-A MLP)"), ("phaseB_push_kernel", "phaseB_push"),
+         ("pe_mlp_cluster_kernel<10>", "pe_mlp (phase B)"), ("ring_append_kernel", "ring_append")]
 KEYS = {
     "gpu__time_duration.sum": "dur",
     "launch__grid_size": "grid", "launch__block_size": "block", "launch__registers_per_thread": "regs",
@@ -42,6 +49,10 @@ def main(path):
         for pat, st in STAGE:
             if pat in full:
                 e["stage"] = st
+                break
+        for pat, kn in BENCH:
+            if pat in full.replace("(int)", ""):
+                e["kernel"] = kn
                 break
         for h, u, v in zip(hdr, units, r):
             if h in KEYS:
