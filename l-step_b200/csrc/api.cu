@@ -47,6 +47,7 @@ const OptName kOpts[] = {
     {"host_memcpy", &Tuning::host_memcpy, "LSTEP_HOST_MEMCPY", 1},
     {"query_dedup", &Tuning::query_dedup, "LSTEP_NO_QUERY_DEDUP", 0},
     {"gather_pipe", &Tuning::gather_pipe, "LSTEP_NO_GATHER_PIPE", 0},
+    {"cos_spread", &Tuning::cos_spread, "LSTEP_COS_SPREAD", 1},
     {"mlp_umma", &Tuning::mlp_umma, "LSTEP_NO_MLP_UMMA", 0},
     {"mlp_umma_min_rows", &Tuning::mlp_umma_min_rows, "LSTEP_MLP_UMMA_MIN_ROWS", -1},
     {"profile", &Tuning::profile, nullptr, 0},

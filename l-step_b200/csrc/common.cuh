@@ -31,6 +31,8 @@ struct Tuning {
   int host_memcpy = 0;        // cudaMemcpyAsync instead of the copy-in kernel in the host-fed step (LSTEP_HOST_MEMCPY)
   int query_dedup = 1;        // identical query sets of a step are computed once                  (LSTEP_NO_QUERY_DEDUP)
   int gather_pipe = 1;        // multi-row gather CTAs with a look-ahead lookup warp (B = 2000)     (LSTEP_NO_GATHER_PIPE)
+  int cos_spread = 0;         // a query row's K * t cosines spread over all threads of its CTA     (LSTEP_COS_SPREAD; measured SLOWER:
+                              // gather 16.4 -> 18.6 us at B=200, 68.6 -> 88.1 us at B=2000 — the cosine phase is issue bound, not chain bound)
   int mlp_umma = 1;           // tcgen05 tensor-core MLP for launches with >= mlp_umma_min_rows rows (LSTEP_NO_MLP_UMMA)
   int mlp_umma_min_rows = 1536;  //                                                                (LSTEP_MLP_UMMA_MIN_ROWS)
   int profile = 0;            // lstep_step_profile(): CUDA events around every kernel of the streaming step

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict_
                                                         const int64_t* __restrict__ src, const int64_t* __restrict__ dst,
                                                         const double* __restrict__ times, int64_t n_edges, float tc,
                                                         const float* __restrict__ tw_u, float* __restrict__ A, int64_t lda,
-                                                        int32_t* __restrict__ counters, int lk_base) {
+                                                        int32_t* __restrict__ counters, int lk_base, int spread) {
   // The kernel in front (the DFT filter, launched with a late trigger: this kernel is resident only after
   // everything before the filter has completed) writes the table and nothing else this kernel touches. Lookups,
   // edge scans and all cosines therefore run BEFORE the dependency wait, next to the HBM-bound filter; only the
@@ -60,10 +60,11 @@ __global__ void __launch_bounds__(512) gather_ab_kernel(const float* __restrict_
   // lk_base > 0: the CTAs walk several query rows each; the warp at threads [lk_base, lk_base + 32) looks one row ahead
   if ((int)blockIdx.x < grid_q) {
     if (lk_base > 0)
-      nbr_aggregate_rows_piped(blockIdx.x, grid_q, true, pe, q_time, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk, t_pad < t ? t_pad : t, lk_base);
+      nbr_aggregate_rows_piped(blockIdx.x, grid_q, true, pe, q_time, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk, t_pad < t ? t_pad : t, lk_base,
+                               spread);
     else
       nbr_aggregate_rows<4, true>(blockIdx.x, grid_q, true, pe, q_time, nullptr, nullptr, n_rows, K, tw_q, d, t, t_pad, S, ldS, period, lk,
-                                  t_pad < t ? t_pad : t);
+                                  t_pad < t ? t_pad : t, spread);
   } else
     edge_aggregate_rows((int64_t)blockIdx.x - grid_q, (int64_t)gridDim.x - grid_q, (int)blockIdx.x == grid_q, true, pe, ids, n_ids, src, dst,
                         times, n_edges, tc, tw_u, d, t, t_pad_e, A, lda, counters);
@@ -306,12 +307,14 @@ int pe_step_core_ex(const lstep_pe_stream* s, const lstep_csr* csr, const int64_
     const int threads_l = piped ? threads + 32 : threads;
     const int64_t cap_q = piped ? (int64_t)num_sms() * (2048 / threads_l) : cap;
     const int grid_q = (int)(rows < cap_q ? rows : cap_q), grid_e = (int)(n_a < cap ? n_a : cap);
-    const size_t smem = std::max((size_t)K * 8 * (piped ? 2 : 1), (size_t)threads_l * kSegPerThread * 8 + 32 * 4);
+    // the K * t cosines of a query row spread over all threads of its CTA (cos_spread; needs K * t floats of shared memory)
+    const bool spread = tuning().cos_spread != 0 && !narrow && (size_t)K * t * 4 <= 16 * 1024;
+    const size_t smem = std::max((size_t)K * 8 * (piped ? 2 : 1) + (spread ? (size_t)K * t * 4 : 0), (size_t)threads_l * kSegPerThread * 8 + 32 * 4);
     if (smem <= 48 * 1024) {
       LookupArgs lk{csr->indptr, csr->nbr, csr->t, csr->num_rows, q, err_flag};
       launch_k(gather_ab_kernel, dim3((unsigned)(grid_q + grid_e)), dim3(threads_l), smem, st, s->cur, tq_q, rows, K, mlp_nbr->tw, d, t, t_pad,
                t_pad_e, w.S, w.lda, q_rows, lk, grid_q, ids_a, n_a, src, dst, tq, n_edges, (float)current_time, mlp_upd->tw, A, ldA, counters,
-               piped ? threads : 0);
+               piped ? threads : 0, spread ? 1 : 0);
       if ((rc = check_launch("gather_ab")) != LSTEP_OK) return rc;
       prof_mark(st, kProfGather);
       edges_done = true;

@@ -1014,15 +1014,17 @@ def test_identical_query_sets_are_computed_once_with_identical_results(torch_cud
         assert torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
 
 
-def test_piped_multi_row_gather_is_bit_identical(torch_cuda):
-    """B = 2000 steps have more query rows (3 distinct sets x 2000) than the fused gather launch has CTAs: its CTAs then walk several
-    rows each with an extra warp looking one row ahead (nbr_aggregate_rows_piped, csrc/gather_bodies.cuh). Outputs, tables and
-    histories must be bit-identical to the one-lookup-then-work form (option gather_pipe = 0), with and without query dedup."""
+@pytest.mark.parametrize("B", [200, 2000])
+def test_gather_variants_are_bit_identical(torch_cuda, B):
+    """Two structural variants of the step's fused gather must not change a bit of the outputs, tables and histories:
+    cos_spread (an experiment, off by default: measured slower) — a query row's K x t cosines are spread over all threads of its
+    CTA and parked in shared memory, the frequency threads add them in the original order k = 0 .. K-1; gather_pipe — at B = 2000 (more query rows than the launch has CTAs)
+    the CTAs walk several rows each with an extra warp looking one row ahead (nbr_aggregate_rows_piped). With and without
+    query dedup, ragged last batch."""
     torch = torch_cuda
     from harness import build_dropin
     from lstep_b200 import NeighborSampler, PEStream, _lib
     lib = _lib.load()
-    B = 2000
     g = synth.make_graph("flights", seed=2, num_edges=60_000)
     V, d, T, K = g.num_nodes, 172, 100, 20
     s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V + 1)
@@ -1033,22 +1035,23 @@ def test_piped_multi_row_gather_is_bit_identical(torch_cuda):
     neg = torch.from_numpy(np.random.default_rng(1).integers(1, V + 1, g.num_edges - e0).astype(np.int64)).cuda()
     res = {}
     try:
-        for dedup in (1, 0):
-            for pipe in (1, 0):
-                _lib.check(lib.lstep_set_option(b"query_dedup", dedup), "opt")
-                _lib.check(lib.lstep_set_option(b"gather_pipe", pipe), "opt")
-                st = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=hist, start=e0)
-                outs = []
-                for b in range(st.num_batches):
-                    lo, hi, _, _ = st.batch_arrays(b)
-                    sv = st.src[lo:hi]
-                    outs.append(st.step(b, [sv, st.dst[lo:hi], sv, neg[lo - e0:hi - e0]]).clone())
-                st.check_errors()
-                res[(dedup, pipe)] = (outs, st.cur.clone(), st.export_history())
+        for dedup, pipe, spread in ((1, 0, 0), (1, 1, 0), (1, 0, 1), (1, 1, 1), (0, 1, 1), (0, 0, 0)):
+            _lib.check(lib.lstep_set_option(b"query_dedup", dedup), "opt")
+            _lib.check(lib.lstep_set_option(b"gather_pipe", pipe), "opt")
+            _lib.check(lib.lstep_set_option(b"cos_spread", spread), "opt")
+            st = PEStream(lstep, g.src_node_ids, g.dst_node_ids, g.node_interact_times, B, K, history=hist, start=e0)
+            outs = []
+            for b in range(st.num_batches):
+                lo, hi, _, _ = st.batch_arrays(b)
+                sv = st.src[lo:hi]
+                outs.append(st.step(b, [sv, st.dst[lo:hi], sv, neg[lo - e0:hi - e0]]).clone())
+            st.check_errors()
+            res[(dedup, pipe, spread)] = (outs, st.cur.clone(), st.export_history())
     finally:
         lib.lstep_set_option(b"query_dedup", 1)
         lib.lstep_set_option(b"gather_pipe", 1)
-    ref = res[(1, 0)]
+        lib.lstep_set_option(b"cos_spread", 0)
+    ref = res[(1, 0, 0)]
     for key, got in res.items():
         for a, b_ in zip(ref[0], got[0]):
             assert torch.equal(a, b_), key
