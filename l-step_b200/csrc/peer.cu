@@ -3,49 +3,52 @@
 // Layout. Every rank holds a REPLICA of the current PE table [V1, d] (6.9 GB at 10 M nodes) and of the temporal CSR, and
 // OWNS the nodes v with v % world == rank: their PE history (change log, csrc/changelog.cu) and every piece of work whose
 // result is a row of an owned node. Replicas are kept equal through PEER MEMORY (CUDA IPC mappings over NVLink / NVSwitch):
-// a rank READS the rows the other owners changed straight out of their change logs, and two flag barriers per step, also in
-// peer memory, order everything. No NCCL call, no staging copy, no host involvement, no data-dependent message size:
+// an owner copies the rows it changes, as contiguous blocks, into small fixed regions of every other rank (inbox, filt and
+// new_rows buffers), each rank scatters what it received into its own replica, and two flag barriers per step, also in
+// peer memory, order everything. No NCCL call, no host involvement, no data-dependent message size:
 //
-//     filter     owned batch nodes: history -> filtered row -> local table AND local filt buffer (at the node's position
-//                in the batch's id list)                                                           (1/world of the rows)
-//     ---------- barrier 1 + refresh (one launch): pull (a) the events of the previous step from every other owner's change
-//                log = the rows that step changed, (b) the other owners' filtered rows of this step, into the local replica
+//     filter     owned batch nodes: history -> filtered row -> local table AND every other rank's filt buffer (at the
+//                node's position in the batch's id list)                                           (1/world of the rows)
+//     ---------- barrier 1 + refresh (one launch): scatter into the local replica (a) the rows the previous step changed on
+//                the other ranks (this rank's inbox blocks), (b) the other owners' filtered rows of this step (filt buffer)
 //     gather     a6 lookup + aggregate of this rank's 1/world share of the query rows  ||  a7 edge aggregate of the owned
 //                batch nodes                                                                     (reads the local replica)
 //     MLP pair   neighbourhood MLP of the share -> outputs  ||  phase-A MLP of the owned batch nodes -> local new_rows
-//     bcast      new_rows[i] -> every rank's new_rows buffer at row pos_mine[i] (2.7 MB per step in total, contiguous)
+//     bcast      new_rows[i] -> every rank's new_rows buffer at row pos_mine[i] (2.7 MB per step in total)
 //     ---------- barrier 2: phase A's rows of ALL batch nodes are in every rank's new_rows buffer --------------------------
 //     push       lookup of ALL batch nodes (replicated: 4 k warp searches), accumulation for the OWNED destinations only
 //                (exact fixed point, csrc/update_push.cu); the owned batch nodes' phase-A rows go into the local table
 //     MLP (B)    owned destinations: table row <- row + tanh(mlp(aggregate))                      (local table)
-//     append     owned changed rows (owned batch nodes, owned destinations, row 0 on rank 0) become events of the change
-//                log — which is also what the other ranks pull after the next barrier 1
+//     append     owned changed rows (owned batch nodes, owned destinations, row 0 on rank 0) become events of the change log
+//     publish    the slot's events (count, node ids, rows) -> this rank's block in every other rank's inbox; in the native
+//                multi-step call on a side stream, next to the next step's filter
 //
 // Why two barriers are enough:
-//   * a rank writes only its OWN memory, except for the phase-A row broadcast and the flags. What others read of it:
-//     the change-log slot of step s (written by append(s), read after barrier 1 of step s+1, rewritten T steps later), the
-//     filt buffer (written by filter(s+1) before barrier 1 of s+1, read right after it, rewritten by filter(s+2), which
-//     follows barrier 2 of s+1 — announced by every rank only after its refresh of s+1), the new_rows buffer (written by
-//     bcast(s) before barrier 2 of s, read by push(s), rewritten by bcast(s+1), which follows barrier 1 of s+1 — announced
-//     by every rank only after its push(s)).
+//   * what a rank writes into another rank, and when it is read: its inbox block (written by publish(s), complete before this
+//     rank announces barrier 1 of s+1, read by the receiver's refresh of s+1, rewritten by publish(s+1), which follows barrier
+//     2 of s+1 — announced by every rank only after its refresh of s+1); the filt buffer (written by filter(s+1) before barrier
+//     1 of s+1, read by the refresh of s+1, rewritten by filter(s+2), which follows barrier 2 of s+1 likewise); the new_rows
+//     buffer (written by bcast(s) before barrier 2 of s, read by push(s), rewritten by bcast(s+1), which follows barrier 1 of
+//     s+1 — announced by every rank only after its push(s)).
 //   * between barrier 2 of a step and the next barrier 1 a rank touches only rows it owns (push applies owned phase-A rows,
 //     the phase-B MLP reads and writes owned destinations, the append reads owned rows); its replica is stale for the rows
 //     OTHER owners change in that interval, which it does not read before the next refresh.
 //   * the refresh writes disjoint rows in its two passes: rows changed by the previous step are skipped when they belong to
 //     the current batch (sorted id list, warp search) — their filtered row is newer.
-// Everything a rank reads remotely is a CONTIGUOUS block (an event slot, the filt buffer): scattered accesses to a multi-GB
-// peer mapping thrash the peer TLB (measured: 43 GB/s scattered against 500 GB/s contiguous, profiles/r02_peer_bw.txt);
-// the first version of this step stored changed rows directly into the other replicas and spent 200 us per step there.
+// Everything that crosses NVLink is a contiguous store into a small fixed region. Measured and dropped (profiles/
+// r02_peer_bw.txt, r02_scaleout_history.md): owners storing changed rows straight into the other 6.9 GB replicas (scattered
+// peer stores thrash the peer TLB: 43 GB/s against 500 GB/s contiguous; 200 us per step), and ranks PULLING the events out of
+// the owners' change logs instead of a publication (peer reads of a different, TLB-cold slot every step: 126 GB/s at 8 ranks).
 //
 // Results equal the single-GPU step's bit for bit: every row is computed by one rank from the same inputs with the same
 // kernels, and phase B's sums are exact 32.32 fixed point (independent of who adds what in which order).
 //
 // Barrier = flag exchange in peer memory: rank r announces epoch e by storing e into flags[g][r] of every rank g
-// (st.release.sys after a system-scope fence); a rank waits by polling its OWN flag block (ld.acquire.sys) until all
-// `world` entries are >= e. The wait is bounded (timeout_ms on the global timer): a missing peer raises
-// LSTEP_FLAG_PEER_TIMEOUT instead of hanging the device. The inserted kernels are programmatic dependent launches that wait
-// first and trigger second, so the successor's pre-wait work (the gather's lookups and cosines, the push kernel's lookups
-// and claims) runs while this rank waits for the others.
+// (st.release.sys after a system-scope fence; the kernels that store into peers fence their own stores too); a rank waits
+// by polling its OWN flag block (ld.acquire.sys) until all `world` entries are >= e. The wait is bounded (timeout_ms on the
+// global timer): a missing peer raises LSTEP_FLAG_PEER_TIMEOUT instead of hanging the device. The inserted kernels are
+// programmatic dependent launches that wait first and trigger second, so the successor's pre-wait work (the gather's
+// lookups and cosines, the push kernel's lookups and claims) runs while this rank waits for the others.
 #include <algorithm>
 #include <cstring>
 
