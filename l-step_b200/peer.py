@@ -181,7 +181,7 @@ class PeerRank:
         return tuple(getattr(self, m).ptr for m in self._SHARED)
 
     def connect_ipc(self, group=None):
-        """One process per GPU: exchange the CUDA IPC handles of the three peer-written blocks through torch.distributed and open
+        """One process per GPU: exchange the CUDA IPC handles of the four peer-written blocks through torch.distributed and open
         the other ranks' (cudaIpcOpenMemHandle enables peer access over NVLink)."""
         import torch.distributed as dist
         mine = (self.rank,) + tuple(getattr(self, m).handle() for m in self._SHARED)
