@@ -930,16 +930,19 @@ def test_tensor_core_mlp_matches_simt_mlp_and_float64(torch_cuda, tag, parity_lo
     parity_log[f"mlp_kernels/{tag}"] = worst
 
 
-def test_stress_2000_steps_pdl_vs_plain_launches_bit_identical(torch_cuda):
+@pytest.mark.parametrize("zipf_s", [0.8, 1.2], ids=["zipf0.8", "hubs-zipf1.2"])
+def test_stress_2000_steps_pdl_vs_plain_launches_bit_identical(torch_cuda, zipf_s):
     """the step depends on work done BEFORE the dependency wait under programmatic dependent launch, on L2-coherent
     loads of predecessor data and on inter-CTA claims in the push kernel. 2000 consecutive steps at the Reddit shape
     (full graph, B = 200, T = 100) with the PDL chain and the same 2000 steps with plain stream launches (kernel
-    boundaries between all kernels) must leave bit-identical tables, histories and outputs."""
+    boundaries between all kernels) must leave bit-identical tables, histories and outputs. zipf 1.2 (SURVEY §8(d)'s skew): a
+    batch collapses onto ~160 nodes, so the push kernel's claims, its same-destination fixed-point reductions and the padding-row
+    partial sums are contended several times harder than in the bench's stream."""
     torch = torch_cuda
     from lstep_b200 import NeighborSampler, PEStream, _lib
     import bench
     lib = _lib.load()
-    g = synth.make_graph("reddit", seed=0)
+    g = synth.make_graph("reddit", seed=0, zipf_s=zipf_s)
     V1, B, K = g.num_nodes + 1, 200, 20
     s = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V1)
     model = bench.make_params_model(g, s, torch.device("cuda"))
