@@ -39,6 +39,7 @@ WORKLOADS = {  # name -> (batch size, K)  (BASELINE.json configs; K=20 is the re
     "enron": (200, 20), "wikipedia": (200, 20), "reddit": (200, 20), "flights": (2000, 20), "tiny_bip": (50, 20),
 }
 D, T_DIM, T_HIST, C_CALLS = 172, 100, 100, 4
+ZIPF_S = 0.8  # endpoint skew of the synthetic stream (--zipf; DESIGN §10: SURVEY §8(d) names 1.2, the hub-heavy regime)
 
 
 def log(*a):
@@ -130,8 +131,9 @@ def make_params_model(graph, sampler, device):
 
 def workload_config(workload, g, B, K, world=1):
     """The `config` both arms print (same string for the CUDA arm and the reference arm: the driver compares them)."""
+    skew = "" if ZIPF_S == 0.8 else f", endpoint skew zipf s={ZIPF_S}"
     return {"workload": f"{workload}-shaped synthetic temporal graph, V={g.num_nodes}, E={g.num_edges}, B={B}, K={K}, "
-                        f"T={T_HIST}, d={D}, t={T_DIM}, C={C_CALLS} neighbourhood calls/batch (eval loop)",
+                        f"T={T_HIST}, d={D}, t={T_DIM}, C={C_CALLS} neighbourhood calls/batch (eval loop){skew}",
             "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (path does not shard at this size)",
             "l2_policy": f"inputs larger than L2: PE history {(g.num_nodes + 1) * T_HIST * D * 4 / 1e6:.0f} MB, a different node set is read each step"}
 
@@ -151,7 +153,7 @@ def run_ours(args, rank, world, own_pg=True):
     lib = _lib.load()
     assert lib.lstep_device_ok() == 1
     B, K = WORKLOADS[args.workload]
-    g = synth.make_graph(args.workload, seed=0 + rank)  # replicas: each rank its own stream of the same shape
+    g = synth.make_graph(args.workload, seed=0 + rank, zipf_s=ZIPF_S)  # replicas: each rank its own stream of the same shape
     V1 = g.num_nodes + 1
     t0 = time.time()
     sampler = NeighborSampler.from_edges(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times, "recent", num_rows=V1)
@@ -654,7 +656,7 @@ def oracle_setup(workload, B, K, n_batches, seed=0):
     from oracle import lstep_oracle as orc
     full = synth.SHAPES[workload]["num_edges"]
     n_edges = min(full, max(40_000, (n_batches + 4) * B * 4))
-    g = synth.make_graph(workload, seed=seed, num_edges=n_edges)
+    g = synth.make_graph(workload, seed=seed, num_edges=n_edges, zipf_s=ZIPF_S)
     adj = orc.build_adjacency(g.src_node_ids, g.dst_node_ids, g.edge_ids, g.node_interact_times)
     p = orc.init_params(D, T_DIM, T_HIST, seed=0)
     V1 = g.num_nodes + 1
@@ -698,7 +700,7 @@ class ReferenceArm:
         ref = self.ref
         torch.set_num_threads(os.cpu_count())
         self.torch, self.B, self.K = torch, B, K
-        self.g = g = synth.make_graph(workload, seed=0)
+        self.g = g = synth.make_graph(workload, seed=0, zipf_s=ZIPF_S)
         V1 = g.num_nodes + 1
         t0 = time.time()
         self.sampler = ref.get_neighbor_sampler(ref.Data(g.src_node_ids, g.dst_node_ids, g.node_interact_times, g.edge_ids, g.labels),
@@ -824,11 +826,11 @@ def run_reference(args, rank, world):
             if i >= warm:
                 tot += dt
                 edges += B
-        g = synth.make_graph(workload, seed=0, num_edges=1000)
+        g = synth.make_graph(workload, seed=0, num_edges=1000, zipf_s=ZIPF_S)
         g_full = synth.SHAPES[workload]
         sample = f"{steps} batches of {B} edges on the first {n_edges} edges of the synthetic stream (oracle port, numpy + BLAS threads)"
     value = edges / tot
-    cfg = workload_config(workload, arm.g if arm is not None else synth.make_graph(workload, seed=0), B, K, 1)
+    cfg = workload_config(workload, arm.g if arm is not None else synth.make_graph(workload, seed=0, zipf_s=ZIPF_S), B, K, 1)
     out = {"impl": "reference", "metric": "temporal edges/sec through PE update+aggregation; % HBM roofline", "value": value,
            "unit": "edges/s", "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": tot / steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -876,8 +878,11 @@ def main():
     ap.add_argument("--no-scaleout", action="store_true", help="N = 1: skip the scale-out sample that rides along with the headline run")
     ap.add_argument("--scaleout-timeout", type=float, default=420.0, help="seconds the scale-out sample may take at N > 1")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--zipf", type=float, default=0.8, help="endpoint skew of the synthetic stream (0.8: the headline workload; 1.2: hub-heavy)")
     ap.add_argument("--cpu-batches", type=int, default=40)
     args = ap.parse_args()
+    global ZIPF_S
+    ZIPF_S = float(args.zipf)
     if args.steps is None:
         args.steps = 1000 if args.workload != "scaleout" else 100
     if args.warmup is None:
