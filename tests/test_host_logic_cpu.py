@@ -134,3 +134,28 @@ def test_header_cites_the_reference_interface_it_replaces():
     for cite in ("utils/utils.py", "models/LSTEP.py", "models/modules.py"):
         assert cite in text, cite
     assert len(re.findall(r"(?:LSTEP|utils|modules|evaluate_model_utils)\.py:\d+", text)) >= 10
+
+
+def test_reference_arm_under_torchrun_prints_one_line_from_rank_0():
+    """bench.py --impl reference launched like the driver launches it for N > 1 (torchrun, one process per rank): rank 0 alone
+    runs the reference's CPU path and prints ONE JSON line, the other ranks exit 0 without work. CPU only (gloo is not even
+    needed: the reference arm creates no process group)."""
+    import json
+    import subprocess
+    import sys
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+           "--warmup", "1", "--workload", "tiny_bip"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["steps"] == 2 and d["warmup"] == 1
+    assert d["unit"] == "edges/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
