@@ -130,3 +130,21 @@ def test_free_running_replay_pe_checksums(tag):
     assert worst_ck < 1e-5, worst_ck
     if n_batches == len(z["ap"]):
         check_updated_table(cur, z["last_pe"], "final table", strict=True)  # (tag small: 60 steps of the small model)
+
+
+def test_committed_goldens_are_what_the_unmodified_reference_produces():
+    """The pin of the pin: tests/golden/verify_golden.py re-runs the UNMODIFIED reference (build container only) and compares
+    every regenerated array bit for bit with the committed fixture — sampler triples, module-boundary outputs in both weight
+    regimes, per-batch negatives, the feature branch (491 arrays; the replays and the run bracket, ~2 min more, are covered by
+    running the script without arguments). Skipped where /root/reference does not exist."""
+    import os
+    import subprocess
+    import sys
+    import pytest
+    if not os.path.isdir(os.environ.get("LSTEP_REFERENCE", "/root/reference")):
+        pytest.skip("no reference checkout here")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "golden", "verify_golden.py"), "sampler", "module", "negatives",
+                          "feature"], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert "0 mismatches" in out.stdout
